@@ -1,0 +1,131 @@
+"""Drop-in mirror of ``FastS.PyTree`` for the hot path (reference: Fast/FastS/FastS/PyTree.py).
+
+``warmup`` (:341-545), ``_compute`` (:42-236), ``_applyBC`` (:1158), ``_fillGhostcells`` (:1162),
+``display_temporal_criteria`` (:2039) keep the reference's names, arguments and tree side effects; the C
+extension modules they call (``fasts``, ``fastc``) are replaced by ``fast_b200.fasts`` / ``fast_b200.fastc``,
+thin ctypes layers over the CUDA C-ABI (include/fastb200.h).  There is no CPU fallback: without a GPU or
+without the built library these calls raise.
+"""
+import numpy
+
+from ..FastC import PyTree as FastC
+from ..FastC.PyTree import Internal
+from .. import VSHARE, geom
+
+__version__ = "0.1-b200"
+
+
+def _zone_arrays(z):
+    own = Internal.getNodeFromName1(z, '.Solver#ownData')
+    pi = Internal.getNodeFromName1(own, 'Parameter_int')[1]
+    pr = Internal.getNodeFromName1(own, 'Parameter_real')[1]
+    gc = Internal.getNodeFromName1(z, Internal.__GridCoordinates__)
+    xyz = [Internal.getNodeFromName1(gc, n)[1] for n in ('CoordinateX', 'CoordinateY', 'CoordinateZ')]
+    return own, pi, pr, xyz
+
+
+def _warmup_host(t, tc=None, Padding=None, verbose=0):
+    """Host half of warmup (PyTree.py:341-470): option freezing, sizes and mesh family (integer part of
+    fasts.allocate_metric), BC compaction, primitive variables, contiguous time levels.  No GPU needed."""
+    FastC._buildOwnData(t, Padding)
+    zones = Internal.getZones(t)
+    for z in zones:
+        own, pi, pr, xyz = _zone_arrays(z)
+        geom.fill_sizes(pi, *xyz)
+        Internal.getNodeFromName1(own, 'type_zone')[1] = numpy.array([pi[VSHARE.ITYPZONE]], Internal.E_NpyInt)
+        if verbose > 0:
+            names = {0: '3D curvilinear', 1: '3D homogenous k direction with constant step',
+                     2: '3D Cartesian with constant step', 3: '2D curvilinear'}
+            print("typezone: %s, %s (%d, %d, %d)" % (names[int(pi[VSHARE.ITYPZONE])], z[0], pi[VSHARE.IJKV],
+                                                      pi[VSHARE.IJKV + 1], pi[VSHARE.IJKV + 2]))
+    FastC._BCcompact(t)
+    first_it = FastC._createPrimVars(t, FastC.OMP_MODE)
+    FastC._compact(t)
+    FastC.FIRST_IT = first_it
+    return zones
+
+
+def host_views(t):
+    """[(Parameter_int, Parameter_real, [ro, ro_M1, ro_P1] blocks, aux block, (x,y,z))] per zone."""
+    out = []
+    for z in Internal.getZones(t):
+        own, pi, pr, xyz = _zone_arrays(z)
+        out.append((pi, pr, [FastC.block_of(z, s) for s in ('', '_M1', '_P1')], FastC.aux_block_of(z), xyz))
+    return out
+
+
+def warmup(t, tc, graph=None, infos_ale=None, Adjoint=False, tmy=None, list_graph=None, Padding=None, verbose=0):
+    """Perform necessary operations to prepare the tree for computation (PyTree.py:341).
+    Returns (t, tc, metrics)."""
+    from .. import fasts, fastc
+    if graph is not None or infos_ale is not None or Adjoint or tmy is not None:
+        raise ValueError("fast_b200: MPI graphs, ALE, adjoint and statistics trees are outside the hot-path scope")
+    zones = _warmup_host(t, tc, Padding, verbose)
+    dtloc = Internal.getNodeFromName1(Internal.getNodeFromName1(t, '.Solver#ownData'), '.Solver#dtloc')[1]
+    FastC.HOOK = FastC.createWorkArrays__(zones, dtloc, FastC.FIRST_IT)
+    nssiter = int(dtloc[0])
+    metrics = [fasts.allocate_metric(z, nssiter, verbose) for z in zones]          # PyTree.py:291
+    fasts.register(zones, metrics, FastC.HOOK, tc)                                   # pointer harvest, once
+    fastc.init_metric(zones, metrics, FastC.HOOK)                                    # PyTree.py:326
+    if tc is not None: fasts.set_joins(FastC.HOOK, tc)                               # miseAPlatDonorTree__ stand-in
+    # first ghost fill on Density (PyTree.py:536) then initial viscosity (:543)
+    _fillGhostcells(zones, tc, metrics, 1, ['Density'], FastC.HOOK)
+    fasts._computePT_mut(zones, metrics, FastC.HOOK)
+    return (t, tc, metrics)
+
+
+def _compute(t, metrics, nitrun, tc=None, graph=None, layer="c", NIT=1, ucData=None, vtune=False):
+    """Compute NIT iterations (PyTree.py:42).  Only the reference's default ``layer="c"`` driver exists here:
+    sub-iterations, match-join transfers and BC fill all run inside fasts._computePT."""
+    from .. import fasts
+    if graph is not None or ucData is not None:
+        raise ValueError("fast_b200: MPI graphs / unsteady chimera data are outside the hot-path scope")
+    if layer != "c": raise ValueError('fast_b200: only layer="c" is built (the Python layer loops in the reference)')
+    zones = Internal.getZones(t)
+    dtloc = FastC.HOOK['dtloc']
+    nitmax = int(dtloc[0])
+    FastC.HOOK['FIRST_IT'] = FastC.FIRST_IT
+    fasts._computePT(zones, metrics, nitrun, 1, nitmax, 1, NIT, FastC.HOOK)          # PyTree.py:219
+    # time levels rotated on the device; rotate the tree's numpys the same way (PyTree.py:226-231)
+    for _ in range(NIT): FastC.switchPointers__(zones, 1, 3)
+    FastC.FIRST_IT = 1
+    FastC.HOOK['FIRST_IT'] = 1
+    return None
+
+
+def _applyBC(t, metrics, hook1, nstep, var="Density"):
+    from .. import fasts
+    zones = Internal.getZones(t)
+    fasts._applyBC(zones, metrics, hook1, nstep, var)
+    return None
+
+
+def _fillGhostcells(zones, tc, metrics, timelevel_target, vars, nstep, omp_mode=0, hook1=None, nitmax=1, rk=1,
+                    exploc=0, num_passage=1, gradP=False, TBLE=False, isWireModel=False):
+    """Match-join transfers then physical BCs on ``vars[0]`` (PyTree.py:1162-1260)."""
+    from .. import fasts
+    if hook1 is None: hook1 = FastC.HOOK if not isinstance(nstep, dict) else nstep
+    if isinstance(nstep, dict): hook1 = nstep
+    if tc is not None: fasts.transfers(zones, hook1, vars[0])
+    fasts._applyBC(zones, metrics, hook1, 1, vars[0])
+    return None
+
+
+def sync_tree(t, levels=('', '_M1', '_P1'), aux=True):
+    """Copy the device-resident state back into the tree's numpys (what save / display / post need)."""
+    from .. import fasts
+    fasts.download(Internal.getZones(t), FastC.HOOK, levels, aux)
+
+
+def display_temporal_criteria(t, metrics, nitrun, format=None, gmres=None, verbose='firstlast', stopAtNan=True):
+    """Display CFL and implicit convergence (PyTree.py:2039).  Returns the per-zone dict that the reference prints."""
+    from .. import fasts
+    zones = Internal.getZones(t)
+    dtloc = FastC.HOOK['dtloc']
+    nssiter = int(dtloc[0])
+    out = fasts.display_ss_iteration(zones, metrics, nitrun, nssiter, 0, {'firstlast': 0, 'all': 1, 'none': 2}.get(verbose, 0))
+    if stopAtNan:
+        for zname, d in out.items():
+            if not numpy.all(numpy.isfinite(d['L2'])):
+                raise FloatingPointError("fast_b200: NaN in the Newton residual of zone %s" % zname)
+    return out

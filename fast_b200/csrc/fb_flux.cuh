@@ -1,0 +1,307 @@
+// fb_flux.cuh -- face flux device functions (MUSCL + AUSM+(P) / SENSOR / Roe inviscid, face-gradient viscous).
+//
+// Reference semantics: S/Compute/template_FluxAndBalance.for:108-190 (constants), {AUSM,SENSOR,ROE}/fluFaceEuler.for,
+// Slope/*_slope_var.for, etat_GD.for, etat_roe_GD.for, Vit_ent/{qn,fluvector,fludiffer}_*, fluvisq_{3dfull,3dhomo,
+// 3dcart}_{i,j,k}.for, mut_interface.for.  The reference generates 96 routines per scheme; here one template
+// <MESH, FLOW, SCHEME, SLOPE, DIR> is instantiated by the launcher.  Everything is FP64; a face is described by the
+// cell l on its upper side (flux through the LOWER face of cell l in direction DIR).
+#pragma once
+#include "fb_common.cuh"
+
+// MESH: 0 3dfull, 1 3dhomo, 2 3dcart.  FLOW: 1 euler, 2 laminar, 3 SA.  SCHEME: 1 ausmpred, 2 senseur, 5 roe.
+// SLOPE: 1 o1, 2 o3, 3 minmod.
+
+__device__ __forceinline__ double avmin(double c, double r)
+{
+    const double s = copysign(1., c);
+    return s * fmax(0., fmin(fabs(c), s * r));
+}
+
+template <int MESH, int DIR>
+__device__ __forceinline__ void face_normal(const ZoneDev &z, int lt, double tc[3], double &s)
+{
+    tc[0] = tc[1] = tc[2] = 0.;
+    if (MESH == 0) {
+        const double *T = DIR == 0 ? z.ti : (DIR == 1 ? z.tj : z.tk);
+        tc[0] = __ldg(T + lt); tc[1] = __ldg(T + lt + z.nm); tc[2] = __ldg(T + lt + 2 * z.nm);
+        s = sqrt(tc[0] * tc[0] + tc[1] * tc[1] + tc[2] * tc[2]);
+    } else if (MESH == 1) {
+        if (DIR < 2) {
+            const double *T = DIR == 0 ? z.ti : z.tj;
+            tc[0] = __ldg(T + lt); tc[1] = __ldg(T + lt + z.nm);
+            s = sqrt(tc[0] * tc[0] + tc[1] * tc[1]);
+        } else { tc[2] = __ldg(z.tk + lt); s = fabs(tc[2]); }
+    } else { tc[DIR] = z.tc0[DIR]; s = fabs(tc[DIR]); }
+}
+
+template <int SLOPE>
+__device__ __forceinline__ void muscl(const ZoneDev &z, double qm2_, double qm1_, double q0, double qp1_, double T0,
+                                      double &qL, double &qR)
+{   // q(l-2), q(l-1), q(l), q(l+1) -> left (qp in the reference) and right (qm) states of the lower face of l
+    if (SLOPE == 2) {
+        const double c6 = 1. / 6., c4 = 5. * c6, c5 = 2. * c6, c6m = -1. * c6;
+        qR = c4 * q0 + c5 * qm1_ + c6m * qp1_;
+        qL = c4 * qm1_ + c6m * qm2_ + c5 * q0;
+    } else if (SLOPE == 3) {
+        const double roff = .5 * fmax(0., fmin(T0 * z.tmin_1 - .5, 1.));
+        const double delm = q0 - qm1_, delp = qp1_ - q0, delq = qm1_ - qm2_;
+        qR = q0 - roff * avmin(delm, delp);
+        qL = qm1_ + roff * avmin(delq, delm);
+    } else { qR = q0; qL = qm1_; }
+}
+
+// laminar viscous flux of one face, added into flu[1..4]; returns volinv (needed by the SA diffusion flux)
+template <int MESH, int FLOW, int DIR>
+__device__ __forceinline__ double visc_face(const ZoneDev &z, const double *__restrict__ rop, int l, int lt,
+                                            const double tc[3], double *flu)
+{
+    const int nd = z.nd;
+    constexpr int D1 = (DIR + 1) % 3, D2 = (DIR + 2) % 3;
+    const int inc[3] = {1, z.incj, z.inck};
+    const int i0 = inc[DIR], i1 = inc[D1], i2 = inc[D2];
+    const int il = l - i0, ir = l;
+    double G[4][3];
+#pragma unroll
+    for (int c = 0; c < 4; c++) { G[c][0] = G[c][1] = G[c][2] = 0.; }
+    double volinv;
+    if (MESH == 2) {
+        volinv = 0.5 / z.vol0;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const double *q = rop + (c + 1) * nd;
+            const double f1 = q[il], f2 = q[ir], fv = f1 + f2;
+            G[c][DIR] = (f2 - f1) * z.tc0[DIR];
+            if (c == 3) continue;
+            if (c == DIR || c == D1) {
+                const double fa = fv + q[il - i1] + q[ir - i1], fb = fv + q[il + i1] + q[ir + i1];
+                G[c][D1] = (fb - fa) * (.25 * z.tc0[D1]);
+            }
+            if (c == DIR || c == D2) {
+                const double fa = fv + q[il - i2] + q[ir - i2], fb = fv + q[il + i2] + q[ir + i2];
+                G[c][D2] = (fb - fa) * (.25 * z.tc0[D2]);
+            }
+        }
+    } else if (MESH == 0) {
+        const int mm[3] = {z.mi, z.mj, z.mk};
+        const int m0 = mm[DIR], m1 = mm[D1], m2 = mm[D2];
+        const double *T0 = DIR == 0 ? z.ti : (DIR == 1 ? z.tj : z.tk);
+        const double *T1 = D1 == 0 ? z.ti : (D1 == 1 ? z.tj : z.tk);
+        const double *T2 = D2 == 0 ? z.ti : (D2 == 1 ? z.tj : z.tk);
+        double tn[3], tn1[3], ta[3], ta1[3], tb[3], tb1[3];
+#pragma unroll
+        for (int e = 0; e < 3; e++) {
+            const int o = e * z.nm;
+            const double t00 = __ldg(T0 + lt + o);
+            tn[e] = .5 * (t00 + __ldg(T0 + lt - m0 + o));
+            tn1[e] = .5 * (t00 + __ldg(T0 + lt + m0 + o));
+            ta[e] = .125 * (__ldg(T1 + lt + o) + __ldg(T1 + lt - m0 + o));
+            ta1[e] = .125 * (__ldg(T1 + lt + m1 + o) + __ldg(T1 + lt + m1 - m0 + o));
+            tb[e] = .125 * (__ldg(T2 + lt + o) + __ldg(T2 + lt - m0 + o));
+            tb1[e] = .125 * (__ldg(T2 + lt + m2 + o) + __ldg(T2 + lt + m2 - m0 + o));
+        }
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const double *q = rop + (c + 1) * nd;
+            const double f1 = q[il], f2 = q[ir];
+            const double f3 = f2 + f1 + q[il - i1] + q[ir - i1];
+            const double f4 = f2 + f1 + q[il + i1] + q[ir + i1];
+            const double f5 = f2 + f1 + q[il - i2] + q[ir - i2];
+            const double f6 = f2 + f1 + q[il + i2] + q[ir + i2];
+#pragma unroll
+            for (int e = 0; e < 3; e++)
+                G[c][e] = (f2 * tn1[e] - f1 * tn[e]) + (f4 * ta1[e] - f3 * ta[e]) + (f6 * tb1[e] - f5 * tb[e]);
+        }
+        volinv = 1. / (__ldg(z.vol + lt) + __ldg(z.vol + lt - m0));
+    } else {   // 3dhomo
+        const int nm = z.nm;
+        if (DIR < 2) {
+            constexpr int DP = 1 - (DIR < 2 ? DIR : 0);
+            const int ip = inc[DP], ik = z.inck;
+            const int m0 = DIR == 0 ? z.mi : z.mj, mp = DP == 0 ? z.mi : z.mj;
+            const double *T0 = DIR == 0 ? z.ti : z.tj, *Tp = DP == 0 ? z.ti : z.tj;
+            double tn[2], tn1[2], tp[2], tp1[2];
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int o = e * nm;
+                const double t00 = __ldg(T0 + lt + o);
+                tn[e] = .5 * (t00 + __ldg(T0 + lt - m0 + o));
+                tn1[e] = .5 * (t00 + __ldg(T0 + lt + m0 + o));
+                tp[e] = .125 * (__ldg(Tp + lt + o) + __ldg(Tp + lt - m0 + o));
+                tp1[e] = .125 * (__ldg(Tp + lt + mp + o) + __ldg(Tp + lt + mp - m0 + o));
+            }
+            const double tkz = .125 * (__ldg(z.tk + lt) + __ldg(z.tk + lt - m0));
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const double *q = rop + (c + 1) * nd;
+                const double f1 = q[il], f2 = q[ir];
+                const double fa = f2 + f1 + q[il - ip] + q[ir - ip], fb = f2 + f1 + q[il + ip] + q[ir + ip];
+#pragma unroll
+                for (int e = 0; e < 2; e++) G[c][e] = (f2 * tn1[e] - f1 * tn[e]) + (fb * tp1[e] - fa * tp[e]);
+                if (c < 3) {
+                    const double fk0 = f2 + f1 + q[il - ik] + q[ir - ik], fk1 = f2 + f1 + q[il + ik] + q[ir + ik];
+                    G[c][2] = (fk1 - fk0) * tkz;
+                }
+            }
+            volinv = 1. / (__ldg(z.vol + lt) + __ldg(z.vol + lt - m0));
+        } else {
+            const int ii = 1, ij = z.incj;
+            const double tiz = __ldg(z.tk + lt);
+            const double tjx = 0.25 * __ldg(z.ti + lt), tjy = 0.25 * __ldg(z.ti + lt + nm);
+            const double tjx1 = 0.25 * __ldg(z.ti + lt + z.mi), tjy1 = 0.25 * __ldg(z.ti + lt + z.mi + nm);
+            const double tkx = 0.25 * __ldg(z.tj + lt), tky = 0.25 * __ldg(z.tj + lt + nm);
+            const double tkx1 = 0.25 * __ldg(z.tj + lt + z.mj), tky1 = 0.25 * __ldg(z.tj + lt + z.mj + nm);
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const double *q = rop + (c + 1) * nd;
+                const double f1 = q[il], f2 = q[ir];
+                G[c][2] = (f2 - f1) * tiz;
+                if (c == 3) continue;
+                const double f3 = f2 + f1 + q[il - ii] + q[ir - ii], f4 = f2 + f1 + q[il + ii] + q[ir + ii];
+                const double f5 = f2 + f1 + q[il - ij] + q[ir - ij], f6 = f2 + f1 + q[il + ij] + q[ir + ij];
+                G[c][0] = ((f4 * tjx1 - f3 * tjx) + (f6 * tkx1 - f5 * tkx));
+                G[c][1] = ((f4 * tjy1 - f3 * tjy) + (f6 * tky1 - f5 * tky));
+            }
+            const double v = __ldg(z.vol + lt);
+            volinv = 1. / (v + v);
+        }
+    }
+    const double div = (G[0][0] + G[1][1] + G[2][2]) * (1. / 3);
+    const double f1 = G[0][0] - div, f2 = G[0][1] + G[1][0], f3 = G[0][2] + G[2][0];
+    const double f4 = G[1][1] - div, f5 = G[1][2] + G[2][1], f6 = G[2][2] - div;
+    double xmutvol, xktvol;
+    const double Tl = rop[il + 4 * nd], Tr = rop[ir + 4 * nd];
+    if (FLOW == 3) {
+        double xmulam = z.coesut * sqrt(Tl * z.temp01) / (1. + z.cmus1 / Tl);
+        xmulam = xmulam + z.coesut * sqrt(Tr * z.temp01) / (1. + z.cmus1 / Tr);
+        const double xmutot = z.xmut[ir] + z.xmut[il];
+        const double xmutur = xmutot - xmulam;
+        xktvol = (xmulam * z.gam3 + xmutur * z.gam4) * volinv;
+        xmutvol = xmutot * volinv;
+    } else {
+        xmutvol = (z.xmut[ir] + z.xmut[il]) * volinv;
+        xktvol = xmutvol * z.gam3;
+    }
+    const double ur = rop[ir + nd] + rop[il + nd], vr = rop[ir + 2 * nd] + rop[il + 2 * nd],
+                 wr = rop[ir + 3 * nd] + rop[il + 3 * nd];
+    double fv, fv5;
+    if (MESH == 0) {
+        fv = -(2. * f1 * tc[0] + f2 * tc[1] + f3 * tc[2]) * xmutvol; fv5 = fv * ur; flu[1] += fv;
+        fv = -(f2 * tc[0] + 2. * f4 * tc[1] + f5 * tc[2]) * xmutvol; fv5 = fv5 + fv * vr; flu[2] += fv;
+        fv = -(f3 * tc[0] + f5 * tc[1] + 2. * f6 * tc[2]) * xmutvol; fv5 = fv5 + fv * wr; flu[3] += fv;
+        fv = fv5 * 0.5 - (G[3][0] * tc[0] + G[3][1] * tc[1] + G[3][2] * tc[2]) * xktvol; flu[4] += fv;
+    } else if (MESH == 1 && DIR < 2) {
+        fv = -(2. * f1 * tc[0] + f2 * tc[1]) * xmutvol; fv5 = fv * ur; flu[1] += fv;
+        fv = -(f2 * tc[0] + 2. * f4 * tc[1]) * xmutvol; fv5 = fv5 + fv * vr; flu[2] += fv;
+        fv = -(f3 * tc[0] + f5 * tc[1]) * xmutvol; fv5 = fv5 + fv * wr; flu[3] += fv;
+        fv = fv5 * 0.5 - (G[3][0] * tc[0] + G[3][1] * tc[1]) * xktvol; flu[4] += fv;
+    } else {
+        const double t0 = tc[DIR];
+        const double fu = (DIR == 0) ? 2. * f1 : (DIR == 1 ? f2 : f3);
+        const double fvv = (DIR == 0) ? f2 : (DIR == 1 ? 2. * f4 : f5);
+        const double fw = (DIR == 0) ? f3 : (DIR == 1 ? f5 : 2. * f6);
+        fv = -(fu * t0) * xmutvol; fv5 = fv * ur; flu[1] += fv;
+        fv = -(fvv * t0) * xmutvol; fv5 = fv5 + fv * vr; flu[2] += fv;
+        fv = -(fw * t0) * xmutvol; fv5 = fv5 + fv * wr; flu[3] += fv;
+        fv = fv5 * 0.5 - (G[3][DIR] * t0) * xktvol; flu[4] += fv;
+    }
+    (void)f6;
+    return volinv;
+}
+
+#include "fb_sa.cuh"
+
+template <int MESH, int FLOW, int SCHEME, int SLOPE, int DIR>
+__device__ __forceinline__ void face_flux(const ZoneDev &z, const double *__restrict__ rop, int l, int lt, double *flu)
+{
+    constexpr int NEQ = FLOW == 3 ? 6 : 5;
+    const int nd = z.nd;
+    const int inc = DIR == 0 ? 1 : (DIR == 1 ? z.incj : z.inck);
+    double tc[3], s;
+    face_normal<MESH, DIR>(z, lt, tc, s);
+    const int nm = l - inc, nm2 = l - 2 * inc, np = l + inc;
+    const double T0 = rop[l + 4 * nd];
+    double qL[NEQ], qR[NEQ];
+#pragma unroll
+    for (int e = 0; e < 5; e++) {
+        const double *q = rop + e * nd;
+        muscl<SLOPE>(z, q[nm2], q[nm], q[l], q[np], T0, qL[e], qR[e]);
+    }
+    const double rgp = z.rgp, gam1 = z.gam1;
+    double qn1 = qL[1] * tc[0] + qL[2] * tc[1] + qL[3] * tc[2];
+    double qn2 = qR[1] * tc[0] + qR[2] * tc[1] + qR[3] * tc[2];
+    if (SCHEME == 5) {
+        const double r1 = qL[0], p1 = r1 * qL[4] * rgp;
+        const double h1 = gam1 * qL[4] * rgp + .5 * (qL[1] * qL[1] + qL[2] * qL[2] + qL[3] * qL[3]);
+        const double r2 = qR[0], p2 = r2 * qR[4] * rgp;
+        const double h2 = gam1 * qR[4] * rgp + .5 * (qR[1] * qR[1] + qR[2] * qR[2] + qR[3] * qR[3]);
+        const double sq1 = sqrt(r1), sq2 = sqrt(r2);
+        const double r = sq1 * sq2, r_1 = 1. / (sq1 + sq2);
+        const double u = (sq1 * qL[1] + sq2 * qR[1]) * r_1, v = (sq1 * qL[2] + sq2 * qR[2]) * r_1,
+                     w = (sq1 * qL[3] + sq2 * qR[3]) * r_1, h = (sq1 * h1 + sq2 * h2) * r_1;
+        const double q = .5 * (u * u + v * v + w * w);
+        const double cc = sqrt((z.gam - 1.) * fabs(h - q));
+        const double du = (qR[1] - qL[1]) * s, dv = (qR[2] - qL[2]) * s, dw = (qR[3] - qL[3]) * s;
+        const double dp = p2 - p1, dqn = qn2 - qn1;
+        const double s_1 = 1.0 / fmax(s, 1.E-30);
+        const double nx = tc[0] * s_1, ny = tc[1] * s_1, nz = tc[2] * s_1;
+        const double qn = u * nx + v * ny + w * nz;
+        double f1 = qn;
+        const double f4 = z.psiroe * (fabs(f1) + cc);
+        double f2 = 0.5 + copysign(0.5, fabs(f1) - f4);
+        double f3 = (f2 - 1.0) * (f1 * f1 / f4 + f4) * 0.5 - f2 * fabs(f1);
+        f1 = (r2 - r1 - dp / (cc * cc)) * s;
+        flu[0] = f3 * (f1);
+        flu[1] = f3 * (f1 * u + r * (du - nx * dqn));
+        flu[2] = f3 * (f1 * v + r * (dv - ny * dqn));
+        flu[3] = f3 * (f1 * w + r * (dw - nz * dqn));
+        flu[4] = f3 * (f1 * q + r * (u * du + v * dv + w * dw - qn * dqn));
+        f1 = qn + cc;
+        f2 = 0.5 + copysign(0.5, fabs(f1) - f4);
+        f3 = (f2 - 1.) * (f1 * f1 / f4 + f4) * 0.5 - f2 * fabs(f1);
+        f1 = (dp + r * cc * dqn * s_1) / (2. * cc * cc) * s * f3;
+        flu[0] += f1; flu[1] += f1 * (u + nx * cc); flu[2] += f1 * (v + ny * cc);
+        flu[3] += f1 * (w + nz * cc); flu[4] += f1 * (h + qn * cc);
+        f1 = qn - cc;
+        f2 = 0.5 + copysign(0.5, fabs(f1) - f4);
+        f3 = (f2 - 1.) * (f1 * f1 / f4 + f4) * 0.5 - f2 * fabs(f1);
+        f1 = (dp - r * cc * dqn * s_1) / (2. * cc * cc) * f3 * s;
+        flu[0] += f1; flu[1] += f1 * (u - nx * cc); flu[2] += f1 * (v - ny * cc);
+        flu[3] += f1 * (w - nz * cc); flu[4] += f1 * (h - qn * cc);
+        const double rou1 = r1 * qn1, rou2 = r2 * qn2, p1p2 = p1 + p2;
+        flu[0] = (flu[0] + rou1 + rou2) * 0.5;
+        flu[1] = (flu[1] + rou1 * qL[1] + rou2 * qR[1] + tc[0] * p1p2) * 0.5;
+        flu[2] = (flu[2] + rou1 * qL[2] + rou2 * qR[2] + tc[1] * p1p2) * 0.5;
+        flu[3] = (flu[3] + rou1 * qL[3] + rou2 * qR[3] + tc[2] * p1p2) * 0.5;
+        flu[4] = (flu[4] + rou1 * h1 + rou2 * h2) * 0.5;
+        if (FLOW == 3) flu[5] = roe_sa_flux<SLOPE>(z, rop, l, inc, qn1, qn2, r1, r2);
+    } else {
+        const double r1 = qL[0], rou1 = r1 * qL[1], rov1 = r1 * qL[2], row1 = r1 * qL[3], p1 = r1 * qL[4] * rgp;
+        const double h1 = gam1 * p1 + .5 * (rou1 * qL[1] + rov1 * qL[2] + row1 * qL[3]);
+        const double r2 = qR[0], rou2 = r2 * qR[1], rov2 = r2 * qR[2], row2 = r2 * qR[3], p2 = r2 * qR[4] * rgp;
+        const double h2 = gam1 * p2 + .5 * (rou2 * qR[1] + rov2 * qR[2] + row2 * qR[3]);
+        double u, tdu;
+        if (SCHEME == 1) {
+            const double cs = rgp * z.gam * T0;
+            const double son = sqrt(qn1 * qn1 / cs);
+            const double tam = -2. * son + s;
+            const double tam1 = fmax(0., tam) * z.c2;
+            u = 0.25 * (qn1 + qn2) - tam1 * (p2 - p1);
+            tdu = fmax(fabs(u), z.c1 * s) * z.wig_cte;
+        } else {
+            const double wg = (double)((z.wigb[l] >> DIR) & 1);
+            u = 0.25 * (qn1 + qn2) - z.c2 * s * (p2 - p1) * (z.opt0 * wg + 1. - z.opt0);
+            tdu = fmax(fabs(u), z.c1 * s) * wg;
+        }
+        const double p1p2 = (p1 + p2) * 0.5;
+        flu[0] = u * (r1 + r2) - tdu * (r2 - r1);
+        flu[1] = u * (rou1 + rou2) - tdu * (rou2 - rou1) + tc[0] * p1p2;
+        flu[2] = u * (rov1 + rov2) - tdu * (rov2 - rov1) + tc[1] * p1p2;
+        flu[3] = u * (row1 + row2) - tdu * (row2 - row1) + tc[2] * p1p2;
+        flu[4] = u * (h1 + h2) - tdu * (h2 - h1);
+        if (FLOW == 3) flu[5] = ausm_sa_flux<SLOPE>(z, rop, l, inc, u, tdu, r1, r2);
+    }
+    if (FLOW >= 2) {
+        const double volinv = visc_face<MESH, FLOW, DIR>(z, rop, l, lt, tc, flu);
+        if (FLOW == 3) flu[5] += sa_visc_flux<MESH, DIR>(z, rop, l, lt, tc, volinv);
+    }
+}

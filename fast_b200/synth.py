@@ -1,0 +1,184 @@
+"""Seeded synthetic cases of BASELINE.json: trees are produced directly in the layout
+FastS.warmup expects (ghost layers included, FlowSolution#Centers in conservative or primitive variables,
+ZoneBC windows in ghosted node numbering, ReferenceState, GoverningEquations).  No CGNS file, no Cassiopee."""
+import math
+import numpy
+from . import Internal
+
+NG = 2  # ghost layers
+
+
+def adim1(MInf=0.5, alphaZ=0., alphaY=0., ReInf=1.e8, MutSMuInf=0.2, Gamma=1.4, Pr=0.72):
+    """Non-dimensional reference state with RoInf = UInf = TInf = 1 (the convention of Cassiopee's KCore.Adim.adim1,
+    restated from its documented definition): p = 1/(gamma M^2), cv = 1/(gamma (gamma-1) M^2), mu(TInf) = 1/Re."""
+    ro, u, T = 1., 1., 1.
+    p = 1. / (Gamma * MInf * MInf)
+    cv = 1. / (Gamma * (Gamma - 1.) * MInf * MInf)
+    az, ay = math.radians(alphaZ), math.radians(alphaY)
+    ux = u * math.cos(az) * math.cos(ay); uy = u * math.sin(az) * math.cos(ay); uz = u * math.sin(ay)
+    roe = p / (Gamma - 1.) + 0.5 * ro * u * u
+    Ts = 1.; Cs = 110.4 / 288.15
+    mus = 1. / ReInf          # Sutherland reference viscosity at Ts = TInf
+    nutilde = _nutilde_from_mut(MutSMuInf) * mus / ro
+    return dict(Density=ro, MomentumX=ro * ux, MomentumY=ro * uy, MomentumZ=ro * uz, EnergyStagnationDensity=roe,
+                Pressure=p, Temperature=T, Cv=cv, Mach=MInf, Reynolds=ReInf, Gamma=Gamma,
+                TurbulentSANuTildeDensity=ro * nutilde, Mus=mus, Cs=Cs, Ts=Ts, Pr=Pr)
+
+
+def _nutilde_from_mut(r):
+    """chi such that chi * fv1(chi) = mut/mu (SA), Newton iterations."""
+    chi = max(r, 1e-3)
+    for _ in range(50):
+        f = chi ** 4 / (chi ** 3 + 357.911) - r
+        df = (4 * chi ** 3 * (chi ** 3 + 357.911) - chi ** 4 * 3 * chi ** 2) / (chi ** 3 + 357.911) ** 2
+        chi -= f / df
+    return chi
+
+
+def add_state(node, state, model):
+    rs = Internal.createUniqueChild(node, 'ReferenceState', 'ReferenceState_t')
+    for k, v in state.items(): Internal.createUniqueChild(rs, k, 'DataArray_t', float(v))
+    fe = Internal.createUniqueChild(node, 'FlowEquationSet', 'FlowEquationSet_t')
+    Internal.createUniqueChild(fe, 'GoverningEquations', 'GoverningEquations_t', model)
+
+
+def _axis(n, L, o, stretch=None):
+    """n interior cells on [o, o+L], NG ghost cells each side (mapping simply continued)."""
+    s = (numpy.arange(-NG, n + NG + 1, dtype=numpy.float64)) / n
+    if stretch is not None: s = stretch(s)
+    return o + L * s
+
+
+def make_block(name, n, L=(1., 1., 1.), origin=(0., 0., 0.), deform=None, stretch=(None, None, None),
+               index_offset=(0, 0, 0), nglob=None):
+    """Structured zone of n=(ni,nj,nk) interior cells + NG ghost layers; `deform(X,Y,Z)->(X,Y,Z)` is applied to the
+    analytic node positions (ghost nodes included, so periodic / matching geometry stays consistent).
+    With nglob the block is the window [index_offset, index_offset+n) of a global nglob-cell mesh."""
+    nglob = nglob or n
+    ax = []
+    for d in range(3):
+        full = _axis(nglob[d], L[d], origin[d], stretch[d])
+        a = index_offset[d]
+        ax.append(full[a:a + n[d] + 2 * NG + 1])
+    X, Y, Z = numpy.meshgrid(ax[0], ax[1], ax[2], indexing='ij')
+    if deform is not None: X, Y, Z = deform(X, Y, Z)
+    z = Internal.newZone(name, n[0] + 2 * NG + 1, n[1] + 2 * NG + 1, n[2] + 2 * NG + 1)
+    gc = Internal.createChild(z, 'GridCoordinates', 'GridCoordinates_t')
+    for nm, a in zip(('CoordinateX', 'CoordinateY', 'CoordinateZ'), (X, Y, Z)):
+        Internal.createChild(gc, nm, 'DataArray_t', numpy.asfortranarray(a))
+    return z
+
+
+def centers(z):
+    gc = Internal.getNodeFromName1(z, 'GridCoordinates')
+    out = []
+    for nm in ('CoordinateX', 'CoordinateY', 'CoordinateZ'):
+        a = Internal.getNodeFromName1(gc, nm)[1]
+        c = 0.125 * (a[:-1, :-1, :-1] + a[1:, :-1, :-1] + a[:-1, 1:, :-1] + a[1:, 1:, :-1]
+                     + a[:-1, :-1, 1:] + a[1:, :-1, 1:] + a[:-1, 1:, 1:] + a[1:, 1:, 1:])
+        out.append(c)
+    return out
+
+
+def set_fields(z, ro, u, v, w, T, nutilde=None, dist=None):
+    sol = Internal.createUniqueChild(z, 'FlowSolution#Centers', 'FlowSolution_t')
+    Internal.createUniqueChild(sol, 'GridLocation', 'GridLocation_t', 'CellCenter')
+    for nm, a in zip(('Density', 'VelocityX', 'VelocityY', 'VelocityZ', 'Temperature'), (ro, u, v, w, T)):
+        Internal.createUniqueChild(sol, nm, 'DataArray_t', numpy.asfortranarray(a, dtype=numpy.float64))
+    if nutilde is not None:
+        Internal.createUniqueChild(sol, 'TurbulentSANuTilde', 'DataArray_t', numpy.asfortranarray(nutilde))
+    if dist is not None:
+        Internal.createUniqueChild(sol, 'TurbulentDistance', 'DataArray_t', numpy.asfortranarray(dist))
+
+
+def add_bc(z, name, btype, face):
+    """face in imin,imax,jmin,jmax,kmin,kmax; window = whole face in ghosted node numbering (1-based)."""
+    ni, nj, nk = z[1][0, 0], z[1][1, 0], z[1][2, 0]
+    r = [[1, ni], [1, nj], [1, nk]]
+    d = 'ijk'.index(face[0])
+    n = (ni, nj, nk)[d]
+    r[d] = [1, 1] if face[1:] == 'min' else [n, n]
+    zbc = Internal.createUniqueChild(z, 'ZoneBC', 'ZoneBC_t')
+    bc = Internal.createChild(zbc, name, 'BC_t', btype)
+    Internal.createChild(bc, 'PointRange', 'IndexRange_t', numpy.array(r, dtype=Internal.E_NpyInt, order='F'))
+    return bc
+
+
+FACES = ('imin', 'imax', 'jmin', 'jmax', 'kmin', 'kmax')
+
+
+def new_tree(zones, state, model):
+    t = Internal.newCGNSTree()
+    b = Internal.newCGNSBase('Base', parent=t)
+    b[2] += zones
+    add_state(b, state, model)
+    return t
+
+
+def vortex_state(xc, yc, zc, state, rng, amp=1e-3, L=1.):
+    """Uniform stream + Lamb-Oseen-like vortex + seeded 1e-3 relative noise."""
+    gam = state['Gamma']; cv = state['Cv']
+    u0 = state['MomentumX'] / state['Density']; v0 = state['MomentumY'] / state['Density']
+    w0 = state['MomentumZ'] / state['Density']
+    r2 = ((xc - 0.5 * L) ** 2 + (yc - 0.5 * L) ** 2) / (0.1 * L) ** 2
+    g = 0.2 * numpy.exp(0.5 * (1. - r2))
+    u = u0 - g * (yc - 0.5 * L) / (0.1 * L); v = v0 + g * (xc - 0.5 * L) / (0.1 * L)
+    w = w0 + 0.05 * numpy.sin(2 * math.pi * zc / L)
+    T = state['Temperature'] * (1. - (gam - 1.) * g * g * 0.5 * state['Mach'] ** 2)
+    ro = state['Density'] * (T / state['Temperature']) ** (1. / (gam - 1.))
+    def noise(a): return a * (1. + amp * rng.standard_normal(a.shape))
+    return noise(ro), noise(u) , noise(v), w + amp * rng.standard_normal(w.shape), noise(T)
+
+
+def case_euler_box(n=64, scheme='ausmpred', deform_amp=0., seed=1234, model='Euler', rk=3, slope='o3',
+                   MInf=0.4, ReInf=1.e8, time_step=None, bcs=None, temporal='explicit', extra_numz=None,
+                   extra_numb=None, n3=None):
+    """C1-style case: n^3 box, periodic (BCautoperiod) unless `bcs` maps faces to BC types."""
+    from .FastC import PyTree as FastC
+    n3 = n3 or (n, n, n)
+    rng = numpy.random.default_rng(seed)
+    state = adim1(MInf=MInf, ReInf=ReInf)
+    deform = None
+    if deform_amp > 0.:
+        def deform(X, Y, Z):
+            tp = 2 * math.pi
+            return (X + deform_amp * numpy.sin(tp * Y) * numpy.sin(tp * Z),
+                    Y + deform_amp * numpy.sin(tp * Z) * numpy.sin(tp * X),
+                    Z + deform_amp * numpy.sin(tp * X) * numpy.sin(tp * Y))
+    z = make_block('cart', n3, deform=deform)
+    xc, yc, zc = centers(z)
+    set_fields(z, *vortex_state(xc, yc, zc, state, rng))
+    for f in FACES:
+        bt = 'BCautoperiod' if bcs is None else bcs[f]
+        add_bc(z, f, bt, f)
+    t = new_tree([z], state, model)
+    h = 1. / n
+    numb = {'temporal_scheme': temporal, 'rk': rk, 'modulo_verif': 1}
+    if temporal == 'implicit': numb['ss_iteration'] = 3
+    if extra_numb: numb.update(extra_numb)
+    numz = {'scheme': scheme, 'slope': slope, 'time_step': time_step if time_step is not None else 1e-3 * h * 100}
+    if extra_numz: numz.update(extra_numz)
+    FastC._setNum2Zones(t, numz); FastC._setNum2Base(t, numb)
+    return t
+
+
+def case_tgv(n=256, seed=7, scheme='senseur', Re=1600., MInf=0.1, time_step=0.002):
+    """C2: laminar Taylor-Green vortex on [0,2pi]^3, fields as in FastS/test/tgvMpi.py:54-58 (restated)."""
+    from .FastC import PyTree as FastC
+    state = adim1(MInf=MInf, ReInf=Re)
+    L = 2 * math.pi
+    z = make_block('tgv', (n, n, n), L=(L, L, L))
+    x, y, zz = centers(z)
+    gam = state['Gamma']; p0 = state['Pressure']; ro0 = 1.; U0 = 1.
+    u = U0 * numpy.sin(x) * numpy.cos(y) * numpy.cos(zz)
+    v = -U0 * numpy.cos(x) * numpy.sin(y) * numpy.cos(zz)
+    w = numpy.zeros_like(u)
+    p = p0 + ro0 * U0 * U0 / 16. * (numpy.cos(2 * x) + numpy.cos(2 * y)) * (numpy.cos(2 * zz) + 2.)
+    ro = p / p0 * ro0
+    T = p / (ro * state['Cv'] * (gam - 1.))
+    set_fields(z, ro, u, v, w, T)
+    for f in FACES: add_bc(z, f, 'BCautoperiod', f)
+    t = new_tree([z], state, 'NSLaminar')
+    FastC._setNum2Zones(t, {'scheme': scheme, 'slope': 'o3', 'time_step': time_step * (256. / n)})
+    FastC._setNum2Base(t, {'temporal_scheme': 'explicit', 'rk': 3, 'modulo_verif': 50})
+    return t

@@ -1,0 +1,98 @@
+/*
+ * fastb200.h -- C ABI of the B200-native FastS residual-and-update hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / numpy / CUDA types.  Each entry
+ * point names the reference interface it replaces (paths relative to onera/Fast, `S/` = Fast/FastS/FastS,
+ * `C/` = Fast/FastC/FastC).  The reference's CPython modules `fasts` / `fastc` bind these (see
+ * INTEGRATION.md); in this repo `fast_b200/fasts.py` / `fastc.py` do so through ctypes.
+ *
+ * Conventions: every function returns 0 on success, a negative FB_E* code otherwise and leaves a
+ * message readable through fb_last_error().  All host arrays are in the reference layout:
+ * Parameter_int / Parameter_real (S/param_solver.h:80-312), rop(NDIMDX,NEQ) variable-major FP64,
+ * node coordinates (NDIMDX_XYZ).  Device memory is owned by the solver object; time levels rotate on
+ * the device in lock-step with the reference's pointer swap (S/Compute/computePT.cpp:675-679).
+ */
+#ifndef FASTB200_H
+#define FASTB200_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FB_OK        0
+#define FB_EINVAL   -1   /* bad argument / option outside the hot-path scope          */
+#define FB_ECUDA    -2   /* CUDA runtime error (incl. "no device": there is no CPU fallback) */
+#define FB_ESTATE   -3   /* call order violated (e.g. compute before init_metric)      */
+
+typedef struct fb_solver fb_solver;
+
+int         fb_version(void);
+const char *fb_last_error(void);
+int         fb_device_count(void);
+
+/* Lifecycle.  Replaces the per-call pointer harvest of S/Compute/computePT.cpp:225-369: zones are
+ * registered once and stay resident in HBM. */
+int  fb_solver_create(int device, int nzones, fb_solver **out);
+void fb_solver_destroy(fb_solver *s);
+
+/* Parameter_int / Parameter_real of zone nd after C/PyTree.py:_buildOwnData + _BCcompact and the integer
+ * part of fasts.allocate_metric (S/Metric/allocate_metric.cpp:124-176). */
+int fb_zone_set_params(fb_solver *s, int nd, const int *param_int, int n_int,
+                       const double *param_real, int n_real);
+/* GridCoordinates/CoordinateX|Y|Z incl. ghost nodes (computePT.cpp:300-310). */
+int fb_zone_set_coords(fb_solver *s, int nd, const double *x, const double *y, const double *z);
+/* FastC.fastc.init_metric (C/Metric/init_metric.cpp:34-366): cp_tijk_, cp_vol_ on the device. */
+int fb_init_metric(fb_solver *s);
+int fb_zone_get_metric(fb_solver *s, int nd, double *ti, double *tj, double *tk, double *vol);
+
+/* FlowSolution#Centers blocks: level 0 = Density (ro), 1 = Density_M1, 2 = Density_P1; n = NDIMDX*NEQ.
+ * aux = [ViscosityEddy | TurbulentDistance] block (S/Compute/src_term.for:96). */
+int fb_zone_upload_state(fb_solver *s, int nd, int level, const double *rop);
+int fb_zone_download_state(fb_solver *s, int nd, int level, double *rop);
+int fb_zone_upload_aux(fb_solver *s, int nd, const double *aux, int n);
+int fb_zone_download_aux(fb_solver *s, int nd, double *aux, int n);
+int fb_zone_download_work(fb_solver *s, int nd, double *drodm, double *coe);
+
+/* Match joins: flattened donor tree in this repo's documented layout (DESIGN.md "match joins"), the
+ * stand-in for Connector's miseAPlatDonorTree__ tables read at C/Com/setInterpTransfersFast.cpp:469-477. */
+int fb_set_joins(fb_solver *s, const int *join_int, int n_int);
+
+/* fasts._computePT(zones, metrics, nitrun, nstep_deb, nstep_fin, layer_mode, nit_c, hook)
+ * (S/Compute/computePT.cpp:44): runs nit_c iterations x sub-iterations nstep_deb..nstep_fin with
+ * layer_mode=1 semantics (transfers + BC inside), rotates the time levels, updates *first_it. */
+int fb_compute(fb_solver *s, int nitrun, int nstep_deb, int nstep_fin, int nit_c, int *first_it);
+/* fasts._applyBC(zones, metrics, hook, nstep, var) (S/BC/applyBC.cpp:33) on time level `level`. */
+int fb_apply_bc(fb_solver *s, int level);
+/* Connector.___setInterpTransfers for match joins (S/PyTree.py:1218) on time level `level`. */
+int fb_transfers(fb_solver *s, int level);
+/* fasts._computePT_mut (S/Compute/LES/computePT_mut.cpp): initial mu / mu+mut into ViscosityEddy. */
+int fb_compute_mut(fb_solver *s);
+
+/* fasts.display_ss_iteration inputs (S/DISPLAY/display_ss_iteration.cpp:29): rdm(nssiter,neq,2) and
+ * CFL (max,min,mean) of zone nd. */
+int fb_zone_get_residuals(fb_solver *s, int nd, double *rdm, int n);
+int fb_zone_get_cfl(fb_solver *s, int nd, double cfl[3]);
+
+/* End-to-end step on HOST buffers (what a reference-side caller holding numpy arrays does): uploads the
+ * three time levels of every zone, runs fb_compute, downloads them back. ro/ro_m1/ro_p1[nd] are host
+ * pointers of NDIMDX*NEQ doubles each (pinned or pageable). */
+int fb_compute_host(fb_solver *s, int nitrun, int nit_c, int *first_it,
+                    double **ro, double **ro_m1, double **ro_p1);
+
+/* Instrumentation for bench.py: CUDA-event time (ms) and launch count accumulated per kernel family
+ * since the last reset. names: "rhs", "lu", "bc", "transfer", "coe", "all". */
+int fb_timing_enable(fb_solver *s, int on);
+int fb_timing_reset(fb_solver *s);
+int fb_timing_get(fb_solver *s, const char *name, double *ms, long long *launches);
+int fb_sync(fb_solver *s);
+/* Device pointer of a zone's state block (uintptr) so the Python host can hand halo buffers to
+ * torch.distributed/NCCL without a host copy. */
+unsigned long long fb_zone_device_ptr(fb_solver *s, int nd, int level);
+/* Multi-GPU halo exchange helpers: pack the donor cells of the cross-rank joins into / unpack from a
+ * contiguous device buffer (FP64, nvar-major per join). */
+int fb_halo_pack(fb_solver *s, int level_or_drodm, unsigned long long dev_buf, long long nbytes);
+int fb_halo_unpack(fb_solver *s, int level_or_drodm, unsigned long long dev_buf, long long nbytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -301,16 +301,17 @@ static void visc_face(const fctx *c, int d0, int l, int lt, const double tc[3], 
     const int d1 = (d0 + 1) % 3, d2 = (d0 + 2) % 3;
     const int i0 = c->inc[d0], i1 = c->inc[d1], i2 = c->inc[d2];
     const int il = l - i0, ir = l;
-    double G[4][3] = {{0}};  /* G[c][e]: d(u,v,w,T)/d(x,y,z) scaled (face gradient * 2 vol) */
+    double G[5][3] = {{0}};  /* G[c][e]: d(u,v,w,T[,nutilde])/d(x,y,z) scaled (face gradient * 2 vol) */
+    const int nv = c->iflow == 3 ? 5 : 4;   /* SA: nutilde gradient with the same metrics (SA/fluvisq_SA_*.for) */
     double volinv;
     if (c->typ == 2) {
         /* fluvisq_3dcart_{i,j,k}.for */
         volinv = c->volinv0;
-        for (int cc = 0; cc < 4; cc++) {
+        for (int cc = 0; cc < nv; cc++) {
             const double *q = rop + (cc + 1) * nd;
             const double f1 = q[il], f2 = q[ir], fv = f1 + f2;
             G[cc][d0] = (f2 - f1) * c->tc0[d0];
-            if (cc == 3) continue;
+            if (cc >= 3) continue;
             for (int t = 0; t < 2; t++) {
                 const int e = t ? d2 : d1, ie = t ? i2 : i1;
                 if (!(cc == d0 || cc == e)) continue;
@@ -333,7 +334,7 @@ static void visc_face(const fctx *c, int d0, int l, int lt, const double tc[3], 
             tb[e] = .125 * (T2[lt + o] + T2[lt - m0 + o]);
             tb1[e] = .125 * (T2[lt + m2 + o] + T2[lt + m2 - m0 + o]);
         }
-        for (int cc = 0; cc < 4; cc++) {
+        for (int cc = 0; cc < nv; cc++) {
             const double *q = rop + (cc + 1) * nd;
             const double f1 = q[il], f2 = q[ir];
             const double f3 = q[ir] + q[il] + q[il - i1] + q[ir - i1];
@@ -360,7 +361,7 @@ static void visc_face(const fctx *c, int d0, int l, int lt, const double tc[3], 
                 tp1[e] = .125 * (Tp[lt + mp + o] + Tp[lt + mp - m0 + o]);
             }
             const double tkz = .125 * (Tk[lt] + Tk[lt - m0]);
-            for (int cc = 0; cc < 4; cc++) {
+            for (int cc = 0; cc < nv; cc++) {
                 const double *q = rop + (cc + 1) * nd;
                 const double f1 = q[il], f2 = q[ir];
                 const double fa = q[ir] + q[il] + q[il - ip] + q[ir - ip];
@@ -382,11 +383,11 @@ static void visc_face(const fctx *c, int d0, int l, int lt, const double tc[3], 
             const double tjx1 = 0.25 * c->t[0][lt + mi], tjy1 = 0.25 * c->t[0][lt + mi + nm];
             const double tkx = 0.25 * c->t[1][lt], tky = 0.25 * c->t[1][lt + nm];
             const double tkx1 = 0.25 * c->t[1][lt + mj], tky1 = 0.25 * c->t[1][lt + mj + nm];
-            for (int cc = 0; cc < 4; cc++) {
+            for (int cc = 0; cc < nv; cc++) {
                 const double *q = rop + (cc + 1) * nd;
                 const double f1 = q[il], f2 = q[ir];
                 G[cc][2] = (f2 - f1) * tiz;
-                if (cc == 3) continue;
+                if (cc >= 3) continue;
                 const double f3 = q[ir] + q[il] + q[il - ii] + q[ir - ii];
                 const double f4 = q[ir] + q[il] + q[il + ii] + q[ir + ii];
                 const double f5 = q[ir] + q[il] + q[il - ij] + q[ir - ij];
@@ -436,6 +437,16 @@ static void visc_face(const fctx *c, int d0, int l, int lt, const double tc[3], 
         fv = -(fvv * t0) * xmutvol; fv5 = fv5 + fv * vr; flu[2] += fv;
         fv = -(fw * t0) * xmutvol; fv5 = fv5 + fv * wr; flu[3] += fv;
         fv = fv5 * 0.5 - (G[3][d0] * t0) * xktvol; flu[4] += fv;
+    }
+    if (c->iflow == 3) {
+        /* SA/mut_interface.for + SA/fluvisq_SA_<mesh>_<dir>.for / assemble_tauij_3dfull.for */
+        double xmulam = c->coesut * sqrt(rop[il + 4 * nd] * c->temp01) / (1. + c->cmus1 / rop[il + 4 * nd]);
+        xmulam = xmulam + c->coesut * sqrt(rop[ir + 4 * nd] * c->temp01) / (1. + c->cmus1 / rop[ir + 4 * nd]);
+        double xsa = xmulam + rop[il + 5 * nd] * rop[il] + rop[ir + 5 * nd] * rop[ir];
+        xsa = xsa * volinv * c->sigma_1;
+        if (c->typ == 0) flu[5] = flu[5] - xsa * (G[4][0] * tc[0] + G[4][1] * tc[1] + G[4][2] * tc[2]);
+        else if (c->typ == 1 && d0 < 2) flu[5] = flu[5] - xsa * (G[4][0] * tc[0] + G[4][1] * tc[1]);
+        else flu[5] = flu[5] - xsa * G[4][d0] * tc[d0];
     }
     *xmutvol_out = xmutvol; *volinv_out = volinv;
 }
@@ -554,28 +565,38 @@ static void face_flux(const fctx *c, int d0, int l, int lt, double *flu)
         flu[4] = u * (h1 + h2) - tdu * (h2 - h1);
         u_conv = u; (void)tdu;
         if (c->neq == 6) {
-            /* AUSM|SENSOR/fluFaceSA.for: nutilde convected with the same u/tdu */
+            /* AUSM|SENSOR/fluFaceSA.for: nutilde reconstructed with the scheme's slope, times the MUSCL densities */
             const double *q = rop + 5 * nd; double qm6, qp6;
             if (c->slope == 2) { qm6 = c->c4 * q[l] + c->c5 * q[nm] + c->c6 * q[np]; qp6 = c->c4 * q[nm] + c->c6 * q[nm2] + c->c5 * q[l]; }
-            else { qm6 = q[l]; qp6 = q[nm]; }
-            flu[5] = u * (qm6 * r2 + qp6 * r1) - tdu * (qm6 * r2 - qp6 * r1);
+            else if (c->slope == 3) {
+                const double roff = .5 * fmax(0., fmin(rop[l + 4 * nd] * c->tmin_1 - .5, 1.));
+                const double delm = q[l] - q[nm], delp = q[np] - q[l], delq = q[nm] - q[nm2];
+                qm6 = q[l] - roff * avmin(delm, delp); qp6 = q[nm] + roff * avmin(delq, delm);
+            } else { qm6 = q[l]; qp6 = q[nm]; }
+            qm6 = qm6 * qm1; qp6 = qp6 * qp1;
+            flu[5] = u * (qm6 + qp6) - tdu * (qm6 - qp6);
         }
     }
     if (c->kflu == 5 && c->neq == 6) {
-        /* ROE/fluFaceSA.for:2-34 */
-        const double *q = rop + 5 * nd;
-        const double r1 = qp1, r2 = qm1;
-        const double qn = 0.5 * (qn1 + qn2);   /* see fo_lu.c notes; restated in roe_sa_flux */
-        (void)qn; (void)q; (void)r1; (void)r2;
-        flu[5] = fo_roe_sa_flux(c->rop, nd, l, inc, qn1, qn2, qp1, qm1, c->slope, c->c4, c->c5, c->c6);
+        /* ROE/fluFaceSA.for:2-34: first-order states, Roe-averaged normal velocity as dissipation speed */
+        double p2 = rop[nm + nd], p3 = rop[nm + 2 * nd], p4 = rop[nm + 3 * nd];
+        const double m2 = rop[l + nd], m3 = rop[l + 2 * nd], m4 = rop[l + 3 * nd];
+        double n1 = p2 * tc[0] + p3 * tc[1] + p4 * tc[2];
+        const double n2 = m2 * tc[0] + m3 * tc[1] + m4 * tc[2];
+        double rp1 = rop[nm], rm1 = rop[l];
+        const double qm6 = rop[l + 5 * nd] * rm1 * n2, qp6 = rop[nm + 5 * nd] * rp1 * n1;
+        rp1 = sqrt(rp1); rm1 = sqrt(rm1);
+        const double r_1 = 1. / (rp1 + rm1);
+        p2 = r_1 * (rp1 * p2 + rm1 * m2); p3 = r_1 * (rp1 * p3 + rm1 * m3); p4 = r_1 * (rp1 * p4 + rm1 * m4);
+        n1 = p2 * tc[0] + p3 * tc[1] + p4 * tc[2];
+        const double s_1 = 1.0 / fmax(s, 1.E-30);
+        const double tdu = fmax(c->c1 / s_1, fabs(n1));
+        flu[5] = 0.5 * (qm6 + qp6 - tdu * (rop[l + 5 * nd] * rop[l] - rop[nm + 5 * nd] * rop[nm]));
     }
     (void)u_conv;
     if (c->iflow >= 2) {
         double xmutvol, volinv;
         visc_face(c, d0, l, lt, tc, flu, &xmutvol, &volinv);
-        if (c->neq == 6)
-            flu[5] += fo_sa_visc_flux(c->rop, c->xmut, c->t, c->inc, c->incm, nd, c->nm, c->typ, c->tc0, d0, l, lt, tc,
-                                      volinv, c->sigma_1);
     }
 }
 

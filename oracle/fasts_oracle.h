@@ -89,6 +89,7 @@ void fo_gsdr3(fo_zone *zones, int nz, int nitcfg, int nssiter, int nitrun, int f
 void fo_compute(fo_zone *zones, int nz, int nitrun, int nit, int nssiter, int modulo_verif,
                 int *first_it, const int *pitc, const double *prtc, int nthreads);
 
+void fo_fill_ghost(fo_zone *zones, int nz, int level, const int *pitc, const double *prtc);
 int fo_max_threads(void);
 #ifdef __cplusplus
 }

@@ -175,3 +175,24 @@ void fo_compute(fo_zone *zones, int nz, int nitrun, int nit, int nssiter, int mo
         }
     }
 }
+
+/* warmup's first ghost fill (S/PyTree.py:536, _fillGhostcells): transfers then BCs on one time level */
+void fo_fill_ghost(fo_zone *zones, int nz, int level, const int *pitc, const double *prtc)
+{
+    if (pitc != NULL) {
+        /* fo_transfers works on rop_CL = ro_p1 at nitcfg 1: alias the requested level there */
+        double **sv = (double **)malloc(nz * sizeof(double *));
+        for (int n = 0; n < nz; n++) { sv[n] = zones[n].ro_p1; zones[n].ro_p1 = level == 0 ? zones[n].ro : (level == 1 ? zones[n].ro_m1 : zones[n].ro_p1); }
+        fo_transfers(zones, nz, pitc, prtc, 0, 1);
+        for (int n = 0; n < nz; n++) zones[n].ro_p1 = sv[n];
+        free(sv);
+    }
+    for (int n = 0; n < nz; n++) {
+        fo_zone *z = &zones[n];
+        double *a = level == 0 ? z->ro : (level == 1 ? z->ro_m1 : z->ro_p1);
+        int dummy[6];
+        fo_bczone(z->pi, z->pr, 0, a, z->ti, z->tj, z->tk, dummy);
+        const int ind[6] = {1, z->pi[FO_IJKV], 1, z->pi[FO_IJKV + 1], 1, z->pi[FO_IJKV + 2]};
+        fo_correct_coins(z->pi, ind, a);
+    }
+}

@@ -34,10 +34,4 @@ void fo_bc_wall_inviscid(const int *pi, const double *pr, int idir, int lrhs, co
 void fo_bc_wall_viscous(const int *pi, const double *pr, int idir, int lrhs, const int w[6], double *rop);
 void fo_bc_farfield(const int *pi, const double *pr, int idir, int lrhs, const int w[6], double *rop, const double *tijk);
 
-/* fo_sa.c */
-double fo_roe_sa_flux(const double *rop, int nd, int l, int inc, double qn1, double qn2, double r1, double r2,
-                      int slope, double c4, double c5, double c6);
-double fo_sa_visc_flux(const double *rop, const double *xmut, const double *const t[3], const int inc[3],
-                       const int incm[3], int nd, int nm, int typ, const double tc0[3], int d0, int l, int lt,
-                       const double tc[3], double volinv, double sigma_1);
 #endif
