@@ -1,0 +1,590 @@
+// fb_api.cu -- C ABI (include/fastb200.h) and the sub-iteration driver.
+//
+// The driver restates the ORDER of S/Compute/gsdr3.cpp:152-444 and computePT.cpp:534-679 for one task per zone:
+//   rhs of every zone -> [lu_match: drodm transfers] -> BC on rhs + corners -> residual norms -> LU + Newton update
+//   -> match-join transfers on rop_CL -> BC ghost fill -> corners, then time-level rotation.
+// Everything is enqueued on one CUDA stream per solver (zones are independent inside a phase; phases are ordered by
+// the stream), no host synchronisation inside fb_compute.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <cmath>
+#include "../../include/fastb200.h"
+#include "fb_kernels.cuh"
+#include "fb_implicit.cuh"
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &m) { g_err = m; return code; }
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+    return fail(FB_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+
+struct Zone {
+    std::vector<int> pi; std::vector<double> pr;
+    ZoneDev d;
+    double *rop[3] = {nullptr, nullptr, nullptr};   // ro, ro_M1, ro_P1 (rotated on the host side of the handle)
+    double *xyz = nullptr, *mtr = nullptr, *aux = nullptr, *drodm = nullptr, *coe = nullptr;
+    unsigned char *wigb = nullptr;
+    double *rdm = nullptr;          // device: nssiter*neq*2
+    double *cflv = nullptr;         // device: 3
+    BcWin *wins = nullptr, *wins_rhs = nullptr;
+    int nwin = 0, nwin_rhs = 0, maxc = 0, maxc_rhs = 0;
+    int lu_box[6];                  // ishift_lu (BCzone.cpp:136-143)
+    int lcorner = 1;
+    LuPlan lu;                      // hyperplane bookkeeping (fb_implicit.cu)
+    bool has_params = false, has_xyz = false;
+    size_t n_state = 0, n_aux = 0;
+};
+
+struct Timer { cudaEvent_t a, b; double ms = 0; long long n = 0; std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pend; };
+
+struct fb_solver {
+    int dev = 0, nz = 0;
+    cudaStream_t st = nullptr;
+    std::vector<Zone> z;
+    bool metric_done = false;
+    JoinSet joins;
+    bool timing = false;
+    Timer tm[6];     // rhs, lu, bc, transfer, coe, all
+    long long launches = 0;
+};
+
+static const char *TNAMES[6] = {"rhs", "lu", "bc", "transfer", "coe", "all"};
+
+struct Scope {   // CUDA-event bracket around one kernel family, resolved lazily (no sync in the hot loop)
+    fb_solver *s; int id; cudaEvent_t a, b; bool on;
+    Scope(fb_solver *s_, int id_) : s(s_), id(id_), on(s_->timing) {
+        if (on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, s->st); }
+    }
+    ~Scope() { if (on) { cudaEventRecord(b, s->st); s->tm[id].pend.push_back({a, b}); } }
+};
+static void resolve(fb_solver *s)
+{
+    for (int i = 0; i < 6; i++) {
+        for (auto &p : s->tm[i].pend) {
+            cudaEventSynchronize(p.second); float ms = 0; cudaEventElapsedTime(&ms, p.first, p.second);
+            s->tm[i].ms += ms; cudaEventDestroy(p.first); cudaEventDestroy(p.second);
+        }
+        s->tm[i].pend.clear();
+    }
+}
+
+extern "C" {
+
+int fb_version(void) { return 100; }
+const char *fb_last_error(void) { return g_err.c_str(); }
+int fb_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
+
+int fb_solver_create(int device, int nzones, fb_solver **out)
+{
+    if (!out || nzones <= 0) return fail(FB_EINVAL, "fb_solver_create: bad arguments");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(FB_ECUDA, "fb_solver_create: no CUDA device visible -- fast_b200 has no CPU fallback");
+    }
+    CK(cudaSetDevice(device));
+    fb_solver *s = new fb_solver();
+    s->dev = device; s->nz = nzones; s->z.resize(nzones);
+    CK(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
+    *out = s;
+    return FB_OK;
+}
+
+void fb_solver_destroy(fb_solver *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->dev);
+    for (auto &z : s->z) {
+        for (int l = 0; l < 3; l++) cudaFree(z.rop[l]);
+        cudaFree(z.xyz); cudaFree(z.mtr); cudaFree(z.aux); cudaFree(z.drodm); cudaFree(z.coe); cudaFree(z.wigb);
+        cudaFree(z.rdm); cudaFree(z.cflv); cudaFree(z.wins); cudaFree(z.wins_rhs);
+        lu_plan_free(z.lu);
+    }
+    joins_free(s->joins);
+    if (s->st) cudaStreamDestroy(s->st);
+    delete s;
+}
+
+// ghost range of one BC window for a whole-zone sub-domain, npass = 0 (C/BC/indice_cl_sdm.for:40-90)
+static bool bc_window(const int *pi, int idir, const int *fen, int out[6])
+{
+    const int nf = pi[PI_NIJK + 3], nfk = pi[PI_NIJK + 4];
+    const int sdm[6] = {1, pi[PI_IJKV], 1, pi[PI_IJKV + 1], 1, pi[PI_IJKV + 2]};
+    for (int d = 0; d < 3; d++) if (!(sdm[2 * d] <= fen[2 * d + 1] && sdm[2 * d + 1] >= fen[2 * d])) return false;
+    for (int d = 0; d < 3; d++) {
+        out[2 * d] = fen[2 * d] > sdm[2 * d] ? fen[2 * d] : sdm[2 * d];
+        out[2 * d + 1] = fen[2 * d + 1] < sdm[2 * d + 1] ? fen[2 * d + 1] : sdm[2 * d + 1];
+    }
+    const int d = (idir - 1) / 2, fic = d == 2 ? nfk : nf;
+    if (idir % 2 == 1) { out[2 * d + 1] = out[2 * d] - 1; out[2 * d] = out[2 * d] - fic; }
+    else { out[2 * d + 1] = out[2 * d] + fic; out[2 * d] = out[2 * d] + 1; }
+    return true;
+}
+static int win_cells(const BcWin &w)
+{
+    const int d = (w.idir - 1) / 2, t1 = d == 0 ? 1 : 0, t2 = d == 2 ? 1 : 2;
+    return (w.w[2 * t1 + 1] - w.w[2 * t1] + 1) * (w.w[2 * t2 + 1] - w.w[2 * t2] + 1);
+}
+
+// BC tables for lrhs=0 (state) and lrhs=1 (rhs before the LU sweep), following S/BC/BCzone.cpp:86-360
+static int build_bc_tables(Zone &z)
+{
+    const int *pi = z.pi.data();
+    const int pt = pi[PI_PT_BC];
+    if (pt <= 0 || pt >= (int)z.pi.size()) return fail(FB_EINVAL, "Parameter_int has no BC table (PT_BC); run _BCcompact first");
+    const int nb = pi[pt];
+    const int ijkv[3] = {pi[PI_IJKV], pi[PI_IJKV + 1], pi[PI_IJKV + 2]};
+    std::vector<BcWin> w0, w1;
+    int lskip[6] = {1, 1, 1, 1, 1, 1}, ificmax[6];
+    const int lum = pi[PI_LU_MATCH] != 0;
+    for (int p = 0; p < 4; p++) ificmax[p] = pi[PI_NIJK + 3] * lum;
+    for (int p = 4; p < 6; p++) ificmax[p] = pi[PI_NIJK + 4] * lum;
+    z.lcorner = 1;
+    for (int b = 0; b < nb; b++) {
+        const int pb = pi[pt + 1 + b], ty = pi[pb + BC_TYPE], ip = pi[pb + BC_IDIR] - 1;
+        if (ip < 0 || ip > 5) return fail(FB_EINVAL, "BC window with idir outside 1..6");
+        const bool ok = ty == 0 || ty == 1 || ty == 3 || ty == 4 || ty == 6 || ty == 11 || ty == 22;
+        if (!ok) return fail(FB_EINVAL, "BC type " + std::to_string(ty) + " is outside the hot-path scope (0,1,3,4,6,11,22)");
+        if ((ty >= 3 && ty <= 7) || ty == 12 || ty == 18 || ty == 30) {
+            lskip[ip] = 0; z.lcorner = 0;
+            if ((ty >= 3 && ty <= 7) || ty == 12) ificmax[ip] = 1;
+        }
+    }
+    for (int p = 0; p < 6; p++) {
+        const int base = (p % 2) ? ijkv[p / 2] : 1;
+        z.lu_box[p] = base + ((p % 2) ? 1 : -1) * (1 - lskip[p]) * ificmax[p];
+    }
+    for (int idir = 0; idir < 6; idir++) {      // default rhs extrapolation on the implicit-ed faces (BCzone.cpp:190-256)
+        if (lskip[idir]) continue;
+        int fen[6] = {1, ijkv[0], 1, ijkv[1], 1, ijkv[2]};
+        const int d = idir / 2;
+        if (idir % 2 == 0) fen[2 * d + 1] = 1; else fen[2 * d] = fen[2 * d + 1];
+        BcWin w; w.type = 0; w.idir = idir + 1;
+        if (bc_window(pi, idir + 1, fen, w.w)) w1.push_back(w);
+    }
+    for (int b = 0; b < nb; b++) {
+        const int pb = pi[pt + 1 + b];
+        BcWin w; w.type = pi[pb + BC_TYPE]; w.idir = pi[pb + BC_IDIR];
+        if (!bc_window(pi, w.idir, pi + pb + BC_FEN, w.w)) continue;
+        w0.push_back(w);
+        if (lskip[w.idir - 1] == 0) {
+            BcWin r = w;
+            const int ty = r.type;
+            if (ty == 0 || ty == 1 || ty == 2 || ty == 10 || ty == 11 || ty == 14 || ty == 16 || ty == 17 || ty == 20 || ty == 21) r.type = 0;
+            w1.push_back(r);
+        }
+    }
+    // The reference applies the windows one after the other; windows of one zone never overlap in scope
+    // (each face ghost cell belongs to one window), except the default rhs extrapolation which must run FIRST.
+    // => rhs table is applied in two launches when both kinds are present (see apply_bc).
+    auto upload = [&](const std::vector<BcWin> &v, BcWin *&dptr, int &n, int &maxc) -> cudaError_t {
+        n = (int)v.size(); maxc = 0;
+        for (auto &w : v) { const int c = win_cells(w); if (c > maxc) maxc = c; }
+        if (n == 0) return cudaSuccess;
+        cudaError_t e = cudaMalloc(&dptr, n * sizeof(BcWin)); if (e != cudaSuccess) return e;
+        return cudaMemcpy(dptr, v.data(), n * sizeof(BcWin), cudaMemcpyHostToDevice);
+    };
+    CK(upload(w0, z.wins, z.nwin, z.maxc));
+    CK(upload(w1, z.wins_rhs, z.nwin_rhs, z.maxc_rhs));
+    // number of leading default-extrapolation windows in the rhs table
+    int ndef = 0; for (int idir = 0; idir < 6; idir++) if (!lskip[idir]) ndef++;
+    z.lu.ndefault_rhs = ndef;
+    return FB_OK;
+}
+
+int fb_zone_set_params(fb_solver *s, int nd, const int *pi, int n_int, const double *pr, int n_real)
+{
+    if (!s || nd < 0 || nd >= s->nz || !pi || !pr || n_int < PI_SIZE || n_real < PR_SIZE)
+        return fail(FB_EINVAL, "fb_zone_set_params: bad arguments");
+    CK(cudaSetDevice(s->dev));
+    Zone &z = s->z[nd];
+    z.pi.assign(pi, pi + n_int); z.pr.assign(pr, pr + n_real);
+    ZoneDev &d = z.d; memset(&d, 0, sizeof(d));
+    d.ni = pi[PI_NIJK]; d.nj = pi[PI_NIJK + 1]; d.nk = pi[PI_NIJK + 2]; d.nf = pi[PI_NIJK + 3]; d.nfk = pi[PI_NIJK + 4];
+    d.iv = pi[PI_IJKV]; d.jv = pi[PI_IJKV + 1]; d.kv = pi[PI_IJKV + 2]; d.nd = pi[PI_NDIMDX];
+    d.incj = d.ni; d.inck = d.ni * d.nj;
+    d.mi = pi[PI_NIJK_MTR]; d.mj = pi[PI_NIJK_MTR + 1]; d.mk = pi[PI_NIJK_MTR + 2]; d.mf = pi[PI_NIJK_MTR + 3];
+    d.mfk = pi[PI_NIJK_MTR + 4]; d.nm = pi[PI_NDIMDX_MTR];
+    d.xi = pi[PI_NIJK_XYZ]; d.xj = pi[PI_NIJK_XYZ + 1]; d.xf = pi[PI_NIJK_XYZ + 3]; d.xfk = pi[PI_NIJK_XYZ + 4];
+    d.ndx = pi[PI_NDIMDX_XYZ];
+    d.typ = pi[PI_ITYPZONE]; d.iflow = pi[PI_IFLOW]; d.kflu = pi[PI_KFLUDOM]; d.slope = pi[PI_SLOPE]; d.neq = pi[PI_NEQ];
+    d.itypcp = pi[PI_ITYPCP]; d.neq_coe = pi[PI_NEQ_COE]; d.rk = pi[PI_RK]; d.dtloc = pi[PI_DTLOC];
+    d.sensortype = pi[PI_SENSORTYPE];
+    if (d.typ < 0 || d.typ > 2) return fail(FB_EINVAL, "zone type " + std::to_string(d.typ) + " not built (3dfull/3dhomo/3dcart only)");
+    if (d.iflow < 1 || d.iflow > 3) return fail(FB_EINVAL, "IFLOW outside 1..3");
+    if (!(d.kflu == 1 || d.kflu == 2 || d.kflu == 5)) return fail(FB_EINVAL, "scheme (KFLUDOM) outside ausmpred/senseur/roe");
+    if (d.slope < 1 || d.slope > 3) return fail(FB_EINVAL, "slope outside o1/o3/minmod");
+    if (pi[PI_LALE] != 0 || pi[PI_EXPLOC] != 0 || pi[PI_ILES] != 0 || pi[PI_IMPLICITSOLVER] != 0 || pi[PI_NB_RELAX] != 1)
+        return fail(FB_EINVAL, "ALE / local explicit / LES / GMRES / nb_relax>1 are outside the hot-path scope");
+    if (d.nf != 2) return fail(FB_EINVAL, "only 2 ghost layers are supported");
+    // constants of template_FluxAndBalance.for:121-153
+    d.gam = pr[PR_GAMMA]; d.cv = pr[PR_CVINF]; d.rgp = d.cv * (d.gam - 1.); d.gam1 = d.gam / (d.gam - 1.);
+    d.gam3 = d.gam1 / pr[PR_PRANDT] * d.rgp; d.gam4 = d.gam1 / pr[PR_PRANDT_TUR] * d.rgp;
+    d.cmus1 = pr[PR_CS]; d.temp01 = 1. / pr[PR_TEMP0];
+    d.coesut = pr[PR_XMUL0] * (1. + d.cmus1 * d.temp01);
+    d.coesut_vis = pr[PR_XMUL0] * (1. + d.cmus1 * d.temp01) * sqrt(d.temp01);
+    d.sigma_1 = 1. / SA_SIGMA;
+    d.c1 = 0.02 * pr[PR_VINF]; d.c2 = 0.02 / (pr[PR_VINF] * pr[PR_ROINF]);
+    d.opt0 = (double)pi[PI_SENSORTYPE]; d.wig_cte = pr[PR_WIG_AMP]; d.psiroe = pr[PR_PSIROE];
+    d.tmin_1 = 100. / pr[PR_TINF]; d.dtc = pr[PR_DTC]; d.ratiom = pr[PR_RATIOM]; d.cfl = pr[PR_CFL];
+    d.roinf = pr[PR_ROINF]; d.xmul0 = pr[PR_XMUL0];
+    d.vinf[0] = pr[PR_VXINF]; d.vinf[1] = pr[PR_VYINF]; d.vinf[2] = pr[PR_VZINF]; d.pinf = pr[PR_PINF];
+    d.ronutildeinf = pr[PR_RONUTILDEINF];
+    // HBM arrays
+    z.n_state = (size_t)d.nd * d.neq;
+    const int naux = d.iflow == 3 ? 2 : (d.iflow == 2 ? 1 : 0);
+    z.n_aux = (size_t)d.nd * naux;
+    for (int l = 0; l < 3; l++) { cudaFree(z.rop[l]); CK(cudaMalloc(&z.rop[l], z.n_state * sizeof(double))); CK(cudaMemset(z.rop[l], 0, z.n_state * sizeof(double))); }
+    cudaFree(z.drodm); CK(cudaMalloc(&z.drodm, z.n_state * sizeof(double))); CK(cudaMemset(z.drodm, 0, z.n_state * sizeof(double)));
+    cudaFree(z.aux); z.aux = nullptr;
+    if (naux) { CK(cudaMalloc(&z.aux, z.n_aux * sizeof(double))); CK(cudaMemset(z.aux, 0, z.n_aux * sizeof(double))); }
+    cudaFree(z.coe); z.coe = nullptr;
+    if (d.itypcp <= 1) { CK(cudaMalloc(&z.coe, (size_t)d.nd * d.neq_coe * sizeof(double))); CK(cudaMemset(z.coe, 0, (size_t)d.nd * d.neq_coe * sizeof(double))); }
+    cudaFree(z.wigb); z.wigb = nullptr;
+    if (d.kflu == 2) { CK(cudaMalloc(&z.wigb, d.nd)); CK(cudaMemset(z.wigb, 0, d.nd)); }
+    const int neq_ij = pi[PI_NEQ_IJ], neq_k = pi[PI_NEQ_K];
+    cudaFree(z.mtr); CK(cudaMalloc(&z.mtr, (size_t)d.nm * (2 * neq_ij + neq_k + 1) * sizeof(double)));
+    d.ti = z.mtr; d.tj = d.ti + (size_t)d.nm * neq_ij; d.tk = d.tj + (size_t)d.nm * neq_ij; d.vol = d.tk + (size_t)d.nm * neq_k;
+    cudaFree(z.xyz); CK(cudaMalloc(&z.xyz, (size_t)3 * d.ndx * sizeof(double)));
+    d.x = z.xyz; d.y = z.xyz + d.ndx; d.z = z.xyz + 2 * (size_t)d.ndx;
+    const int nss = pi[PI_NSSITER] > 0 ? pi[PI_NSSITER] : 1;
+    cudaFree(z.rdm); CK(cudaMalloc(&z.rdm, (size_t)nss * d.neq * 2 * sizeof(double))); CK(cudaMemset(z.rdm, 0, (size_t)nss * d.neq * 2 * sizeof(double)));
+    cudaFree(z.cflv); CK(cudaMalloc(&z.cflv, 3 * sizeof(double))); CK(cudaMemset(z.cflv, 0, 3 * sizeof(double)));
+    d.xmut = z.aux; d.drodm = z.drodm; d.coe = z.coe; d.wigb = z.wigb;
+    cudaFree(z.wins); cudaFree(z.wins_rhs); z.wins = z.wins_rhs = nullptr;
+    int rc = build_bc_tables(z); if (rc) return rc;
+    if (d.itypcp <= 1) { rc = lu_plan_build(z.lu, d, z.lu_box); if (rc) return fail(FB_ECUDA, "lu_plan_build failed"); }
+    z.has_params = true; s->metric_done = false;
+    return FB_OK;
+}
+
+int fb_zone_set_coords(fb_solver *s, int nd, const double *x, const double *y, const double *zc)
+{
+    if (!s || nd < 0 || nd >= s->nz || !x || !y || !zc) return fail(FB_EINVAL, "fb_zone_set_coords: bad arguments");
+    Zone &z = s->z[nd]; if (!z.has_params) return fail(FB_ESTATE, "fb_zone_set_coords before fb_zone_set_params");
+    CK(cudaSetDevice(s->dev));
+    const size_t n = (size_t)z.d.ndx * sizeof(double);
+    CK(cudaMemcpy(z.xyz, x, n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(z.xyz + z.d.ndx, y, n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(z.xyz + 2 * (size_t)z.d.ndx, zc, n, cudaMemcpyHostToDevice));
+    z.has_xyz = true;
+    return FB_OK;
+}
+
+int fb_init_metric(fb_solver *s)
+{
+    if (!s) return fail(FB_EINVAL, "null solver");
+    CK(cudaSetDevice(s->dev));
+    for (auto &z : s->z) {
+        if (!z.has_params || !z.has_xyz) return fail(FB_ESTATE, "fb_init_metric: every zone needs params and coordinates");
+        launch_metric(z.d, s->st);
+    }
+    CK(cudaStreamSynchronize(s->st));
+    for (auto &z : s->z) {   // 3dcart constants live in the descriptor (template_FluxAndBalance.for:112-119)
+        if (z.d.typ == 2) {
+            double h[4];
+            CK(cudaMemcpy(h, z.mtr, 4 * sizeof(double), cudaMemcpyDeviceToHost));   // ti|tj|tk|vol, one value each
+            z.d.tc0[0] = h[0]; z.d.tc0[1] = h[1]; z.d.tc0[2] = h[2]; z.d.vol0 = h[3];
+        }
+    }
+    CK(cudaGetLastError());
+    s->metric_done = true;
+    return FB_OK;
+}
+
+int fb_zone_get_metric(fb_solver *s, int nd, double *ti, double *tj, double *tk, double *vol)
+{
+    if (!s || nd < 0 || nd >= s->nz) return fail(FB_EINVAL, "bad zone");
+    Zone &z = s->z[nd]; if (!s->metric_done) return fail(FB_ESTATE, "metrics not computed");
+    CK(cudaSetDevice(s->dev));
+    const int nij = z.pi[PI_NEQ_IJ], nk = z.pi[PI_NEQ_K]; const size_t nm = z.d.nm;
+    if (ti) CK(cudaMemcpy(ti, z.d.ti, nm * nij * sizeof(double), cudaMemcpyDeviceToHost));
+    if (tj) CK(cudaMemcpy(tj, z.d.tj, nm * nij * sizeof(double), cudaMemcpyDeviceToHost));
+    if (tk) CK(cudaMemcpy(tk, z.d.tk, nm * nk * sizeof(double), cudaMemcpyDeviceToHost));
+    if (vol) CK(cudaMemcpy(vol, z.d.vol, nm * sizeof(double), cudaMemcpyDeviceToHost));
+    return FB_OK;
+}
+
+static int chk_zone(fb_solver *s, int nd, int level)
+{
+    if (!s || nd < 0 || nd >= s->nz || level < 0 || level > 2) return fail(FB_EINVAL, "bad zone / level");
+    if (!s->z[nd].has_params) return fail(FB_ESTATE, "zone has no parameters yet");
+    return FB_OK;
+}
+int fb_zone_upload_state(fb_solver *s, int nd, int level, const double *rop)
+{
+    int rc = chk_zone(s, nd, level); if (rc) return rc;
+    CK(cudaSetDevice(s->dev));
+    CK(cudaMemcpyAsync(s->z[nd].rop[level], rop, s->z[nd].n_state * sizeof(double), cudaMemcpyHostToDevice, s->st));
+    CK(cudaStreamSynchronize(s->st));
+    return FB_OK;
+}
+int fb_zone_download_state(fb_solver *s, int nd, int level, double *rop)
+{
+    int rc = chk_zone(s, nd, level); if (rc) return rc;
+    CK(cudaSetDevice(s->dev));
+    CK(cudaMemcpyAsync(rop, s->z[nd].rop[level], s->z[nd].n_state * sizeof(double), cudaMemcpyDeviceToHost, s->st));
+    CK(cudaStreamSynchronize(s->st));
+    return FB_OK;
+}
+int fb_zone_upload_aux(fb_solver *s, int nd, const double *aux, int n)
+{
+    int rc = chk_zone(s, nd, 0); if (rc) return rc;
+    Zone &z = s->z[nd]; if ((size_t)n != z.n_aux) return fail(FB_EINVAL, "aux size mismatch");
+    if (n == 0) return FB_OK;
+    CK(cudaSetDevice(s->dev));
+    CK(cudaMemcpyAsync(z.aux, aux, z.n_aux * sizeof(double), cudaMemcpyHostToDevice, s->st));
+    CK(cudaStreamSynchronize(s->st));
+    return FB_OK;
+}
+int fb_zone_download_aux(fb_solver *s, int nd, double *aux, int n)
+{
+    int rc = chk_zone(s, nd, 0); if (rc) return rc;
+    Zone &z = s->z[nd]; if ((size_t)n != z.n_aux) return fail(FB_EINVAL, "aux size mismatch");
+    if (n == 0) return FB_OK;
+    CK(cudaSetDevice(s->dev));
+    CK(cudaMemcpyAsync(aux, z.aux, z.n_aux * sizeof(double), cudaMemcpyDeviceToHost, s->st));
+    CK(cudaStreamSynchronize(s->st));
+    return FB_OK;
+}
+int fb_zone_download_work(fb_solver *s, int nd, double *drodm, double *coe)
+{
+    int rc = chk_zone(s, nd, 0); if (rc) return rc;
+    Zone &z = s->z[nd];
+    CK(cudaSetDevice(s->dev));
+    CK(cudaStreamSynchronize(s->st));
+    if (drodm) CK(cudaMemcpy(drodm, z.drodm, z.n_state * sizeof(double), cudaMemcpyDeviceToHost));
+    if (coe && z.coe) CK(cudaMemcpy(coe, z.coe, (size_t)z.d.nd * z.d.neq_coe * sizeof(double), cudaMemcpyDeviceToHost));
+    return FB_OK;
+}
+
+int fb_set_joins(fb_solver *s, const int *ji, int n)
+{
+    if (!s || !ji || n < 1) return fail(FB_EINVAL, "fb_set_joins: bad arguments");
+    CK(cudaSetDevice(s->dev));
+    std::vector<int> nds(s->nz), neqs(s->nz);
+    for (int i = 0; i < s->nz; i++) { nds[i] = s->z[i].d.nd; neqs[i] = s->z[i].d.neq; }
+    std::string err;
+    if (joins_build(s->joins, ji, n, s->nz, nds.data(), neqs.data(), err)) return fail(FB_EINVAL, "fb_set_joins: " + err);
+    return FB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------- driver
+static void apply_bc_zone(fb_solver *s, Zone &z, double *rop, int lrhs)
+{
+    if (lrhs == 0) {
+        launch_bc(z.d, z.wins, z.nwin, z.maxc, rop, 0, s->st); s->launches += z.nwin > 0;
+        int box[6] = {1, z.d.iv, 1, z.d.jv, 1, z.d.kv};
+        launch_corners(z.d, rop, box, s->st); s->launches++;
+    } else {
+        const int nd0 = z.lu.ndefault_rhs;
+        if (nd0 > 0) { launch_bc(z.d, z.wins_rhs, nd0, z.maxc_rhs, rop, 1, s->st); s->launches++; }
+        if (z.nwin_rhs > nd0) { launch_bc(z.d, z.wins_rhs + nd0, z.nwin_rhs - nd0, z.maxc_rhs, rop, 1, s->st); s->launches++; }
+        if (z.lcorner == 0) { launch_corners(z.d, rop, z.lu_box, s->st); s->launches++; }
+    }
+}
+
+static void transfers(fb_solver *s, int which, int level_ssiter_dummy, double **target)
+{
+    (void)level_ssiter_dummy;
+    if (s->joins.njoin == 0) return;
+    Scope t(s, 3);
+    std::vector<double *> ptr(s->nz);
+    for (int i = 0; i < s->nz; i++) ptr[i] = which == 1 ? s->z[i].drodm : target[i];
+    s->launches += joins_apply(s->joins, ptr.data(), s->nz, s->st);
+}
+
+static int gsdr3(fb_solver *s, int nitcfg, int nssiter, int nitrun, int first_it, int lssiter_verif, int lexit_lu)
+{
+    (void)nitrun; (void)nssiter;
+    const bool implicit = s->z[0].d.itypcp <= 1;
+    std::vector<double *> cl(s->nz);
+    {
+        Scope all(s, 5);
+        for (int n = 0; n < s->nz; n++) {
+            Zone &z = s->z[n];
+            // gsdr3.cpp:162-173: flux input and array receiving transfers + BC
+            double *ssiter, *clp;
+            if (nitcfg == 1) { ssiter = z.rop[0]; clp = z.rop[2]; }
+            else if (implicit) { ssiter = z.rop[2]; clp = z.rop[2]; }
+            else if (nitcfg % 2 == 0) { ssiter = z.rop[2]; clp = z.rop[0]; }
+            else { ssiter = z.rop[0]; clp = z.rop[2]; }
+            cl[n] = clp;
+            if (nitcfg == 1) {   // navier_stokes_struct.for:216-301
+                Scope c(s, 4);
+                if (z.d.iflow >= 2) { launch_invist(z.d, ssiter, implicit || z.d.iflow == 3 ? z.d.nf : 1, s->st); s->launches++; }
+                if (implicit) { launch_coe(z.d, ssiter, first_it, lssiter_verif, z.cflv, s->st); s->launches++; }
+                if (z.d.kflu == 2) { launch_sensor(z.d, ssiter, s->st); s->launches++; }
+            }
+            {
+                Scope r(s, 0);
+                if (implicit && z.d.iflow == 3 && nitcfg == 1) { launch_sa_ring(z.d, ssiter, s->st); s->launches++; }
+                double *out = implicit ? nullptr : clp;   // explicit: the stage writes the array that then gets the BCs
+                launch_rhs(z.d, ssiter, out, z.rop[0], z.rop[1], nitcfg, first_it, s->st); s->launches++;
+            }
+        }
+        if (implicit) {
+            if (s->z[0].pi[PI_LU_MATCH] == 1) transfers(s, 1, 0, nullptr);   // lhs.cpp:1-15
+            for (int n = 0; n < s->nz; n++) {
+                Zone &z = s->z[n];
+                { Scope b(s, 2); apply_bc_zone(s, z, z.drodm, 1); }           // lhs.cpp:57-67
+                if (lssiter_verif == 1) { launch_resid(z.d, z.rdm, nitcfg, s->st); s->launches++; }   // cprdu3s1
+                if (lexit_lu == 0) {
+                    Scope l(s, 1);
+                    double *ssiter = nitcfg == 1 ? z.rop[0] : z.rop[2];
+                    s->launches += launch_lu(z.d, z.lu, ssiter, z.rop[2], s->st);   // invlu_ + mjr_newton
+                }
+            }
+        }
+        if (lexit_lu == 0) {
+            transfers(s, 0, 0, cl.data());                                     // transfert_multiblock.cpp
+            Scope b(s, 2);
+            for (int n = 0; n < s->nz; n++) apply_bc_zone(s, s->z[n], cl[n], 0);   // bcs.cpp:32-40
+        }
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(FB_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
+    return FB_OK;
+}
+
+int fb_compute(fb_solver *s, int nitrun, int nstep_deb, int nstep_fin, int nit_c, int *first_it)
+{
+    if (!s || !first_it || nit_c < 1) return fail(FB_EINVAL, "fb_compute: bad arguments");
+    if (!s->metric_done) return fail(FB_ESTATE, "fb_compute before fb_init_metric");
+    CK(cudaSetDevice(s->dev));
+    const int itypcp = s->z[0].d.itypcp, nssiter = s->z[0].pi[PI_NSSITER];
+    for (auto &z : s->z) if ((z.d.itypcp <= 1) != (itypcp <= 1)) return fail(FB_EINVAL, "mixed explicit/implicit zones");
+    int modulo_verif = s->z[0].lu.modulo_verif > 0 ? s->z[0].lu.modulo_verif : 200;
+    for (int it = 0; it < nit_c; it++) {
+        const int nitrun_loc = nitrun * nit_c + it;
+        for (int nstep = nstep_deb; nstep <= nstep_fin; nstep++) {
+            int verif = 0, lexit = 0;                       // C/Compute/souszones_list.cpp:36-83
+            if (nitrun_loc % modulo_verif == 0) { verif = 1; if (nstep == nssiter && itypcp != 2) lexit = 1; }
+            if (verif == 0 && nstep == nssiter && itypcp == 1) continue;   // computePT.cpp:582
+            int rc = gsdr3(s, nstep, nssiter, nitrun_loc, *first_it, verif, lexit); if (rc) return rc;
+        }
+        *first_it = 1;
+        for (auto &z : s->z) { double *sv = z.rop[1]; z.rop[1] = z.rop[0]; z.rop[0] = z.rop[2]; z.rop[2] = sv; }   // computePT.cpp:675-679
+    }
+    return FB_OK;
+}
+
+int fb_set_modulo_verif(fb_solver *s, int m) { if (!s || m < 1) return fail(FB_EINVAL, "bad modulo_verif"); for (auto &z : s->z) z.lu.modulo_verif = m; return FB_OK; }
+
+int fb_apply_bc(fb_solver *s, int level)
+{
+    if (!s || level < 0 || level > 2) return fail(FB_EINVAL, "bad level");
+    if (!s->metric_done) return fail(FB_ESTATE, "fb_apply_bc before fb_init_metric");
+    CK(cudaSetDevice(s->dev));
+    for (auto &z : s->z) apply_bc_zone(s, z, z.rop[level], 0);
+    CK(cudaGetLastError());
+    return FB_OK;
+}
+int fb_transfers(fb_solver *s, int level)
+{
+    if (!s || level < 0 || level > 2) return fail(FB_EINVAL, "bad level");
+    CK(cudaSetDevice(s->dev));
+    std::vector<double *> t(s->nz); for (int i = 0; i < s->nz; i++) t[i] = s->z[i].rop[level];
+    transfers(s, 0, 0, t.data());
+    CK(cudaGetLastError());
+    return FB_OK;
+}
+int fb_compute_mut(fb_solver *s)
+{
+    if (!s) return fail(FB_EINVAL, "null solver");
+    CK(cudaSetDevice(s->dev));
+    for (auto &z : s->z) if (z.d.iflow >= 2) { launch_invist(z.d, z.rop[0], z.d.nf, s->st); s->launches++; }
+    CK(cudaGetLastError());
+    return FB_OK;
+}
+
+int fb_zone_get_residuals(fb_solver *s, int nd, double *rdm, int n)
+{
+    int rc = chk_zone(s, nd, 0); if (rc) return rc;
+    Zone &z = s->z[nd];
+    const int nss = z.pi[PI_NSSITER] > 0 ? z.pi[PI_NSSITER] : 1;
+    if (n != nss * z.d.neq * 2) return fail(FB_EINVAL, "rdm size must be nssiter*neq*2");
+    CK(cudaSetDevice(s->dev)); CK(cudaStreamSynchronize(s->st));
+    CK(cudaMemcpy(rdm, z.rdm, n * sizeof(double), cudaMemcpyDeviceToHost));
+    return FB_OK;
+}
+int fb_zone_get_cfl(fb_solver *s, int nd, double cfl[3])
+{
+    int rc = chk_zone(s, nd, 0); if (rc) return rc;
+    CK(cudaSetDevice(s->dev)); CK(cudaStreamSynchronize(s->st));
+    CK(cudaMemcpy(cfl, s->z[nd].cflv, 3 * sizeof(double), cudaMemcpyDeviceToHost));
+    const double cells = (double)s->z[nd].d.iv * s->z[nd].d.jv * s->z[nd].d.kv;
+    cfl[2] /= cells;   // computePT.cpp:645
+    return FB_OK;
+}
+
+int fb_compute_host(fb_solver *s, int nitrun, int nit_c, int *first_it, double **ro, double **ro_m1, double **ro_p1)
+{
+    if (!s || !ro || !ro_m1 || !ro_p1) return fail(FB_EINVAL, "fb_compute_host: bad arguments");
+    CK(cudaSetDevice(s->dev));
+    double **h[3] = {ro, ro_m1, ro_p1};
+    for (int n = 0; n < s->nz; n++)
+        for (int l = 0; l < 3; l++)
+            CK(cudaMemcpyAsync(s->z[n].rop[l], h[l][n], s->z[n].n_state * sizeof(double), cudaMemcpyHostToDevice, s->st));
+    const int nssiter = s->z[0].pi[PI_NSSITER];
+    int rc = fb_compute(s, nitrun, 1, nssiter, nit_c, first_it); if (rc) return rc;
+    // after the rotation device level l holds what the caller's rotated pointers expect: write back in place
+    for (int n = 0; n < s->nz; n++)
+        for (int l = 0; l < 3; l++)
+            CK(cudaMemcpyAsync(h[l][n], s->z[n].rop[l], s->z[n].n_state * sizeof(double), cudaMemcpyDeviceToHost, s->st));
+    CK(cudaStreamSynchronize(s->st));
+    return FB_OK;
+}
+
+int fb_timing_enable(fb_solver *s, int on) { if (!s) return fail(FB_EINVAL, "null"); s->timing = on != 0; return FB_OK; }
+int fb_timing_reset(fb_solver *s)
+{
+    if (!s) return fail(FB_EINVAL, "null");
+    cudaSetDevice(s->dev); cudaStreamSynchronize(s->st); resolve(s);
+    for (int i = 0; i < 6; i++) { s->tm[i].ms = 0; s->tm[i].n = 0; }
+    s->launches = 0;
+    return FB_OK;
+}
+int fb_timing_get(fb_solver *s, const char *name, double *ms, long long *launches)
+{
+    if (!s || !name) return fail(FB_EINVAL, "null");
+    cudaSetDevice(s->dev); cudaStreamSynchronize(s->st); resolve(s);
+    for (int i = 0; i < 6; i++) if (!strcmp(name, TNAMES[i])) { if (ms) *ms = s->tm[i].ms; if (launches) *launches = s->launches; return FB_OK; }
+    return fail(FB_EINVAL, "unknown timer name");
+}
+int fb_sync(fb_solver *s) { if (!s) return fail(FB_EINVAL, "null"); CK(cudaSetDevice(s->dev)); CK(cudaStreamSynchronize(s->st)); CK(cudaGetLastError()); return FB_OK; }
+unsigned long long fb_zone_device_ptr(fb_solver *s, int nd, int level)
+{
+    if (!s || nd < 0 || nd >= s->nz || level < 0 || level > 3) return 0;
+    return (unsigned long long)(level == 3 ? s->z[nd].drodm : s->z[nd].rop[level]);
+}
+int fb_halo_pack(fb_solver *s, int which, unsigned long long buf, long long nbytes)
+{
+    if (!s) return fail(FB_EINVAL, "null");
+    CK(cudaSetDevice(s->dev));
+    std::vector<double *> t(s->nz); for (int i = 0; i < s->nz; i++) t[i] = which == 3 ? s->z[i].drodm : s->z[i].rop[which];
+    if (joins_pack(s->joins, t.data(), (double *)buf, nbytes, s->st)) return fail(FB_EINVAL, "halo buffer too small");
+    s->launches++;
+    return FB_OK;
+}
+int fb_halo_unpack(fb_solver *s, int which, unsigned long long buf, long long nbytes)
+{
+    if (!s) return fail(FB_EINVAL, "null");
+    CK(cudaSetDevice(s->dev));
+    std::vector<double *> t(s->nz); for (int i = 0; i < s->nz; i++) t[i] = which == 3 ? s->z[i].drodm : s->z[i].rop[which];
+    if (joins_unpack(s->joins, t.data(), (const double *)buf, nbytes, s->st)) return fail(FB_EINVAL, "halo buffer too small");
+    s->launches++;
+    return FB_OK;
+}
+unsigned long long fb_stream(fb_solver *s) { return s ? (unsigned long long)s->st : 0; }
+
+}   // extern "C"
+extern "C" int fb_halo_sizes(fb_solver *s, long long *send_doubles, long long *recv_doubles)
+{
+    if (!s) return -1;
+    if (send_doubles) *send_doubles = s->joins.send_doubles;
+    if (recv_doubles) *recv_doubles = s->joins.recv_doubles;
+    return 0;
+}

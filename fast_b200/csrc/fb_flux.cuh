@@ -60,18 +60,19 @@ __device__ __forceinline__ double visc_face(const ZoneDev &z, const double *__re
     const int inc[3] = {1, z.incj, z.inck};
     const int i0 = inc[DIR], i1 = inc[D1], i2 = inc[D2];
     const int il = l - i0, ir = l;
-    double G[4][3];
+    constexpr int NV = FLOW == 3 ? 5 : 4;   // SA: nutilde gradient with the same averaged metrics (SA/fluvisq_SA_*.for)
+    double G[NV][3];
 #pragma unroll
-    for (int c = 0; c < 4; c++) { G[c][0] = G[c][1] = G[c][2] = 0.; }
+    for (int c = 0; c < NV; c++) { G[c][0] = G[c][1] = G[c][2] = 0.; }
     double volinv;
     if (MESH == 2) {
         volinv = 0.5 / z.vol0;
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
+        for (int c = 0; c < NV; c++) {
             const double *q = rop + (c + 1) * nd;
             const double f1 = q[il], f2 = q[ir], fv = f1 + f2;
             G[c][DIR] = (f2 - f1) * z.tc0[DIR];
-            if (c == 3) continue;
+            if (c >= 3) continue;
             if (c == DIR || c == D1) {
                 const double fa = fv + q[il - i1] + q[ir - i1], fb = fv + q[il + i1] + q[ir + i1];
                 G[c][D1] = (fb - fa) * (.25 * z.tc0[D1]);
@@ -100,7 +101,7 @@ __device__ __forceinline__ double visc_face(const ZoneDev &z, const double *__re
             tb1[e] = .125 * (__ldg(T2 + lt + m2 + o) + __ldg(T2 + lt + m2 - m0 + o));
         }
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
+        for (int c = 0; c < NV; c++) {
             const double *q = rop + (c + 1) * nd;
             const double f1 = q[il], f2 = q[ir];
             const double f3 = f2 + f1 + q[il - i1] + q[ir - i1];
@@ -131,7 +132,7 @@ __device__ __forceinline__ double visc_face(const ZoneDev &z, const double *__re
             }
             const double tkz = .125 * (__ldg(z.tk + lt) + __ldg(z.tk + lt - m0));
 #pragma unroll
-            for (int c = 0; c < 4; c++) {
+            for (int c = 0; c < NV; c++) {
                 const double *q = rop + (c + 1) * nd;
                 const double f1 = q[il], f2 = q[ir];
                 const double fa = f2 + f1 + q[il - ip] + q[ir - ip], fb = f2 + f1 + q[il + ip] + q[ir + ip];
@@ -151,11 +152,11 @@ __device__ __forceinline__ double visc_face(const ZoneDev &z, const double *__re
             const double tkx = 0.25 * __ldg(z.tj + lt), tky = 0.25 * __ldg(z.tj + lt + nm);
             const double tkx1 = 0.25 * __ldg(z.tj + lt + z.mj), tky1 = 0.25 * __ldg(z.tj + lt + z.mj + nm);
 #pragma unroll
-            for (int c = 0; c < 4; c++) {
+            for (int c = 0; c < NV; c++) {
                 const double *q = rop + (c + 1) * nd;
                 const double f1 = q[il], f2 = q[ir];
                 G[c][2] = (f2 - f1) * tiz;
-                if (c == 3) continue;
+                if (c >= 3) continue;
                 const double f3 = f2 + f1 + q[il - ii] + q[ir - ii], f4 = f2 + f1 + q[il + ii] + q[ir + ii];
                 const double f5 = f2 + f1 + q[il - ij] + q[ir - ij], f6 = f2 + f1 + q[il + ij] + q[ir + ij];
                 G[c][0] = ((f4 * tjx1 - f3 * tjx) + (f6 * tkx1 - f5 * tkx));
@@ -205,6 +206,16 @@ __device__ __forceinline__ double visc_face(const ZoneDev &z, const double *__re
         fv = fv5 * 0.5 - (G[3][DIR] * t0) * xktvol; flu[4] += fv;
     }
     (void)f6;
+    if (FLOW == 3) {
+        double xmulam = z.coesut * sqrt(Tl * z.temp01) / (1. + z.cmus1 / Tl);
+        xmulam = xmulam + z.coesut * sqrt(Tr * z.temp01) / (1. + z.cmus1 / Tr);
+        double xsa = xmulam + rop[il + 5 * nd] * rop[il] + rop[ir + 5 * nd] * rop[ir];
+        xsa = xsa * volinv * z.sigma_1;
+        constexpr int C = NV - 1;
+        if (MESH == 0) flu[5] = flu[5] - xsa * (G[C][0] * tc[0] + G[C][1] * tc[1] + G[C][2] * tc[2]);
+        else if (MESH == 1 && DIR < 2) flu[5] = flu[5] - xsa * (G[C][0] * tc[0] + G[C][1] * tc[1]);
+        else flu[5] = flu[5] - xsa * G[C][DIR] * tc[DIR];
+    }
     return volinv;
 }
 
@@ -273,7 +284,7 @@ __device__ __forceinline__ void face_flux(const ZoneDev &z, const double *__rest
         flu[2] = (flu[2] + rou1 * qL[2] + rou2 * qR[2] + tc[1] * p1p2) * 0.5;
         flu[3] = (flu[3] + rou1 * qL[3] + rou2 * qR[3] + tc[2] * p1p2) * 0.5;
         flu[4] = (flu[4] + rou1 * h1 + rou2 * h2) * 0.5;
-        if (FLOW == 3) flu[5] = roe_sa_flux<SLOPE>(z, rop, l, inc, qn1, qn2, r1, r2);
+        if (FLOW == 3) flu[5] = roe_sa_flux(z, rop, l, inc, tc, s_1);
     } else {
         const double r1 = qL[0], rou1 = r1 * qL[1], rov1 = r1 * qL[2], row1 = r1 * qL[3], p1 = r1 * qL[4] * rgp;
         const double h1 = gam1 * p1 + .5 * (rou1 * qL[1] + rov1 * qL[2] + row1 * qL[3]);
@@ -298,10 +309,7 @@ __device__ __forceinline__ void face_flux(const ZoneDev &z, const double *__rest
         flu[2] = u * (rov1 + rov2) - tdu * (rov2 - rov1) + tc[1] * p1p2;
         flu[3] = u * (row1 + row2) - tdu * (row2 - row1) + tc[2] * p1p2;
         flu[4] = u * (h1 + h2) - tdu * (h2 - h1);
-        if (FLOW == 3) flu[5] = ausm_sa_flux<SLOPE>(z, rop, l, inc, u, tdu, r1, r2);
+        if (FLOW == 3) flu[5] = ausm_sa_flux<SLOPE>(z, rop, l, inc, T0, u, tdu, r1, r2);
     }
-    if (FLOW >= 2) {
-        const double volinv = visc_face<MESH, FLOW, DIR>(z, rop, l, lt, tc, flu);
-        if (FLOW == 3) flu[5] += sa_visc_flux<MESH, DIR>(z, rop, l, lt, tc, volinv);
-    }
+    if (FLOW >= 2) visc_face<MESH, FLOW, DIR>(z, rop, l, lt, tc, flu);
 }

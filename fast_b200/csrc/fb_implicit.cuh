@@ -1,0 +1,37 @@
+// fb_implicit.cuh -- implicit chain (LU-SGS coefficients, residual norms, hyperplane LU sweep) and match-join
+// transfers; implemented in fb_implicit.cu / fb_joins.cu.
+#pragma once
+#include <string>
+#include <vector>
+#include "fb_common.cuh"
+
+struct LuPlan {
+    int box[6] = {0, 0, 0, 0, 0, 0};   // sweep box = ishift_lu (S/BC/BCzone.cpp:136-143)
+    int nplanes = 0;
+    int ndefault_rhs = 0;             // leading default-extrapolation windows of the rhs BC table
+    int modulo_verif = 0;
+    void *scratch = nullptr;
+};
+int  lu_plan_build(LuPlan &p, const ZoneDev &z, const int box[6]);
+void lu_plan_free(LuPlan &p);
+void launch_coe(const ZoneDev &z, const double *rop, int first_it, int lssiter_verif, double *cfl, cudaStream_t st);
+void launch_sa_ring(const ZoneDev &z, const double *rop, cudaStream_t st);
+void launch_resid(const ZoneDev &z, double *rdm, int nitcfg, cudaStream_t st);
+int  launch_lu(const ZoneDev &z, const LuPlan &p, const double *rop_ssiter, double *rop_out, cudaStream_t st);
+
+// match joins (1 donor, coefficient 1: C/Com/setInterpTransfersFast.cpp:440-955 for interpolation type 0/1)
+struct JoinSet {
+    int njoin = 0;
+    int *d_desc = nullptr;     // njoin x 8 ints: kind, dz, rz, npts, off_d, off_r, boff, neq
+    int *d_idx = nullptr;      // donor / receiver cell addresses (0-based l)
+    int maxpts = 0;
+    std::vector<int> h_desc;
+    long long send_doubles = 0, recv_doubles = 0;
+    double **d_ptrs = nullptr; // per-zone base pointers (refreshed at every apply)
+    int nz = 0;
+};
+int  joins_build(JoinSet &j, const int *ji, int n, int nz, const int *ndimdx, const int *neqs, std::string &err);
+void joins_free(JoinSet &j);
+int  joins_apply(JoinSet &j, double **zone_ptr, int nz, cudaStream_t st);          // kind 0 (local) joins
+int  joins_pack(JoinSet &j, double **zone_ptr, double *buf, long long nbytes, cudaStream_t st);      // kind 1
+int  joins_unpack(JoinSet &j, double **zone_ptr, const double *buf, long long nbytes, cudaStream_t st); // kind 2

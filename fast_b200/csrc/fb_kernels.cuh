@@ -1,0 +1,17 @@
+// fb_kernels.cuh -- launchers shared between fb_kernels.cu / fb_implicit.cu and the C-ABI driver (fb_api.cu).
+#pragma once
+#include "fb_common.cuh"
+
+struct BcWin {          // one BC window, ghost range already resolved (C/BC/indice_cl_sdm.for, npass = 0)
+    int type, idir;     // reference tag (C/PyTree.py:30-70), 1..6
+    int w[6];           // ghost cells imin..kmax (1-based interior numbering, ghosts <= 0 or > n)
+};
+
+void launch_metric(const ZoneDev &z, cudaStream_t st);
+void launch_invist(const ZoneDev &z, const double *rop, int ext, cudaStream_t st);
+void launch_sensor(const ZoneDev &z, const double *rop, cudaStream_t st);
+// explicit stage (init_rhs + flux balance + core3ark3) or implicit rhs (src + flux balance + core3as2)
+void launch_rhs(const ZoneDev &z, const double *rop, double *rop_out, const double *ro_n, const double *ro_n1,
+                int nitcfg, int first_it, cudaStream_t st);
+void launch_bc(const ZoneDev &z, const BcWin *d_wins, int nwin, int maxcells, double *rop, int lrhs, cudaStream_t st);
+void launch_corners(const ZoneDev &z, double *rop, const int box[6], cudaStream_t st);

@@ -1,0 +1,177 @@
+// fb_source.cuh -- per-cell source / assembly pieces fused into k_rhs: SA eddy viscosity (SA/vispalart.for),
+// SA source (SA/spsource_SA.for + sourceSA_grad_*.for + sourceSA_prod_dest.for + sourceSA_LU.for) and the
+// Newton residual assembly (core3as2.for).
+#pragma once
+#include "fb_common.cuh"
+
+__device__ __forceinline__ double mulam(const ZoneDev &z, double T)
+{   // S/Compute/mulam.for
+    return z.coesut * sqrt(T * z.temp01) / (1. + z.cmus1 / T);
+}
+
+// SA/vispalart.for: mu + min(max(rho nutilde fv1, 0), ratiom mu)
+__device__ __forceinline__ double vispalart_cell(const ZoneDev &z, const double *__restrict__ rop, int l)
+{
+    const int nd = z.nd;
+    const double amulam = mulam(z, rop[l + 4 * nd]);
+    const double anulam = rop[l] / amulam;
+    const double anutild = fmax(rop[l + 5 * nd], 1.e-27);
+    const double chi = fmax(anutild * anulam, 1.e-7);
+    const double fvv1 = 1. / (1. + SA_CV1 / (chi * chi * chi));
+    const double amut = rop[l] * anutild * fvv1;
+    const double xmuprov = fmax(amut, 0.);
+    return amulam + fmin(xmuprov, z.ratiom * amulam);
+}
+
+// SA source of cell l: returns vol*tsource; when STORE the LU diagonal coe(:,6) is updated (nitcfg<=1, implicit)
+template <int MESH>
+__device__ __forceinline__ double sa_source_cell(const ZoneDev &z, const double *__restrict__ rop, int l, int lt,
+                                                 bool store, double coe1)
+{
+    const int nd = z.nd, nm = z.nm;
+    const int l1 = l + 1, l2 = l - 1, l3 = l + z.incj, l4 = l - z.incj, l5 = l + z.inck, l6 = l - z.inck;
+    const double c1 = SA_CB2 / SA_SIGMA;
+    const double cw1 = (SA_CB1 / SA_CKARM / SA_CKARM) + (1. + SA_CB2) / SA_SIGMA;
+    double g[4][3];      // u,v,w,nutilde gradients (x 2 vol)
+    double h[3];         // rho*nutilde gradient (x 2 vol)
+    double vol;
+    if (MESH == 2) {
+        vol = z.vol0;
+        const double tix = z.tc0[0], tjy = z.tc0[1], tkz = z.tc0[2];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const double *q = rop + (c < 3 ? c + 1 : 5) * nd;
+            const double q0 = q[l];
+            const double u1 = q0 + q[l2], u2 = q0 + q[l3], u3 = q0 + q[l1], u4 = q0 + q[l4], u5 = q0 + q[l5], u6 = q0 + q[l6];
+            g[c][0] = (u3 - u1) * tix; g[c][1] = (u2 - u4) * tjy; g[c][2] = (u5 - u6) * tkz;
+        }
+        const double *q = rop + 5 * nd;
+        const double q0 = q[l] * rop[l];
+        const double u1 = q0 + q[l2] * rop[l2], u2 = q0 + q[l3] * rop[l3], u3 = q0 + q[l1] * rop[l1],
+                     u4 = q0 + q[l4] * rop[l4], u5 = q0 + q[l5] * rop[l5], u6 = q0 + q[l6] * rop[l6];
+        h[0] = g[3][0] * (u3 - u1) * tix; h[1] = g[3][1] * (u2 - u4) * tjy; h[2] = g[3][2] * (u5 - u6) * tkz;
+    } else if (MESH == 1) {
+        vol = __ldg(z.vol + lt);
+        const double tix = __ldg(z.ti + lt), tiy = __ldg(z.ti + lt + nm), tix1 = __ldg(z.ti + lt + z.mi), tiy1 = __ldg(z.ti + lt + z.mi + nm);
+        const double tjx = __ldg(z.tj + lt), tjy = __ldg(z.tj + lt + nm), tjx1 = __ldg(z.tj + lt + z.mj), tjy1 = __ldg(z.tj + lt + z.mj + nm);
+        const double tkz = __ldg(z.tk + lt);
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const double *q = rop + (c < 3 ? c + 1 : 5) * nd;
+            const double q0 = q[l];
+            const double u1 = q0 + q[l2], u2 = q0 + q[l3], u3 = q0 + q[l1], u4 = q0 + q[l4], u5 = q0 + q[l5], u6 = q0 + q[l6];
+            g[c][0] = (u3 * tix1 - u1 * tix + u2 * tjx1 - u4 * tjx);
+            g[c][1] = (u3 * tiy1 - u1 * tiy + u2 * tjy1 - u4 * tjy);
+            g[c][2] = (u5 - u6) * tkz;
+        }
+        const double *q = rop + 5 * nd;
+        const double q0 = q[l] * rop[l];
+        const double u1 = q0 + q[l2] * rop[l2], u2 = q0 + q[l3] * rop[l3], u3 = q0 + q[l1] * rop[l1],
+                     u4 = q0 + q[l4] * rop[l4], u5 = q0 + q[l5] * rop[l5], u6 = q0 + q[l6] * rop[l6];
+        h[0] = g[3][0] * (u3 * tix1 - u1 * tix + u2 * tjx1 - u4 * tjx);
+        h[1] = g[3][1] * (u3 * tiy1 - u1 * tiy + u2 * tjy1 - u4 * tjy);
+        h[2] = g[3][2] * (u5 - u6) * tkz;
+    } else {
+        vol = __ldg(z.vol + lt);
+        double ti0[3], ti1[3], tj0[3], tj1[3], tk0[3], tk1[3];
+#pragma unroll
+        for (int e = 0; e < 3; e++) {
+            ti0[e] = __ldg(z.ti + lt + e * nm); ti1[e] = __ldg(z.ti + lt + z.mi + e * nm);
+            tj0[e] = __ldg(z.tj + lt + e * nm); tj1[e] = __ldg(z.tj + lt + z.mj + e * nm);
+            tk0[e] = __ldg(z.tk + lt + e * nm); tk1[e] = __ldg(z.tk + lt + z.mk + e * nm);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const double *q = rop + (c < 3 ? c + 1 : 5) * nd;
+            const double q0 = q[l];
+            const double u1 = q0 + q[l2], u2 = q0 + q[l3], u3 = q0 + q[l1], u4 = q0 + q[l4], u5 = q0 + q[l5], u6 = q0 + q[l6];
+#pragma unroll
+            for (int e = 0; e < 3; e++)
+                g[c][e] = (u3 * ti1[e] - u1 * ti0[e] + u2 * tj1[e] - u4 * tj0[e] + u5 * tk1[e] - u6 * tk0[e]);
+        }
+        const double *q = rop + 5 * nd;
+        const double q0 = q[l] * rop[l];
+        const double u1 = q0 + q[l2] * rop[l2], u2 = q0 + q[l3] * rop[l3], u3 = q0 + q[l1] * rop[l1],
+                     u4 = q0 + q[l4] * rop[l4], u5 = q0 + q[l5] * rop[l5], u6 = q0 + q[l6] * rop[l6];
+#pragma unroll
+        for (int e = 0; e < 3; e++)
+            h[e] = g[3][e] * (u3 * ti1[e] - u1 * ti0[e] + u2 * tj1[e] - u4 * tj0[e] + u5 * tk1[e] - u6 * tk0[e]);
+    }
+    const double xvol = 0.5 / vol;
+    const double rotx = g[2][1] - g[1][2], roty = g[0][2] - g[2][0], rotz = g[1][0] - g[0][1];
+    const double rot = sqrt(rotx * rotx + roty * roty + rotz * rotz) * xvol;
+    const double anvisc = c1 * (h[0] + h[1] + h[2]) * xvol * xvol;
+    // sourceSA_prod_dest.for
+    const double amulam = mulam(z, rop[l + 4 * nd]);
+    const double anulam = rop[l] / amulam;
+    const double anutild = fmax(rop[l + 5 * nd], 1.e-27);
+    const double chi = fmax(anutild * anulam, 1.e-7);
+    const double f1 = 1. / (1. + SA_CV1 / (chi * chi * chi));
+    const double f2 = 1. - chi / (1. + chi * f1);
+    const double dist = fmax(z.xmut[l + nd], 1.e-27);
+    double stild = rot + (anutild * f2) / (SA_CKARM * SA_CKARM * dist * dist);
+    const double prod = rop[l] * SA_CB1 * stild * anutild;
+    stild = fmax(stild, 0.00000000000000000001);
+    double r = anutild / (stild * SA_CKARM * SA_CKARM * dist * dist);
+    r = fmin(r, 10.);
+    const double r5 = r * r * r * r * r - 1.;
+    const double gg = r * (1. + SA_CW2 * r5);
+    const double g2 = gg * gg, g6 = g2 * g2 * g2;
+    const double fwg = gg * pow((1. + SA_CW3) / (g6 + SA_CW3), 1. / 6.);
+    const double destruc = rop[l] * cw1 * fwg * (anutild / dist) * (anutild / dist);
+    const double tsource = (prod + anvisc - destruc);
+    if (store) {   // sourceSA_LU.for
+        const double tsourceb = prod - destruc;
+        double amutild = anutild * rop[l];
+        amutild = fmax(amutild, 0.0000000000000001);
+        const double tsourcenu = vol * tsourceb / amutild;
+        z.coe[l + 5 * nd] = z.coe[l + 4 * nd] - fmin(tsourcenu, 0.) * coe1;
+    }
+    return vol * tsource;
+}
+
+template <int MESH, bool IMPL>
+__device__ __forceinline__ void sa_source(const ZoneDev &z, const double *__restrict__ rop, int l, int lt, int i, int j,
+                                          int k, int nitcfg, double coe1, double *acc)
+{
+    (void)i; (void)j; (void)k;
+    acc[5] += sa_source_cell<MESH>(z, rop, l, lt, IMPL && nitcfg <= 1, coe1);
+}
+
+// core3as2.for:37-195: Newton residual from the flux balance and the BDF time terms (conservative variables)
+template <int NEQ>
+__device__ __forceinline__ void implicit_assemble(const ZoneDev &z, const double *__restrict__ r0,
+                                                  const double *__restrict__ rn, const double *__restrict__ rm, int l,
+                                                  double coe1, double c1, double c2, double c3, double *acc)
+{
+    const int nd = z.nd; const double cv = z.cv;
+    const bool first = (rn == r0);   // nitcfg == 1: rop_ssiter is ro itself => c4 = c1 + c2
+    if (first && z.dtloc == 1) {
+#pragma unroll
+        for (int e = 0; e < NEQ; e++) acc[e] = coe1 * acc[e];
+        return;
+    }
+    const double a0 = r0[l], a1 = r0[l + nd], a2 = r0[l + 2 * nd], a3 = r0[l + 3 * nd], a4 = r0[l + 4 * nd];
+    const double m0 = rm[l], m1 = rm[l + nd], m2 = rm[l + 2 * nd], m3 = rm[l + 3 * nd], m4 = rm[l + 4 * nd];
+    const double roe = a0 * (cv * a4 + 0.5 * (a1 * a1 + a2 * a2 + a3 * a3));
+    const double roe_n1 = m0 * (cv * m4 + 0.5 * (m1 * m1 + m2 * m2 + m3 * m3));
+    if (first) {
+        const double c4 = c1 + c2;
+        acc[0] = coe1 * acc[0] + c4 * a0 + c3 * m0;
+        acc[1] = coe1 * acc[1] + c4 * a1 * a0 + c3 * m1 * m0;
+        acc[2] = coe1 * acc[2] + c4 * a2 * a0 + c3 * m2 * m0;
+        acc[3] = coe1 * acc[3] + c4 * a3 * a0 + c3 * m3 * m0;
+        acc[4] = coe1 * acc[4] + c4 * roe + c3 * roe_n1;
+        if (NEQ == 6) acc[NEQ - 1] = coe1 * acc[NEQ - 1] + c4 * r0[l + 5 * nd] * a0 + c3 * rm[l + 5 * nd] * m0;
+    } else {
+        const double n0 = rn[l], n1 = rn[l + nd], n2 = rn[l + 2 * nd], n3 = rn[l + 3 * nd], n4 = rn[l + 4 * nd];
+        const double roe_n = n0 * (cv * n4 + 0.5 * (n1 * n1 + n2 * n2 + n3 * n3));
+        acc[0] = coe1 * acc[0] + c1 * a0 + c2 * n0 + c3 * m0;
+        acc[1] = coe1 * acc[1] + c1 * a1 * a0 + c2 * n1 * n0 + c3 * m1 * m0;
+        acc[2] = coe1 * acc[2] + c1 * a2 * a0 + c2 * n2 * n0 + c3 * m2 * m0;
+        acc[3] = coe1 * acc[3] + c1 * a3 * a0 + c2 * n3 * n0 + c3 * m3 * m0;
+        acc[4] = coe1 * acc[4] + c1 * roe + c2 * roe_n + c3 * roe_n1;
+        if (NEQ == 6)
+            acc[NEQ - 1] = coe1 * acc[NEQ - 1] + c1 * r0[l + 5 * nd] * a0 + c2 * rn[l + 5 * nd] * n0 + c3 * rm[l + 5 * nd] * m0;
+    }
+}

@@ -1,0 +1,147 @@
+"""Stand-in for the reference's CPython extension ``fasts`` (method table: FastS/FastS/fastS.cpp:26-66) on top of
+the CUDA C-ABI.  Same method names and argument order as the entries FastS.PyTree calls on the hot path."""
+import ctypes
+import numpy
+
+from . import _lib, VSHARE as V
+from .FastC import PyTree as FastC
+from .FastC.PyTree import Internal
+
+_vp = ctypes.c_void_p
+
+
+def _dp(a):
+    return a.ctypes.data_as(_lib.c_dp)
+
+
+def _solver(hook):
+    s = hook.get('solver') if hook is not None else None
+    if s is None: raise _lib.FastError("fast_b200: zones are not registered on a GPU solver (call FastS.warmup first)")
+    return s
+
+
+def allocate_metric(z, nssiter, verbose=0):
+    """fasts.allocate_metric(zone, nssiter) (S/Metric/allocate_metric.cpp:34): the integer part (sizes, mesh family,
+    NEQ...) has already been written into Parameter_int by FastS._warmup_host; returns the ``metrics`` list of the
+    zone in the reference's order [ti|tj|tk|vol, ti0, venti, ti_df, rdm, ind_dm, it_lu_ssdom, degen]
+    (S/param_solver.h:338-345).  The metric block itself stays in HBM; the numpy is filled on demand."""
+    own = Internal.getNodeFromName1(z, '.Solver#ownData')
+    pi = Internal.getNodeFromName1(own, 'Parameter_int')[1]
+    nm = int(pi[V.NDIMDX_MTR]); nij = int(pi[V.NEQ_IJ]); nk = int(pi[V.NEQ_K])
+    mtr = numpy.zeros((nm, 2 * nij + nk + 1), numpy.float64, order='F')
+    rdm = numpy.zeros(int(nssiter) * int(pi[V.NEQ]) * 2, numpy.float64)
+    ind_dm = numpy.array([1, pi[V.IJKV], 1, pi[V.IJKV + 1], 1, pi[V.IJKV + 2]], Internal.E_NpyInt)
+    return [mtr, mtr, None, None, rdm, ind_dm, numpy.zeros(1, Internal.E_NpyInt), None]
+
+
+def register(zones, metrics, hook, tc=None, device=0):
+    """Pointer harvest of computePT.cpp:225-369 done ONCE: create the device-resident solver, upload parameters,
+    coordinates, the three time levels and [ViscosityEddy|TurbulentDistance]."""
+    L = _lib.lib()
+    s = _vp()
+    _lib.check(L.fb_solver_create(int(device), len(zones), ctypes.byref(s)))
+    hook['solver'] = s
+    hook['nzones'] = len(zones)
+    for nd, z in enumerate(zones):
+        own = Internal.getNodeFromName1(z, '.Solver#ownData')
+        pi = numpy.ascontiguousarray(Internal.getNodeFromName1(own, 'Parameter_int')[1], dtype=numpy.int32)
+        pr = numpy.ascontiguousarray(Internal.getNodeFromName1(own, 'Parameter_real')[1], dtype=numpy.float64)
+        _lib.check(L.fb_zone_set_params(s, nd, pi.ctypes.data_as(_lib.c_ip), pi.size, _dp(pr), pr.size))
+        gc = Internal.getNodeFromName1(z, Internal.__GridCoordinates__)
+        xyz = [numpy.ascontiguousarray(Internal.getNodeFromName1(gc, n)[1].ravel(order='F')) for n in
+               ('CoordinateX', 'CoordinateY', 'CoordinateZ')]
+        _lib.check(L.fb_zone_set_coords(s, nd, _dp(xyz[0]), _dp(xyz[1]), _dp(xyz[2])))
+        for lev, suf in enumerate(('', '_M1', '_P1')):
+            _lib.check(L.fb_zone_upload_state(s, nd, lev, _dp(FastC.block_of(z, suf))))
+        aux = FastC.aux_block_of(z)
+        if aux is not None: _lib.check(L.fb_zone_upload_aux(s, nd, _dp(aux), aux.size))
+    dtloc = hook['dtloc']
+    _lib.check(L.fb_set_modulo_verif(s, int(dtloc[1])))
+    return s
+
+
+def set_joins(hook, tc):
+    """tc = flattened match-join table (numpy int32, layout in csrc/fb_joins.cu) -- stand-in for Connector's
+    miseAPlatDonorTree__ output stored in HOOK['param_int_tc'] (S/PyTree.py:495)."""
+    L = _lib.lib()
+    ji = numpy.ascontiguousarray(tc, dtype=numpy.int32)
+    hook['param_int_tc'] = ji
+    _lib.check(L.fb_set_joins(_solver(hook), ji.ctypes.data_as(_lib.c_ip), ji.size))
+
+
+def _computePT(zones, metrics, nitrun, nstep_deb, nstep_fin, layer_mode, nit_c, hook):
+    """fasts._computePT (S/Compute/computePT.cpp:44).  Returns the time spent in transfers (0.: they are on-stream)."""
+    if layer_mode != 1: raise _lib.FastError("fast_b200: only layer_mode=1 (C layer) is built")
+    L = _lib.lib()
+    fi = ctypes.c_int(int(hook.get('FIRST_IT', 0)))
+    _lib.check(L.fb_compute(_solver(hook), int(nitrun), int(nstep_deb), int(nstep_fin), int(nit_c), ctypes.byref(fi)))
+    hook['FIRST_IT'] = fi.value
+    return 0.
+
+
+_LEVEL = {'Density': 0, 'Density_M1': 1, 'Density_P1': 2}
+
+
+def _applyBC(zones, metrics, hook, nstep, var="Density"):
+    """fasts._applyBC (S/BC/applyBC.cpp:33)."""
+    _lib.check(_lib.lib().fb_apply_bc(_solver(hook), _LEVEL[var]))
+
+
+def transfers(zones, hook, var="Density"):
+    """Connector.___setInterpTransfers restricted to match joins (S/PyTree.py:1218)."""
+    _lib.check(_lib.lib().fb_transfers(_solver(hook), _LEVEL[var]))
+
+
+def _computePT_mut(zones, metrics, hook):
+    """fasts._computePT_mut (S/Compute/LES/computePT_mut.cpp): initial mu (+mut) into ViscosityEddy."""
+    _lib.check(_lib.lib().fb_compute_mut(_solver(hook)))
+
+
+def allocate_ssor(zones, metrics, hook):
+    """fasts.allocate_ssor (S/Compute/LU/allocate_ssor.cpp): only needed for nb_relax>1 (not built)."""
+    return None
+
+
+def download(zones, hook, levels=('', '_M1', '_P1'), aux=True):
+    L = _lib.lib(); s = _solver(hook)
+    for nd, z in enumerate(zones):
+        for suf in levels:
+            lev = {'': 0, '_M1': 1, '_P1': 2}[suf]
+            _lib.check(L.fb_zone_download_state(s, nd, lev, _dp(FastC.block_of(z, suf))))
+        if aux:
+            a = FastC.aux_block_of(z)
+            if a is not None: _lib.check(L.fb_zone_download_aux(s, nd, _dp(a), a.size))
+
+
+def get_metric(zones, metrics, hook):
+    """Fill the host numpy of the metrics list from HBM (tests / post-processing)."""
+    L = _lib.lib(); s = _solver(hook)
+    out = []
+    for nd, z in enumerate(zones):
+        pi = Internal.getNodeFromName1(Internal.getNodeFromName1(z, '.Solver#ownData'), 'Parameter_int')[1]
+        nm = int(pi[V.NDIMDX_MTR]); nij = int(pi[V.NEQ_IJ]); nk = int(pi[V.NEQ_K])
+        ti = numpy.zeros(nm * nij); tj = numpy.zeros(nm * nij); tk = numpy.zeros(nm * max(nk, 1)); vol = numpy.zeros(nm)
+        _lib.check(L.fb_zone_get_metric(s, nd, _dp(ti), _dp(tj), _dp(tk), _dp(vol)))
+        out.append((ti, tj, tk[:nm * nk], vol))
+    return out
+
+
+def display_ss_iteration(zones, metrics, nitrun, nssiter, lft, iverb):
+    """fasts.display_ss_iteration (S/DISPLAY/display_ss_iteration.cpp:29): returns {zone: {'L2','Loo','CFL'}} with
+    L2 = sqrt(sum drodm^2 / ncells) and Loo = max|drodm| per sub-iteration and equation (dpssiter.for)."""
+    L = _lib.lib(); s = _solver(FastC.HOOK)
+    out = {}
+    for nd, z in enumerate(zones):
+        pi = Internal.getNodeFromName1(Internal.getNodeFromName1(z, '.Solver#ownData'), 'Parameter_int')[1]
+        neq = int(pi[V.NEQ]); n = int(nssiter) * neq * 2
+        rdm = metrics[nd][V.METRIC_RDM]
+        if rdm.size != n: rdm = numpy.zeros(n)
+        _lib.check(L.fb_zone_get_residuals(s, nd, _dp(rdm), n))
+        cfl = numpy.zeros(3); _lib.check(L.fb_zone_get_cfl(s, nd, _dp(cfl)))
+        own = Internal.getNodeFromName1(z, '.Solver#ownData')
+        Internal.getNodeFromName1(own, 'CFL_minmaxmoy')[1][:] = [cfl[1], cfl[0], cfl[2]]
+        r = rdm.reshape((int(nssiter), neq, 2), order='F')
+        ncell = float(pi[V.IJKV]) * float(pi[V.IJKV + 1]) * float(pi[V.IJKV + 2])
+        out[z[0]] = {'L2': numpy.sqrt(r[:, :, 0] / ncell), 'Loo': r[:, :, 1].copy(), 'CFL': cfl}
+        if iverb == 1: print("zone %s nitrun %d: L2 %s" % (z[0], nitrun, out[z[0]]['L2'][:, 0]))
+    return out

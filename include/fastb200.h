@@ -91,6 +91,11 @@ unsigned long long fb_zone_device_ptr(fb_solver *s, int nd, int level);
  * contiguous device buffer (FP64, nvar-major per join). */
 int fb_halo_pack(fb_solver *s, int level_or_drodm, unsigned long long dev_buf, long long nbytes);
 int fb_halo_unpack(fb_solver *s, int level_or_drodm, unsigned long long dev_buf, long long nbytes);
+int fb_halo_sizes(fb_solver *s, long long *send_doubles, long long *recv_doubles);
+/* dtloc[1] of .Solver#dtloc (C/PyTree.py:1188-1200): residual / CFL check every modulo_verif iterations. */
+int fb_set_modulo_verif(fb_solver *s, int modulo_verif);
+/* cudaStream_t of the solver (uintptr) so that torch/NCCL work can be ordered against it. */
+unsigned long long fb_stream(fb_solver *s);
 
 #ifdef __cplusplus
 }
