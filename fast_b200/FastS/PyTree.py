@@ -69,7 +69,7 @@ def warmup(t, tc, graph=None, infos_ale=None, Adjoint=False, tmy=None, list_grap
     fastc.init_metric(zones, metrics, FastC.HOOK)                                    # PyTree.py:326
     if tc is not None: fasts.set_joins(FastC.HOOK, tc)                               # miseAPlatDonorTree__ stand-in
     # first ghost fill on Density (PyTree.py:536) then initial viscosity (:543)
-    _fillGhostcells(zones, tc, metrics, 1, ['Density'], FastC.HOOK)
+    _fillGhostcells(zones, tc, metrics, 1, ['Density'], 1, hook1=FastC.HOOK)
     fasts._computePT_mut(zones, metrics, FastC.HOOK)
     return (t, tc, metrics)
 
@@ -104,8 +104,7 @@ def _fillGhostcells(zones, tc, metrics, timelevel_target, vars, nstep, omp_mode=
                     exploc=0, num_passage=1, gradP=False, TBLE=False, isWireModel=False):
     """Match-join transfers then physical BCs on ``vars[0]`` (PyTree.py:1162-1260)."""
     from .. import fasts
-    if hook1 is None: hook1 = FastC.HOOK if not isinstance(nstep, dict) else nstep
-    if isinstance(nstep, dict): hook1 = nstep
+    if hook1 is None: hook1 = FastC.HOOK
     if tc is not None: fasts.transfers(zones, hook1, vars[0])
     fasts._applyBC(zones, metrics, hook1, 1, vars[0])
     return None

@@ -219,6 +219,9 @@ int fb_zone_set_params(fb_solver *s, int nd, const int *pi, int n_int, const dou
     if (pi[PI_LALE] != 0 || pi[PI_EXPLOC] != 0 || pi[PI_ILES] != 0 || pi[PI_IMPLICITSOLVER] != 0 || pi[PI_NB_RELAX] != 1)
         return fail(FB_EINVAL, "ALE / local explicit / LES / GMRES / nb_relax>1 are outside the hot-path scope");
     if (d.nf != 2) return fail(FB_EINVAL, "only 2 ghost layers are supported");
+    if (pi[PI_LU_MATCH] == 1 && d.iflow == 3) return fail(FB_EINVAL, "lu_match with SA (extrap_coe) is not built");
+    if (d.dtloc == 1 && d.iflow == 1) return fail(FB_EINVAL, "local time step needs a viscous model (dtloc.for divides by mu)");
+    if (d.dtloc == 1 && d.itypcp == 2) return fail(FB_EINVAL, "explicit local time step (tstb3_expli) is not built");
     // constants of template_FluxAndBalance.for:121-153
     d.gam = pr[PR_GAMMA]; d.cv = pr[PR_CVINF]; d.rgp = d.cv * (d.gam - 1.); d.gam1 = d.gam / (d.gam - 1.);
     d.gam3 = d.gam1 / pr[PR_PRANDT] * d.rgp; d.gam4 = d.gam1 / pr[PR_PRANDT_TUR] * d.rgp;
@@ -229,7 +232,7 @@ int fb_zone_set_params(fb_solver *s, int nd, const int *pi, int n_int, const dou
     d.c1 = 0.02 * pr[PR_VINF]; d.c2 = 0.02 / (pr[PR_VINF] * pr[PR_ROINF]);
     d.opt0 = (double)pi[PI_SENSORTYPE]; d.wig_cte = pr[PR_WIG_AMP]; d.psiroe = pr[PR_PSIROE];
     d.tmin_1 = 100. / pr[PR_TINF]; d.dtc = pr[PR_DTC]; d.ratiom = pr[PR_RATIOM]; d.cfl = pr[PR_CFL];
-    d.roinf = pr[PR_ROINF]; d.xmul0 = pr[PR_XMUL0];
+    d.roinf = pr[PR_ROINF]; d.xmul0 = pr[PR_XMUL0]; d.prandt = pr[PR_PRANDT];
     d.vinf[0] = pr[PR_VXINF]; d.vinf[1] = pr[PR_VYINF]; d.vinf[2] = pr[PR_VZINF]; d.pinf = pr[PR_PINF];
     d.ronutildeinf = pr[PR_RONUTILDEINF];
     // HBM arrays
@@ -430,11 +433,11 @@ static int gsdr3(fb_solver *s, int nitcfg, int nssiter, int nitrun, int first_it
             for (int n = 0; n < s->nz; n++) {
                 Zone &z = s->z[n];
                 { Scope b(s, 2); apply_bc_zone(s, z, z.drodm, 1); }           // lhs.cpp:57-67
-                if (lssiter_verif == 1) { launch_resid(z.d, z.rdm, nitcfg, s->st); s->launches++; }   // cprdu3s1
+                if (lssiter_verif == 1) { launch_resid(z.d, z.rdm, nitcfg, z.pi[PI_NSSITER], s->st); s->launches += 2; }   // cprdu3s1
                 if (lexit_lu == 0) {
                     Scope l(s, 1);
                     double *ssiter = nitcfg == 1 ? z.rop[0] : z.rop[2];
-                    s->launches += launch_lu(z.d, z.lu, ssiter, z.rop[2], s->st);   // invlu_ + mjr_newton
+                    s->launches += launch_lu(z.d, z.lu, ssiter, z.rop[2], z.pi[PI_LU_MATCH] == 1, s->st);   // invlu_ + mjr_newton
                 }
             }
         }

@@ -47,7 +47,7 @@ struct ZoneDev {
     double *xmut, *drodm, *coe;
     unsigned char *wigb;
     double gam, rgp, gam1, gam3, gam4, cmus1, temp01, coesut, coesut_vis, sigma_1;
-    double c1, c2, opt0, wig_cte, psiroe, tmin_1, cv, dtc, ratiom, cfl, roinf, xmul0;
+    double c1, c2, opt0, wig_cte, psiroe, tmin_1, cv, dtc, ratiom, cfl, roinf, xmul0, prandt;
     double tc0[3], vol0;
     double vinf[3], pinf, ronutildeinf;   // DEFAULT_STATE of the BCs (S/BC/BCzone.cpp:26-40)
 };

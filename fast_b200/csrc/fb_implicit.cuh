@@ -16,8 +16,8 @@ int  lu_plan_build(LuPlan &p, const ZoneDev &z, const int box[6]);
 void lu_plan_free(LuPlan &p);
 void launch_coe(const ZoneDev &z, const double *rop, int first_it, int lssiter_verif, double *cfl, cudaStream_t st);
 void launch_sa_ring(const ZoneDev &z, const double *rop, cudaStream_t st);
-void launch_resid(const ZoneDev &z, double *rdm, int nitcfg, cudaStream_t st);
-int  launch_lu(const ZoneDev &z, const LuPlan &p, const double *rop_ssiter, double *rop_out, cudaStream_t st);
+void launch_resid(const ZoneDev &z, double *rdm, int nitcfg, int nss, cudaStream_t st);
+int  launch_lu(const ZoneDev &z, const LuPlan &p, const double *rop_ssiter, double *rop_out, int lu_match, cudaStream_t st);
 
 // match joins (1 donor, coefficient 1: C/Com/setInterpTransfersFast.cpp:440-955 for interpolation type 0/1)
 struct JoinSet {

@@ -182,3 +182,132 @@ def case_tgv(n=256, seed=7, scheme='senseur', Re=1600., MInf=0.1, time_step=0.00
     FastC._setNum2Zones(t, {'scheme': scheme, 'slope': 'o3', 'time_step': time_step * (256. / n)})
     FastC._setNum2Base(t, {'temporal_scheme': 'explicit', 'rk': 3, 'modulo_verif': 50})
     return t
+
+
+def case_flatplate(n=(64, 48, 8), seed=2025, MInf=0.2, ReInf=25.e6, ss_iteration=5, cfl=7., sheared=False,
+                   scheme='ausmpred', modulo_verif=1, nblocks=(1, 1, 1)):
+    """C3 / C5-style RANS-SA flat plate: x geometric stretch, y tanh clustering toward the wall (jmin = viscous wall),
+    z uniform => typezone 1 (3dhomo); `sheared=True` adds a smooth 3-D shear => typezone 0 (3dfull).
+    Farfield on imin/imax/jmax, autoperiodic in k.  nblocks splits the plate into match-joined blocks."""
+    from .FastC import PyTree as FastC
+    rng = numpy.random.default_rng(seed)
+    state = adim1(MInf=MInf, ReInf=ReInf, MutSMuInf=15.)
+    Lx, H, Lz = 2., 1., 0.25
+    ax, by = 2.0, 3.2
+    sx = lambda s: (numpy.exp(ax * s) - 1.) / (math.exp(ax) - 1.)
+    sy = lambda s: 1. + numpy.tanh(by * (s - 1.)) / math.tanh(by)
+    deform = None
+    if sheared:
+        def deform(X, Y, Z):
+            return X + 0.02 * numpy.sin(6. * Z) * Y, Y * (1. + 0.03 * numpy.cos(5. * Z) * numpy.sin(3. * X)), Z + 0.01 * numpy.sin(4. * X) * Y
+    zones, layout = [], {}
+    nb = nblocks
+    nloc = [n[d] // nb[d] for d in range(3)]
+    for bk in range(nb[2]):
+        for bj in range(nb[1]):
+            for bi in range(nb[0]):
+                name = 'plate' if nb == (1, 1, 1) else 'plate_%d_%d_%d' % (bi, bj, bk)
+                z = make_block(name, tuple(nloc), L=(Lx, H, Lz), stretch=(sx, sy, None), deform=deform,
+                               index_offset=(bi * nloc[0], bj * nloc[1], bk * nloc[2]), nglob=n)
+                xc, yc, zc = centers(z)
+                d = numpy.abs(yc) + 1e-12
+                delta = 0.05
+                prof = numpy.tanh(numpy.abs(yc) / delta)
+                u = prof * (1. + 1e-3 * rng.standard_normal(xc.shape))
+                v = 1e-3 * rng.standard_normal(xc.shape) * prof
+                w = 1e-3 * rng.standard_normal(xc.shape) * prof
+                ro = numpy.ones_like(xc) * (1. + 1e-4 * rng.standard_normal(xc.shape))
+                T = numpy.ones_like(xc) * (1. + 0.2 * (state['Gamma'] - 1.) * MInf ** 2 * (1. - prof ** 2))
+                nut = state['TurbulentSANuTildeDensity'] * (0.1 + 3. * prof * numpy.exp(-numpy.abs(yc) / (4 * delta))) \
+                    * (1. + 1e-2 * rng.random(xc.shape))
+                set_fields(z, ro, u, v, w, T, nutilde=nut, dist=d)
+                layout[(bi, bj, bk)] = len(zones)
+                zones.append(z)
+                if bi == 0: add_bc(z, 'imin', 'BCFarfield', 'imin')
+                if bi == nb[0] - 1: add_bc(z, 'imax', 'BCFarfield', 'imax')
+                if bj == 0: add_bc(z, 'jmin', 'BCWallViscous', 'jmin')
+                if bj == nb[1] - 1: add_bc(z, 'jmax', 'BCFarfield', 'jmax')
+                if nb[2] == 1:
+                    add_bc(z, 'kmin', 'BCautoperiod', 'kmin'); add_bc(z, 'kmax', 'BCautoperiod', 'kmax')
+    t = new_tree(zones, state, 'NSTurbulent')
+    FastC._setNum2Zones(t, {'scheme': scheme, 'slope': 'o3', 'time_step_nature': 'local', 'cfl': cfl, 'nb_relax': 1})
+    FastC._setNum2Base(t, {'temporal_scheme': 'implicit', 'ss_iteration': ss_iteration, 'modulo_verif': modulo_verif})
+    joins = build_joins(layout, nb, tuple(nloc), periodic=(False, False, nb[2] > 1))
+    return t, joins
+
+
+def case_multiblock(nblk=(2, 2, 2), n=16, seed=99, scheme='roe', model='NSLaminar', deform_amp=0.015, lu_match=1,
+                    ss_iteration=3, ReInf=5000., MInf=0.3, time_step=None, temporal='implicit', modulo_verif=1):
+    """C4-style case: nblk blocks of n^3 cells, smooth sinusoidal deformation (3dfull), match joins inside, farfield
+    outside, Roe o3, implicit LU-SGS with lu_match."""
+    from .FastC import PyTree as FastC
+    rng = numpy.random.default_rng(seed)
+    state = adim1(MInf=MInf, ReInf=ReInf)
+    ng = tuple(n * b for b in nblk)
+    L = tuple(float(b) for b in nblk)
+    deform = None
+    if deform_amp > 0.:
+        def deform(X, Y, Z):
+            tp = math.pi
+            return (X + deform_amp * numpy.sin(tp * Y) * numpy.sin(tp * Z), Y + deform_amp * numpy.sin(tp * Z) * numpy.sin(tp * X),
+                    Z + deform_amp * numpy.sin(tp * X) * numpy.sin(tp * Y))
+    zones, layout = [], {}
+    for bk in range(nblk[2]):
+        for bj in range(nblk[1]):
+            for bi in range(nblk[0]):
+                z = make_block('blk_%d_%d_%d' % (bi, bj, bk), (n, n, n), L=L, deform=deform,
+                               index_offset=(bi * n, bj * n, bk * n), nglob=ng)
+                xc, yc, zc = centers(z)
+                set_fields(z, *vortex_state(xc, yc, zc, state, rng, L=L[0]))
+                for d, f in enumerate(('i', 'j', 'k')):
+                    b = (bi, bj, bk)[d]
+                    if b == 0: add_bc(z, f + 'min', 'BCFarfield', f + 'min')
+                    if b == nblk[d] - 1: add_bc(z, f + 'max', 'BCFarfield', f + 'max')
+                layout[(bi, bj, bk)] = len(zones)
+                zones.append(z)
+    t = new_tree(zones, state, model)
+    h = 1. / n
+    numz = {'scheme': scheme, 'slope': 'o3', 'time_step': time_step if time_step is not None else 0.1 * h, 'psiroe': 0.1}
+    numb = {'temporal_scheme': temporal, 'modulo_verif': modulo_verif}
+    if temporal == 'implicit':
+        numz['lu_match'] = lu_match; numb['ss_iteration'] = ss_iteration
+    FastC._setNum2Zones(t, numz); FastC._setNum2Base(t, numb)
+    return t, build_joins(layout, nblk, (n, n, n))
+
+
+def build_joins(layout, nblk, nloc, periodic=(False, False, False), rank_of=None, rank=0):
+    """Flattened match-join table (csrc/fb_joins.cu layout).  For every pair of face-adjacent blocks the NG ghost
+    layers of the receiver (interior tangential extent) are copied from the matching interior cells of the donor.
+    rank_of: block zone id -> rank; local joins are kind 0, cross-rank joins are split into a send (kind 1) entry on the
+    donor's rank and a receive (kind 2) entry on the receiver's rank with matching buffer offsets per peer.
+    Returns None when the case has no join; with rank_of returns (table, peers) where peers[r] = (send_off, send_n,
+    recv_off, recv_n) in doubles are filled by the caller from the neq of the zones."""
+    ni, nj, nk = [nloc[d] + 2 * NG for d in range(3)]
+
+    def addr(i, j, k):   # 1-based interior numbering -> 0-based cell address
+        return (i + NG - 1) + (j + NG - 1) * ni + (k + NG - 1) * ni * nj
+    recs = []
+    for (bi, bj, bk), rz in sorted(layout.items(), key=lambda kv: kv[1]):
+        for d in range(3):
+            for side in (-1, 1):
+                nb = [bi, bj, bk]; nb[d] += side
+                if nb[d] < 0 or nb[d] >= nblk[d]:
+                    if not periodic[d]: continue
+                    nb[d] %= nblk[d]
+                dz = layout[tuple(nb)]
+                rng = [numpy.arange(1, nloc[0] + 1), numpy.arange(1, nloc[1] + 1), numpy.arange(1, nloc[2] + 1)]
+                g = numpy.arange(1 - NG, 1) if side < 0 else numpy.arange(nloc[d] + 1, nloc[d] + NG + 1)
+                src = g + nloc[d] if side < 0 else g - nloc[d]
+                r = list(rng); r[d] = g
+                s = list(rng); s[d] = src
+                R = numpy.meshgrid(*r, indexing='ij'); S = numpy.meshgrid(*s, indexing='ij')
+                recs.append((dz, rz, addr(S[0], S[1], S[2]).ravel(order='F').astype(numpy.int32),
+                             addr(R[0], R[1], R[2]).ravel(order='F').astype(numpy.int32)))
+    if not recs: return None
+    if rank_of is None:
+        desc, idx, off = [], [], 0
+        for dz, rz, s, r in recs:
+            desc += [0, dz, rz, s.size, off, off + s.size, 0]
+            idx += [s, r]; off += 2 * s.size
+        return numpy.concatenate([numpy.array([len(recs), off], numpy.int32), numpy.array(desc, numpy.int32)] + idx)
+    raise NotImplementedError("use fast_b200.dist.partition_joins for multi-rank tables")

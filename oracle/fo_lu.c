@@ -1,16 +1,307 @@
-/* fo_lu.c -- implicit chain (TEST INFRASTRUCTURE, see fasts_oracle.h); filled in below. */
+/*
+ * fo_lu.c -- implicit chain of the CPU oracle: LU spectral radii / diagonal (tstb3c, tstb3_impli), Newton
+ * residual assembly (core3as2), residual norms (cprdu3s1), LU-SGS sweeps + Newton update (invlu_l / invlu_u and the
+ * lu_ and mjr_ bodies), match-join transfers.  TEST INFRASTRUCTURE, see fasts_oracle.h.
+ */
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include "fo_internal.h"
 #include "fasts_oracle.h"
-#define NOTYET(name) { fprintf(stderr, #name ": not restated yet\n"); abort(); }
-void fo_vispalart(const int *pi, const double *pr, const int ind[6], const double *rop, double *xmut) NOTYET(fo_vispalart)
-void fo_tstb3c(const int *pi, const double *pr, int first_it, const int ind[6], const double *rop, double *coe, const double *xmut, const double *ti, const double *tj, const double *tk, const double *vol) NOTYET(fo_tstb3c)
-void fo_tstb3_impli(const int *pi, const double *pr, int first_it, const int ind[6], const double *rop, double *coe, const double *xmut, const double *ti, const double *tj, const double *tk, const double *vol) NOTYET(fo_tstb3_impli)
-void fo_tstb3_expli(const int *pi, const double *pr, const int ind[6], const double *rop, double *coe, const double *xmut, const double *ti, const double *tj, const double *tk, const double *vol) NOTYET(fo_tstb3_expli)
-void fo_spsource_SA(const int *pi, const double *pr, int nitcfg, const int ind[6], const double *xmut, const double *rop, double *coe, const double *ti, const double *tj, const double *tk, const double *vol, const double *dist, double *drodm) NOTYET(fo_spsource_SA)
-void fo_core3as2(const int *pi, const double *pr, int nitcfg, int first_it, const int ind[6], const double *rop_1, const double *rop_n, const double *rop_n1, double *drodm, const double *coe) NOTYET(fo_core3as2)
-void fo_cprdu3s1(const int *pi, int nitcfg, const int ind[6], const double *drodm, double *rdm_blk) NOTYET(fo_cprdu3s1)
-void fo_invlu(const int *pi, const double *pr, const int ind_lu[6], const double *rop, double *rop_out, double *drodm, const double *coe, const double *ti, const double *tj, const double *tk) NOTYET(fo_invlu)
-void fo_transfers(fo_zone *zones, int nz, const int *pitc, const double *prtc, int which, int nitcfg) NOTYET(fo_transfers)
+
+/* ---------------------------------------------------------------------------------------------------------
+ * FastS/Compute/tstb3c.for:77-300 (global dt: coe(:,1) already = dt/vol) and tstb3_impli.for:60-330 with
+ * dtloc.for (local dt: coe(:,1) = CFL*min(dt_conv, dt_visc)); fixed mesh, E_SCALAR_COMPUTER branch.
+ * ------------------------------------------------------------------------------------------------------- */
+static void coe_kernel(const int *pi, const double *pr, int first_it, const int ind[6], const double *rop,
+                       double *coe, const double *xmut, const double *ti, const double *tj, const double *tk,
+                       const double *vol, int local)
+{
+    const int nd = pi[FO_NDIMDX], nm = pi[FO_NDIMDX_MTR], typ = pi[FO_ITYPZONE];
+    const int mi = pi[FO_NIJK_MTR], mj = pi[FO_NIJK_MTR + 1], mk = pi[FO_NIJK_MTR + 2];
+    const double cut0x = local ? 1e-30 : 1e-20;
+    const double gamma = pr[FO_GAMMA], rgp = pr[FO_CVINF] * (gamma - 1.), prandt = pr[FO_PRANDT];
+    double xid = 1.5; if (first_it == 0) xid = 1.;
+    if (local) xid = 1.;
+    double gam1 = gamma / prandt;
+    if (pi[FO_IFLOW] == 1) gam1 = local ? cut0x : 0.;
+    const double gam1_1 = local ? 1. / gam1 : 0.;
+    const double gam2 = gamma * rgp;
+    double tcxi0 = 0, tcyj0 = 0, tczk0 = 0, tc2i0 = 0, tc2j0 = 0, tc2k0 = 0;
+    if (typ == 2) { tcxi0 = ti[0]; tcyj0 = tj[0]; tczk0 = tk[0]; tc2i0 = sqrt(tcxi0 * tcxi0); tc2j0 = sqrt(tcyj0 * tcyj0); tc2k0 = sqrt(tczk0 * tczk0); }
+    FO_LOOP(ind) {
+        const int l = fo_inddm(pi, i, j, k);
+        const int lt = typ == 2 ? 0 : fo_indmtr(pi, i, j, k);
+        const int li = lt + mi, lj = lt + mj, lk = lt + mk;
+        const double r = rop[l], detj = fmax(vol[lt], cut0x);
+        const double u = rop[l + nd], v = rop[l + 2 * nd], w = rop[l + 3 * nd];
+        const double c = sqrt(gam2 * rop[l + 4 * nd]);
+        const double vmu = gam1 * (xmut ? xmut[l] : 0.);
+        const double volu = detj * r;
+        const double xmvis = vmu / volu;
+        double tc2i, tc2j, tc2k, qni, qnj, qnk;
+        if (typ == 0) {
+            const double tcxi = .5 * (ti[lt] + ti[li]), tcyi = .5 * (ti[lt + nm] + ti[li + nm]), tczi = .5 * (ti[lt + 2 * nm] + ti[li + 2 * nm]);
+            tc2i = .5 * (sqrt(ti[lt] * ti[lt] + ti[lt + nm] * ti[lt + nm] + ti[lt + 2 * nm] * ti[lt + 2 * nm])
+                       + sqrt(ti[li] * ti[li] + ti[li + nm] * ti[li + nm] + ti[li + 2 * nm] * ti[li + 2 * nm]));
+            qni = tcxi * u + tcyi * v + tczi * w;
+            const double tcxj = .5 * (tj[lt] + tj[lj]), tcyj = .5 * (tj[lt + nm] + tj[lj + nm]), tczj = .5 * (tj[lt + 2 * nm] + tj[lj + 2 * nm]);
+            tc2j = .5 * (sqrt(tj[lt] * tj[lt] + tj[lt + nm] * tj[lt + nm] + tj[lt + 2 * nm] * tj[lt + 2 * nm])
+                       + sqrt(tj[lj] * tj[lj] + tj[lj + nm] * tj[lj + nm] + tj[lj + 2 * nm] * tj[lj + 2 * nm]));
+            qnj = tcxj * u + tcyj * v + tczj * w;
+            const double tcxk = .5 * (tk[lt] + tk[lk]), tcyk = .5 * (tk[lt + nm] + tk[lk + nm]), tczk = .5 * (tk[lt + 2 * nm] + tk[lk + 2 * nm]);
+            tc2k = .5 * (sqrt(tk[lt] * tk[lt] + tk[lt + nm] * tk[lt + nm] + tk[lt + 2 * nm] * tk[lt + 2 * nm])
+                       + sqrt(tk[lk] * tk[lk] + tk[lk + nm] * tk[lk + nm] + tk[lk + 2 * nm] * tk[lk + 2 * nm]));
+            qnk = tcxk * u + tcyk * v + tczk * w;
+        } else if (typ == 1) {
+            const double tcxi = .5 * (ti[lt] + ti[li]), tcyi = .5 * (ti[lt + nm] + ti[li + nm]);
+            tc2i = .5 * (sqrt(ti[lt] * ti[lt] + ti[lt + nm] * ti[lt + nm]) + sqrt(ti[li] * ti[li] + ti[li + nm] * ti[li + nm]));
+            qni = tcxi * u + tcyi * v;
+            const double tcxj = .5 * (tj[lt] + tj[lj]), tcyj = .5 * (tj[lt + nm] + tj[lj + nm]);
+            tc2j = .5 * (sqrt(tj[lt] * tj[lt] + tj[lt + nm] * tj[lt + nm]) + sqrt(tj[lj] * tj[lj] + tj[lj + nm] * tj[lj + nm]));
+            qnj = tcxj * u + tcyj * v;
+            const double tczk = tk[lt];
+            tc2k = sqrt(tk[lt] * tk[lt]);
+            qnk = tczk * w;
+        } else {
+            tc2i = tc2i0; tc2j = tc2j0; tc2k = tc2k0;
+            qni = tcxi0 * u; qnj = tcyj0 * v; qnk = tczk0 * w;
+        }
+        const double vmi = fabs(qni) + c * tc2i, vmj = fabs(qnj) + c * tc2j, vmk = fabs(qnk) + c * tc2k;
+        coe[l + nd] = vmi * 2. + xmvis * tc2i * tc2i * 4.;
+        coe[l + 2 * nd] = vmj * 2. + xmvis * tc2j * tc2j * 4.;
+        coe[l + 3 * nd] = vmk * 2. + xmvis * tc2k * tc2k * 4.;
+        if (local) {   /* dtloc.for */
+            const double d = 1. / (tc2i * tc2i + tc2j * tc2j + tc2k * tc2k);
+            const double dtvis = 0.5 * detj * d * gam1_1 / (xmut ? xmut[l] : 0.) * r;
+            const double sp = sqrt(u * u + v * v + w * w) + c;
+            const double dtconv = sqrt(d) / sp;
+            coe[l] = pr[FO_CFL] * fmin(dtconv, dtvis);
+        }
+        coe[l + 4 * nd] = xid + coe[l] * (coe[l + nd] + coe[l + 2 * nd] + coe[l + 3 * nd]) * 0.5;
+    }
+}
+
+void fo_tstb3c(const int *pi, const double *pr, int first_it, const int ind[6], const double *rop, double *coe,
+               const double *xmut, const double *ti, const double *tj, const double *tk, const double *vol)
+{ coe_kernel(pi, pr, first_it, ind, rop, coe, pi[FO_IFLOW] == 1 ? NULL : xmut, ti, tj, tk, vol, 0); }
+
+void fo_tstb3_impli(const int *pi, const double *pr, int first_it, const int ind[6], const double *rop, double *coe,
+                    const double *xmut, const double *ti, const double *tj, const double *tk, const double *vol)
+{
+    if (pi[FO_IFLOW] == 1) { fprintf(stderr, "oracle: local time step needs a viscous model (dtloc.for divides by xmut)\n"); abort(); }
+    coe_kernel(pi, pr, first_it, ind, rop, coe, xmut, ti, tj, tk, vol, 1);
+}
+
+void fo_tstb3_expli(const int *pi, const double *pr, const int ind[6], const double *rop, double *coe,
+                    const double *xmut, const double *ti, const double *tj, const double *tk, const double *vol)
+{ (void)pi; (void)pr; (void)ind; (void)rop; (void)coe; (void)xmut; (void)ti; (void)tj; (void)tk; (void)vol;
+  fprintf(stderr, "oracle: explicit local time step (tstb3_expli) is out of scope\n"); abort(); }
+
+/* FastS/Compute/core3as2.for:37-195 */
+void fo_core3as2(const int *pi, const double *pr, int nitcfg, int first_it, const int ind[6], const double *rop,
+                 const double *rop_n, const double *rop_n1, double *drodm, const double *coe)
+{
+    const int nd = pi[FO_NDIMDX], neq = pi[FO_NEQ];
+    const double cv = pr[FO_CVINF];
+    double c1, c2, c3;
+    if (first_it == 0 || pi[FO_DTLOC] == 1) { c1 = -1.; c2 = 1.; c3 = 0.; } else { c1 = -1.5; c2 = 2.; c3 = -0.5; }
+    if (nitcfg == 1) {
+        const double c4 = c1 + c2;
+        if (pi[FO_DTLOC] == 1) {
+            FO_LOOP(ind) { const int l = fo_inddm(pi, i, j, k); for (int e = 0; e < neq; e++) drodm[l + e * nd] = coe[l] * drodm[l + e * nd]; }
+            return;
+        }
+        FO_LOOP(ind) {
+            const int l = fo_inddm(pi, i, j, k);
+            drodm[l] = coe[l] * drodm[l] + c4 * rop[l] + c3 * rop_n1[l];
+            for (int e = 1; e < 4; e++)
+                drodm[l + e * nd] = coe[l] * drodm[l + e * nd] + c4 * rop[l + e * nd] * rop[l] + c3 * rop_n1[l + e * nd] * rop_n1[l];
+            const double roe = rop[l] * (cv * rop[l + 4 * nd] + 0.5 * (rop[l + nd] * rop[l + nd] + rop[l + 2 * nd] * rop[l + 2 * nd] + rop[l + 3 * nd] * rop[l + 3 * nd]));
+            const double roe_n1 = rop_n1[l] * (cv * rop_n1[l + 4 * nd] + 0.5 * (rop_n1[l + nd] * rop_n1[l + nd] + rop_n1[l + 2 * nd] * rop_n1[l + 2 * nd] + rop_n1[l + 3 * nd] * rop_n1[l + 3 * nd]));
+            drodm[l + 4 * nd] = coe[l] * drodm[l + 4 * nd] + c4 * roe + c3 * roe_n1;
+            if (neq == 6) drodm[l + 5 * nd] = coe[l] * drodm[l + 5 * nd] + c4 * rop[l + 5 * nd] * rop[l] + c3 * rop_n1[l + 5 * nd] * rop_n1[l];
+        }
+    } else {
+        FO_LOOP(ind) {
+            const int l = fo_inddm(pi, i, j, k);
+            drodm[l] = coe[l] * drodm[l] + c1 * rop[l] + c2 * rop_n[l] + c3 * rop_n1[l];
+            for (int e = 1; e < 4; e++)
+                drodm[l + e * nd] = coe[l] * drodm[l + e * nd] + c1 * rop[l + e * nd] * rop[l] + c2 * rop_n[l + e * nd] * rop_n[l]
+                                  + c3 * rop_n1[l + e * nd] * rop_n1[l];
+            const double roe = rop[l] * (cv * rop[l + 4 * nd] + 0.5 * (rop[l + nd] * rop[l + nd] + rop[l + 2 * nd] * rop[l + 2 * nd] + rop[l + 3 * nd] * rop[l + 3 * nd]));
+            const double roe_n = rop_n[l] * (cv * rop_n[l + 4 * nd] + 0.5 * (rop_n[l + nd] * rop_n[l + nd] + rop_n[l + 2 * nd] * rop_n[l + 2 * nd] + rop_n[l + 3 * nd] * rop_n[l + 3 * nd]));
+            const double roe_n1 = rop_n1[l] * (cv * rop_n1[l + 4 * nd] + 0.5 * (rop_n1[l + nd] * rop_n1[l + nd] + rop_n1[l + 2 * nd] * rop_n1[l + 2 * nd] + rop_n1[l + 3 * nd] * rop_n1[l + 3 * nd]));
+            drodm[l + 4 * nd] = coe[l] * drodm[l + 4 * nd] + c1 * roe + c2 * roe_n + c3 * roe_n1;
+            if (neq == 6)
+                drodm[l + 5 * nd] = coe[l] * drodm[l + 5 * nd] + c1 * rop[l + 5 * nd] * rop[l] + c2 * rop_n[l + 5 * nd] * rop_n[l]
+                                  + c3 * rop_n1[l + 5 * nd] * rop_n1[l];
+        }
+    }
+}
+
+/* FastS/Compute/cprdu3s1.for + cprdu3s1_incl.for:100-140, one residual block = the whole zone:
+   rdm(nitcfg, ne, 1) = sum drodm^2, rdm(nitcfg, ne, 2) = max |drodm|  (Fortran order (nssiter, neq, 2)) */
+void fo_cprdu3s1(const int *pi, int nitcfg, const int ind[6], const double *drodm, double *rdm)
+{
+    const int nd = pi[FO_NDIMDX], neq = pi[FO_NEQ], nss = pi[FO_NSSITER];
+    for (int e = 0; e < neq; e++) {
+        double s = 0., m = 0.;
+        FO_LOOP(ind) { const double x = drodm[fo_inddm(pi, i, j, k) + e * nd]; const double xp = fabs(x); if (xp > m) m = xp; s += x * x; }
+        rdm[(nitcfg - 1) + e * nss] = s;
+        rdm[(nitcfg - 1) + e * nss + neq * nss] = m;
+    }
+}
+
+/* ---------------------------------------------------------------------------------------------------------
+ * LU-SGS.  B_d(l1) dW(l1): LU/lu_{i,j,k}_{3dfull,3dhomogene,3dcart}[_SA].for restated once with the cell-centred
+ * mean normal tc of the NEIGHBOUR cell l1 (zero components for 3dhomo / 3dcart), signe = +0.5 (L) / -0.5 (U).
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    const int *pi; const double *rop, *coe, *t[3];
+    int inc[3], incm[3], nd, nm, typ, neq;
+    double gam1, gamm1, gam2, cp, tc0[3];
+} luctx;
+
+static void lu_term(const luctx *c, int d, int l1, int lta, int ltb, double signe, const double *dw, double b[6])
+{
+    const int nd = c->nd, nm = c->nm;
+    double tcx = 0., tcy = 0., tcz = 0.;
+    const double *T = c->t[d];
+    if (c->typ == 0) { tcx = 0.5 * (T[ltb] + T[lta]); tcy = 0.5 * (T[ltb + nm] + T[lta + nm]); tcz = 0.5 * (T[ltb + 2 * nm] + T[lta + 2 * nm]); }
+    else if (c->typ == 1) { if (d < 2) { tcx = 0.5 * (T[ltb] + T[lta]); tcy = 0.5 * (T[ltb + nm] + T[lta + nm]); } else tcz = T[ltb]; }
+    else { if (d == 0) tcx = c->tc0[0]; else if (d == 1) tcy = c->tc0[1]; else tcz = c->tc0[2]; }
+    const double *rop = c->rop;
+    const double u = rop[l1 + nd], v = rop[l1 + 2 * nd], w = rop[l1 + 3 * nd], t = rop[l1 + 4 * nd];
+    const double q2 = .5 * (u * u + v * v + w * w), h = c->cp * t + q2, ph2 = c->gamm1 * q2;
+    const double qn = tcx * u + tcy * v + tcz * w;
+    const double cd = c->coe[l1 + (d + 1) * nd] * signe;
+    const double gamm1 = c->gamm1, gam2 = c->gam2, gam1 = c->gam1;
+    const double b11 = cd, b12 = tcx, b13 = tcy, b14 = tcz;
+    const double b21 = (tcx * ph2 - u * qn), b22 = (qn - tcx * gam2 * u) + cd, b23 = (tcy * u - tcx * gamm1 * v), b24 = (tcz * u - tcx * gamm1 * w), b25 = tcx * gamm1;
+    const double b31 = (tcy * ph2 - v * qn), b32 = (tcx * v - tcy * gamm1 * u), b33 = (qn - tcy * gam2 * v) + cd, b34 = (tcz * v - tcy * gamm1 * w), b35 = tcy * gamm1;
+    const double b41 = (tcz * ph2 - w * qn), b42 = (tcx * w - tcz * gamm1 * u), b43 = (tcy * w - tcz * gamm1 * v), b44 = (qn - tcz * gam2 * w) + cd, b45 = tcz * gamm1;
+    const double b51 = qn * (ph2 - h), b52 = (tcx * h - gamm1 * u * qn), b53 = (tcy * h - gamm1 * v * qn), b54 = (tcz * h - gamm1 * w * qn), b55 = (gam1 * qn) + cd;
+    const double d1 = dw[l1], d2 = dw[l1 + nd], d3 = dw[l1 + 2 * nd], d4 = dw[l1 + 3 * nd], d5 = dw[l1 + 4 * nd];
+    b[0] = b11 * d1 + b12 * d2 + b13 * d3 + b14 * d4;
+    b[1] = b21 * d1 + b22 * d2 + b23 * d3 + b24 * d4 + b25 * d5;
+    b[2] = b31 * d1 + b32 * d2 + b33 * d3 + b34 * d4 + b35 * d5;
+    b[3] = b41 * d1 + b42 * d2 + b43 * d3 + b44 * d4 + b45 * d5;
+    b[4] = b51 * d1 + b52 * d2 + b53 * d3 + b54 * d4 + b55 * d5;
+    if (c->neq == 6) b[5] = (qn + cd) * dw[l1 + 5 * nd];
+}
+
+/* LU/mjr_newton.for / mjr_newton_SA.for */
+static void mjr_newton(const int *pi, const double *pr, int l, const double *rop, double *rop_1, const double *dw)
+{
+    const int nd = pi[FO_NDIMDX], neq = pi[FO_NEQ];
+    const double cvinv = 1. / pr[FO_CVINF], cvinv2 = 0.5 * cvinv;
+    const double ro_old = rop[l], u_old = rop[l + nd], v_old = rop[l + 2 * nd], w_old = rop[l + 3 * nd], t_old = rop[l + 4 * nd];
+    const double nu_old = neq == 6 ? rop[l + 5 * nd] : 0.;
+    rop_1[l] = rop[l] + dw[l];
+    const double r_1 = 1. / rop_1[l];
+    rop_1[l + nd] = (ro_old * u_old + dw[l + nd]) * r_1;
+    rop_1[l + 2 * nd] = (ro_old * v_old + dw[l + 2 * nd]) * r_1;
+    rop_1[l + 3 * nd] = (ro_old * w_old + dw[l + 3 * nd]) * r_1;
+    const double roe_old = ro_old * (pr[FO_CVINF] * t_old + 0.5 * (u_old * u_old + v_old * v_old + w_old * w_old));
+    rop_1[l + 4 * nd] = (roe_old + dw[l + 4 * nd]) * r_1 * cvinv
+        - cvinv2 * (rop_1[l + nd] * rop_1[l + nd] + rop_1[l + 2 * nd] * rop_1[l + 2 * nd] + rop_1[l + 3 * nd] * rop_1[l + 3 * nd]);
+    if (neq == 6) {
+        const double cmus1 = pr[FO_CS], temp01 = 1. / pr[FO_TEMP0], coesut = pr[FO_XMUL0] * (1. + cmus1 * temp01);
+        double anulam = coesut * sqrt(rop_1[l + 4 * nd] * temp01) / (1. + cmus1 / rop_1[l + 4 * nd]);
+        anulam = anulam * r_1 * pr[FO_RATIOM];
+        double t = (ro_old * nu_old + dw[l + 5 * nd]) * r_1;
+        t = fmin(t, anulam);
+        rop_1[l + 5 * nd] = fmax(t, 0.);
+    }
+}
+
+/* LU/invlu.for:6-344 (nb_relax = 1, fixed mesh): invlu_l[_SA] then invlu_u[_SA]; lu_match = 1 selects the "overlap"
+   variants whose only effect for a whole-zone box is the i,j,k accumulation order and a Newton update restricted to
+   the interior (invlu_overlap_u.for).  In place: drodm holds rhs -> dW* -> dW. */
+void fo_invlu(const int *pi, const double *pr, const int box[6], const double *rop, double *rop_out, double *drodm,
+              const double *coe, const double *ti, const double *tj, const double *tk)
+{
+    if (box[1] < box[0]) return;
+    luctx c;
+    c.pi = pi; c.rop = rop; c.coe = coe; c.t[0] = ti; c.t[1] = tj; c.t[2] = tk;
+    c.inc[0] = 1; c.inc[1] = pi[FO_NIJK]; c.inc[2] = pi[FO_NIJK] * pi[FO_NIJK + 1];
+    c.incm[0] = pi[FO_NIJK_MTR]; c.incm[1] = pi[FO_NIJK_MTR + 1]; c.incm[2] = pi[FO_NIJK_MTR + 2];
+    c.nd = pi[FO_NDIMDX]; c.nm = pi[FO_NDIMDX_MTR]; c.typ = pi[FO_ITYPZONE]; c.neq = pi[FO_NEQ];
+    c.gam1 = pr[FO_GAMMA]; c.gamm1 = c.gam1 - 1.; c.cp = pr[FO_GAMMA] * pr[FO_CVINF]; c.gam2 = c.gamm1 - 1.;
+    c.tc0[0] = ti[0]; c.tc0[1] = tj[0]; c.tc0[2] = tk[0];
+    const int nd = c.nd, neq = c.neq, overlap = pi[FO_LU_MATCH] == 1;
+    if (overlap && neq == 6) { fprintf(stderr, "oracle: lu_match with SA (extrap_coe) is not restated\n"); abort(); }
+    const int ideb = box[0], ifin = box[1], jdeb = box[2], jfin = box[3], kdeb = box[4], kfin = box[5];
+    double b[6];
+    /* ---- lower sweep (invlu_l.for:79-215): normals 0.5*(t(lt)+t(lt-m)) of the cell l-d */
+    for (int k = kdeb; k <= kfin; k++) for (int j = jdeb; j <= jfin; j++) for (int i = ideb; i <= ifin; i++) {
+        const int l = fo_inddm(pi, i, j, k), lt = c.typ == 2 ? 0 : fo_indmtr(pi, i, j, k);
+        const double xal = coe[l] * 0.5;
+        int order[3], n = 0;
+        const int hi = i > ideb, hj = j > jdeb, hk = k > kdeb;
+        if (overlap) { if (hi) order[n++] = 0; if (hj) order[n++] = 1; if (hk) order[n++] = 2; }
+        else if (c.typ == 2 && hj && hk) { order[n++] = 1; order[n++] = 2; if (hi) order[n++] = 0; }
+        else { if (hk) order[n++] = 2; if (hj) order[n++] = 1; if (hi) order[n++] = 0; }
+        for (int q = 0; q < n; q++) {
+            const int d = order[q];
+            lu_term(&c, d, l - c.inc[d], lt - c.incm[d], lt, 0.5, drodm, b);
+            for (int e = 0; e < neq; e++) drodm[l + e * nd] = drodm[l + e * nd] + b[e] * xal;
+        }
+        const double diag = 1. / coe[l + 4 * nd];
+        for (int e = 0; e < 5; e++) drodm[l + e * nd] = drodm[l + e * nd] * diag;
+        if (neq == 6) drodm[l + 5 * nd] = drodm[l + 5 * nd] / coe[l + 5 * nd];
+    }
+    /* ---- upper sweep (invlu_u.for:60-215): normals 0.5*(t(lt+2m)+t(lt+m)) of the cell l+d, Newton update plane
+       by plane (so the k term of plane k reads the already updated state of plane k+1 when rop aliases rop_out) */
+    int nb[6];
+    for (int q = 0; q < 6; q++) nb[q] = box[q];
+    if (overlap) { nb[0] = 1; nb[1] = pi[FO_IJKV]; nb[2] = 1; nb[3] = pi[FO_IJKV + 1]; nb[4] = 1; nb[5] = pi[FO_IJKV + 2]; }
+    for (int k = kfin; k >= kdeb; k--) {
+        for (int j = jfin; j >= jdeb; j--) for (int i = ifin; i >= ideb; i--) {
+            const int l = fo_inddm(pi, i, j, k), lt = c.typ == 2 ? 0 : fo_indmtr(pi, i, j, k);
+            const double xal = coe[l] * -0.5;
+            const double dg = coe[l + 4 * nd];
+            for (int e = 0; e < 5; e++) drodm[l + e * nd] = drodm[l + e * nd] * dg;
+            if (neq == 6) drodm[l + 5 * nd] = drodm[l + 5 * nd] * coe[l + 5 * nd];
+            int order[3], n = 0;
+            const int hi = i < ifin, hj = j < jfin, hk = k < kfin;
+            if (overlap) { if (hi) order[n++] = 0; if (hj) order[n++] = 1; if (hk) order[n++] = 2; }
+            else { if (hk) order[n++] = 2; if (hj) order[n++] = 1; if (hi) order[n++] = 0; }
+            for (int q = 0; q < n; q++) {
+                const int d = order[q];
+                lu_term(&c, d, l + c.inc[d], lt + c.incm[d], c.typ == 1 && d == 2 ? lt : lt + 2 * c.incm[d], -0.5, drodm, b);
+                for (int e = 0; e < neq; e++) drodm[l + e * nd] = drodm[l + e * nd] + b[e] * xal;
+            }
+            const double diag = 1. / coe[l + 4 * nd];
+            for (int e = 0; e < 5; e++) drodm[l + e * nd] = drodm[l + e * nd] * diag;
+            if (neq == 6) drodm[l + 5 * nd] = drodm[l + 5 * nd] / coe[l + 5 * nd];
+        }
+        if (k >= nb[4] && k <= nb[5])
+            for (int j = nb[2]; j <= nb[3]; j++) for (int i = nb[0]; i <= nb[1]; i++)
+                mjr_newton(pi, pr, fo_inddm(pi, i, j, k), rop, rop_out, drodm);
+    }
+}
+
+/* Match joins restricted to one donor / coefficient 1 (C/Com/setInterpTransfersFast.cpp:440-955 for interpolation
+   type 0/1, ST/tgvMpi.py:136-139).  Table layout = csrc/fb_joins.cu (kind 0 joins only on the CPU side). */
+void fo_transfers(fo_zone *zones, int nz, const int *ji, const double *prtc, int which, int nitcfg)
+{
+    (void)prtc; (void)nz;
+    const int nj = ji[0];
+    const int *idx = ji + 2 + 7 * nj;
+    for (int q = 0; q < nj; q++) {
+        const int *s = ji + 2 + 7 * q;
+        if (s[0] != 0) continue;
+        fo_zone *zd = &zones[s[1]], *zr = &zones[s[2]];
+        const int neq = zd->pi[FO_NEQ], ndd = zd->pi[FO_NDIMDX], ndr = zr->pi[FO_NDIMDX];
+        const int implicit = zd->pi[FO_ITYPCP] <= 1;
+        const double *src; double *dst;
+        if (which == 1) { src = zd->drodm; dst = zr->drodm; }
+        else if (nitcfg == 1 || implicit) { src = zd->ro_p1; dst = zr->ro_p1; }
+        else if (nitcfg % 2 == 0) { src = zd->ro; dst = zr->ro; }
+        else { src = zd->ro_p1; dst = zr->ro_p1; }
+        for (int n = 0; n < s[3]; n++)
+            for (int e = 0; e < neq; e++) dst[idx[s[5] + n] + e * ndr] = src[idx[s[4] + n] + e * ndd];
+    }
+}

@@ -1,0 +1,53 @@
+"""GPU parity against the CPU oracle: implicit chain (coe, BDF residual, LU-SGS wavefront, Newton update), SA,
+wall / farfield BCs, match joins."""
+import numpy
+import pytest
+from helpers import oracle_from_tree, interior, relerr, FastS, FastC, V
+from fast_b200 import synth
+from fast_b200.FastC.PyTree import Internal
+
+TOL = 1e-10
+
+
+def _box(**kw):
+    return lambda: (synth.case_euler_box(**kw), None)
+
+
+CASES = {
+    'euler_cart_roe_bdf': _box(n=12, scheme='roe', temporal='implicit'),
+    'lamin_full_roe_bdf': _box(n=12, scheme='roe', model='NSLaminar', ReInf=1000., deform_amp=0.02, temporal='implicit'),
+    'lamin_cart_ausm_dtloc': _box(n=12, scheme='ausmpred', model='NSLaminar', ReInf=1000., temporal='implicit',
+                                  extra_numz={'time_step_nature': 'local', 'cfl': 4.}),
+    'lamin_full_senseur_minmod': _box(n=10, scheme='senseur', model='NSLaminar', ReInf=500., deform_amp=0.02, temporal='implicit'),
+    'sa_plate_homo': lambda: synth.case_flatplate(n=(24, 16, 6)),
+    'sa_plate_full': lambda: synth.case_flatplate(n=(20, 12, 6), sheared=True),
+    'sa_plate_roe': lambda: synth.case_flatplate(n=(16, 12, 4), scheme='roe'),
+    'sa_plate_blocks': lambda: synth.case_flatplate(n=(24, 16, 8), nblocks=(2, 2, 2)),
+    'multiblock_roe_lumatch': lambda: synth.case_multiblock(nblk=(2, 2, 1), n=8),
+    'multiblock_explicit': lambda: synth.case_multiblock(nblk=(2, 1, 2), n=8, temporal='explicit', scheme='senseur'),
+}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', sorted(CASES))
+def test_implicit_parity(name):
+    t1, j1 = CASES[name](); t2, j2 = CASES[name]()
+    o = oracle_from_tree(t1, joins=j1)
+    (t2, tc, metrics) = FastS.warmup(t2, j2)
+    nss = int(o.zones[0].pi[V.NSSITER])
+    for it in range(1, 4):
+        o.compute(it, 1, nss, 1)
+        FastS._compute(t2, metrics, it)
+    FastS.sync_tree(t2)
+    crit = FastS.display_temporal_criteria(t2, metrics, 3)
+    for zo, z in zip(o.zones, Internal.getZones(t2)):
+        for lev, suf in enumerate(('', '_M1')):
+            a = interior(zo.pi, FastC.block_of(z, suf)); b = interior(zo.pi, zo.lev[lev])
+            assert numpy.isfinite(a).all()
+            assert relerr(a, b) <= TOL, (name, z[0], suf, relerr(a, b))
+        if int(zo.pi[V.ITYPCP]) <= 1:
+            r = zo.rdm.reshape((nss, zo.neq, 2), order='F')
+            ncell = float(zo.pi[V.IJKV]) * float(zo.pi[V.IJKV + 1]) * float(zo.pi[V.IJKV + 2])
+            l2 = numpy.sqrt(r[:, :, 0] / ncell)
+            assert numpy.allclose(crit[z[0]]['L2'], l2, rtol=1e-8, atol=1e-300)
+            assert numpy.allclose(crit[z[0]]['Loo'], r[:, :, 1], rtol=1e-8, atol=1e-300)
