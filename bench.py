@@ -1,0 +1,226 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the FastS residual-and-update hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload tgv256|plate|multiblock]
+
+A "step" is one full time iteration of the hot path (all sub-iterations: 3 RK stages, or ss_iteration Newton
+sub-iterations incl. LU sweeps, plus match-join transfers and BC fill) over one synthetic case.  Default workload at
+N=1 = BASELINE.json configs[1]: laminar Taylor-Green vortex 256^3, SENSOR scheme, explicit RK3.
+`value` is Mcell.it/s = interior cells x time iterations / second with the state resident in HBM; `e2e` is the same
+metric through the reference-facing C-ABI call with HOST buffers (fb_compute_host: H2D of the input time levels and
+D2H of the new one inside the timed region).  `--impl reference` times the CPU oracle (the reference's Fortran cannot
+be built here: no Fortran compiler, no Cassiopee) with all host threads on a bounded sample of the same workload.
+"""
+import argparse, ctypes, json, os, subprocess, sys, threading, time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import numpy  # noqa: E402
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        with open(p) as f: return float(json.load(f)['hbm_gbs']), 'measured'
+    return 6650., 'fallback'
+
+
+def make_case(workload, n=None, rank=0, world=1):
+    from fast_b200 import synth
+    if workload == 'tgv256':
+        n = n or 256
+        return synth.case_tgv(n=n), None, 'laminar TGV %d^3, SENSOR o3, explicit RK3 (BASELINE configs[1])' % n
+    if workload == 'plate':
+        n = n or (512, 256, 64)
+        t, j = synth.case_flatplate(n=n, modulo_verif=1000)
+        return t, j, 'RANS-SA flat plate %dx%dx%d (3dhomo), AUSM o3, implicit LU-SGS 5 sub-iterations, local dt (BASELINE configs[2])' % n
+    if workload == 'multiblock':
+        n = n or 128
+        t, j = synth.case_multiblock(nblk=(2, 2, 2), n=n, modulo_verif=1000)
+        return t, j, '8 x %d^3 blocks, match joins, Roe o3, implicit LU-SGS 3 sub-iterations, lu_match (BASELINE configs[3])' % n
+    raise ValueError(workload)
+
+
+def algorithmic_bytes(pi):
+    """doubles moved once per irreducible phase, per cell-update (sub-iteration)."""
+    from fast_b200 import VSHARE as V
+    neq = int(pi[V.NEQ]); typ = int(pi[V.ITYPZONE]); iflow = int(pi[V.IFLOW])
+    m = 10 if typ == 0 else 0
+    a = (1 if iflow >= 2 else 0) + (1 if iflow == 3 else 0)
+    if int(pi[V.ITYPCP]) == 2:
+        c = 0 if typ == 2 else 1
+        return 8. * ((11. / 3.) * neq + m + 0 * a + c), 8. * ((11. / 3.) * neq + m + c)   # (whole sub-iteration, rhs kernel)
+    return 8. * (13 * neq + 1 + a + 3 * m), 8. * (4 * neq + 1 + a + m)   # rhs: 3 neq read + neq write + coe1 + a + m
+
+
+class Clocks(threading.Thread):
+    def __init__(self):
+        super().__init__(daemon=True); self.stop = False; self.samples = []; self.reasons = set(); self.maxmhz = None
+    def run(self):
+        q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+            'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+        while not self.stop:
+            try:
+                o = subprocess.run(['nvidia-smi', '--query-gpu=' + q, '--format=csv,noheader,nounits', '-i', os.environ.get('LOCAL_RANK', '0')],
+                                   capture_output=True, text=True, timeout=5).stdout.strip().split(',')
+                self.samples.append(float(o[0])); self.maxmhz = float(o[1])
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), o[2:6]):
+                    if 'Active' in v and 'Not' not in v: self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.2)
+    def summary(self):
+        s = sorted(self.samples)
+        return {'sm_mhz': s[len(s) // 2] if s else None, 'sm_max_mhz': self.maxmhz, 'reasons': sorted(self.reasons)}
+
+
+def cpu_oracle_rate(workload, seconds=15., threads=None):
+    """Mcell.it/s of the CPU oracle (OpenMP: k slabs for the rhs, one zone per thread for the LU) on a bounded sample."""
+    sys.path.insert(0, os.path.join(ROOT, 'tests')); sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    from helpers import oracle_from_tree, V
+    sample_n = {'tgv256': 96, 'plate': (128, 64, 16), 'multiblock': 32}[workload]
+    t, j, desc = make_case(workload, n=sample_n)
+    o = oracle_from_tree(t, joins=j, fast=True)
+    nthreads = threads or o.L.fo_max_threads()
+    nss = int(o.zones[0].pi[V.NSSITER])
+    cells = sum(int(z.pi[V.IJKV]) * int(z.pi[V.IJKV + 1]) * int(z.pi[V.IJKV + 2]) for z in o.zones)
+    o.compute(1, 1, nss, 1000, nthreads=nthreads)                     # warm-up / first touch
+    t0 = time.perf_counter(); o.compute(2, 1, nss, 1000, nthreads=nthreads); dt1 = time.perf_counter() - t0
+    nit = max(1, min(200, int(seconds / max(dt1, 1e-6))))
+    t0 = time.perf_counter()
+    for it in range(nit): o.compute(3 + it, 1, nss, 1000, nthreads=nthreads)
+    dt = time.perf_counter() - t0
+    return cells * nit / dt / 1e6, nthreads, '%s for %d iterations (%.1f s)' % (desc, nit, dt), nss
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0: return
+    rates = []
+    for s in range(args.warmup + args.steps):
+        r, nth, sample, nss = cpu_oracle_rate(args.workload, seconds=max(2., 60. / (args.warmup + args.steps)))
+        if s >= args.warmup: rates.append(r)
+    v = float(numpy.mean(rates))
+    out = {'impl': 'reference', 'metric': 'FP64 cell-updates/sec', 'value': v, 'unit': 'Mcell.it/s', 'n_gpus': args.gpus,
+           'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': None, 'higher_is_better': True, 'scaling': 'weak',
+           'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+           'config': {'workload': sample, 'note': 'CPU oracle (port of the reference Fortran; the reference itself cannot be built here)'},
+           'cpu_baseline': {'value': v, 'unit': 'Mcell.it/s', 'cores': nth, 'kind': 'port', 'sample': sample},
+           'e2e': {'value': v, 'unit': 'Mcell.it/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(out))
+
+
+def run_gpu(args):
+    import torch
+    from fast_b200 import _lib, VSHARE as V
+    from fast_b200.FastS import PyTree as FastS
+    from fast_b200.FastC import PyTree as FastC
+    from fast_b200.FastC.PyTree import Internal
+    rank = int(os.environ.get('RANK', '0')); world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    torch.cuda.set_device(local)
+    if world > 1:
+        from fast_b200 import dist as fdist
+        return fdist.bench_multi(args, rank, world, local)
+
+    t, joins, desc = make_case(args.workload)
+    os.environ['FAST_B200_DEVICE'] = str(local)
+    (t, tc, metrics) = FastS.warmup(t, joins)
+    zones = Internal.getZones(t)
+    L = _lib.lib(); s = FastC.HOOK['solver']
+    pi0 = Internal.getNodeFromName1(Internal.getNodeFromName1(zones[0], '.Solver#ownData'), 'Parameter_int')[1]
+    nss = int(pi0[V.NSSITER]); implicit = int(pi0[V.ITYPCP]) <= 1
+    nsub = nss - 1 if implicit else nss
+    cells = 0
+    for z in zones:
+        pi = Internal.getNodeFromName1(Internal.getNodeFromName1(z, '.Solver#ownData'), 'Parameter_int')[1]
+        cells += int(pi[V.IJKV]) * int(pi[V.IJKV + 1]) * int(pi[V.IJKV + 2])
+    stream = torch.cuda.ExternalStream(L.fb_stream(s))
+    nit = 1
+    for w in range(args.warmup):
+        FastS._compute(t, metrics, nit); nit += 1
+    _lib.check(L.fb_sync(s))
+    _lib.check(L.fb_timing_enable(s, 1)); _lib.check(L.fb_timing_reset(s))
+    clk = Clocks(); clk.start()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record(stream)
+    for k in range(args.steps):
+        FastS._compute(t, metrics, nit); nit += 1
+    e1.record(stream); torch.cuda.synchronize(); _lib.check(L.fb_sync(s))
+    ms = e0.elapsed_time(e1)
+    clk.stop = True; clk.join(timeout=2)
+    tm = {}
+    launches = ctypes.c_longlong(0)
+    for name in ('rhs', 'lu', 'bc', 'transfer', 'coe', 'all'):
+        v = ctypes.c_double(0); _lib.check(L.fb_timing_get(s, name.encode(), ctypes.byref(v), ctypes.byref(launches)))
+        tm[name] = v.value
+    _lib.check(L.fb_timing_enable(s, 0))
+    value = cells * args.steps / (ms * 1e-3) / 1e6
+    # roofline of the dominant kernel (k_rhs): algorithmic bytes per launch / average launch duration
+    b_sub, b_rhs = algorithmic_bytes(pi0)
+    n_rhs = args.steps * nsub * len(zones)
+    avg_rhs_ms = tm['rhs'] / n_rhs
+    peak, pk = peaks()
+    ach = (cells / len(zones)) * b_rhs / (avg_rhs_ms * 1e-3) / 1e9
+    dominant = 'k_rhs' if tm['rhs'] >= tm['lu'] else 'k_lu'
+    roof = {'bound': 'hbm', 'kernel': 'k_rhs', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'traffic': None,
+            'peak_source': pk, 'bytes_per_cell_update': b_rhs, 'avg_launch_ms': avg_rhs_ms,
+            'whole_subiteration_GBs': cells * b_sub * nsub * args.steps / (ms * 1e-3) / 1e9,
+            'step_share': {k: (v / tm['all'] if tm['all'] else None) for k, v in tm.items()}, 'dominant': dominant}
+
+    # end to end through the C-ABI with host buffers (pinned): H2D inputs + D2H result every step
+    nz = len(zones)
+    hb = [[torch.empty(FastC.block_of(z, suf).size, dtype=torch.float64, pin_memory=True) for z in zones] for suf in ('', '_M1', '_P1')]
+    FastS.sync_tree(t)
+    for li, suf in enumerate(('', '_M1', '_P1')):
+        for zi, z in enumerate(zones): hb[li][zi].numpy()[:] = FastC.block_of(z, suf)
+    PtrArr = ctypes.c_void_p * nz
+    def ptrs(li): return PtrArr(*[hb[li][zi].data_ptr() for zi in range(nz)])
+    fi = ctypes.c_int(1)
+    e2e_steps = max(2, min(args.steps, 5))
+    order = [0, 1, 2]
+    def host_step(n):
+        _lib.check(L.fb_compute_host(s, n, 1, ctypes.byref(fi), ptrs(order[0]), ptrs(order[1]), ptrs(order[2])))
+        order[:] = [order[2], order[0], order[1]]      # switchPointers__ on the host arrays
+    host_step(nit); nit += 1
+    torch.cuda.synchronize(); e0.record(stream)
+    for k in range(e2e_steps):
+        host_step(nit); nit += 1
+    e1.record(stream); torch.cuda.synchronize()
+    ms2 = e0.elapsed_time(e1)
+    state_bytes = sum(x.numel() * 8 for x in hb[0])
+    h2d = state_bytes * (2 if implicit else 1); d2h = state_bytes
+    e2e = {'value': cells * e2e_steps / (ms2 * 1e-3) / 1e6, 'unit': 'Mcell.it/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+           'steps': e2e_steps, 'ms_per_step': ms2 / e2e_steps}
+    a = hb[order[0]][0].numpy()
+    assert numpy.isfinite(a).all(), "non-finite state after the benchmark"
+
+    cpu = None
+    if not args.no_cpu:
+        r, nth, sample, _ = cpu_oracle_rate(args.workload, seconds=12.)
+        cpu = {'value': r, 'unit': 'Mcell.it/s', 'cores': nth, 'kind': 'port', 'sample': sample}
+    out = {'metric': 'FP64 cell-updates/sec', 'value': value, 'unit': 'Mcell.it/s', 'n_gpus': 1, 'steps': args.steps,
+           'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+           'dtype': 'f64', 'data': 'synthetic',
+           'config': {'workload': desc, 'cells': cells, 'sub_iterations_per_step': nsub, 'l2': 'working set >> 126 MB L2 (no flush needed)',
+                      'cell_updates_per_s': cells * nsub * args.steps / (ms * 1e-3)},
+           'roofline': roof, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches.value), 'clocks': clk.summary()}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1); ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3); ap.add_argument('--impl', default='fast_b200')
+    ap.add_argument('--workload', default=None); ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+    if args.workload is None: args.workload = 'tgv256' if args.gpus == 1 else 'multiblock'
+    if args.impl == 'reference': run_reference(args)
+    else: run_gpu(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -525,18 +525,21 @@ int fb_zone_get_cfl(fb_solver *s, int nd, double cfl[3])
 
 int fb_compute_host(fb_solver *s, int nitrun, int nit_c, int *first_it, double **ro, double **ro_m1, double **ro_p1)
 {
-    if (!s || !ro || !ro_m1 || !ro_p1) return fail(FB_EINVAL, "fb_compute_host: bad arguments");
+    if (!s || !ro || !ro_m1 || !ro_p1 || !first_it) return fail(FB_EINVAL, "fb_compute_host: bad arguments");
+    if (nit_c != 1) return fail(FB_EINVAL, "fb_compute_host: nit_c must be 1 (the host rotates its pointers after every iteration)");
     CK(cudaSetDevice(s->dev));
-    double **h[3] = {ro, ro_m1, ro_p1};
-    for (int n = 0; n < s->nz; n++)
-        for (int l = 0; l < 3; l++)
-            CK(cudaMemcpyAsync(s->z[n].rop[l], h[l][n], s->z[n].n_state * sizeof(double), cudaMemcpyHostToDevice, s->st));
+    // inputs of one iteration: ro always, ro_M1 for the BDF2 time term (implicit); ro_P1 is pure output
+    const bool implicit = s->z[0].d.itypcp <= 1;
+    for (int n = 0; n < s->nz; n++) {
+        CK(cudaMemcpyAsync(s->z[n].rop[0], ro[n], s->z[n].n_state * sizeof(double), cudaMemcpyHostToDevice, s->st));
+        if (implicit) CK(cudaMemcpyAsync(s->z[n].rop[1], ro_m1[n], s->z[n].n_state * sizeof(double), cudaMemcpyHostToDevice, s->st));
+    }
     const int nssiter = s->z[0].pi[PI_NSSITER];
-    int rc = fb_compute(s, nitrun, 1, nssiter, nit_c, first_it); if (rc) return rc;
-    // after the rotation device level l holds what the caller's rotated pointers expect: write back in place
+    int rc = fb_compute(s, nitrun, 1, nssiter, 1, first_it); if (rc) return rc;
+    // after the device-side rotation level 0 is the new solution: it lands in the caller's ro_P1 buffer, and the caller
+    // rotates its three pointers exactly like FastC.switchPointers__ (ro_M1 <- ro <- ro_P1 <- old ro_M1)
     for (int n = 0; n < s->nz; n++)
-        for (int l = 0; l < 3; l++)
-            CK(cudaMemcpyAsync(h[l][n], s->z[n].rop[l], s->z[n].n_state * sizeof(double), cudaMemcpyDeviceToHost, s->st));
+        CK(cudaMemcpyAsync(ro_p1[n], s->z[n].rop[0], s->z[n].n_state * sizeof(double), cudaMemcpyDeviceToHost, s->st));
     CK(cudaStreamSynchronize(s->st));
     return FB_OK;
 }

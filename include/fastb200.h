@@ -72,9 +72,10 @@ int fb_compute_mut(fb_solver *s);
 int fb_zone_get_residuals(fb_solver *s, int nd, double *rdm, int n);
 int fb_zone_get_cfl(fb_solver *s, int nd, double cfl[3]);
 
-/* End-to-end step on HOST buffers (what a reference-side caller holding numpy arrays does): uploads the
- * three time levels of every zone, runs fb_compute, downloads them back. ro/ro_m1/ro_p1[nd] are host
- * pointers of NDIMDX*NEQ doubles each (pinned or pageable). */
+/* End-to-end iteration on HOST buffers (what a reference-side caller holding the tree's numpy arrays does):
+ * uploads the input time levels of every zone (ro; ro_M1 too for the implicit BDF term), runs one fb_compute
+ * iteration (nit_c must be 1), downloads the new solution into the caller's ro_P1 buffers.  The caller then rotates
+ * its three pointers like FastC.switchPointers__ (C/PyTree.py:2298).  ro/ro_m1/ro_p1[nd]: NDIMDX*NEQ doubles each. */
 int fb_compute_host(fb_solver *s, int nitrun, int nit_c, int *first_it,
                     double **ro, double **ro_m1, double **ro_p1);
 
