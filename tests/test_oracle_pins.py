@@ -1,0 +1,131 @@
+"""CPU tests of the oracle against the pins available without the reference's (unshipped) fixtures: in-source
+constants, analytic invariants and the committed regression fixtures in tests/golden/."""
+import ctypes, os
+import numpy
+import pytest
+from helpers import oracle_from_tree, interior, relerr, orc, V, ROOT
+from fast_b200 import synth
+from fast_b200.FastC.PyTree import Internal
+
+_dp = ctypes.POINTER(ctypes.c_double); _ip = ctypes.POINTER(ctypes.c_int)
+
+
+def _uniform(t, vals=(1., 1., 0.3, -0.2, 1.)):
+    for z in Internal.getZones(t):
+        sol = Internal.getNodeFromName1(z, 'FlowSolution#Centers')
+        for n, v in zip(('Density', 'VelocityX', 'VelocityY', 'VelocityZ', 'Temperature'), vals):
+            Internal.getNodeFromName1(sol, n)[1][...] = v
+
+
+@pytest.mark.parametrize('kw', [dict(scheme='ausmpred'), dict(scheme='roe', deform_amp=0.03),
+                                dict(scheme='senseur', model='NSLaminar', ReInf=500., deform_amp=0.03),
+                                dict(scheme='roe', model='NSLaminar', ReInf=500., temporal='implicit', deform_amp=0.02)])
+def test_free_stream_preserved(kw):
+    """Uniform flow on a closed (periodic) mesh => drodm == 0 to round-off, Cartesian and curvilinear."""
+    t = synth.case_euler_box(n=10, **kw); _uniform(t)
+    o = oracle_from_tree(t); z = o.zones[0]
+    nss = int(z.pi[V.NSSITER])
+    for it in (1, 2): o.compute(it, 1, nss, 1)
+    a = interior(z.pi, z.lev[0])
+    for e, v in enumerate((1., 1., 0.3, -0.2, 1.)):
+        assert numpy.abs(a[e] - v).max() < 5e-13
+
+
+def test_conservation_periodic():
+    """Telescoping fluxes: total mass, momentum and energy constant to round-off in a periodic Cartesian box (Euler:
+    the viscous cross terms read the edge ghost cells, which correct_coins replaces by averages -- reference behaviour)."""
+    t = synth.case_euler_box(n=12, scheme='senseur')
+    o = oracle_from_tree(t); z = o.zones[0]
+    def totals():
+        a = interior(z.pi, z.lev[0]); cv = z.pr[V.CVINF]
+        ro = a[0]; e = ro * (cv * a[4] + 0.5 * (a[1] ** 2 + a[2] ** 2 + a[3] ** 2))
+        return numpy.array([ro.sum(), (ro * a[1]).sum(), (ro * a[2]).sum(), (ro * a[3]).sum(), e.sum()])
+    t0 = totals()
+    for it in range(1, 6): o.compute(it, 1, 3, 1)
+    t1 = totals()
+    assert numpy.abs(t1 - t0).max() <= 1e-12 * numpy.abs(t0).max()
+
+
+def test_metric_pins():
+    """vol of a Cartesian cell = hx*hy*hz, |ti| = hy*hz; closed curvilinear cells: sum of face vectors = 0."""
+    t = synth.case_euler_box(n=8, n3=(8, 10, 12))
+    o = oracle_from_tree(t); z = o.zones[0]
+    hx, hy, hz = 1. / 8, 1. / 10, 1. / 12
+    assert abs(z.vol[0] - hx * hy * hz) < 1e-17 and abs(abs(z.ti[0]) - hy * hz) < 1e-16
+    t = synth.case_euler_box(n=8, deform_amp=0.04)
+    o = oracle_from_tree(t); z = o.zones[0]; pi = z.pi
+    assert int(pi[V.ITYPZONE]) == 0
+    nm = int(pi[V.NDIMDX_MTR]); nx, ny, nz = [int(pi[V.NIJK_XYZ + d]) for d in range(3)]
+    for e in range(3):
+        a3 = [q[e * nm:(e + 1) * nm].reshape((nx, ny, nz), order='F') for q in (z.ti, z.tj, z.tk)]
+        s = (a3[0][1:, :-1, :-1] - a3[0][:-1, :-1, :-1] + a3[1][:-1, 1:, :-1] - a3[1][:-1, :-1, :-1]
+             + a3[2][:-1, :-1, 1:] - a3[2][:-1, :-1, :-1])
+        assert numpy.abs(s).max() < 1e-16
+    assert z.vol[:nm].reshape((nx, ny, nz), order='F')[:-1, :-1, :-1].min() > 0
+
+
+def test_sensor_zero_on_monotone_data():
+    """wiggle2001: no double sign change => wig == 0 everywhere; a saw-tooth sets it to 1."""
+    t = synth.case_euler_box(n=8, scheme='senseur')
+    o = oracle_from_tree(t); z = o.zones[0]; L = o.L; pi = z.pi
+    nd = int(pi[V.NDIMDX]); ni, nj, nk = int(pi[V.NIJK]), int(pi[V.NIJK + 1]), int(pi[V.NIJK + 2])
+    ii = numpy.arange(nd) % ni
+    rop = numpy.zeros(5 * nd)
+    for e in range(5): rop[e * nd:(e + 1) * nd] = 1. + 0.01 * (e + 1) * ii          # monotone in i, constant in j,k
+    ind = (ctypes.c_int * 6)(1, int(pi[V.IJKV]), 1, int(pi[V.IJKV + 1]), 1, int(pi[V.IJKV + 2]))
+    wig = numpy.full(3 * nd, -1.)
+    L.fo_wiggle2001(pi.ctypes.data_as(_ip), z.pr.ctypes.data_as(_dp), ind, rop.ctypes.data_as(_dp), wig.ctypes.data_as(_dp))
+    assert (wig[wig >= 0] == 0).all()
+    rop[:nd] = 1. + 0.01 * (ii % 2)                                                  # saw-tooth density
+    L.fo_wiggle2001(pi.ctypes.data_as(_ip), z.pr.ctypes.data_as(_dp), ind, rop.ctypes.data_as(_dp), wig.ctypes.data_as(_dp))
+    assert interior(pi, wig[:nd].copy())[0].min() == 1.
+
+
+def test_lu_sgs_reduces_to_diagonal():
+    """invlu with zero metrics (A = 0) and zero spectral radii => dW = drodm / coe5 (SURVEY 8c pin)."""
+    t = synth.case_euler_box(n=6, scheme='roe', temporal='implicit', deform_amp=0.02)
+    o = oracle_from_tree(t); z = o.zones[0]; L = o.L; pi = z.pi
+    nd = int(pi[V.NDIMDX]); rng = numpy.random.default_rng(0)
+    drodm = rng.standard_normal(5 * nd); ref = drodm.copy()
+    coe = numpy.zeros(5 * nd); coe[:nd] = 0.01; coe[4 * nd:] = 1.5 + rng.random(nd)
+    zero = numpy.zeros_like(z.ti); zk = numpy.zeros_like(z.tk)
+    box = (ctypes.c_int * 6)(1, int(pi[V.IJKV]), 1, int(pi[V.IJKV + 1]), 1, int(pi[V.IJKV + 2]))
+    out = z.lev[0].copy()
+    L.fo_invlu(pi.ctypes.data_as(_ip), z.pr.ctypes.data_as(_dp), box, z.lev[0].ctypes.data_as(_dp), out.ctypes.data_as(_dp),
+               drodm.ctypes.data_as(_dp), coe.ctypes.data_as(_dp), zero.ctypes.data_as(_dp), zero.ctypes.data_as(_dp), zk.ctypes.data_as(_dp))
+    a = interior(pi, drodm); b = interior(pi, ref) / interior(pi, coe[4 * nd:].copy())[0][None]
+    assert numpy.abs(a - b).max() < 1e-14
+    # Newton update of density is rho + dW1
+    assert numpy.abs(interior(pi, out)[0] - (interior(pi, z.lev[0])[0] + a[0])).max() < 1e-14
+
+
+def test_newton_converges_and_bdf_first_iteration():
+    """Implicit dual time stepping: the Newton residual drops monotonically over the sub-iterations."""
+    t = synth.case_euler_box(n=10, scheme='roe', temporal='implicit')
+    o = oracle_from_tree(t); z = o.zones[0]
+    nss = int(z.pi[V.NSSITER])
+    o.compute(1, 1, nss, 1)
+    r = z.rdm.reshape((nss, z.neq, 2), order='F')[:, 0, 0]
+    assert (numpy.diff(r) < 0).all() and r[-1] < 1e-3 * r[0]
+
+
+def test_openmp_slabs_equal_serial():
+    """The timed CPU baseline (k slabs / zone-parallel LU) gives the serial result (same per-cell accumulation order)."""
+    ts = [synth.case_euler_box(n=10, scheme='senseur', model='NSLaminar', ReInf=500., deform_amp=0.02) for _ in range(2)]
+    o1 = oracle_from_tree(ts[0]); o2 = oracle_from_tree(ts[1])
+    for it in (1, 2):
+        o1.compute(it, 1, 3, 1, nthreads=1); o2.compute(it, 1, 3, 1, nthreads=3)
+    assert numpy.array_equal(interior(o1.zones[0].pi, o1.zones[0].lev[0]), interior(o2.zones[0].pi, o2.zones[0].lev[0]))
+
+
+GOLDEN = os.path.join(ROOT, 'tests', 'golden', 'oracle_regression.npz')
+
+
+@pytest.mark.skipif(not os.path.exists(GOLDEN), reason="fixtures not generated")
+def test_golden_regression():
+    """The committed fixtures (tests/golden/make_golden.py) are reproduced bit-for-bit by the strict-FP oracle build."""
+    import sys; sys.path.insert(0, os.path.join(ROOT, "tests", "golden")); import make_golden
+    g = numpy.load(GOLDEN)
+    for name in make_golden.CASES:
+        a = make_golden.run(name)
+        assert numpy.allclose(a, g[name], rtol=1e-13, atol=1e-15), name
