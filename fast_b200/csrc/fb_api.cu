@@ -283,6 +283,7 @@ int fb_init_metric(fb_solver *s)
     for (auto &z : s->z) {
         if (!z.has_params || !z.has_xyz) return fail(FB_ESTATE, "fb_init_metric: every zone needs params and coordinates");
         launch_metric(z.d, s->st);
+        if (z.d.itypcp <= 1) lu_plan_metrics(z.lu, z.d, s->st);
     }
     CK(cudaStreamSynchronize(s->st));
     for (auto &z : s->z) {   // 3dcart constants live in the descriptor (template_FluxAndBalance.for:112-119)
@@ -310,6 +311,7 @@ int fb_zone_get_metric(fb_solver *s, int nd, double *ti, double *tj, double *tk,
     return FB_OK;
 }
 
+static int check_lu(fb_solver *s);
 static int chk_zone(fb_solver *s, int nd, int level)
 {
     if (!s || nd < 0 || nd >= s->nz || level < 0 || level > 2) return fail(FB_EINVAL, "bad zone / level");
@@ -330,7 +332,7 @@ int fb_zone_download_state(fb_solver *s, int nd, int level, double *rop)
     CK(cudaSetDevice(s->dev));
     CK(cudaMemcpyAsync(rop, s->z[nd].rop[level], s->z[nd].n_state * sizeof(double), cudaMemcpyDeviceToHost, s->st));
     CK(cudaStreamSynchronize(s->st));
-    return FB_OK;
+    return check_lu(s);
 }
 int fb_zone_upload_aux(fb_solver *s, int nd, const double *aux, int n)
 {
@@ -560,7 +562,13 @@ int fb_timing_get(fb_solver *s, const char *name, double *ms, long long *launche
     for (int i = 0; i < 6; i++) if (!strcmp(name, TNAMES[i])) { if (ms) *ms = s->tm[i].ms; if (launches) *launches = s->launches; return FB_OK; }
     return fail(FB_EINVAL, "unknown timer name");
 }
-int fb_sync(fb_solver *s) { if (!s) return fail(FB_EINVAL, "null"); CK(cudaSetDevice(s->dev)); CK(cudaStreamSynchronize(s->st)); CK(cudaGetLastError()); return FB_OK; }
+static int check_lu(fb_solver *s)
+{
+    for (auto &z : s->z) if (z.d.itypcp <= 1 && lu_plan_error(z.lu))
+        return fail(FB_ECUDA, "LU wavefront: a tile timed out waiting for its neighbour (results invalid)");
+    return FB_OK;
+}
+int fb_sync(fb_solver *s) { if (!s) return fail(FB_EINVAL, "null"); CK(cudaSetDevice(s->dev)); CK(cudaStreamSynchronize(s->st)); CK(cudaGetLastError()); return check_lu(s); }
 unsigned long long fb_zone_device_ptr(fb_solver *s, int nd, int level)
 {
     if (!s || nd < 0 || nd >= s->nz || level < 0 || level > 3) return 0;

@@ -10,6 +10,7 @@
 // The reference sweeps i fastest, then j, then k; a cell only depends on its three lower (upper) neighbours, so all
 // cells of a hyperplane i+j+k = const are independent and the wavefront reproduces exactly the sequential result.
 #include <cstdio>
+#include <cstdlib>
 #include "fb_implicit.cuh"
 #include "fb_source.cuh"
 
@@ -288,14 +289,6 @@ __global__ void k_newton(ZoneDev z, const double *__restrict__ rop, double *__re
     }
 }
 
-int lu_plan_build(LuPlan &p, const ZoneDev &z, const int box[6])
-{
-    for (int i = 0; i < 6; i++) p.box[i] = box[i];
-    p.nplanes = (box[1] - box[0] + 1) + (box[3] - box[2] + 1) + (box[5] - box[4] + 1) - 2;
-    (void)z;
-    return 0;
-}
-void lu_plan_free(LuPlan &p) { if (p.scratch) cudaFree(p.scratch); p.scratch = nullptr; }
 
 template <int MESH, int NEQ>
 static int run_lu(const ZoneDev &z, const LuPlan &p, const double *rop, double *rop_out, int lu_match, cudaStream_t st)
@@ -321,6 +314,9 @@ static int run_lu(const ZoneDev &z, const LuPlan &p, const double *rop, double *
 
 int launch_lu(const ZoneDev &z, const LuPlan &p, const double *rop, double *rop_out, int lu_match, cudaStream_t st)
 {
+    // default: tile-pipelined wavefront (fb_lu.cu); FAST_B200_LU=plane keeps the one-launch-per-hyperplane kernels for A/B checks
+    static const int use_plane = [] { const char *e = getenv("FAST_B200_LU"); return e && e[0] == 'p'; }();
+    if (!use_plane) return launch_lu_tiles(z, p, rop, rop_out, lu_match, st);
     if (z.neq == 6) {
         if (z.typ == 0) return run_lu<0, 6>(z, p, rop, rop_out, lu_match, st);
         if (z.typ == 1) return run_lu<1, 6>(z, p, rop, rop_out, lu_match, st);

@@ -10,10 +10,20 @@ struct LuPlan {
     int nplanes = 0;
     int ndefault_rhs = 0;             // leading default-extrapolation windows of the rhs BC table
     int modulo_verif = 0;
-    void *scratch = nullptr;
+    // tile-pipelined wavefront (fb_lu.cu)
+    int tk = 8, NJ = 0, NK = 0;       // tile height in k, tiles per direction of the (j,k) cross-section
+    int *d_order = nullptr;           // ticket -> tile, i+j+k order
+    int *d_ctl = nullptr;             // [ticket lower, ticket upper, error flag, pad]
+    double *d_mb = nullptr;           // inter-tile mailboxes: j interfaces then k interfaces
+    size_t n_ifj = 0, n_ifk = 0;
+    double *d_tcm = nullptr;          // cell-centred mean normals (3dfull: 9 x NDIMDX, 3dhomo: 5 x ni*nj)
+    long long tstride = 0;
 };
 int  lu_plan_build(LuPlan &p, const ZoneDev &z, const int box[6]);
 void lu_plan_free(LuPlan &p);
+void lu_plan_metrics(LuPlan &p, const ZoneDev &z, cudaStream_t st);   // after the metrics exist
+int  lu_plan_error(const LuPlan &p);
+int  launch_lu_tiles(const ZoneDev &z, const LuPlan &p, const double *rop_ssiter, double *rop_out, int lu_match, cudaStream_t st);
 void launch_coe(const ZoneDev &z, const double *rop, int first_it, int lssiter_verif, double *cfl, cudaStream_t st);
 void launch_sa_ring(const ZoneDev &z, const double *rop, cudaStream_t st);
 void launch_resid(const ZoneDev &z, double *rdm, int nitcfg, int nss, cudaStream_t st);
