@@ -23,8 +23,10 @@
 // HBM traffic per cell: lower reads rhs+coe+(u,v,w,T)+normals, writes dW*; upper reads dW*+coe+state+normals and
 // writes ro_P1 directly (mjr_newton fused, dW itself is never stored).
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 #include <algorithm>
+#include <type_traits>
 #include "fb_implicit.cuh"
 
 #define LU_CI 8            // cells per line per staged chunk
@@ -32,6 +34,8 @@
 #define LU_MB 6            // doubles per mailbox entry
 #define LU_EMPTY 0xFFF7DEADBEEF5A5AULL   // signalling NaN: never produced by arithmetic
 #define LU_SPIN_MAX (1 << 21)
+#define LU_NC 256          // compute threads: 4 lanes per line
+#define LU_NT 320          // + 2 service warps
 
 template <int MESH, int NEQ, bool UPPER>
 struct LuCfg {
@@ -44,7 +48,7 @@ struct LuCfg {
     static constexpr int NT = MESH == 0 ? 9 : (MESH == 1 ? 5 : 0);
     static constexpr int A_DW = 0, A_COE = NEQ, A_ST = NEQ + NC, A_T = NEQ + NC + NS;
     static constexpr int A = NEQ + NC + NS + NT;
-    static constexpr size_t SMEM = (size_t)(2 * A * L * LU_CI + 2 * 2 * L * NEQ) * sizeof(double);
+    static constexpr size_t SMEM = (size_t)(2 * A * L * LU_CI + 2 * 3 * L * LU_MB + 4 * 16 * LU_MB) * sizeof(double);
 };
 
 int lu_tile_tk(int mesh, int neq) { return (mesh == 0 && neq == 6) ? 6 : 8; }
@@ -64,7 +68,10 @@ struct LuTileArgs {
     int bi, bj, bk, NJ, NK;
     int alias, order_mode;
     int plane;              // ni*nj (3dhomo: tcm is a plane array)
+    unsigned long long *dbg;   // FAST_B200_LU_DEBUG: per tile {start, first step, end, smid} (globaltimer ns)
 };
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned smid() { unsigned r; asm volatile("mov.u32 %0, %smid;" : "=r"(r)); return r; }
 
 __device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
 {
@@ -74,62 +81,46 @@ __device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-__device__ __forceinline__ void mb_load(const double *p, unsigned long long *v)
-{
-    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];\n" : "=l"(v[0]), "=l"(v[1]) : "l"(p) : "memory");
-    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];\n" : "=l"(v[2]), "=l"(v[3]) : "l"(p + 2) : "memory");
-    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];\n" : "=l"(v[4]), "=l"(v[5]) : "l"(p + 4) : "memory");
-}
-__device__ __forceinline__ void mb_store(double *p, const unsigned long long *v)
-{
-    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};\n" ::"l"(p), "l"(v[0]), "l"(v[1]) : "memory");
-    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};\n" ::"l"(p + 2), "l"(v[2]), "l"(v[3]) : "memory");
-    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};\n" ::"l"(p + 4), "l"(v[4]), "l"(v[5]) : "memory");
-}
-template <int NEQ> __device__ __forceinline__ bool mb_ready(const unsigned long long *v)
-{
-    bool ok = true;
-#pragma unroll
-    for (int e = 0; e < NEQ; e++) ok = ok && (v[e] != LU_EMPTY);
-    return ok;
-}
+// mailbox accesses: strong (volatile) 8-byte accesses served by L2; an entry validates itself word by word
+__device__ __forceinline__ bool mb_empty(unsigned long long v) { return v == LU_EMPTY; }
 
-// B_d(l) . dW(l) with the cell-centred mean normal (tcx,tcy,tcz) of cell l: lu_{i,j,k}_*.for, signe folded into cd
+// B_d(l) . dW(l) with the cell-centred mean normal (tcx,tcy,tcz) of cell l (lu_{i,j,k}_*.for; signe folded into cd).
+// The reference spells out the 5x5 flux Jacobian; the product is evaluated here in its factored form
+//   theta = n.dm - qn drho,  dp = (g-1)(q2 drho - q.dm + dE),  A dW = [n.dm, qn dm + q theta + n dp, qn (dE + dp) + h theta]
+// (identical algebra, ~4x fewer FP64 operations, differences at round-off level).
 template <int NEQ>
 __device__ __forceinline__ void lu_prod(double tcx, double tcy, double tcz, double u, double v, double w, double t,
                                         double cd, double gam, double cp, const double *d, double *b)
 {
-    const double gam1 = gam, gamm1 = gam1 - 1., gam2 = gamm1 - 1.;
-    const double q2 = .5 * (u * u + v * v + w * w), h = cp * t + q2, ph2 = gamm1 * q2;
+    const double gamm1 = gam - 1.;
+    const double q2 = .5 * (u * u + v * v + w * w), h = cp * t + q2;
     const double qn = tcx * u + tcy * v + tcz * w;
-    const double d1 = d[0], d2 = d[1], d3 = d[2], d4 = d[3], d5 = d[4];
-    const double b11 = cd, b12 = tcx, b13 = tcy, b14 = tcz;
-    const double b21 = (tcx * ph2 - u * qn), b22 = (qn - tcx * gam2 * u) + cd, b23 = (tcy * u - tcx * gamm1 * v), b24 = (tcz * u - tcx * gamm1 * w), b25 = tcx * gamm1;
-    const double b31 = (tcy * ph2 - v * qn), b32 = (tcx * v - tcy * gamm1 * u), b33 = (qn - tcy * gam2 * v) + cd, b34 = (tcz * v - tcy * gamm1 * w), b35 = tcy * gamm1;
-    const double b41 = (tcz * ph2 - w * qn), b42 = (tcx * w - tcz * gamm1 * u), b43 = (tcy * w - tcz * gamm1 * v), b44 = (qn - tcz * gam2 * w) + cd, b45 = tcz * gamm1;
-    const double b51 = qn * (ph2 - h), b52 = (tcx * h - gamm1 * u * qn), b53 = (tcy * h - gamm1 * v * qn), b54 = (tcz * h - gamm1 * w * qn), b55 = (gam1 * qn) + cd;
-    b[0] = b11 * d1 + b12 * d2 + b13 * d3 + b14 * d4;
-    b[1] = b21 * d1 + b22 * d2 + b23 * d3 + b24 * d4 + b25 * d5;
-    b[2] = b31 * d1 + b32 * d2 + b33 * d3 + b34 * d4 + b35 * d5;
-    b[3] = b41 * d1 + b42 * d2 + b43 * d3 + b44 * d4 + b45 * d5;
-    b[4] = b51 * d1 + b52 * d2 + b53 * d3 + b54 * d4 + b55 * d5;
+    const double ndm = tcx * d[1] + tcy * d[2] + tcz * d[3];
+    const double theta = ndm - qn * d[0];
+    const double dp = gamm1 * ((q2 * d[0] - (u * d[1] + v * d[2] + w * d[3])) + d[4]);
+    b[0] = ndm + cd * d[0];
+    b[1] = (qn * d[1] + u * theta) + (tcx * dp + cd * d[1]);
+    b[2] = (qn * d[2] + v * theta) + (tcy * dp + cd * d[2]);
+    b[3] = (qn * d[3] + w * theta) + (tcz * dp + cd * d[3]);
+    b[4] = (qn * (d[4] + dp) + h * theta) + cd * d[4];
     if (NEQ == 6) b[NEQ - 1] = (qn + cd) * d[NEQ - 1];
 }
 
 template <int MESH, int NEQ, bool UPPER>
-__global__ void __launch_bounds__(128, 1) k_lu_tile(ZoneDev z, LuTileArgs a)
+__global__ void __launch_bounds__(LU_NT, 1) k_lu_tile(ZoneDev z, LuTileArgs a)
 {
     using C = LuCfg<MESH, NEQ, UPPER>;
-    constexpr int TJ = C::TJ, TK = C::TK, L = C::L, A = C::A, CI = LU_CI;
+    constexpr int TJ = C::TJ, TK = C::TK, L = C::L, A = C::A, CI = LU_CI, EX = LU_MB;
     extern __shared__ double smem[];
     double *ring = smem;                              // [2][A][L][CI]
-    double *exj = smem + 2 * A * L * CI;              // [2][L][NEQ]
-    double *exk = exj + 2 * L * NEQ;                  // [2][L][NEQ]
+    double *exb = smem + 2 * A * L * CI;              // [2][3][L][EX] products handed to (ii+1), (jj+1), (kk+1)
+    unsigned long long *mbs = (unsigned long long *)(exb + 2 * 3 * L * EX);   // [4][16][EX] prefetched mailbox entries
     __shared__ int s_tile;
     const int tid = threadIdx.x;
     if (tid == 0) s_tile = a.order[atomicAdd(a.ticket, 1)];
     __syncthreads();
     const int J = s_tile & 0xffff, K = s_tile >> 16;
+    if (a.dbg && tid == 0) { a.dbg[4 * (K * a.NJ + J)] = gtime(); a.dbg[4 * (K * a.NJ + J) + 3] = smid(); }
     const int bi = a.bi, bj = a.bj, bk = a.bk;
     const int nst = bi + TJ + TK - 2;
     const int nd = z.nd;
@@ -137,9 +128,9 @@ __global__ void __launch_bounds__(128, 1) k_lu_tile(ZoneDev z, LuTileArgs a)
     // cell address of sweep coordinates (ii, jjg, kkg): l0 + sg * (ii + jjg * incj + kkg * inck)
     const int l0 = UPPER ? inddm(z, a.box[1], a.box[3], a.box[5]) : inddm(z, a.box[0], a.box[2], a.box[4]);
 
-    if (tid >= 64) {
+    if (tid >= LU_NC) {
         // ------------------------------------------------------------------------------------ service warps
-        const int st = tid - 64;
+        const int st = tid - LU_NC;
         const int q = st / CI, cell = st % CI;           // line slot (= kk) and cell inside the chunk
         const bool qok = q < TK;
         const int kk = q, kkg = K * TK + kk;
@@ -191,10 +182,35 @@ __global__ void __launch_bounds__(128, 1) k_lu_tile(ZoneDev z, LuTileArgs a)
                 }
             }
         };
+        // mailbox prefetch: thread st < 48 fetches 16 bytes of the entry that interface line il needs at step sp and
+        // parks them in shared memory (slot sp & 3); the load is issued before the refill work of the iteration and
+        // consumed after it, so its L2 latency overlaps with the cp.async issue
+        const int il = st / 3, part = st % 3;
+        const bool isj = il < 8;
+        const int mjj = isj ? 0 : il - 8, mkk = isj ? il : 0;
+        const int mjg = J * TJ + mjj, mkg = K * TK + mkk;
+        const bool mvalid = st < 48 && mjg < bj && mkg < bk && mkk < TK && (isj ? J > 0 : K > 0);
+        const unsigned long long *mrow = nullptr;
+        if (mvalid) mrow = (const unsigned long long *)(isj ? a.ifj + ((size_t)((J - 1) * bk + mkg) * bi) * LU_MB
+                                                              : a.ifk + ((size_t)((K - 1) * bj + mjg) * bi) * LU_MB) + 2 * part;
+        const int msig = mjj + mkk;
         for (int t = -CI; t <= -2; t++) { rule(t); cp_async_commit(); }
+        for (int sp = 0; sp < 2; sp++) {
+            const int ii = sp - msig;
+            if (mvalid && ii >= 0 && ii < bi) {
+                const volatile unsigned long long *p = mrow + (size_t)ii * LU_MB;
+                unsigned long long *dst = mbs + ((size_t)((sp & 3) * 16 + il) * EX) + 2 * part;
+                dst[0] = p[0]; dst[1] = p[1];
+            }
+        }
         for (int s = 0; s < nst; s++) {
+            const int sp = s + 2, ii = sp - msig;
+            const bool doit = mvalid && ii >= 0 && ii < bi;
+            unsigned long long v0 = LU_EMPTY, v1 = LU_EMPTY;
+            if (doit) { const volatile unsigned long long *p = mrow + (size_t)ii * LU_MB; v0 = p[0]; v1 = p[1]; }
             rule(s - 1);
             cp_async_commit();
+            if (doit) { unsigned long long *dst = mbs + ((size_t)((sp & 3) * 16 + il) * EX) + 2 * part; dst[0] = v0; dst[1] = v1; }
             cp_async_wait<CI - 1>();
             __syncthreads();
         }
@@ -205,153 +221,138 @@ __global__ void __launch_bounds__(128, 1) k_lu_tile(ZoneDev z, LuTileArgs a)
     }
 
     // ---------------------------------------------------------------------------------------- compute warps
-    const int jj = tid % TJ, kk = tid / TJ;
+    // 4 lanes per line: lane r < 3 evaluates the product of direction r, all lanes redo the (cheap) dW* of the line, so
+    // that the three Jacobian products run on different lanes of the same instruction stream and the 8 compute warps
+    // keep two warps per scheduler on the FP64 pipe.
+    const int lam = tid >> 2, r = tid & 3;
+    const int jj = lam % TJ, kk = lam / TJ;
     const int jjg = J * TJ + jj, kkg = K * TK + kk;
-    const bool lvalid = tid < L && jjg < bj && kkg < bk;
+    const bool lvalid = lam < L && jjg < bj && kkg < bk;
     const int sigma = jj + kk;
     const bool has_j = jjg > 0, has_k = kkg > 0;
     const bool mbj_in = lvalid && jj == 0 && J > 0, mbk_in = lvalid && kk == 0 && K > 0;
-    const bool mbj_out = lvalid && jj == TJ - 1 && J + 1 < a.NJ, mbk_out = lvalid && kk == TK - 1 && K + 1 < a.NK;
-    double *mbj_r = mbj_in ? a.ifj + ((size_t)((J - 1) * bk + kkg) * bi) * LU_MB : nullptr;
-    double *mbk_r = mbk_in ? a.ifk + ((size_t)((K - 1) * bj + jjg) * bi) * LU_MB : nullptr;
-    double *mbj_w = mbj_out ? a.ifj + ((size_t)(J * bk + kkg) * bi) * LU_MB : nullptr;
-    double *mbk_w = mbk_out ? a.ifk + ((size_t)(K * bj + jjg) * bi) * LU_MB : nullptr;
-    unsigned long long pj1[LU_MB], pj2[LU_MB], pk1[LU_MB], pk2[LU_MB];
-#pragma unroll
-    for (int e = 0; e < LU_MB; e++) { pj1[e] = pj2[e] = pk1[e] = pk2[e] = LU_EMPTY; }
-    auto prefetch = [&](int s) {   // entry needed at step s+2
-        const int ii2 = s - sigma + 2;
-#pragma unroll
-        for (int e = 0; e < LU_MB; e++) { pj1[e] = pj2[e]; pk1[e] = pk2[e]; }
-        if (ii2 >= 0 && ii2 < bi) {
-            if (mbj_in) mb_load(mbj_r + (size_t)ii2 * LU_MB, pj2);
-            if (mbk_in) mb_load(mbk_r + (size_t)ii2 * LU_MB, pk2);
-        }
-    };
-    prefetch(-2); prefetch(-1);
+    const bool mbj_out = lvalid && r == 1 && jj == TJ - 1 && J + 1 < a.NJ, mbk_out = lvalid && r == 2 && kk == TK - 1 && K + 1 < a.NK;
+    volatile unsigned long long *mbj_r = mbj_in ? (unsigned long long *)(a.ifj + ((size_t)((J - 1) * bk + kkg) * bi) * LU_MB) : nullptr;
+    volatile unsigned long long *mbk_r = mbk_in ? (unsigned long long *)(a.ifk + ((size_t)((K - 1) * bj + jjg) * bi) * LU_MB) : nullptr;
+    volatile unsigned long long *mb_w = nullptr;
+    if (mbj_out) mb_w = (unsigned long long *)(a.ifj + ((size_t)(J * bk + kkg) * bi) * LU_MB);
+    if (mbk_out) mb_w = (unsigned long long *)(a.ifk + ((size_t)(K * bj + jjg) * bi) * LU_MB);
     // Newton box test of the own line (upper only)
     const int jg = UPPER ? a.box[3] - jjg : a.box[2] + jjg, kg = UPPER ? a.box[5] - kkg : a.box[4] + kkg;
     const bool line_in_nb = jg >= a.nbx[2] && jg <= a.nbx[3] && kg >= a.nbx[4] && kg <= a.nbx[5];
     const double signe = UPPER ? -0.5 : 0.5;
     const double gam = z.gam, cp = z.gam * z.cv;
-    double bprev[NEQ];
-#pragma unroll
-    for (int e = 0; e < NEQ; e++) bprev[e] = 0.;
-    unsigned long long empty[LU_MB];
-#pragma unroll
-    for (int e = 0; e < LU_MB; e++) empty[e] = LU_EMPTY;
+    // accumulation order of the reference (invlu_l.for / invlu_u.for: k,j,i; overlap variants: i,j,k; 3dcart lower: j,k,i
+    // when both exist): which product sits at position 0, 1, 2 of the sum
+    int ord0 = 2, ord1 = 1, ord2 = 0;
+    if (a.order_mode == 1) { ord0 = 0; ord1 = 1; ord2 = 2; }
+    else if (a.order_mode == 2 && has_j && has_k) { ord0 = 1; ord1 = 2; ord2 = 0; }
+    const int rr = r < 3 ? r : 2;                      // lane 3 repeats the k product (not stored)
 
+    // one incoming product: from shared memory (neighbour line of the tile), from the prefetched mailbox entry (tile
+    // boundary; falls back to polling global memory while the producer tile has not delivered), or zero (box boundary)
+    auto mailbox = [&](volatile unsigned long long *row, const unsigned long long *pre, int ii, double *bv) {
+        unsigned long long v[NEQ];
+        bool ok = true;
+#pragma unroll
+        for (int e = 0; e < NEQ; e++) { v[e] = pre[e]; ok = ok && !mb_empty(v[e]); }
+        volatile unsigned long long *p = row + (size_t)ii * LU_MB;
+        int spin = 0;
+        while (!ok) {
+            ok = true;
+#pragma unroll
+            for (int e = 0; e < NEQ; e++) { v[e] = p[e]; ok = ok && !mb_empty(v[e]); }
+            if (++spin > LU_SPIN_MAX || (((spin & 1023) == 0) && *(volatile int *)a.err)) { *a.err = 1; break; }
+        }
+#pragma unroll
+        for (int e = 0; e < NEQ; e++) bv[e] = __longlong_as_double((long long)v[e]);
+        if (r == 0) {
+#pragma unroll
+            for (int e = 0; e < LU_MB; e++) p[e] = LU_EMPTY;      // self-cleaning: ready for the next sweep
+        }
+    };
+
+    if (a.dbg && tid == 0) a.dbg[4 * (K * a.NJ + J) + 1] = gtime();
     for (int s = 0; s < nst; s++) {
         __syncthreads();
         const int ii = s - sigma;
-        const bool active = lvalid && ii >= 0 && ii < bi;
-        unsigned long long cj[LU_MB], ck[LU_MB];
-#pragma unroll
-        for (int e = 0; e < LU_MB; e++) { cj[e] = pj1[e]; ck[e] = pk1[e]; }
-        prefetch(s);
-        if (!active) continue;
+        if (!(lvalid && ii >= 0 && ii < bi)) continue;
         const int c = ii / CI, slot = ii % CI;
-        const double *R = ring + ((size_t)((c & 1) * A) * L + tid) * CI + slot;
+        const double *R = ring + ((size_t)((c & 1) * A) * L + lam) * CI + slot;
 #define RING(arr) R[(size_t)(arr) * L * CI]
-        double acc[NEQ], b[NEQ], bj_[NEQ], bk_[NEQ];
+        double acc[NEQ], bi_[EX], bj_[EX], bk_[EX];
 #pragma unroll
         for (int e = 0; e < NEQ; e++) acc[e] = RING(C::A_DW + e);
         const double coe1 = RING(C::A_COE), coe5 = RING(C::A_COE + 4);
         double coe6 = 1.;
         if (NEQ == 6) coe6 = RING(C::A_COE + 5);
+        // state, mean normal and spectral radius of the lane's direction
+        double ro = 0., u, v, w, t, nut = 0.;
+        if (UPPER) { ro = RING(C::A_ST); u = RING(C::A_ST + 1); v = RING(C::A_ST + 2); w = RING(C::A_ST + 3); t = RING(C::A_ST + 4); if (NEQ == 6) nut = RING(C::A_ST + 5); }
+        else { u = RING(C::A_ST); v = RING(C::A_ST + 1); w = RING(C::A_ST + 2); t = RING(C::A_ST + 3); }
+        double tcx = 0., tcy = 0., tcz = 0.;
+        if (MESH == 0) { tcx = RING(C::A_T + 3 * rr); tcy = RING(C::A_T + 3 * rr + 1); tcz = RING(C::A_T + 3 * rr + 2); }
+        else if (MESH == 1) {
+            if (rr < 2) { tcx = RING(C::A_T + 2 * rr); tcy = RING(C::A_T + 2 * rr + 1); } else tcz = RING(C::A_T + 4);
+        } else { if (rr == 0) tcx = z.tc0[0]; else if (rr == 1) tcy = z.tc0[1]; else tcz = z.tc0[2]; }
+        const double cd = RING(C::A_COE + 1 + rr) * signe;
+        // incoming products (zero where the neighbour is outside the sweep box: adding 0 leaves acc unchanged)
+        const double *xin = exb + (size_t)((s + 1) & 1) * 3 * L * EX;
+        {
+            const double2 *p = (const double2 *)(xin + (size_t)lam * EX);
+            const double2 x0 = p[0], x1 = p[1], x2 = p[2];
+            const bool h = ii > 0;
+            bi_[0] = h ? x0.x : 0.; bi_[1] = h ? x0.y : 0.; bi_[2] = h ? x1.x : 0.; bi_[3] = h ? x1.y : 0.; bi_[4] = h ? x2.x : 0.; bi_[5] = h ? x2.y : 0.;
+        }
+        if (jj > 0) {
+            const double2 *p = (const double2 *)(xin + (size_t)(L + lam - 1) * EX);
+            const double2 x0 = p[0], x1 = p[1], x2 = p[2];
+            bj_[0] = x0.x; bj_[1] = x0.y; bj_[2] = x1.x; bj_[3] = x1.y; bj_[4] = x2.x; bj_[5] = x2.y;
+        } else if (has_j) mailbox(mbj_r, mbs + (size_t)((s & 3) * 16 + kk) * EX, ii, bj_);
+        else {
+#pragma unroll
+            for (int e = 0; e < EX; e++) bj_[e] = 0.;
+        }
+        if (kk > 0) {
+            const double2 *p = (const double2 *)(xin + (size_t)(2 * L + lam - TJ) * EX);
+            const double2 x0 = p[0], x1 = p[1], x2 = p[2];
+            bk_[0] = x0.x; bk_[1] = x0.y; bk_[2] = x1.x; bk_[3] = x1.y; bk_[4] = x2.x; bk_[5] = x2.y;
+        } else if (has_k) mailbox(mbk_r, mbs + (size_t)((s & 3) * 16 + 8 + jj) * EX, ii, bk_);
+        else {
+#pragma unroll
+            for (int e = 0; e < EX; e++) bk_[e] = 0.;
+        }
         if (UPPER) {
 #pragma unroll
             for (int e = 0; e < 5; e++) acc[e] = acc[e] * coe5;
             if (NEQ == 6) acc[NEQ - 1] = acc[NEQ - 1] * coe6;
         }
         const double xal = coe1 * signe;
-        // incoming products
-        const bool hi = ii > 0;
-        if (has_j) {
-            if (jj > 0) {
-                const double *p = exj + ((size_t)((s + 1) & 1) * L + tid - 1) * NEQ;
 #pragma unroll
-                for (int e = 0; e < NEQ; e++) bj_[e] = p[e];
-            } else {
-                double *p = mbj_r + (size_t)ii * LU_MB;
-                int spin = 0;
-                while (!mb_ready<NEQ>(cj)) {
-                    mb_load(p, cj);
-                    if (++spin > LU_SPIN_MAX || (((spin & 1023) == 0) && *(volatile int *)a.err)) { *a.err = 1; break; }
-                }
-#pragma unroll
-                for (int e = 0; e < NEQ; e++) bj_[e] = __longlong_as_double((long long)cj[e]);
-                mb_store(p, empty);
-            }
-        }
-        if (has_k) {
-            if (kk > 0) {
-                const double *p = exk + ((size_t)((s + 1) & 1) * L + tid - TJ) * NEQ;
-#pragma unroll
-                for (int e = 0; e < NEQ; e++) bk_[e] = p[e];
-            } else {
-                double *p = mbk_r + (size_t)ii * LU_MB;
-                int spin = 0;
-                while (!mb_ready<NEQ>(ck)) {
-                    mb_load(p, ck);
-                    if (++spin > LU_SPIN_MAX || (((spin & 1023) == 0) && *(volatile int *)a.err)) { *a.err = 1; break; }
-                }
-#pragma unroll
-                for (int e = 0; e < NEQ; e++) bk_[e] = __longlong_as_double((long long)ck[e]);
-                mb_store(p, empty);
-            }
-        }
-        // accumulation order of the reference (invlu_l.for / invlu_u.for; overlap variants: i,j,k)
-        int ord0 = 2, ord1 = 1, ord2 = 0;
-        if (a.order_mode == 1) { ord0 = 0; ord1 = 1; ord2 = 2; }
-        else if (a.order_mode == 2 && has_j && has_k) { ord0 = 1; ord1 = 2; ord2 = 0; }
-#pragma unroll
-        for (int qq = 0; qq < 3; qq++) {
-            const int d = qq == 0 ? ord0 : (qq == 1 ? ord1 : ord2);
-            if (d == 0) { if (hi) {
-#pragma unroll
-                for (int e = 0; e < NEQ; e++) acc[e] = acc[e] + bprev[e] * xal; } }
-            else if (d == 1) { if (has_j) {
-#pragma unroll
-                for (int e = 0; e < NEQ; e++) acc[e] = acc[e] + bj_[e] * xal; } }
-            else { if (has_k) {
-#pragma unroll
-                for (int e = 0; e < NEQ; e++) acc[e] = acc[e] + bk_[e] * xal; } }
+        for (int e = 0; e < NEQ; e++) {
+            const double t0 = ord0 == 0 ? bi_[e] : (ord0 == 1 ? bj_[e] : bk_[e]);
+            const double t1 = ord1 == 0 ? bi_[e] : (ord1 == 1 ? bj_[e] : bk_[e]);
+            const double t2 = ord2 == 0 ? bi_[e] : (ord2 == 1 ? bj_[e] : bk_[e]);
+            acc[e] = ((acc[e] + t0 * xal) + t1 * xal) + t2 * xal;
         }
         const double diag = 1. / coe5;
         double dwn[NEQ];
 #pragma unroll
         for (int e = 0; e < 5; e++) dwn[e] = acc[e] * diag;
         if (NEQ == 6) dwn[NEQ - 1] = acc[NEQ - 1] / coe6;
-
-        // state of the own cell
-        double ro = 0., u, v, w, t, nut = 0.;
-        if (UPPER) { ro = RING(C::A_ST); u = RING(C::A_ST + 1); v = RING(C::A_ST + 2); w = RING(C::A_ST + 3); t = RING(C::A_ST + 4); if (NEQ == 6) nut = RING(C::A_ST + 5); }
-        else { u = RING(C::A_ST); v = RING(C::A_ST + 1); w = RING(C::A_ST + 2); t = RING(C::A_ST + 3); }
-        double tix = 0., tiy = 0., tiz = 0., tjx = 0., tjy = 0., tjz = 0., tkx = 0., tky = 0., tkz = 0.;
-        if (MESH == 0) {
-            tix = RING(C::A_T); tiy = RING(C::A_T + 1); tiz = RING(C::A_T + 2);
-            tjx = RING(C::A_T + 3); tjy = RING(C::A_T + 4); tjz = RING(C::A_T + 5);
-            tkx = RING(C::A_T + 6); tky = RING(C::A_T + 7); tkz = RING(C::A_T + 8);
-        } else if (MESH == 1) {
-            tix = RING(C::A_T); tiy = RING(C::A_T + 1); tjx = RING(C::A_T + 2); tjy = RING(C::A_T + 3); tkz = RING(C::A_T + 4);
-        } else { tix = z.tc0[0]; tjy = z.tc0[1]; tkz = z.tc0[2]; }
-        const double cdi = RING(C::A_COE + 1) * signe, cdj = RING(C::A_COE + 2) * signe, cdk = RING(C::A_COE + 3) * signe;
         // Newton update of the own cell (mjr_newton[_SA].for); with rop aliased to rop_out the reference has already
         // updated plane k+1 when it sweeps plane k, i.e. the k product of a cell uses its UPDATED state
-        double un = u, vn = v, wn = w, tn = t;
-        bool in_nb = false;
         if (UPPER) {
             const int ig = a.box[1] - ii;
-            in_nb = line_in_nb && ig >= a.nbx[0] && ig <= a.nbx[1];
+            const bool in_nb = line_in_nb && ig >= a.nbx[0] && ig <= a.nbx[1];
             const double cvinv = 1. / z.cv, cvinv2 = 0.5 * cvinv;
             const double rn = ro + dwn[0];
             const double r_1 = 1. / rn;
-            un = (ro * u + dwn[1]) * r_1; vn = (ro * v + dwn[2]) * r_1; wn = (ro * w + dwn[3]) * r_1;
+            const double un = (ro * u + dwn[1]) * r_1, vn = (ro * v + dwn[2]) * r_1, wn = (ro * w + dwn[3]) * r_1;
             const double roe_old = ro * (z.cv * t + 0.5 * (u * u + v * v + w * w));
-            tn = (roe_old + dwn[4]) * r_1 * cvinv - cvinv2 * (un * un + vn * vn + wn * wn);
-            double *W = const_cast<double *>(R);
-            if (in_nb) {
+            const double tn = (roe_old + dwn[4]) * r_1 * cvinv - cvinv2 * (un * un + vn * vn + wn * wn);
+            if (in_nb && r == 3) {
+                double *W = const_cast<double *>(R);
                 W[(size_t)(C::A_DW) * L * CI] = rn; W[(size_t)(C::A_DW + 1) * L * CI] = un; W[(size_t)(C::A_DW + 2) * L * CI] = vn;
                 W[(size_t)(C::A_DW + 3) * L * CI] = wn; W[(size_t)(C::A_DW + 4) * L * CI] = tn;
                 if (NEQ == 6) {
@@ -362,41 +363,29 @@ __global__ void __launch_bounds__(128, 1) k_lu_tile(ZoneDev z, LuTileArgs a)
                     W[(size_t)(C::A_DW + 5) * L * CI] = fmax(tt, 0.);
                 }
             }
-        } else {
+            if (a.alias && in_nb && rr == 2) { u = un; v = vn; w = wn; t = tn; }
+        } else if (r == 3) {
             double *W = const_cast<double *>(R);
 #pragma unroll
             for (int e = 0; e < NEQ; e++) W[(size_t)(C::A_DW + e) * L * CI] = dwn[e];
         }
-        // outgoing products
-        lu_prod<NEQ>(tix, tiy, tiz, u, v, w, t, cdi, gam, cp, dwn, bprev);
-        lu_prod<NEQ>(tjx, tjy, tjz, u, v, w, t, cdj, gam, cp, dwn, b);
-        {
-            double *p = exj + ((size_t)(s & 1) * L + tid) * NEQ;
+        // outgoing product of the lane's direction
+        double b[EX];
+        b[EX - 1] = 0.;
+        lu_prod<NEQ>(tcx, tcy, tcz, u, v, w, t, cd, gam, cp, dwn, b);
+        if (r < 3) {
+            double2 *p = (double2 *)(exb + ((size_t)((s & 1) * 3 + r) * L + lam) * EX);
+            p[0] = make_double2(b[0], b[1]); p[1] = make_double2(b[2], b[3]); p[2] = make_double2(b[4], b[5]);
+            if (mb_w) {
+                volatile unsigned long long *o = mb_w + (size_t)ii * LU_MB;
 #pragma unroll
-            for (int e = 0; e < NEQ; e++) p[e] = b[e];
-            if (mbj_out) {
-                unsigned long long o[LU_MB];
-#pragma unroll
-                for (int e = 0; e < LU_MB; e++) o[e] = e < NEQ ? (unsigned long long)__double_as_longlong(b[e < NEQ ? e : 0]) : 0ULL;
-                mb_store(mbj_w + (size_t)ii * LU_MB, o);
-            }
-        }
-        const bool upd = UPPER && a.alias && in_nb;
-        lu_prod<NEQ>(tkx, tky, tkz, upd ? un : u, upd ? vn : v, upd ? wn : w, upd ? tn : t, cdk, gam, cp, dwn, b);
-        {
-            double *p = exk + ((size_t)(s & 1) * L + tid) * NEQ;
-#pragma unroll
-            for (int e = 0; e < NEQ; e++) p[e] = b[e];
-            if (mbk_out) {
-                unsigned long long o[LU_MB];
-#pragma unroll
-                for (int e = 0; e < LU_MB; e++) o[e] = e < NEQ ? (unsigned long long)__double_as_longlong(b[e < NEQ ? e : 0]) : 0ULL;
-                mb_store(mbk_w + (size_t)ii * LU_MB, o);
+                for (int e = 0; e < LU_MB; e++) o[e] = (unsigned long long)__double_as_longlong(b[e]);
             }
         }
 #undef RING
     }
     __syncthreads();
+    if (a.dbg && tid == 0) a.dbg[4 * (K * a.NJ + J) + 2] = gtime();
 }
 
 // cell-centred mean normals 0.5*(t_d(l) + t_d(l + d)) of every cell (lu_{i,j,k}_*.for build them on the fly)
@@ -497,10 +486,32 @@ static int run_lu_tiles(const ZoneDev &z, const LuPlan &p, const double *rop, do
     }
     cudaMemsetAsync(p.d_ctl, 0, 2 * sizeof(int), st);
     const int ntiles = p.NJ * p.NK;
+    static const bool dbg = getenv("FAST_B200_LU_DEBUG") != nullptr;
+    static unsigned long long *d_dbg = nullptr; static int dbg_calls = 0;
+    a.dbg = nullptr;
+    if (dbg && dbg_calls < 3) { if (!d_dbg) cudaMalloc(&d_dbg, 2 * 4 * 65536 * sizeof(unsigned long long)); a.dbg = d_dbg; }
     a.ticket = p.d_ctl; a.order_mode = lu_match ? 1 : (MESH == 2 ? 2 : 0);
-    k_lu_tile<MESH, NEQ, false><<<ntiles, 128, LuCfg<MESH, NEQ, false>::SMEM, st>>>(z, a);
+    k_lu_tile<MESH, NEQ, false><<<ntiles, LU_NT, LuCfg<MESH, NEQ, false>::SMEM, st>>>(z, a);
     a.ticket = p.d_ctl + 1; a.order_mode = lu_match ? 1 : 0;
-    k_lu_tile<MESH, NEQ, true><<<ntiles, 128, LuCfg<MESH, NEQ, true>::SMEM, st>>>(z, a);
+    if (a.dbg) a.dbg += 4 * 65536;
+    k_lu_tile<MESH, NEQ, true><<<ntiles, LU_NT, LuCfg<MESH, NEQ, true>::SMEM, st>>>(z, a);
+    if (a.dbg) {
+        cudaStreamSynchronize(st);
+        std::vector<unsigned long long> h(2 * 4 * 65536);
+        cudaMemcpy(h.data(), d_dbg, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+        for (int sw = 0; sw < 2; sw++) {
+            const unsigned long long *q = h.data() + sw * 4 * 65536; unsigned long long t0 = ~0ULL, t1 = 0;
+            for (int t = 0; t < ntiles; t++) { t0 = std::min(t0, q[4 * t]); t1 = std::max(t1, q[4 * t + 2]); }
+            fprintf(stderr, "LUDBG sweep %d call %d: NJ %d NK %d tiles %d bi %d total %.1f us\n", sw, dbg_calls, p.NJ, p.NK, ntiles, a.bi, (t1 - t0) * 1e-3);
+            for (int t = 0; t < ntiles; t++) {
+                const int J = t % p.NJ, K = t / p.NJ;
+                if (dbg_calls == 1 && (J % 4 == 0) && (K % 2 == 0 || K == p.NK - 1))
+                    fprintf(stderr, "LUDBG   tile J %2d K %2d sm %3llu start %8.1f first %8.1f end %8.1f dur %8.1f\n", J, K, q[4 * t + 3],
+                            (q[4 * t] - t0) * 1e-3, (q[4 * t + 1] - t0) * 1e-3, (q[4 * t + 2] - t0) * 1e-3, (q[4 * t + 2] - q[4 * t]) * 1e-3);
+            }
+        }
+        dbg_calls++;
+    }
     return 3;
 }
 
