@@ -35,7 +35,8 @@
 #define LU_EMPTY 0xFFF7DEADBEEF5A5AULL   // signalling NaN: never produced by arithmetic
 #define LU_SPIN_MAX (1 << 21)
 #define LU_NC 256          // compute threads: 4 lanes per line
-#define LU_NT 320          // + 2 service warps
+#define LU_NR 128          // refill threads (cp.async, lanes along i)
+#define LU_NT 448          // + 64 write-back / mailbox threads
 
 template <int MESH, int NEQ, bool UPPER>
 struct LuCfg {
@@ -48,7 +49,7 @@ struct LuCfg {
     static constexpr int NT = MESH == 0 ? 9 : (MESH == 1 ? 5 : 0);
     static constexpr int A_DW = 0, A_COE = NEQ, A_ST = NEQ + NC, A_T = NEQ + NC + NS;
     static constexpr int A = NEQ + NC + NS + NT;
-    static constexpr size_t SMEM = (size_t)(2 * A * L * LU_CI + 2 * 3 * L * LU_MB + 4 * 16 * LU_MB) * sizeof(double);
+    static constexpr size_t SMEM = (size_t)(2 * A * L * LU_CI + 2 * 3 * L * LU_MB + 6 * 16 * LU_MB) * sizeof(double);
 };
 
 int lu_tile_tk(int mesh, int neq) { return (mesh == 0 && neq == 6) ? 6 : 8; }
@@ -113,11 +114,14 @@ __global__ void __launch_bounds__(LU_NT, 1) k_lu_tile(ZoneDev z, LuTileArgs a)
     constexpr int TJ = C::TJ, TK = C::TK, L = C::L, A = C::A, CI = LU_CI, EX = LU_MB;
     extern __shared__ double smem[];
     double *ring = smem;                              // [2][A][L][CI]
-    double *exb = smem + 2 * A * L * CI;              // [2][3][L][EX] products handed to (ii+1), (jj+1), (kk+1)
-    unsigned long long *mbs = (unsigned long long *)(exb + 2 * 3 * L * EX);   // [4][16][EX] prefetched mailbox entries
+    double *exb = smem + 2 * A * L * CI;              // [2][L][3][EX] products handed to (ii+1), (jj+1), (kk+1)
+    unsigned long long *mbs = (unsigned long long *)(exb + 2 * 3 * L * EX);   // [4][16][EX] prefetched mailbox words
+    double *mbx = (double *)(mbs + 4 * 16 * EX);      // [2][16][EX] validated products of the neighbour tiles
     __shared__ int s_tile;
     const int tid = threadIdx.x;
     if (tid == 0) s_tile = a.order[atomicAdd(a.ticket, 1)];
+    // exchange buffers start at zero: products that are multiplied by a zero weight (box boundary) must be finite
+    for (int i = tid; i < 2 * 3 * L * EX + 6 * 16 * EX; i += LU_NT) exb[i] = 0.;
     __syncthreads();
     const int J = s_tile & 0xffff, K = s_tile >> 16;
     if (a.dbg && tid == 0) { a.dbg[4 * (K * a.NJ + J)] = gtime(); a.dbg[4 * (K * a.NJ + J) + 3] = smid(); }
@@ -130,48 +134,39 @@ __global__ void __launch_bounds__(LU_NT, 1) k_lu_tile(ZoneDev z, LuTileArgs a)
 
     if (tid >= LU_NC) {
         // ------------------------------------------------------------------------------------ service warps
+        // Line bookkeeping shared by the roles.  rule(t): the line of row kk with (t - sigma) % CI == 0 finished chunk
+        // m-1 at step t-1 (m = (t - sigma) / CI): chunk m-1 is written back (one iteration later, t = s-1, so that the
+        // barrier of iteration s-1 orders it after the compute step that produced it) and its buffer refilled with
+        // chunk m+1 (two iterations later, t = s-2, after the write-back has read it).
         const int st = tid - LU_NC;
-        const int q = st / CI, cell = st % CI;           // line slot (= kk) and cell inside the chunk
-        const bool qok = q < TK;
+        const int q = (st / CI) % 8, cell = st % CI;     // line slot (= kk) and cell inside the chunk
         const int kk = q, kkg = K * TK + kk;
-        // rule(t): the line of row kk with (t - sigma) % CI == 0 finished chunk m-1 at step t-1 (m = (t-sigma)/CI):
-        // write chunk m-1 back, refill its buffer with chunk m+1.  Executed one iteration late (t = s-1) so that the
-        // barrier of iteration s-1 orders it after the compute step that produced the data.
-        auto rule = [&](int t) {
-            if (!qok) return;
+        struct Ln { int lam, lrow, m, jjg; bool ok; };
+        auto line_of = [&](int t) {
+            Ln o;
             const int jj = ((t - kk) % TJ + TJ) % TJ;          // TJ == CI
-            const int jjg = J * TJ + jj;
-            if (jjg >= bj || kkg >= bk) return;
-            const int sigma = jj + kk;
-            const int m = (t - sigma) / CI;                     // exact: (t - sigma) is a multiple of CI (may be < 0)
-            const int lam = kk * TJ + jj;
-            const int lrow = l0 + sg * (jjg * z.incj + kkg * z.inck);
-            {   // write back chunk m-1
-                const int c = m - 1, ii = c * CI + cell;
-                if (c >= 0 && ii < bi) {
-                    const int l = lrow + sg * ii;
-                    const double *src = ring + ((size_t)((c & 1) * A + C::A_DW) * L + lam) * CI + cell;
-                    if (!UPPER) {
-#pragma unroll
-                        for (int e = 0; e < NEQ; e++) a.dw[l + e * nd] = src[(size_t)e * L * CI];
-                    } else {
-                        const int i = a.box[1] - ii, j = a.box[3] - jjg, k = a.box[5] - kkg;
-                        if (i >= a.nbx[0] && i <= a.nbx[1] && j >= a.nbx[2] && j <= a.nbx[3] && k >= a.nbx[4] && k <= a.nbx[5]) {
-#pragma unroll
-                            for (int e = 0; e < NEQ; e++) a.rop_out[l + e * nd] = src[(size_t)e * L * CI];
-                        }
-                    }
-                }
-            }
-            {   // refill with chunk m+1
-                const int c = m + 1, ii = c * CI + cell;
-                if (c >= 0 && ii < bi) {
-                    const int l = lrow + sg * ii;
-                    double *dst = ring + ((size_t)((c & 1) * A) * L + lam) * CI + cell;
+            o.jjg = J * TJ + jj;
+            o.ok = q < TK && o.jjg < bj && kkg < bk;
+            o.m = (t - (jj + kk)) / CI;                         // exact: a multiple of CI (may be < 0)
+            o.lam = kk * TJ + jj;
+            o.lrow = l0 + sg * (o.jjg * z.incj + kkg * z.inck);
+            return o;
+        };
+        if (st < LU_NR) {
+            // ---- refill role: 128 threads, lanes along i, the staged arrays split in two halves
+            const int half = st / 64;
+            auto refill = [&](int t) {
+                const Ln o = line_of(t);
+                const int c = o.m + 1, ii = c * CI + cell;
+                if (!(o.ok && c >= 0 && ii < bi)) return;
+                const int l = o.lrow + sg * ii;
+                double *dst = ring + ((size_t)((c & 1) * A) * L + o.lam) * CI + cell;
+                if (half == 0) {
 #pragma unroll
                     for (int e = 0; e < NEQ; e++) cp_async8(dst + (size_t)(C::A_DW + e) * L * CI, a.dw + l + e * nd);
 #pragma unroll
                     for (int e = 0; e < C::NC; e++) cp_async8(dst + (size_t)(C::A_COE + e) * L * CI, a.coe + l + e * nd);
+                } else {
 #pragma unroll
                     for (int e = 0; e < C::NS; e++) cp_async8(dst + (size_t)(C::A_ST + e) * L * CI, a.rop + l + (C::S0 + e) * nd);
                     if (MESH != 2) {
@@ -180,201 +175,209 @@ __global__ void __launch_bounds__(LU_NT, 1) k_lu_tile(ZoneDev z, LuTileArgs a)
                         for (int e = 0; e < C::NT; e++) cp_async8(dst + (size_t)(C::A_T + e) * L * CI, a.tcm + lt + e * a.tstride);
                     }
                 }
+            };
+            for (int t = -CI; t <= -3; t++) { refill(t); cp_async_commit(); }
+            for (int s = 0; s < nst; s++) {
+                refill(s - 2);
+                cp_async_commit();
+                cp_async_wait<CI - 2>();
+                __syncthreads();
             }
+            __syncthreads();
+            cp_async_wait<0>();
+            return;
+        }
+        // ---- write-back + mailbox role: 64 threads
+        auto writeback = [&](int t) {   // upper sweep: Newton update mjr_newton[_SA].for applied here, off the compute warps
+            const Ln o = line_of(t);
+            const int c = o.m - 1, ii = c * CI + cell;
+            if (!(o.ok && c >= 0 && ii < bi)) return;
+            const int l = o.lrow + sg * ii;
+            const double *src = ring + ((size_t)((c & 1) * A) * L + o.lam) * CI + cell;
+#define SRC(arr) src[(size_t)(arr) * L * CI]
+            if (!UPPER) {
+#pragma unroll
+                for (int e = 0; e < NEQ; e++) a.dw[l + e * nd] = SRC(C::A_DW + e);
+            } else {
+                const int i = a.box[1] - ii, j = a.box[3] - o.jjg, k = a.box[5] - kkg;
+                if (i >= a.nbx[0] && i <= a.nbx[1] && j >= a.nbx[2] && j <= a.nbx[3] && k >= a.nbx[4] && k <= a.nbx[5]) {
+                    const double ro = SRC(C::A_ST), u = SRC(C::A_ST + 1), v = SRC(C::A_ST + 2), w = SRC(C::A_ST + 3), t_ = SRC(C::A_ST + 4);
+                    const double cvinv = 1. / z.cv, cvinv2 = 0.5 * cvinv;
+                    const double rn = ro + SRC(C::A_DW);
+                    const double r_1 = 1. / rn;
+                    const double un = (ro * u + SRC(C::A_DW + 1)) * r_1, vn = (ro * v + SRC(C::A_DW + 2)) * r_1, wn = (ro * w + SRC(C::A_DW + 3)) * r_1;
+                    const double roe_old = ro * (z.cv * t_ + 0.5 * (u * u + v * v + w * w));
+                    const double tn = (roe_old + SRC(C::A_DW + 4)) * r_1 * cvinv - cvinv2 * (un * un + vn * vn + wn * wn);
+                    a.rop_out[l] = rn; a.rop_out[l + nd] = un; a.rop_out[l + 2 * nd] = vn; a.rop_out[l + 3 * nd] = wn; a.rop_out[l + 4 * nd] = tn;
+                    if (NEQ == 6) {
+                        double anulam = z.coesut * sqrt(tn * z.temp01) * tn / (tn + z.cmus1);   // = coesut sqrt(T/T0) / (1 + Cs/T)
+                        anulam = anulam * r_1 * z.ratiom;
+                        double tt = (ro * SRC(C::A_ST + NEQ - 1) + SRC(C::A_DW + NEQ - 1)) * r_1;
+                        tt = fmin(tt, anulam);
+                        a.rop_out[l + 5 * nd] = fmax(tt, 0.);
+                    }
+                }
+            }
+#undef SRC
         };
-        // mailbox prefetch: thread st < 48 fetches 16 bytes of the entry that interface line il needs at step sp and
-        // parks them in shared memory (slot sp & 3); the load is issued before the refill work of the iteration and
-        // consumed after it, so its L2 latency overlaps with the cp.async issue
-        const int il = st / 3, part = st % 3;
+        // mailboxes: thread sw < 48 owns 16 bytes of the entry of interface line il (0..7: j interface, row kk = il;
+        // 8..15: k interface, column jj = il-8).  Words needed at step X are loaded at iteration X-3 (registers carried
+        // over the loop edge, no stall), parked in shared memory at X-2 and, before the barrier of step X, delivered
+        // validated into mbx (polling global memory while the producer tile has not delivered); the entry is re-armed.
+        // The compute warps never see a mailbox.
+        const int sw = st - LU_NR;
+        const int il = sw / 3, part = sw % 3;
         const bool isj = il < 8;
         const int mjj = isj ? 0 : il - 8, mkk = isj ? il : 0;
         const int mjg = J * TJ + mjj, mkg = K * TK + mkk;
-        const bool mvalid = st < 48 && mjg < bj && mkg < bk && mkk < TK && (isj ? J > 0 : K > 0);
-        const unsigned long long *mrow = nullptr;
-        if (mvalid) mrow = (const unsigned long long *)(isj ? a.ifj + ((size_t)((J - 1) * bk + mkg) * bi) * LU_MB
-                                                              : a.ifk + ((size_t)((K - 1) * bj + mjg) * bi) * LU_MB) + 2 * part;
+        const bool mvalid = sw < 48 && mjg < bj && mkg < bk && mkk < TK && (isj ? J > 0 : K > 0);
+        volatile unsigned long long *mrow = (volatile unsigned long long *)a.order;   // harmless readable dummy
+        if (mvalid) mrow = (unsigned long long *)(isj ? a.ifj + ((size_t)((J - 1) * bk + mkg) * bi) * LU_MB
+                                                        : a.ifk + ((size_t)((K - 1) * bj + mjg) * bi) * LU_MB) + 2 * part;
         const int msig = mjj + mkk;
-        for (int t = -CI; t <= -2; t++) { rule(t); cp_async_commit(); }
-        for (int sp = 0; sp < 2; sp++) {
-            const int ii = sp - msig;
-            if (mvalid && ii >= 0 && ii < bi) {
-                const volatile unsigned long long *p = mrow + (size_t)ii * LU_MB;
-                unsigned long long *dst = mbs + ((size_t)((sp & 3) * 16 + il) * EX) + 2 * part;
-                dst[0] = p[0]; dst[1] = p[1];
+        unsigned long long *mpre = mbs + (size_t)il * EX + 2 * part;        // + (step & 3) * 16 * EX
+        double *mout = mbx + (size_t)il * EX + 2 * part;                     // + (step & 1) * 16 * EX
+        auto entry = [&](int X) {    // clamped: always a readable address
+            int ii = X - msig; ii = ii < 0 ? 0 : (ii >= bi ? bi - 1 : ii);
+            return mrow + (mvalid ? (size_t)ii * LU_MB : 0);
+        };
+        auto needed = [&](int X) { const int ii = X - msig; return mvalid && ii >= 0 && ii < bi; };
+        auto deliver = [&](int X) {
+            if (!needed(X)) return;
+            const unsigned long long *pre = mpre + (size_t)(X & 3) * 16 * EX;
+            unsigned long long v0 = pre[0], v1 = pre[1];
+            volatile unsigned long long *p = entry(X);
+            int spin = 0;
+            while (mb_empty(v0) || mb_empty(v1)) {
+                v0 = p[0]; v1 = p[1];
+                if (++spin > LU_SPIN_MAX || (((spin & 1023) == 0) && *(volatile int *)a.err)) { *a.err = 1; break; }
             }
+            double *o = mout + (size_t)(X & 1) * 16 * EX;
+            o[0] = __longlong_as_double((long long)v0); o[1] = __longlong_as_double((long long)v1);
+            p[0] = LU_EMPTY; p[1] = LU_EMPTY;                                  // self-cleaning: ready for the next sweep
+        };
+        const bool mth = sw < 48;                                            // threads 48..63 only write back
+        for (int X = 0; X < 2; X++) {
+            volatile unsigned long long *p = entry(X);
+            unsigned long long *d = mpre + (size_t)(X & 3) * 16 * EX;
+            if (mth) { d[0] = p[0]; d[1] = p[1]; }
         }
+        unsigned long long w0, w1;
+        { volatile unsigned long long *p = entry(2); w0 = p[0]; w1 = p[1]; }
         for (int s = 0; s < nst; s++) {
-            const int sp = s + 2, ii = sp - msig;
-            const bool doit = mvalid && ii >= 0 && ii < bi;
-            unsigned long long v0 = LU_EMPTY, v1 = LU_EMPTY;
-            if (doit) { const volatile unsigned long long *p = mrow + (size_t)ii * LU_MB; v0 = p[0]; v1 = p[1]; }
-            rule(s - 1);
-            cp_async_commit();
-            if (doit) { unsigned long long *dst = mbs + ((size_t)((sp & 3) * 16 + il) * EX) + 2 * part; dst[0] = v0; dst[1] = v1; }
-            cp_async_wait<CI - 1>();
+            if (mth) { unsigned long long *d = mpre + (size_t)((s + 2) & 3) * 16 * EX; d[0] = w0; d[1] = w1; }
+            { volatile unsigned long long *p = entry(s + 3); w0 = p[0]; w1 = p[1]; }
+            writeback(s - 1);
+            deliver(s);
             __syncthreads();
         }
         __syncthreads();
-        for (int s = nst; s <= nst + CI; s++) rule(s - 1);
-        cp_async_wait<0>();
+        for (int s = nst; s <= nst + CI; s++) writeback(s - 1);
         return;
     }
 
     // ---------------------------------------------------------------------------------------- compute warps
     // 4 lanes per line: lane r < 3 evaluates the product of direction r, all lanes redo the (cheap) dW* of the line, so
     // that the three Jacobian products run on different lanes of the same instruction stream and the 8 compute warps
-    // keep two warps per scheduler on the FP64 pipe.
+    // keep two warps per scheduler on the FP64 pipe.  The step is branch-free: products from outside the sweep box are
+    // zeros, products from neighbour tiles arrive validated in mbx (service warps).
     const int lam = tid >> 2, r = tid & 3;
     const int jj = lam % TJ, kk = lam / TJ;
     const int jjg = J * TJ + jj, kkg = K * TK + kk;
     const bool lvalid = lam < L && jjg < bj && kkg < bk;
     const int sigma = jj + kk;
     const bool has_j = jjg > 0, has_k = kkg > 0;
-    const bool mbj_in = lvalid && jj == 0 && J > 0, mbk_in = lvalid && kk == 0 && K > 0;
-    const bool mbj_out = lvalid && r == 1 && jj == TJ - 1 && J + 1 < a.NJ, mbk_out = lvalid && r == 2 && kk == TK - 1 && K + 1 < a.NK;
-    volatile unsigned long long *mbj_r = mbj_in ? (unsigned long long *)(a.ifj + ((size_t)((J - 1) * bk + kkg) * bi) * LU_MB) : nullptr;
-    volatile unsigned long long *mbk_r = mbk_in ? (unsigned long long *)(a.ifk + ((size_t)((K - 1) * bj + jjg) * bi) * LU_MB) : nullptr;
     volatile unsigned long long *mb_w = nullptr;
-    if (mbj_out) mb_w = (unsigned long long *)(a.ifj + ((size_t)(J * bk + kkg) * bi) * LU_MB);
-    if (mbk_out) mb_w = (unsigned long long *)(a.ifk + ((size_t)(K * bj + jjg) * bi) * LU_MB);
-    // Newton box test of the own line (upper only)
+    if (lvalid && r == 1 && jj == TJ - 1 && J + 1 < a.NJ) mb_w = (unsigned long long *)(a.ifj + ((size_t)(J * bk + kkg) * bi) * LU_MB);
+    if (lvalid && r == 2 && kk == TK - 1 && K + 1 < a.NK) mb_w = (unsigned long long *)(a.ifk + ((size_t)(K * bj + jjg) * bi) * LU_MB);
+    // Newton box test of the own line (upper, aliased state only)
     const int jg = UPPER ? a.box[3] - jjg : a.box[2] + jjg, kg = UPPER ? a.box[5] - kkg : a.box[4] + kkg;
     const bool line_in_nb = jg >= a.nbx[2] && jg <= a.nbx[3] && kg >= a.nbx[4] && kg <= a.nbx[5];
     const double signe = UPPER ? -0.5 : 0.5;
     const double gam = z.gam, cp = z.gam * z.cv;
-    // accumulation order of the reference (invlu_l.for / invlu_u.for: k,j,i; overlap variants: i,j,k; 3dcart lower: j,k,i
-    // when both exist): which product sits at position 0, 1, 2 of the sum
-    int ord0 = 2, ord1 = 1, ord2 = 0;
-    if (a.order_mode == 1) { ord0 = 0; ord1 = 1; ord2 = 2; }
-    else if (a.order_mode == 2 && has_j && has_k) { ord0 = 1; ord1 = 2; ord2 = 0; }
-    const int rr = r < 3 ? r : 2;                      // lane 3 repeats the k product (not stored)
-
-    // one incoming product: from shared memory (neighbour line of the tile), from the prefetched mailbox entry (tile
-    // boundary; falls back to polling global memory while the producer tile has not delivered), or zero (box boundary)
-    auto mailbox = [&](volatile unsigned long long *row, const unsigned long long *pre, int ii, double *bv) {
-        unsigned long long v[NEQ];
-        bool ok = true;
-#pragma unroll
-        for (int e = 0; e < NEQ; e++) { v[e] = pre[e]; ok = ok && !mb_empty(v[e]); }
-        volatile unsigned long long *p = row + (size_t)ii * LU_MB;
-        int spin = 0;
-        while (!ok) {
-            ok = true;
-#pragma unroll
-            for (int e = 0; e < NEQ; e++) { v[e] = p[e]; ok = ok && !mb_empty(v[e]); }
-            if (++spin > LU_SPIN_MAX || (((spin & 1023) == 0) && *(volatile int *)a.err)) { *a.err = 1; break; }
-        }
-#pragma unroll
-        for (int e = 0; e < NEQ; e++) bv[e] = __longlong_as_double((long long)v[e]);
-        if (r == 0) {
-#pragma unroll
-            for (int e = 0; e < LU_MB; e++) p[e] = LU_EMPTY;      // self-cleaning: ready for the next sweep
-        }
-    };
-
+    const int rr = r < 3 ? r : 2;                      // lane 3 repeats the k product (not stored) and writes dW back
+    // where the j / k products come from: neighbour line of the tile (exb) or neighbour tile (mbx); offsets in doubles
+    // relative to the buffer of the step parity
+    const int offj = jj > 0 ? ((lam - 1) * 3 + 1) * EX : -1, offk = kk > 0 ? ((lam - TJ) * 3 + 2) * EX : -1;
+    const int mofj = kk * EX, mofk = (8 + jj) * EX;
     if (a.dbg && tid == 0) a.dbg[4 * (K * a.NJ + J) + 1] = gtime();
     for (int s = 0; s < nst; s++) {
         __syncthreads();
         const int ii = s - sigma;
         if (!(lvalid && ii >= 0 && ii < bi)) continue;
         const int c = ii / CI, slot = ii % CI;
-        const double *R = ring + ((size_t)((c & 1) * A) * L + lam) * CI + slot;
+        double *R = ring + ((size_t)((c & 1) * A) * L + lam) * CI + slot;
 #define RING(arr) R[(size_t)(arr) * L * CI]
-        double acc[NEQ], bi_[EX], bj_[EX], bk_[EX];
+        double acc[NEQ];
 #pragma unroll
         for (int e = 0; e < NEQ; e++) acc[e] = RING(C::A_DW + e);
         const double coe1 = RING(C::A_COE), coe5 = RING(C::A_COE + 4);
         double coe6 = 1.;
         if (NEQ == 6) coe6 = RING(C::A_COE + 5);
         // state, mean normal and spectral radius of the lane's direction
-        double ro = 0., u, v, w, t, nut = 0.;
-        if (UPPER) { ro = RING(C::A_ST); u = RING(C::A_ST + 1); v = RING(C::A_ST + 2); w = RING(C::A_ST + 3); t = RING(C::A_ST + 4); if (NEQ == 6) nut = RING(C::A_ST + 5); }
+        double ro = 0., u, v, w, t;
+        if (UPPER) { ro = RING(C::A_ST); u = RING(C::A_ST + 1); v = RING(C::A_ST + 2); w = RING(C::A_ST + 3); t = RING(C::A_ST + 4); }
         else { u = RING(C::A_ST); v = RING(C::A_ST + 1); w = RING(C::A_ST + 2); t = RING(C::A_ST + 3); }
+        // every lane loads all normals / radii (broadcast, conflict-free) and keeps those of its direction
         double tcx = 0., tcy = 0., tcz = 0.;
-        if (MESH == 0) { tcx = RING(C::A_T + 3 * rr); tcy = RING(C::A_T + 3 * rr + 1); tcz = RING(C::A_T + 3 * rr + 2); }
-        else if (MESH == 1) {
-            if (rr < 2) { tcx = RING(C::A_T + 2 * rr); tcy = RING(C::A_T + 2 * rr + 1); } else tcz = RING(C::A_T + 4);
-        } else { if (rr == 0) tcx = z.tc0[0]; else if (rr == 1) tcy = z.tc0[1]; else tcz = z.tc0[2]; }
-        const double cd = RING(C::A_COE + 1 + rr) * signe;
-        // incoming products (zero where the neighbour is outside the sweep box: adding 0 leaves acc unchanged)
+        if (MESH == 0) {
+            const double a0 = RING(C::A_T), a1 = RING(C::A_T + 1), a2 = RING(C::A_T + 2), b0 = RING(C::A_T + 3), b1 = RING(C::A_T + 4),
+                         b2 = RING(C::A_T + 5), c0 = RING(C::A_T + 6), c1 = RING(C::A_T + 7), c2 = RING(C::A_T + 8);
+            tcx = rr == 0 ? a0 : (rr == 1 ? b0 : c0); tcy = rr == 0 ? a1 : (rr == 1 ? b1 : c1); tcz = rr == 0 ? a2 : (rr == 1 ? b2 : c2);
+        } else if (MESH == 1) {
+            const double a0 = RING(C::A_T), a1 = RING(C::A_T + 1), b0 = RING(C::A_T + 2), b1 = RING(C::A_T + 3), c2 = RING(C::A_T + 4);
+            tcx = rr == 0 ? a0 : (rr == 1 ? b0 : 0.); tcy = rr == 0 ? a1 : (rr == 1 ? b1 : 0.); tcz = rr == 2 ? c2 : 0.;
+        } else { tcx = rr == 0 ? z.tc0[0] : 0.; tcy = rr == 1 ? z.tc0[1] : 0.; tcz = rr == 2 ? z.tc0[2] : 0.; }
+        const double cd0 = RING(C::A_COE + 1), cd1 = RING(C::A_COE + 2), cd2 = RING(C::A_COE + 3);
+        const double cd = (rr == 0 ? cd0 : (rr == 1 ? cd1 : cd2)) * signe;
+        // incoming products; the sum follows the reference's k, j, i order (invlu_l.for / invlu_u.for); the overlap and
+        // 3dcart variants only permute the three additions (a last-bit effect, inside the stated 1e-10 tolerance)
         const double *xin = exb + (size_t)((s + 1) & 1) * 3 * L * EX;
-        {
-            const double2 *p = (const double2 *)(xin + (size_t)lam * EX);
-            const double2 x0 = p[0], x1 = p[1], x2 = p[2];
-            const bool h = ii > 0;
-            bi_[0] = h ? x0.x : 0.; bi_[1] = h ? x0.y : 0.; bi_[2] = h ? x1.x : 0.; bi_[3] = h ? x1.y : 0.; bi_[4] = h ? x2.x : 0.; bi_[5] = h ? x2.y : 0.;
-        }
-        if (jj > 0) {
-            const double2 *p = (const double2 *)(xin + (size_t)(L + lam - 1) * EX);
-            const double2 x0 = p[0], x1 = p[1], x2 = p[2];
-            bj_[0] = x0.x; bj_[1] = x0.y; bj_[2] = x1.x; bj_[3] = x1.y; bj_[4] = x2.x; bj_[5] = x2.y;
-        } else if (has_j) mailbox(mbj_r, mbs + (size_t)((s & 3) * 16 + kk) * EX, ii, bj_);
-        else {
-#pragma unroll
-            for (int e = 0; e < EX; e++) bj_[e] = 0.;
-        }
-        if (kk > 0) {
-            const double2 *p = (const double2 *)(xin + (size_t)(2 * L + lam - TJ) * EX);
-            const double2 x0 = p[0], x1 = p[1], x2 = p[2];
-            bk_[0] = x0.x; bk_[1] = x0.y; bk_[2] = x1.x; bk_[3] = x1.y; bk_[4] = x2.x; bk_[5] = x2.y;
-        } else if (has_k) mailbox(mbk_r, mbs + (size_t)((s & 3) * 16 + 8 + jj) * EX, ii, bk_);
-        else {
-#pragma unroll
-            for (int e = 0; e < EX; e++) bk_[e] = 0.;
-        }
+        const double *xmb = mbx + (size_t)(s & 1) * 16 * EX;
+        const double2 *pi_ = (const double2 *)(xin + (size_t)lam * 3 * EX);
+        const double2 *pj_ = (const double2 *)(offj >= 0 ? xin + offj : xmb + mofj);
+        const double2 *pk_ = (const double2 *)(offk >= 0 ? xin + offk : xmb + mofk);
+        const double2 i0 = pi_[0], i1 = pi_[1], i2 = pi_[2], j0 = pj_[0], j1 = pj_[1], j2 = pj_[2], k0 = pk_[0], k1 = pk_[1], k2 = pk_[2];
+        const double xal = coe1 * signe;
+        const double xi = ii > 0 ? xal : 0., xj = has_j ? xal : 0., xk = has_k ? xal : 0.;
         if (UPPER) {
 #pragma unroll
             for (int e = 0; e < 5; e++) acc[e] = acc[e] * coe5;
             if (NEQ == 6) acc[NEQ - 1] = acc[NEQ - 1] * coe6;
         }
-        const double xal = coe1 * signe;
-#pragma unroll
-        for (int e = 0; e < NEQ; e++) {
-            const double t0 = ord0 == 0 ? bi_[e] : (ord0 == 1 ? bj_[e] : bk_[e]);
-            const double t1 = ord1 == 0 ? bi_[e] : (ord1 == 1 ? bj_[e] : bk_[e]);
-            const double t2 = ord2 == 0 ? bi_[e] : (ord2 == 1 ? bj_[e] : bk_[e]);
-            acc[e] = ((acc[e] + t0 * xal) + t1 * xal) + t2 * xal;
-        }
+        acc[0] = ((acc[0] + k0.x * xk) + j0.x * xj) + i0.x * xi;
+        acc[1] = ((acc[1] + k0.y * xk) + j0.y * xj) + i0.y * xi;
+        acc[2] = ((acc[2] + k1.x * xk) + j1.x * xj) + i1.x * xi;
+        acc[3] = ((acc[3] + k1.y * xk) + j1.y * xj) + i1.y * xi;
+        acc[4] = ((acc[4] + k2.x * xk) + j2.x * xj) + i2.x * xi;
+        if (NEQ == 6) acc[NEQ - 1] = ((acc[NEQ - 1] + k2.y * xk) + j2.y * xj) + i2.y * xi;
         const double diag = 1. / coe5;
         double dwn[NEQ];
 #pragma unroll
         for (int e = 0; e < 5; e++) dwn[e] = acc[e] * diag;
         if (NEQ == 6) dwn[NEQ - 1] = acc[NEQ - 1] / coe6;
-        // Newton update of the own cell (mjr_newton[_SA].for); with rop aliased to rop_out the reference has already
-        // updated plane k+1 when it sweeps plane k, i.e. the k product of a cell uses its UPDATED state
-        if (UPPER) {
+        if (r == 3) {
+#pragma unroll
+            for (int e = 0; e < NEQ; e++) RING(C::A_DW + e) = dwn[e];
+        }
+        // with rop aliased to rop_out the reference has already Newton-updated plane k+1 when it sweeps plane k
+        // (invlu_u.for), i.e. the k product of a cell uses its UPDATED state
+        if (UPPER && a.alias) {
             const int ig = a.box[1] - ii;
-            const bool in_nb = line_in_nb && ig >= a.nbx[0] && ig <= a.nbx[1];
+            const bool in_nb = line_in_nb && ig >= a.nbx[0] && ig <= a.nbx[1] && rr == 2;
             const double cvinv = 1. / z.cv, cvinv2 = 0.5 * cvinv;
-            const double rn = ro + dwn[0];
-            const double r_1 = 1. / rn;
+            const double r_1 = 1. / (ro + dwn[0]);
             const double un = (ro * u + dwn[1]) * r_1, vn = (ro * v + dwn[2]) * r_1, wn = (ro * w + dwn[3]) * r_1;
             const double roe_old = ro * (z.cv * t + 0.5 * (u * u + v * v + w * w));
             const double tn = (roe_old + dwn[4]) * r_1 * cvinv - cvinv2 * (un * un + vn * vn + wn * wn);
-            if (in_nb && r == 3) {
-                double *W = const_cast<double *>(R);
-                W[(size_t)(C::A_DW) * L * CI] = rn; W[(size_t)(C::A_DW + 1) * L * CI] = un; W[(size_t)(C::A_DW + 2) * L * CI] = vn;
-                W[(size_t)(C::A_DW + 3) * L * CI] = wn; W[(size_t)(C::A_DW + 4) * L * CI] = tn;
-                if (NEQ == 6) {
-                    double anulam = z.coesut * sqrt(tn * z.temp01) / (1. + z.cmus1 / tn);
-                    anulam = anulam * r_1 * z.ratiom;
-                    double tt = (ro * nut + dwn[NEQ - 1]) * r_1;
-                    tt = fmin(tt, anulam);
-                    W[(size_t)(C::A_DW + 5) * L * CI] = fmax(tt, 0.);
-                }
-            }
-            if (a.alias && in_nb && rr == 2) { u = un; v = vn; w = wn; t = tn; }
-        } else if (r == 3) {
-            double *W = const_cast<double *>(R);
-#pragma unroll
-            for (int e = 0; e < NEQ; e++) W[(size_t)(C::A_DW + e) * L * CI] = dwn[e];
+            u = in_nb ? un : u; v = in_nb ? vn : v; w = in_nb ? wn : w; t = in_nb ? tn : t;
         }
         // outgoing product of the lane's direction
         double b[EX];
         b[EX - 1] = 0.;
         lu_prod<NEQ>(tcx, tcy, tcz, u, v, w, t, cd, gam, cp, dwn, b);
         if (r < 3) {
-            double2 *p = (double2 *)(exb + ((size_t)((s & 1) * 3 + r) * L + lam) * EX);
+            double2 *p = (double2 *)(exb + ((size_t)((s & 1) * L + lam) * 3 + r) * EX);
             p[0] = make_double2(b[0], b[1]); p[1] = make_double2(b[2], b[3]); p[2] = make_double2(b[4], b[5]);
             if (mb_w) {
                 volatile unsigned long long *o = mb_w + (size_t)ii * LU_MB;
