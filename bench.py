@@ -5,7 +5,9 @@
 
 A "step" is one full time iteration of the hot path (all sub-iterations: 3 RK stages, or ss_iteration Newton
 sub-iterations incl. LU sweeps, plus match-join transfers and BC fill) over one synthetic case.  Default workload at
-N=1 = BASELINE.json configs[1]: laminar Taylor-Green vortex 256^3, SENSOR scheme, explicit RK3.
+N=1 = BASELINE.json configs[1]: laminar Taylor-Green vortex 256^3, SENSOR scheme, explicit RK3; at N>1 (launched by
+torchrun, one rank per GPU) the same case with one 256^3 block per GPU joined periodically (weak scaling), ghost cells of
+the cut faces exchanged by NCCL point-to-point every RK stage.
 `value` is Mcell.it/s = interior cells x time iterations / second with the state resident in HBM; `e2e` is the same
 metric through the reference-facing C-ABI call with HOST buffers (fb_compute_host: H2D of the input time levels and
 D2H of the new one inside the timed region).  `--impl reference` times the CPU oracle (the reference's Fortran cannot
@@ -118,17 +120,19 @@ def run_gpu(args):
     from fast_b200.FastC.PyTree import Internal
     rank = int(os.environ.get('RANK', '0')); world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    os.environ['FAST_B200_DEVICE'] = str(local)
+    dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-    torch.cuda.set_device(local)
-    if world > 1:
         from fast_b200 import dist as fdist
-        return fdist.bench_multi(args, rank, world, local)
-
-    t, joins, desc = make_case(args.workload)
-    os.environ['FAST_B200_DEVICE'] = str(local)
-    (t, tc, metrics) = FastS.warmup(t, joins)
+        t, table, peers, desc, cells_total = fdist.local_case(args.workload, rank, world)
+        t, metrics, hx = fdist.warmup_rank(t, table, peers, local)
+    else:
+        t, joins, desc = make_case(args.workload)
+        (t, tc, metrics) = FastS.warmup(t, joins)
+        hx, cells_total = None, None
     zones = Internal.getZones(t)
     L = _lib.lib(); s = FastC.HOOK['solver']
     pi0 = Internal.getNodeFromName1(Internal.getNodeFromName1(zones[0], '.Solver#ownData'), 'Parameter_int')[1]
@@ -138,19 +142,29 @@ def run_gpu(args):
     for z in zones:
         pi = Internal.getNodeFromName1(Internal.getNodeFromName1(z, '.Solver#ownData'), 'Parameter_int')[1]
         cells += int(pi[V.IJKV]) * int(pi[V.IJKV + 1]) * int(pi[V.IJKV + 2])
+    if cells_total is None: cells_total = cells
     stream = torch.cuda.ExternalStream(L.fb_stream(s))
+
+    def fence():
+        torch.cuda.synchronize(); _lib.check(L.fb_sync(s))
+        if dist is not None: dist.barrier(); torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None: return x
+        tt = torch.tensor([x], dtype=torch.float64, device='cuda'); dist.all_reduce(tt, op=dist.ReduceOp.MAX); return float(tt.item())
+
     nit = 1
     for w in range(args.warmup):
         FastS._compute(t, metrics, nit); nit += 1
-    _lib.check(L.fb_sync(s))
+    fence()
     _lib.check(L.fb_timing_enable(s, 1)); _lib.check(L.fb_timing_reset(s))
     clk = Clocks(); clk.start()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize(); e0.record(stream)
+    fence(); e0.record(stream)
     for k in range(args.steps):
         FastS._compute(t, metrics, nit); nit += 1
-    e1.record(stream); torch.cuda.synchronize(); _lib.check(L.fb_sync(s))
-    ms = e0.elapsed_time(e1)
+    e1.record(stream); fence()
+    ms = max_over_ranks(e0.elapsed_time(e1))
     clk.stop = True; clk.join(timeout=2)
     tm = {}
     launches = ctypes.c_longlong(0)
@@ -158,18 +172,27 @@ def run_gpu(args):
         v = ctypes.c_double(0); _lib.check(L.fb_timing_get(s, name.encode(), ctypes.byref(v), ctypes.byref(launches)))
         tm[name] = v.value
     _lib.check(L.fb_timing_enable(s, 0))
-    value = cells * args.steps / (ms * 1e-3) / 1e6
-    # roofline of the dominant kernel (k_rhs): algorithmic bytes per launch / average launch duration
+    nlaunch = int(launches.value)
+    if dist is not None:
+        tt = torch.tensor([nlaunch], dtype=torch.int64, device='cuda'); dist.all_reduce(tt); nlaunch = int(tt.item())
+    value = cells_total * args.steps / (ms * 1e-3) / 1e6
+    # roofline of the dominant kernel: algorithmic bytes per launch / mean launch duration (CUDA events on the solver's stream)
     b_sub, b_rhs = algorithmic_bytes(pi0)
-    n_rhs = args.steps * nsub * len(zones)
-    avg_rhs_ms = tm['rhs'] / n_rhs
     peak, pk = peaks()
-    ach = (cells / len(zones)) * b_rhs / (avg_rhs_ms * 1e-3) / 1e9
-    dominant = 'k_rhs' if tm['rhs'] >= tm['lu'] else 'k_lu'
-    roof = {'bound': 'hbm', 'kernel': 'k_rhs', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'traffic': None,
-            'peak_source': pk, 'bytes_per_cell_update': b_rhs, 'avg_launch_ms': avg_rhs_ms,
-            'whole_subiteration_GBs': cells * b_sub * nsub * args.steps / (ms * 1e-3) / 1e9,
-            'step_share': {k: (v / tm['all'] if tm['all'] else None) for k, v in tm.items()}, 'dominant': dominant}
+    cz = cells / len(zones)
+    if tm['lu'] > tm['rhs']:
+        kern, nl, bpl = 'k_lu_tile', 2 * args.steps * nsub * len(zones), (b_sub - b_rhs) / 2.   # lower + upper launch
+        avg_ms = tm['lu'] / nl
+    else:
+        kern, nl, bpl = 'k_rhs2', args.steps * nsub * len(zones), b_rhs
+        avg_ms = tm['rhs'] / nl
+    ach = cz * bpl / (avg_ms * 1e-3) / 1e9
+    roof = {'bound': 'hbm', 'kernel': kern, 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'traffic': None,
+            'peak_source': pk + ' (MEASURED_PEAKS.json hbm_gbs)' if pk == 'measured' else pk, 'bytes_per_cell_per_launch': bpl,
+            'avg_launch_ms': avg_ms,
+            'whole_subiteration': {'bytes_per_cell_update': b_sub, 'GBs': cells_total * b_sub * nsub * args.steps / (ms * 1e-3) / 1e9,
+                                   'frac': cells_total * b_sub * nsub * args.steps / (ms * 1e-3) / 1e9 / (peak * world)},
+            'step_share': {k: (v / tm['all'] if tm['all'] else None) for k, v in tm.items()}}
 
     # end to end through the C-ABI with host buffers (pinned): H2D inputs + D2H result every step
     nz = len(zones)
@@ -186,29 +209,36 @@ def run_gpu(args):
         _lib.check(L.fb_compute_host(s, n, 1, ctypes.byref(fi), ptrs(order[0]), ptrs(order[1]), ptrs(order[2])))
         order[:] = [order[2], order[0], order[1]]      # switchPointers__ on the host arrays
     host_step(nit); nit += 1
-    torch.cuda.synchronize(); e0.record(stream)
+    fence(); e0.record(stream)
     for k in range(e2e_steps):
         host_step(nit); nit += 1
-    e1.record(stream); torch.cuda.synchronize()
-    ms2 = e0.elapsed_time(e1)
+    e1.record(stream); fence()
+    ms2 = max_over_ranks(e0.elapsed_time(e1))
     state_bytes = sum(x.numel() * 8 for x in hb[0])
-    h2d = state_bytes * (2 if implicit else 1); d2h = state_bytes
-    e2e = {'value': cells * e2e_steps / (ms2 * 1e-3) / 1e6, 'unit': 'Mcell.it/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+    h2d = state_bytes * (2 if implicit else 1) * world; d2h = state_bytes * world
+    e2e = {'value': cells_total * e2e_steps / (ms2 * 1e-3) / 1e6, 'unit': 'Mcell.it/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
            'steps': e2e_steps, 'ms_per_step': ms2 / e2e_steps}
     a = hb[order[0]][0].numpy()
     assert numpy.isfinite(a).all(), "non-finite state after the benchmark"
 
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:
         r, nth, sample, _ = cpu_oracle_rate(args.workload, seconds=12.)
         cpu = {'value': r, 'unit': 'Mcell.it/s', 'cores': nth, 'kind': 'port', 'sample': sample}
-    out = {'metric': 'FP64 cell-updates/sec', 'value': value, 'unit': 'Mcell.it/s', 'n_gpus': 1, 'steps': args.steps,
+    if rank != 0:
+        if dist is not None: dist.destroy_process_group()
+        return
+    cfg = {'workload': desc, 'cells': cells_total, 'sub_iterations_per_step': nsub, 'l2': 'working set >> 126 MB L2 (no flush needed)',
+           'cell_updates_per_s': cells_total * nsub * args.steps / (ms * 1e-3)}
+    if hx is not None:
+        cfg['halo'] = {'transport': 'NCCL isend/irecv per neighbour on the solver stream', 'bytes_per_exchange_per_rank': hx.bytes_per_exchange,
+                       'exchanges_per_step': nsub * (2 if implicit and int(pi0[V.LU_MATCH]) else 1)}
+    out = {'metric': 'FP64 cell-updates/sec', 'value': value, 'unit': 'Mcell.it/s', 'n_gpus': world, 'steps': args.steps,
            'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-           'dtype': 'f64', 'data': 'synthetic',
-           'config': {'workload': desc, 'cells': cells, 'sub_iterations_per_step': nsub, 'l2': 'working set >> 126 MB L2 (no flush needed)',
-                      'cell_updates_per_s': cells * nsub * args.steps / (ms * 1e-3)},
-           'roofline': roof, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches.value), 'clocks': clk.summary()}
+           'dtype': 'f64', 'data': 'synthetic', 'config': cfg,
+           'roofline': roof, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': nlaunch, 'clocks': clk.summary()}
     print(json.dumps(out))
+    if dist is not None: dist.destroy_process_group()
 
 
 def main():
@@ -217,7 +247,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3); ap.add_argument('--impl', default='fast_b200')
     ap.add_argument('--workload', default=None); ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()
-    if args.workload is None: args.workload = 'tgv256' if args.gpus == 1 else 'multiblock'
+    if args.workload is None: args.workload = 'tgv256'
     if args.impl == 'reference': run_reference(args)
     else: run_gpu(args)
 

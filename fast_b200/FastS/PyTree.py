@@ -54,9 +54,12 @@ def host_views(t):
     return out
 
 
-def warmup(t, tc, graph=None, infos_ale=None, Adjoint=False, tmy=None, list_graph=None, Padding=None, verbose=0):
+def warmup(t, tc, graph=None, infos_ale=None, Adjoint=False, tmy=None, list_graph=None, Padding=None, verbose=0,
+           exchange=None):
     """Perform necessary operations to prepare the tree for computation (PyTree.py:341).
-    Returns (t, tc, metrics)."""
+    Returns (t, tc, metrics).  One process per GPU (the reference's FastS.Mpi.warmup, S/Mpi.py): `exchange(solver)` builds
+    the cross-rank transport (fast_b200.dist.HaloExchange) once the join table -- with its pack / unpack entries -- is
+    on the device and before the first ghost fill."""
     from .. import fasts, fastc
     if graph is not None or infos_ale is not None or Adjoint or tmy is not None:
         raise ValueError("fast_b200: MPI graphs, ALE, adjoint and statistics trees are outside the hot-path scope")
@@ -68,6 +71,7 @@ def warmup(t, tc, graph=None, infos_ale=None, Adjoint=False, tmy=None, list_grap
     fasts.register(zones, metrics, FastC.HOOK, tc)                                   # pointer harvest, once
     fastc.init_metric(zones, metrics, FastC.HOOK)                                    # PyTree.py:326
     if tc is not None: fasts.set_joins(FastC.HOOK, tc)                               # miseAPlatDonorTree__ stand-in
+    if exchange is not None: FastC.HOOK['halo_exchange'] = exchange(FastC.HOOK['solver'])
     # first ghost fill on Density (PyTree.py:536) then initial viscosity (:543)
     _fillGhostcells(zones, tc, metrics, 1, ['Density'], 1, hook1=FastC.HOOK)
     fasts._computePT_mut(zones, metrics, FastC.HOOK)

@@ -45,6 +45,8 @@ struct fb_solver {
     std::vector<Zone> z;
     bool metric_done = false;
     JoinSet joins;
+    fb_exchange_fn xcb = nullptr; void *xuser = nullptr;   // cross-rank halo exchange (fb_set_exchange_cb)
+    double *halo_send = nullptr, *halo_recv = nullptr;
     bool timing = false;
     Timer tm[6];     // rhs, lu, bc, transfer, coe, all
     long long launches = 0;
@@ -103,6 +105,7 @@ void fb_solver_destroy(fb_solver *s)
         lu_plan_free(z.lu);
     }
     joins_free(s->joins);
+    cudaFree(s->halo_send); cudaFree(s->halo_recv);
     if (s->st) cudaStreamDestroy(s->st);
     delete s;
 }
@@ -373,6 +376,9 @@ int fb_set_joins(fb_solver *s, const int *ji, int n)
     for (int i = 0; i < s->nz; i++) { nds[i] = s->z[i].d.nd; neqs[i] = s->z[i].d.neq; }
     std::string err;
     if (joins_build(s->joins, ji, n, s->nz, nds.data(), neqs.data(), err)) return fail(FB_EINVAL, "fb_set_joins: " + err);
+    cudaFree(s->halo_send); cudaFree(s->halo_recv); s->halo_send = s->halo_recv = nullptr;
+    if (s->joins.send_doubles) CK(cudaMalloc(&s->halo_send, s->joins.send_doubles * sizeof(double)));
+    if (s->joins.recv_doubles) CK(cudaMalloc(&s->halo_recv, s->joins.recv_doubles * sizeof(double)));
     return FB_OK;
 }
 
@@ -398,7 +404,15 @@ static void transfers(fb_solver *s, int which, int level_ssiter_dummy, double **
     Scope t(s, 3);
     std::vector<double *> ptr(s->nz);
     for (int i = 0; i < s->nz; i++) ptr[i] = which == 1 ? s->z[i].drodm : target[i];
+    // cross-rank joins (C/Com/setInterpTransfersFast.cpp:962 setInterpTransfersInter): pack the donor cells, let the host
+    // transport exchange the two device buffers on this stream, unpack into the ghost cells; local joins in between
+    const bool cross = s->xcb && (s->joins.send_doubles || s->joins.recv_doubles);
+    if (cross && s->joins.send_doubles) { joins_pack(s->joins, ptr.data(), s->halo_send, s->joins.send_doubles * 8, s->st); s->launches++; }
     s->launches += joins_apply(s->joins, ptr.data(), s->nz, s->st);
+    if (cross) {
+        s->xcb(s->xuser, which);
+        if (s->joins.recv_doubles) { joins_unpack(s->joins, ptr.data(), s->halo_recv, s->joins.recv_doubles * 8, s->st); s->launches++; }
+    }
 }
 
 static int gsdr3(fb_solver *s, int nitcfg, int nssiter, int nitrun, int first_it, int lssiter_verif, int lexit_lu)
@@ -593,6 +607,19 @@ int fb_halo_unpack(fb_solver *s, int which, unsigned long long buf, long long nb
     return FB_OK;
 }
 unsigned long long fb_stream(fb_solver *s) { return s ? (unsigned long long)s->st : 0; }
+int fb_set_exchange_cb(fb_solver *s, fb_exchange_fn cb, void *user)
+{
+    if (!s) return fail(FB_EINVAL, "null");
+    s->xcb = cb; s->xuser = user;
+    return FB_OK;
+}
+int fb_halo_buffers(fb_solver *s, unsigned long long *send_ptr, unsigned long long *recv_ptr)
+{
+    if (!s) return fail(FB_EINVAL, "null");
+    if (send_ptr) *send_ptr = (unsigned long long)s->halo_send;
+    if (recv_ptr) *recv_ptr = (unsigned long long)s->halo_recv;
+    return FB_OK;
+}
 
 }   // extern "C"
 extern "C" int fb_halo_sizes(fb_solver *s, long long *send_doubles, long long *recv_doubles)

@@ -34,9 +34,12 @@ def allocate_metric(z, nssiter, verbose=0):
     return [mtr, mtr, None, None, rdm, ind_dm, numpy.zeros(1, Internal.E_NpyInt), None]
 
 
-def register(zones, metrics, hook, tc=None, device=0):
+def register(zones, metrics, hook, tc=None, device=None):
     """Pointer harvest of computePT.cpp:225-369 done ONCE: create the device-resident solver, upload parameters,
-    coordinates, the three time levels and [ViscosityEddy|TurbulentDistance]."""
+    coordinates, the three time levels and [ViscosityEddy|TurbulentDistance].  Device: FAST_B200_DEVICE, else
+    LOCAL_RANK (one process per GPU), else 0."""
+    import os
+    if device is None: device = int(os.environ.get('FAST_B200_DEVICE', os.environ.get('LOCAL_RANK', '0')))
     L = _lib.lib()
     s = _vp()
     _lib.check(L.fb_solver_create(int(device), len(zones), ctypes.byref(s)))

@@ -162,12 +162,7 @@ def case_euler_box(n=64, scheme='ausmpred', deform_amp=0., seed=1234, model='Eul
     return t
 
 
-def case_tgv(n=256, seed=7, scheme='senseur', Re=1600., MInf=0.1, time_step=0.002):
-    """C2: laminar Taylor-Green vortex on [0,2pi]^3, fields as in FastS/test/tgvMpi.py:54-58 (restated)."""
-    from .FastC import PyTree as FastC
-    state = adim1(MInf=MInf, ReInf=Re)
-    L = 2 * math.pi
-    z = make_block('tgv', (n, n, n), L=(L, L, L))
+def _tgv_fields(z, state):
     x, y, zz = centers(z)
     gam = state['Gamma']; p0 = state['Pressure']; ro0 = 1.; U0 = 1.
     u = U0 * numpy.sin(x) * numpy.cos(y) * numpy.cos(zz)
@@ -177,11 +172,48 @@ def case_tgv(n=256, seed=7, scheme='senseur', Re=1600., MInf=0.1, time_step=0.00
     ro = p / p0 * ro0
     T = p / (ro * state['Cv'] * (gam - 1.))
     set_fields(z, ro, u, v, w, T)
+
+
+def case_tgv(n=256, seed=7, scheme='senseur', Re=1600., MInf=0.1, time_step=0.002):
+    """C2: laminar Taylor-Green vortex on [0,2pi]^3, fields as in FastS/test/tgvMpi.py:54-58 (restated)."""
+    from .FastC import PyTree as FastC
+    state = adim1(MInf=MInf, ReInf=Re)
+    L = 2 * math.pi
+    z = make_block('tgv', (n, n, n), L=(L, L, L))
+    _tgv_fields(z, state)
     for f in FACES: add_bc(z, f, 'BCautoperiod', f)
     t = new_tree([z], state, 'NSLaminar')
     FastC._setNum2Zones(t, {'scheme': scheme, 'slope': 'o3', 'time_step': time_step * (256. / n)})
     FastC._setNum2Base(t, {'temporal_scheme': 'explicit', 'rk': 3, 'modulo_verif': 50})
     return t
+
+
+def case_tgv_blocks(n=256, nblk=(2, 1, 1), only=None, scheme='senseur', Re=1600., MInf=0.1, time_step=0.002):
+    """Weak-scaling family of C2: nblk blocks of n^3 cells, one Taylor-Green period per block (domain 2 pi nblk), periodic
+    everywhere: BCautoperiod where a direction has one block, match joins otherwise (the hand-built donor tree of
+    FastS/test/tgvMpi.py:125-195).  `only` = global zone ids to build (the others belong to other ranks).
+    Returns (tree with the `only` zones, layout {(bi,bj,bk): zone id})."""
+    from .FastC import PyTree as FastC
+    state = adim1(MInf=MInf, ReInf=Re)
+    L = 2 * math.pi
+    ng = tuple(n * b for b in nblk)
+    layout, zones = {}, []
+    for bk in range(nblk[2]):
+        for bj in range(nblk[1]):
+            for bi in range(nblk[0]):
+                zid = len(layout); layout[(bi, bj, bk)] = zid
+                if only is not None and zid not in only: continue
+                z = make_block('tgv_%d_%d_%d' % (bi, bj, bk), (n, n, n), L=tuple(L * b for b in nblk),
+                               index_offset=(bi * n, bj * n, bk * n), nglob=ng)
+                _tgv_fields(z, state)
+                for d, f in enumerate('ijk'):
+                    if nblk[d] == 1:
+                        add_bc(z, f + 'min', 'BCautoperiod', f + 'min'); add_bc(z, f + 'max', 'BCautoperiod', f + 'max')
+                zones.append(z)
+    t = new_tree(zones, state, 'NSLaminar')
+    FastC._setNum2Zones(t, {'scheme': scheme, 'slope': 'o3', 'time_step': time_step * (256. / n)})
+    FastC._setNum2Base(t, {'temporal_scheme': 'explicit', 'rk': 3, 'modulo_verif': 50})
+    return t, layout
 
 
 def case_flatplate(n=(64, 48, 8), seed=2025, MInf=0.2, ReInf=25.e6, ss_iteration=5, cfl=7., sheared=False,
@@ -237,7 +269,8 @@ def case_flatplate(n=(64, 48, 8), seed=2025, MInf=0.2, ReInf=25.e6, ss_iteration
 
 
 def case_multiblock(nblk=(2, 2, 2), n=16, seed=99, scheme='roe', model='NSLaminar', deform_amp=0.015, lu_match=1,
-                    ss_iteration=3, ReInf=5000., MInf=0.3, time_step=None, temporal='implicit', modulo_verif=1):
+                    ss_iteration=3, ReInf=5000., MInf=0.3, time_step=None, temporal='implicit', modulo_verif=1,
+                    only=None, return_layout=False):
     """C4-style case: nblk blocks of n^3 cells, smooth sinusoidal deformation (3dfull), match joins inside, farfield
     outside, Roe o3, implicit LU-SGS with lu_match."""
     from .FastC import PyTree as FastC
@@ -255,15 +288,20 @@ def case_multiblock(nblk=(2, 2, 2), n=16, seed=99, scheme='roe', model='NSLamina
     for bk in range(nblk[2]):
         for bj in range(nblk[1]):
             for bi in range(nblk[0]):
+                zid = len(layout)
+                brng = numpy.random.default_rng(seed + 7919 * zid) if only is not None else rng   # per-block stream when sharded
+                if only is not None and zid not in only:
+                    layout[(bi, bj, bk)] = zid
+                    continue
                 z = make_block('blk_%d_%d_%d' % (bi, bj, bk), (n, n, n), L=L, deform=deform,
                                index_offset=(bi * n, bj * n, bk * n), nglob=ng)
                 xc, yc, zc = centers(z)
-                set_fields(z, *vortex_state(xc, yc, zc, state, rng, L=L[0]))
+                set_fields(z, *vortex_state(xc, yc, zc, state, brng, L=L[0]))
                 for d, f in enumerate(('i', 'j', 'k')):
                     b = (bi, bj, bk)[d]
                     if b == 0: add_bc(z, f + 'min', 'BCFarfield', f + 'min')
                     if b == nblk[d] - 1: add_bc(z, f + 'max', 'BCFarfield', f + 'max')
-                layout[(bi, bj, bk)] = len(zones)
+                layout[(bi, bj, bk)] = zid
                 zones.append(z)
     t = new_tree(zones, state, model)
     h = 1. / n
@@ -272,16 +310,14 @@ def case_multiblock(nblk=(2, 2, 2), n=16, seed=99, scheme='roe', model='NSLamina
     if temporal == 'implicit':
         numz['lu_match'] = lu_match; numb['ss_iteration'] = ss_iteration
     FastC._setNum2Zones(t, numz); FastC._setNum2Base(t, numb)
+    if return_layout: return t, layout
     return t, build_joins(layout, nblk, (n, n, n))
 
 
-def build_joins(layout, nblk, nloc, periodic=(False, False, False), rank_of=None, rank=0):
-    """Flattened match-join table (csrc/fb_joins.cu layout).  For every pair of face-adjacent blocks the NG ghost
-    layers of the receiver (interior tangential extent) are copied from the matching interior cells of the donor.
-    rank_of: block zone id -> rank; local joins are kind 0, cross-rank joins are split into a send (kind 1) entry on the
-    donor's rank and a receive (kind 2) entry on the receiver's rank with matching buffer offsets per peer.
-    Returns None when the case has no join; with rank_of returns (table, peers) where peers[r] = (send_off, send_n,
-    recv_off, recv_n) in doubles are filled by the caller from the neq of the zones."""
+def join_records(layout, nblk, nloc, periodic=(False, False, False)):
+    """Global, deterministically ordered list of match joins (donor zone, receiver zone, donor cells, receiver cells):
+    for every pair of face-adjacent blocks the NG ghost layers of the receiver (interior tangential extent) are copied
+    from the matching interior cells of the donor."""
     ni, nj, nk = [nloc[d] + 2 * NG for d in range(3)]
 
     def addr(i, j, k):   # 1-based interior numbering -> 0-based cell address
@@ -303,11 +339,48 @@ def build_joins(layout, nblk, nloc, periodic=(False, False, False), rank_of=None
                 R = numpy.meshgrid(*r, indexing='ij'); S = numpy.meshgrid(*s, indexing='ij')
                 recs.append((dz, rz, addr(S[0], S[1], S[2]).ravel(order='F').astype(numpy.int32),
                              addr(R[0], R[1], R[2]).ravel(order='F').astype(numpy.int32)))
-    if not recs: return None
+    return recs
+
+
+def build_joins(layout, nblk, nloc, periodic=(False, False, False), rank_of=None, rank=0, neq=5):
+    """Flattened match-join table (csrc/fb_joins.cu layout).
+    Without rank_of: every join is local (kind 0); returns the table, or None when the case has no join.
+    With rank_of (global zone id -> rank): the table of `rank`, zones renumbered locally in global-id order; a join whose
+    donor and receiver live on different ranks is split into a pack entry (kind 1) on the donor's rank and an unpack
+    entry (kind 2) on the receiver's rank.  The send (receive) buffer is the concatenation, peer by peer in rank order,
+    of the joins to (from) that peer in global join order, each join var-major [neq][npts] FP64 -- so both sides agree
+    on the offsets without talking.  Returns (table, peers) with peers = {peer: (send_off, send_n, recv_off, recv_n)}
+    in doubles."""
+    recs = join_records(layout, nblk, nloc, periodic)
     if rank_of is None:
+        if not recs: return None
         desc, idx, off = [], [], 0
         for dz, rz, s, r in recs:
             desc += [0, dz, rz, s.size, off, off + s.size, 0]
             idx += [s, r]; off += 2 * s.size
         return numpy.concatenate([numpy.array([len(recs), off], numpy.int32), numpy.array(desc, numpy.int32)] + idx)
-    raise NotImplementedError("use fast_b200.dist.partition_joins for multi-rank tables")
+    mine = sorted(z for z, r in rank_of.items() if r == rank)
+    lz = {z: n for n, z in enumerate(mine)}
+    send_n, recv_n = {}, {}
+    for dz, rz, s, r in recs:
+        rd, rr = rank_of[dz], rank_of[rz]
+        if rd == rr: continue
+        if rd == rank: send_n[rr] = send_n.get(rr, 0) + s.size * neq
+        if rr == rank: recv_n[rd] = recv_n.get(rd, 0) + s.size * neq
+    peers, so, ro = {}, 0, 0
+    for p in sorted(set(send_n) | set(recv_n)):
+        peers[p] = (so, send_n.get(p, 0), ro, recv_n.get(p, 0))
+        so += send_n.get(p, 0); ro += recv_n.get(p, 0)
+    cur_s = {p: v[0] for p, v in peers.items()}; cur_r = {p: v[2] for p, v in peers.items()}
+    desc, idx, off, nj = [], [], 0, 0
+    for dz, rz, s, r in recs:
+        rd, rr = rank_of[dz], rank_of[rz]
+        if rd == rank and rr == rank:
+            desc += [0, lz[dz], lz[rz], s.size, off, off + s.size, 0]; idx += [s, r]; off += 2 * s.size; nj += 1
+        elif rd == rank:
+            desc += [1, lz[dz], -1, s.size, off, -1, cur_s[rr]]; idx += [s]; off += s.size; cur_s[rr] += s.size * neq; nj += 1
+        elif rr == rank:
+            desc += [2, -1, lz[rz], s.size, -1, off, cur_r[rd]]; idx += [r]; off += r.size; cur_r[rd] += r.size * neq; nj += 1
+    table = numpy.concatenate([numpy.array([nj, off], numpy.int32), numpy.array(desc, numpy.int32).reshape(-1)] + idx) \
+        if nj else numpy.array([0, 0], numpy.int32)
+    return table.astype(numpy.int32), peers

@@ -93,6 +93,15 @@ unsigned long long fb_zone_device_ptr(fb_solver *s, int nd, int level);
 int fb_halo_pack(fb_solver *s, int level_or_drodm, unsigned long long dev_buf, long long nbytes);
 int fb_halo_unpack(fb_solver *s, int level_or_drodm, unsigned long long dev_buf, long long nbytes);
 int fb_halo_sizes(fb_solver *s, long long *send_doubles, long long *recv_doubles);
+/* Cross-rank match joins (one process per GPU).  The join table may contain kind 1 (pack into the send buffer) and
+ * kind 2 (unpack from the receive buffer) entries; inside fb_compute / fb_transfers, at the two points where the
+ * reference exchanges MPI messages (drodm before the LU sweep when lu_match=1, S/Compute/lhs.cpp:1-15; rop_CL after
+ * it, S/Compute/gsdr3.cpp:362 -> C/Com/setInterpTransfersFast.cpp:962), the library packs on its stream, calls
+ * cb(user, which) (which: 0 state, 1 drodm) -- the host transport moves fb_halo_buffers() send -> peers' recv, ordered
+ * on fb_stream() -- and unpacks.  Without a callback cross-rank entries are ignored. */
+typedef void (*fb_exchange_fn)(void *user, int which);
+int fb_set_exchange_cb(fb_solver *s, fb_exchange_fn cb, void *user);
+int fb_halo_buffers(fb_solver *s, unsigned long long *send_ptr, unsigned long long *recv_ptr);
 /* dtloc[1] of .Solver#dtloc (C/PyTree.py:1188-1200): residual / CFL check every modulo_verif iterations. */
 int fb_set_modulo_verif(fb_solver *s, int modulo_verif);
 /* cudaStream_t of the solver (uintptr) so that torch/NCCL work can be ordered against it. */
