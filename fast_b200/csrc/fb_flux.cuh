@@ -7,6 +7,7 @@
 // cell l on its upper side (flux through the LOWER face of cell l in direction DIR).
 #pragma once
 #include "fb_common.cuh"
+#include "fb_view.cuh"
 
 // MESH: 0 3dfull, 1 3dhomo, 2 3dcart.  FLOW: 1 euler, 2 laminar, 3 SA.  SCHEME: 1 ausmpred, 2 senseur, 5 roe.
 // SLOPE: 1 o1, 2 o3, 3 minmod.
@@ -51,15 +52,14 @@ __device__ __forceinline__ void muscl(const ZoneDev &z, double qm2_, double qm1_
 }
 
 // laminar viscous flux of one face, added into flu[1..4]; returns volinv (needed by the SA diffusion flux)
-template <int MESH, int FLOW, int DIR>
-__device__ __forceinline__ double visc_face(const ZoneDev &z, const double *__restrict__ rop, int l, int lt,
-                                            const double tc[3], double *flu)
+template <int MESH, int FLOW, int DIR, class V>
+__device__ __forceinline__ double visc_face(const ZoneDev &z, const V &v, int l, int lt, const double tc[3], double *flu)
 {
-    const int nd = z.nd;
     constexpr int D1 = (DIR + 1) % 3, D2 = (DIR + 2) % 3;
-    const int inc[3] = {1, z.incj, z.inck};
-    const int i0 = inc[DIR], i1 = inc[D1], i2 = inc[D2];
-    const int il = l - i0, ir = l;
+    const int il = v.template dn<DIR>(l), ir = l;
+    // the eight cross neighbours of the face (il, ir) in the two tangential directions
+    const int ilm1 = v.template dn<D1>(il), irm1 = v.template dn<D1>(ir), ilp1 = v.template up<D1>(il), irp1 = v.template up<D1>(ir);
+    const int ilm2 = v.template dn<D2>(il), irm2 = v.template dn<D2>(ir), ilp2 = v.template up<D2>(il), irp2 = v.template up<D2>(ir);
     constexpr int NV = FLOW == 3 ? 5 : 4;   // SA: nutilde gradient with the same averaged metrics (SA/fluvisq_SA_*.for)
     double G[NV][3];
 #pragma unroll
@@ -69,16 +69,16 @@ __device__ __forceinline__ double visc_face(const ZoneDev &z, const double *__re
         volinv = 0.5 / z.vol0;
 #pragma unroll
         for (int c = 0; c < NV; c++) {
-            const double *q = rop + (c + 1) * nd;
-            const double f1 = q[il], f2 = q[ir], fv = f1 + f2;
+            const int e = c + 1;
+            const double f1 = v.q(e, il), f2 = v.q(e, ir), fv = f1 + f2;
             G[c][DIR] = (f2 - f1) * z.tc0[DIR];
             if (c >= 3) continue;
             if (c == DIR || c == D1) {
-                const double fa = fv + q[il - i1] + q[ir - i1], fb = fv + q[il + i1] + q[ir + i1];
+                const double fa = fv + v.q(e, ilm1) + v.q(e, irm1), fb = fv + v.q(e, ilp1) + v.q(e, irp1);
                 G[c][D1] = (fb - fa) * (.25 * z.tc0[D1]);
             }
             if (c == DIR || c == D2) {
-                const double fa = fv + q[il - i2] + q[ir - i2], fb = fv + q[il + i2] + q[ir + i2];
+                const double fa = fv + v.q(e, ilm2) + v.q(e, irm2), fb = fv + v.q(e, ilp2) + v.q(e, irp2);
                 G[c][D2] = (fb - fa) * (.25 * z.tc0[D2]);
             }
         }
@@ -102,12 +102,12 @@ __device__ __forceinline__ double visc_face(const ZoneDev &z, const double *__re
         }
 #pragma unroll
         for (int c = 0; c < NV; c++) {
-            const double *q = rop + (c + 1) * nd;
-            const double f1 = q[il], f2 = q[ir];
-            const double f3 = f2 + f1 + q[il - i1] + q[ir - i1];
-            const double f4 = f2 + f1 + q[il + i1] + q[ir + i1];
-            const double f5 = f2 + f1 + q[il - i2] + q[ir - i2];
-            const double f6 = f2 + f1 + q[il + i2] + q[ir + i2];
+            const int e_ = c + 1;
+            const double f1 = v.q(e_, il), f2 = v.q(e_, ir);
+            const double f3 = f2 + f1 + v.q(e_, ilm1) + v.q(e_, irm1);
+            const double f4 = f2 + f1 + v.q(e_, ilp1) + v.q(e_, irp1);
+            const double f5 = f2 + f1 + v.q(e_, ilm2) + v.q(e_, irm2);
+            const double f6 = f2 + f1 + v.q(e_, ilp2) + v.q(e_, irp2);
 #pragma unroll
             for (int e = 0; e < 3; e++)
                 G[c][e] = (f2 * tn1[e] - f1 * tn[e]) + (f4 * ta1[e] - f3 * ta[e]) + (f6 * tb1[e] - f5 * tb[e]);
@@ -117,7 +117,9 @@ __device__ __forceinline__ double visc_face(const ZoneDev &z, const double *__re
         const int nm = z.nm;
         if (DIR < 2) {
             constexpr int DP = 1 - (DIR < 2 ? DIR : 0);
-            const int ip = inc[DP], ik = z.inck;
+            // DP is D1 for DIR = 0 and D2 for DIR = 1; k is the other tangential direction
+            const int ilmp = DIR == 0 ? ilm1 : ilm2, irmp = DIR == 0 ? irm1 : irm2, ilpp = DIR == 0 ? ilp1 : ilp2, irpp = DIR == 0 ? irp1 : irp2;
+            const int ilmk = DIR == 0 ? ilm2 : ilm1, irmk = DIR == 0 ? irm2 : irm1, ilpk = DIR == 0 ? ilp2 : ilp1, irpk = DIR == 0 ? irp2 : irp1;
             const int m0 = DIR == 0 ? z.mi : z.mj, mp = DP == 0 ? z.mi : z.mj;
             const double *T0 = DIR == 0 ? z.ti : z.tj, *Tp = DP == 0 ? z.ti : z.tj;
             double tn[2], tn1[2], tp[2], tp1[2];
@@ -133,19 +135,18 @@ __device__ __forceinline__ double visc_face(const ZoneDev &z, const double *__re
             const double tkz = .125 * (__ldg(z.tk + lt) + __ldg(z.tk + lt - m0));
 #pragma unroll
             for (int c = 0; c < NV; c++) {
-                const double *q = rop + (c + 1) * nd;
-                const double f1 = q[il], f2 = q[ir];
-                const double fa = f2 + f1 + q[il - ip] + q[ir - ip], fb = f2 + f1 + q[il + ip] + q[ir + ip];
+                const int e_ = c + 1;
+                const double f1 = v.q(e_, il), f2 = v.q(e_, ir);
+                const double fa = f2 + f1 + v.q(e_, ilmp) + v.q(e_, irmp), fb = f2 + f1 + v.q(e_, ilpp) + v.q(e_, irpp);
 #pragma unroll
                 for (int e = 0; e < 2; e++) G[c][e] = (f2 * tn1[e] - f1 * tn[e]) + (fb * tp1[e] - fa * tp[e]);
                 if (c < 3) {
-                    const double fk0 = f2 + f1 + q[il - ik] + q[ir - ik], fk1 = f2 + f1 + q[il + ik] + q[ir + ik];
+                    const double fk0 = f2 + f1 + v.q(e_, ilmk) + v.q(e_, irmk), fk1 = f2 + f1 + v.q(e_, ilpk) + v.q(e_, irpk);
                     G[c][2] = (fk1 - fk0) * tkz;
                 }
             }
             volinv = 1. / (__ldg(z.vol + lt) + __ldg(z.vol + lt - m0));
         } else {
-            const int ii = 1, ij = z.incj;
             const double tiz = __ldg(z.tk + lt);
             const double tjx = 0.25 * __ldg(z.ti + lt), tjy = 0.25 * __ldg(z.ti + lt + nm);
             const double tjx1 = 0.25 * __ldg(z.ti + lt + z.mi), tjy1 = 0.25 * __ldg(z.ti + lt + z.mi + nm);
@@ -153,12 +154,12 @@ __device__ __forceinline__ double visc_face(const ZoneDev &z, const double *__re
             const double tkx1 = 0.25 * __ldg(z.tj + lt + z.mj), tky1 = 0.25 * __ldg(z.tj + lt + z.mj + nm);
 #pragma unroll
             for (int c = 0; c < NV; c++) {
-                const double *q = rop + (c + 1) * nd;
-                const double f1 = q[il], f2 = q[ir];
+                const int e_ = c + 1;
+                const double f1 = v.q(e_, il), f2 = v.q(e_, ir);
                 G[c][2] = (f2 - f1) * tiz;
                 if (c >= 3) continue;
-                const double f3 = f2 + f1 + q[il - ii] + q[ir - ii], f4 = f2 + f1 + q[il + ii] + q[ir + ii];
-                const double f5 = f2 + f1 + q[il - ij] + q[ir - ij], f6 = f2 + f1 + q[il + ij] + q[ir + ij];
+                const double f3 = f2 + f1 + v.q(e_, ilm1) + v.q(e_, irm1), f4 = f2 + f1 + v.q(e_, ilp1) + v.q(e_, irp1);
+                const double f5 = f2 + f1 + v.q(e_, ilm2) + v.q(e_, irm2), f6 = f2 + f1 + v.q(e_, ilp2) + v.q(e_, irp2);
                 G[c][0] = ((f4 * tjx1 - f3 * tjx) + (f6 * tkx1 - f5 * tkx));
                 G[c][1] = ((f4 * tjy1 - f3 * tjy) + (f6 * tky1 - f5 * tky));
             }
@@ -170,20 +171,19 @@ __device__ __forceinline__ double visc_face(const ZoneDev &z, const double *__re
     const double f1 = G[0][0] - div, f2 = G[0][1] + G[1][0], f3 = G[0][2] + G[2][0];
     const double f4 = G[1][1] - div, f5 = G[1][2] + G[2][1], f6 = G[2][2] - div;
     double xmutvol, xktvol;
-    const double Tl = rop[il + 4 * nd], Tr = rop[ir + 4 * nd];
+    const double Tl = v.q(4, il), Tr = v.q(4, ir);
     if (FLOW == 3) {
         double xmulam = z.coesut * sqrt(Tl * z.temp01) / (1. + z.cmus1 / Tl);
         xmulam = xmulam + z.coesut * sqrt(Tr * z.temp01) / (1. + z.cmus1 / Tr);
-        const double xmutot = z.xmut[ir] + z.xmut[il];
+        const double xmutot = v.mu(ir) + v.mu(il);
         const double xmutur = xmutot - xmulam;
         xktvol = (xmulam * z.gam3 + xmutur * z.gam4) * volinv;
         xmutvol = xmutot * volinv;
     } else {
-        xmutvol = (z.xmut[ir] + z.xmut[il]) * volinv;
+        xmutvol = (v.mu(ir) + v.mu(il)) * volinv;
         xktvol = xmutvol * z.gam3;
     }
-    const double ur = rop[ir + nd] + rop[il + nd], vr = rop[ir + 2 * nd] + rop[il + 2 * nd],
-                 wr = rop[ir + 3 * nd] + rop[il + 3 * nd];
+    const double ur = v.q(1, ir) + v.q(1, il), vr = v.q(2, ir) + v.q(2, il), wr = v.q(3, ir) + v.q(3, il);
     double fv, fv5;
     if (MESH == 0) {
         fv = -(2. * f1 * tc[0] + f2 * tc[1] + f3 * tc[2]) * xmutvol; fv5 = fv * ur; flu[1] += fv;
@@ -209,7 +209,7 @@ __device__ __forceinline__ double visc_face(const ZoneDev &z, const double *__re
     if (FLOW == 3) {
         double xmulam = z.coesut * sqrt(Tl * z.temp01) / (1. + z.cmus1 / Tl);
         xmulam = xmulam + z.coesut * sqrt(Tr * z.temp01) / (1. + z.cmus1 / Tr);
-        double xsa = xmulam + rop[il + 5 * nd] * rop[il] + rop[ir + 5 * nd] * rop[ir];
+        double xsa = xmulam + v.q(5, il) * v.q(0, il) + v.q(5, ir) * v.q(0, ir);
         xsa = xsa * volinv * z.sigma_1;
         constexpr int C = NV - 1;
         if (MESH == 0) flu[5] = flu[5] - xsa * (G[C][0] * tc[0] + G[C][1] * tc[1] + G[C][2] * tc[2]);
@@ -221,22 +221,19 @@ __device__ __forceinline__ double visc_face(const ZoneDev &z, const double *__re
 
 #include "fb_sa.cuh"
 
-template <int MESH, int FLOW, int SCHEME, int SLOPE, int DIR>
-__device__ __forceinline__ void face_flux(const ZoneDev &z, const double *__restrict__ rop, int l, int lt, double *flu)
+// l: cell index in the view v; lg: the reference's global cell index (SENSOR switch, stores); lt: metric index
+template <int MESH, int FLOW, int SCHEME, int SLOPE, int DIR, class V>
+__device__ __forceinline__ void face_flux(const ZoneDev &z, const V &vw, int l, int lg, int lt, double *flu)
 {
     constexpr int NEQ = FLOW == 3 ? 6 : 5;
-    const int nd = z.nd;
-    const int inc = DIR == 0 ? 1 : (DIR == 1 ? z.incj : z.inck);
     double tc[3], s;
     face_normal<MESH, DIR>(z, lt, tc, s);
-    const int nm = l - inc, nm2 = l - 2 * inc, np = l + inc;
-    const double T0 = rop[l + 4 * nd];
+    const int nm = vw.template dn<DIR>(l), np = vw.template up<DIR>(l);
+    const double T0 = vw.q(4, l);
     double qL[NEQ], qR[NEQ];
 #pragma unroll
-    for (int e = 0; e < 5; e++) {
-        const double *q = rop + e * nd;
-        muscl<SLOPE>(z, q[nm2], q[nm], q[l], q[np], T0, qL[e], qR[e]);
-    }
+    for (int e = 0; e < 5; e++)
+        muscl<SLOPE>(z, vw.template qm2<DIR>(e, l), vw.q(e, nm), vw.q(e, l), vw.q(e, np), T0, qL[e], qR[e]);
     const double rgp = z.rgp, gam1 = z.gam1;
     double qn1 = qL[1] * tc[0] + qL[2] * tc[1] + qL[3] * tc[2];
     double qn2 = qR[1] * tc[0] + qR[2] * tc[1] + qR[3] * tc[2];
@@ -284,7 +281,7 @@ __device__ __forceinline__ void face_flux(const ZoneDev &z, const double *__rest
         flu[2] = (flu[2] + rou1 * qL[2] + rou2 * qR[2] + tc[1] * p1p2) * 0.5;
         flu[3] = (flu[3] + rou1 * qL[3] + rou2 * qR[3] + tc[2] * p1p2) * 0.5;
         flu[4] = (flu[4] + rou1 * h1 + rou2 * h2) * 0.5;
-        if (FLOW == 3) flu[5] = roe_sa_flux(z, rop, l, inc, tc, s_1);
+        if (FLOW == 3) flu[5] = roe_sa_flux(z, vw, l, nm, tc, s_1);
     } else {
         const double r1 = qL[0], rou1 = r1 * qL[1], rov1 = r1 * qL[2], row1 = r1 * qL[3], p1 = r1 * qL[4] * rgp;
         const double h1 = gam1 * p1 + .5 * (rou1 * qL[1] + rov1 * qL[2] + row1 * qL[3]);
@@ -299,7 +296,7 @@ __device__ __forceinline__ void face_flux(const ZoneDev &z, const double *__rest
             u = 0.25 * (qn1 + qn2) - tam1 * (p2 - p1);
             tdu = fmax(fabs(u), z.c1 * s) * z.wig_cte;
         } else {
-            const double wg = (double)((z.wigb[l] >> DIR) & 1);
+            const double wg = (double)((z.wigb[lg] >> DIR) & 1);
             u = 0.25 * (qn1 + qn2) - z.c2 * s * (p2 - p1) * (z.opt0 * wg + 1. - z.opt0);
             tdu = fmax(fabs(u), z.c1 * s) * wg;
         }
@@ -309,7 +306,7 @@ __device__ __forceinline__ void face_flux(const ZoneDev &z, const double *__rest
         flu[2] = u * (rov1 + rov2) - tdu * (rov2 - rov1) + tc[1] * p1p2;
         flu[3] = u * (row1 + row2) - tdu * (row2 - row1) + tc[2] * p1p2;
         flu[4] = u * (h1 + h2) - tdu * (h2 - h1);
-        if (FLOW == 3) flu[5] = ausm_sa_flux<SLOPE>(z, rop, l, inc, T0, u, tdu, r1, r2);
+        if (FLOW == 3) flu[5] = ausm_sa_flux<SLOPE, DIR>(z, vw, l, nm, np, T0, u, tdu, r1, r2);
     }
-    if (FLOW >= 2) visc_face<MESH, FLOW, DIR>(z, rop, l, lt, tc, flu);
+    if (FLOW >= 2) visc_face<MESH, FLOW, DIR>(z, vw, l, lt, tc, flu);
 }

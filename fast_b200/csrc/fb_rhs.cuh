@@ -1,73 +1,35 @@
-// fb_rhs.cuh -- fused rhs kernel template; instantiated per (MESH, FLOW) in fb_rhs_m*f*.cu so that the 81 x 2
+// fb_rhs.cuh -- fused rhs kernel templates; instantiated per (MESH, FLOW) in fb_rhs_m*f*.cu so that the 81 x 2
 // variants compile in parallel.
+//   k_rhs3: k-marching, state planes staged by TMA into a shared-memory ring (default whenever the zone's strides
+//           can be encoded in a tensor map: ni and NDIMDX even);
+//   k_rhs2: k-marching, state read through L1 (any zone size).
+// Both evaluate every face flux once and share it between its two cells, and sum in the reference's order
+// +F_k +F_j +F_i -F_i(i+1) -F_j(j+1) -F_k(k+1) (template_FluxAndBalance.for:192-271), so they agree bit for bit.
 #pragma once
 #include <cstdlib>
+#include <cuda.h>
 #include "fb_kernels.cuh"
 #include "fb_flux.cuh"
 #include "fb_source.cuh"
+#include "fb_rhs_decl.cuh"
+
 
 static inline dim3 grid3r(int ni, int nj, int nk, dim3 b) { return dim3((ni + b.x - 1) / b.x, (nj + b.y - 1) / b.y, nk); }
 
-// ------------------------------------------------------------------------------------------------ fused rhs
-// One thread per interior cell, gather form: the six face fluxes of the cell are evaluated and summed in the
-// reference's accumulation order (+Fk +Fj +Fi -Fi(i+1) -Fj(j+1) -Fk(k+1), template_FluxAndBalance.for:192-271),
-// then the time-integration step is applied in registers so that drodm and rop_out are written once.
-#include "fb_rhs_decl.cuh"
-
-template <int MESH, int FLOW, int SCHEME, int SLOPE, bool IMPL>
-__global__ void __launch_bounds__(128) k_rhs(ZoneDev z, RhsArgs a)
+// ------------------------------------------------------------------------------------------------ cell epilogue
+// explicit: core3ark3.for:108-154 (+203-236 for nutilde) -- the stage is updated from its own input
+// (navier_stokes_struct.for:477-483); implicit: core3as2.for:70-100.  l: cell in the view, lg: global cell index.
+template <int MESH, int FLOW, bool IMPL, class V>
+__device__ __forceinline__ void rhs_finish(const ZoneDev &z, const RhsArgs &a, const V &v, int l, int lg, double coe1, double *acc)
 {
     constexpr int NEQ = FLOW == 3 ? 6 : 5;
-    const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
-    const int k = 1 + blockIdx.z;
-    if (i > z.iv || j > z.jv) return;
     const int nd = z.nd;
-    const int l = inddm(z, i, j, k);
-    const int lt = MESH == 2 ? 0 : indmtr(z, i, j, k);
-    const double *__restrict__ rop = a.rop;
-    double acc[NEQ], f[NEQ];
-    // init_rhs.for:85-129
-    if (IMPL || a.nitcfg == 1) {
-#pragma unroll
-        for (int e = 0; e < NEQ; e++) acc[e] = 0.;
-    } else {
-#pragma unroll
-        for (int e = 0; e < NEQ; e++) acc[e] = z.drodm[l + e * nd] * a.coefH;
-    }
-    double coe1;   // dt/vol (tstb3_global.for) -- explicit: recomputed, implicit: from coe(:,1)
-    if (IMPL) coe1 = z.coe[l];
-    else coe1 = MESH == 2 ? z.dtc / z.vol0 : z.dtc / __ldg(z.vol + lt);
-    if (FLOW == 3) sa_source<MESH, IMPL>(z, rop, l, lt, i, j, k, a.nitcfg, coe1, acc);
-    // lower faces
-    face_flux<MESH, FLOW, SCHEME, SLOPE, 2>(z, rop, l, lt, f);
-#pragma unroll
-    for (int e = 0; e < NEQ; e++) acc[e] += f[e];
-    face_flux<MESH, FLOW, SCHEME, SLOPE, 1>(z, rop, l, lt, f);
-#pragma unroll
-    for (int e = 0; e < NEQ; e++) acc[e] += f[e];
-    face_flux<MESH, FLOW, SCHEME, SLOPE, 0>(z, rop, l, lt, f);
-#pragma unroll
-    for (int e = 0; e < NEQ; e++) acc[e] += f[e];
-    // upper faces = lower faces of the next cell
-    face_flux<MESH, FLOW, SCHEME, SLOPE, 0>(z, rop, l + 1, MESH == 2 ? 0 : lt + z.mi, f);
-#pragma unroll
-    for (int e = 0; e < NEQ; e++) acc[e] -= f[e];
-    face_flux<MESH, FLOW, SCHEME, SLOPE, 1>(z, rop, l + z.incj, MESH == 2 ? 0 : lt + z.mj, f);
-#pragma unroll
-    for (int e = 0; e < NEQ; e++) acc[e] -= f[e];
-    face_flux<MESH, FLOW, SCHEME, SLOPE, 2>(z, rop, l + z.inck, MESH == 2 ? 0 : lt + z.mk, f);
-#pragma unroll
-    for (int e = 0; e < NEQ; e++) acc[e] -= f[e];
-
     const double cv = z.cv;
     if (!IMPL) {
-        // core3ark3.for:108-154 (+203-236 for nutilde)
 #pragma unroll
-        for (int e = 0; e < NEQ; e++) z.drodm[l + e * nd] = acc[e];
-        const double *__restrict__ ro = a.rop;   // the stage is updated from its own input (navier_stokes_struct.for:477-483)
+        for (int e = 0; e < NEQ; e++) z.drodm[lg + e * nd] = acc[e];
         double r_1 = a.coefW * coe1;
-        const double ro_old = ro[l], u_old = ro[l + nd], v_old = ro[l + 2 * nd], w_old = ro[l + 3 * nd], t_old = ro[l + 4 * nd];
+        const double ro_old = v.q(0, l), u_old = v.q(1, l), v_old = v.q(2, l), w_old = v.q(3, l), t_old = v.q(4, l);
         const double tab1 = acc[0] * r_1, tab2 = acc[1] * r_1, tab3 = acc[2] * r_1, tab4 = acc[3] * r_1, tab5 = acc[4] * r_1;
         const double cvinv = 1. / cv, cvinv2 = 0.5 * cvinv;
         const double rn = ro_old + tab1;
@@ -76,73 +38,31 @@ __global__ void __launch_bounds__(128) k_rhs(ZoneDev z, RhsArgs a)
         const double roe_old = ro_old * (cv * t_old + 0.5 * (u_old * u_old + v_old * v_old + w_old * w_old));
         const double tn = (roe_old + tab5) * r1n * cvinv - cvinv2 * (un * un + vn * vn + wn * wn);
         double *__restrict__ out = a.rop_out;
-        out[l] = rn; out[l + nd] = un; out[l + 2 * nd] = vn; out[l + 3 * nd] = wn; out[l + 4 * nd] = tn;
+        out[lg] = rn; out[lg + nd] = un; out[lg + 2 * nd] = vn; out[lg + 3 * nd] = wn; out[lg + 4 * nd] = tn;
         if (FLOW == 3) {
             const double tab6 = acc[NEQ - 1] * r_1;
             double anulam = z.coesut * sqrt(tn * z.temp01) / (1. + z.cmus1 / tn);
             anulam = anulam * r1n * z.ratiom;
-            double t = (ro_old * ro[l + 5 * nd] + tab6) * r1n;
+            double t = (ro_old * v.q(5, l) + tab6) * r1n;
             t = fmin(t, anulam);
-            out[l + 5 * nd] = fmax(t, 0.);
+            out[lg + 5 * nd] = fmax(t, 0.);
         }
     } else {
-        // core3as2.for:70-100: drodm = coe1*drodm + c1 W(rop_ssiter) + c2 W(ro) + c3 W(ro_M1)
-        const double *__restrict__ r0 = a.rop, *__restrict__ rn = a.ro_n, *__restrict__ rm = a.ro_n1;
-        implicit_assemble<NEQ>(z, r0, rn, rm, l, coe1, a.c1, a.c2, a.c3, acc);
+        implicit_assemble<NEQ>(z, v, l, a.rop, a.ro_n, a.ro_n1, lg, coe1, a.c1, a.c2, a.c3, acc);
 #pragma unroll
-        for (int e = 0; e < NEQ; e++) z.drodm[l + e * nd] = acc[e];
+        for (int e = 0; e < NEQ; e++) z.drodm[lg + e * nd] = acc[e];
     }
 }
 
-// ------------------------------------------------------------------------------------------------ fused rhs, v2
+// ------------------------------------------------------------------------------------------------ fused rhs, L1 path
 // k-marching kernel: every face flux is evaluated ONCE and shared by its two cells.
 //   CTA = 32 x (RJ+1) threads over a tile of 31 x RJ cells, marching over a chunk of k planes.
 //   thread (li, m): lower i face and lower j face of cell (i0+li, j0+m, k) and its lower k face;
 //     F_i(i+1) comes from lane li+1 (warp shuffle; lane 31 only owns a face), F_j(j+1) from row m+1 (shared memory,
 //     double-buffered by plane parity: one __syncthreads per plane; row RJ only owns faces), F_k(k+1) is the lower k
 //     face of the next plane: the cell of plane k-1 is finished (and written) when plane k has produced it.
-//   The sum keeps the reference's order +F_k +F_j +F_i -F_i(i+1) -F_j(j+1) -F_k(k+1)
-//   (template_FluxAndBalance.for:192-271), so the result is bitwise the one of the gather kernel above.
 #define RHS2_RJ 8
 #define RHS2_KC 32
-
-template <int MESH, int FLOW, bool IMPL>
-__device__ __forceinline__ void rhs_finish(const ZoneDev &z, const RhsArgs &a, int l, double coe1, double *acc)
-{
-    constexpr int NEQ = FLOW == 3 ? 6 : 5;
-    const int nd = z.nd;
-    const double cv = z.cv;
-    if (!IMPL) {
-        // core3ark3.for:108-154 (+203-236 for nutilde)
-#pragma unroll
-        for (int e = 0; e < NEQ; e++) z.drodm[l + e * nd] = acc[e];
-        const double *__restrict__ ro = a.rop;
-        double r_1 = a.coefW * coe1;
-        const double ro_old = ro[l], u_old = ro[l + nd], v_old = ro[l + 2 * nd], w_old = ro[l + 3 * nd], t_old = ro[l + 4 * nd];
-        const double tab1 = acc[0] * r_1, tab2 = acc[1] * r_1, tab3 = acc[2] * r_1, tab4 = acc[3] * r_1, tab5 = acc[4] * r_1;
-        const double cvinv = 1. / cv, cvinv2 = 0.5 * cvinv;
-        const double rn = ro_old + tab1;
-        const double r1n = 1. / rn;
-        const double un = (ro_old * u_old + tab2) * r1n, vn = (ro_old * v_old + tab3) * r1n, wn = (ro_old * w_old + tab4) * r1n;
-        const double roe_old = ro_old * (cv * t_old + 0.5 * (u_old * u_old + v_old * v_old + w_old * w_old));
-        const double tn = (roe_old + tab5) * r1n * cvinv - cvinv2 * (un * un + vn * vn + wn * wn);
-        double *__restrict__ out = a.rop_out;
-        out[l] = rn; out[l + nd] = un; out[l + 2 * nd] = vn; out[l + 3 * nd] = wn; out[l + 4 * nd] = tn;
-        if (FLOW == 3) {
-            const double tab6 = acc[NEQ - 1] * r_1;
-            double anulam = z.coesut * sqrt(tn * z.temp01) / (1. + z.cmus1 / tn);
-            anulam = anulam * r1n * z.ratiom;
-            double t = (ro_old * ro[l + 5 * nd] + tab6) * r1n;
-            t = fmin(t, anulam);
-            out[l + 5 * nd] = fmax(t, 0.);
-        }
-    } else {
-        // core3as2.for:70-100: drodm = coe1*drodm + c1 W(rop_ssiter) + c2 W(ro) + c3 W(ro_M1)
-        implicit_assemble<NEQ>(z, a.rop, a.ro_n, a.ro_n1, l, coe1, a.c1, a.c2, a.c3, acc);
-#pragma unroll
-        for (int e = 0; e < NEQ; e++) z.drodm[l + e * nd] = acc[e];
-    }
-}
 
 template <int MESH, int FLOW, int SCHEME, int SLOPE, bool IMPL>
 __global__ void __launch_bounds__(32 * (RHS2_RJ + 1)) k_rhs2(ZoneDev z, RhsArgs a)
@@ -156,7 +76,7 @@ __global__ void __launch_bounds__(32 * (RHS2_RJ + 1)) k_rhs2(ZoneDev z, RhsArgs 
     const bool fi = m < RJ && j <= z.jv && i <= z.iv + 1;               // owns a lower i face that somebody needs
     const bool fj = li < 31 && i <= z.iv && j <= z.jv + 1;              // owns a lower j face that somebody needs
     const int nd = z.nd;
-    const double *__restrict__ rop = a.rop;
+    const GView v(z, a.rop);
     double acc[NEQ], f[NEQ];
 #pragma unroll
     for (int e = 0; e < NEQ; e++) acc[e] = 0.;
@@ -167,11 +87,11 @@ __global__ void __launch_bounds__(32 * (RHS2_RJ + 1)) k_rhs2(ZoneDev z, RhsArgs 
         const bool last = k == k1 + 1;
         // lower k face: finishes the cell of plane k-1, starts the cell of plane k
         if (cell) {
-            face_flux<MESH, FLOW, SCHEME, SLOPE, 2>(z, rop, l, lt, f);
+            face_flux<MESH, FLOW, SCHEME, SLOPE, 2>(z, v, l, l, lt, f);
             if (k > k0) {
 #pragma unroll
                 for (int e = 0; e < NEQ; e++) acc[e] -= f[e];
-                rhs_finish<MESH, FLOW, IMPL>(z, a, l - z.inck, coe1p, acc);
+                rhs_finish<MESH, FLOW, IMPL>(z, a, v, l - z.inck, l - z.inck, coe1p, acc);
             }
         }
         if (last) break;      // uniform
@@ -187,14 +107,14 @@ __global__ void __launch_bounds__(32 * (RHS2_RJ + 1)) k_rhs2(ZoneDev z, RhsArgs 
             }
             if (IMPL) coe1 = z.coe[l];
             else coe1 = MESH == 2 ? z.dtc / z.vol0 : z.dtc / __ldg(z.vol + lt);
-            if (FLOW == 3) sa_source<MESH, IMPL>(z, rop, l, lt, i, j, k, a.nitcfg, coe1, acc);
+            if (FLOW == 3) sa_source<MESH, IMPL>(z, v, l, l, lt, a.nitcfg, coe1, acc);
 #pragma unroll
             for (int e = 0; e < NEQ; e++) acc[e] += f[e];
         }
         coe1p = coe1;
         // lower j face -> shared memory
         if (fj) {
-            face_flux<MESH, FLOW, SCHEME, SLOPE, 1>(z, rop, l, lt, f);
+            face_flux<MESH, FLOW, SCHEME, SLOPE, 1>(z, v, l, l, lt, f);
 #pragma unroll
             for (int e = 0; e < NEQ; e++) sFj[k & 1][m][e][li] = f[e];
             if (cell) {
@@ -203,7 +123,7 @@ __global__ void __launch_bounds__(32 * (RHS2_RJ + 1)) k_rhs2(ZoneDev z, RhsArgs 
             }
         }
         // lower i face; the upper one comes from the next lane
-        if (fi) face_flux<MESH, FLOW, SCHEME, SLOPE, 0>(z, rop, l, lt, f);
+        if (fi) face_flux<MESH, FLOW, SCHEME, SLOPE, 0>(z, v, l, l, lt, f);
         else {
 #pragma unroll
             for (int e = 0; e < NEQ; e++) f[e] = 0.;
@@ -221,6 +141,185 @@ __global__ void __launch_bounds__(32 * (RHS2_RJ + 1)) k_rhs2(ZoneDev z, RhsArgs 
     }
 }
 
+// ------------------------------------------------------------------------------------------------ fused rhs, TMA path
+// Same thread <-> face mapping as k_rhs2, but the primitive state (and mu+mut) of the tile, halo included, is staged
+// plane by plane into a shared-memory ring by TMA (one cp.async.bulk.tensor box of 36 x (RJ+4) x 1 x NEQ doubles per
+// plane and array, completion on an mbarrier).  Iteration k works on planes k-1, k, k+1 (the own column at k-2, which
+// only the k-face MUSCL stencil needs, is carried in registers) while plane k+2 is in flight; the slot of plane k-1
+// is re-armed for plane k+3 behind the end-of-plane barrier.  All stencil reads are LDS with immediate offsets: no
+// address arithmetic, no L1 tag traffic, HBM sees every plane once per tile (+ halo, served by L2).
+#ifndef RHS3_NS
+#define RHS3_NS 4           // ring slots
+#endif
+#ifndef RHS3_RJ_NS
+#define RHS3_RJ_NS 8        // tile rows, Euler / laminar
+#endif
+#ifndef RHS3_RJ_SA
+#define RHS3_RJ_SA 6        // tile rows, Spalart-Allmaras (7 staged variables)
+#endif
+#ifndef RHS3_MINB
+#define RHS3_MINB 2         // resident CTAs per SM the register allocation aims at
+#endif
+#ifndef RHS3_KC
+#define RHS3_KC 64          // k planes per CTA
+#endif
+
+template <int FLOW, int RJ>
+struct Rhs3Cfg {
+    static constexpr int NEQ = FLOW == 3 ? 6 : 5;
+    static constexpr int NV = NEQ + (FLOW >= 2 ? 1 : 0);
+    static constexpr int BI = 36, ROWS = RJ + 4;          // box: 2 halo columns / rows on each side (+1 face lane, +1 pad)
+    static constexpr int RS = BI, VS = RS * ROWS;
+    static constexpr int PS = (NV * VS + 15) / 16 * 16;   // slot stride: TMA destinations must be 128-byte aligned
+    static_assert((NEQ * VS) % 16 == 0, "the mu box lands behind the rop box: NEQ*VS must be a multiple of 16 doubles");
+    static constexpr int NT = 32 * (RJ + 1);
+    static constexpr unsigned TX = (unsigned)(NV * VS * sizeof(double));   // bytes one plane brings in
+    static constexpr size_t SMEM = (size_t)(RHS3_NS * PS + 2 * (RJ + 1) * NEQ * 32) * sizeof(double) + RHS3_NS * sizeof(unsigned long long);
+};
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+                 ::"r"(b), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *tm, int c0, int c1, int c2, int c3, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+                   "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+template <int MESH, int FLOW, int SCHEME, int SLOPE, bool IMPL, int RJ>
+__global__ void __launch_bounds__(32 * (RJ + 1), RHS3_MINB)
+k_rhs3(const __grid_constant__ CUtensorMap tm_rop, const __grid_constant__ CUtensorMap tm_mu, ZoneDev z, RhsArgs a)
+{
+    using C = Rhs3Cfg<FLOW, RJ>;
+    constexpr int NEQ = C::NEQ, NS = RHS3_NS, PS = C::PS, RS = C::RS, VS = C::VS;
+    extern __shared__ __align__(128) double ring[];
+    double (*sFj)[RJ + 1][NEQ][32] = (double (*)[RJ + 1][NEQ][32])(ring + NS * PS);
+    unsigned long long *bar = (unsigned long long *)(ring + NS * PS + 2 * (RJ + 1) * NEQ * 32);
+    const int li = threadIdx.x, m = threadIdx.y;
+    const bool leader = li == 0 && m == 0;
+    const int i = 1 + blockIdx.x * 31 + li, j = 1 + blockIdx.y * RJ + m;
+    const int k0 = 1 + blockIdx.z * RHS3_KC, k1 = min(k0 + RHS3_KC - 1, z.kv);
+    const bool cell = li < 31 && m < RJ && i <= z.iv && j <= z.jv;
+    const bool fi = m < RJ && j <= z.jv && i <= z.iv + 1;
+    const bool fj = li < 31 && i <= z.iv && j <= z.jv + 1;
+    const int nd = z.nd;
+    // array coordinates of the box origin (cell i0-2, j0-2) and planes k0-1 .. k1+2
+    // (TMA needs a 16-byte aligned global start: an odd first column is shifted one to the left -- the 36-wide box
+    // still covers the 35 columns i0-2 .. i0+32 the tile reads)
+    const int ca0 = blockIdx.x * 31 + z.nf - 2, cb = blockIdx.y * RJ + z.nf - 2;
+    const int sh = ca0 & 1, ca = ca0 - sh;
+    const int pfirst = k0 - 1, plast = k1 + 2;
+    auto issue = [&](int p) {
+        const int slot = (p - pfirst) % NS;
+        mbar_expect_tx(bar + slot, C::TX);
+        tma_load_4d(ring + slot * PS, &tm_rop, ca, cb, p + z.nfk - 1, 0, bar + slot);
+        if (FLOW >= 2) tma_load_4d(ring + slot * PS + NEQ * VS, &tm_mu, ca, cb, p + z.nfk - 1, 0, bar + slot);
+    };
+    if (leader) {
+        for (int s = 0; s < NS; s++) mbar_init(bar + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (leader)
+        for (int p = pfirst; p < pfirst + NS && p <= plast; p++) issue(p);
+    // own column at plane k0-2 (registers)
+    double km2[NEQ];
+    {
+        const int l = inddm(z, cell ? i : 1, cell ? j : 1, k0 - 2);
+#pragma unroll
+        for (int e = 0; e < NEQ; e++) km2[e] = a.rop[l + e * nd];
+    }
+    double acc[NEQ], f[NEQ];
+#pragma unroll
+    for (int e = 0; e < NEQ; e++) acc[e] = 0.;
+    double coe1p = 0.;
+    mbar_wait(bar + 0, 0);
+    mbar_wait(bar + 1, 0);
+    const int lcol = (m + 2) * RS + li + 2 + sh;
+    for (int k = k0; k <= k1 + 1; k++) {
+        const int pk = k - pfirst;                       // >= 1
+        const int sk = pk % NS, su = (pk + 1) % NS, sd = (pk - 1) % NS;
+        mbar_wait(bar + su, ((pk + 1) / NS) & 1);        // plane k+1 has landed
+        SView<RS, VS, NEQ> v;
+        v.s = ring; v.kup = (su - sk) * PS; v.kdn = (sd - sk) * PS; v.km2 = km2;
+        const int ls = sk * PS + lcol;
+        const int l = inddm(z, i, j, k);
+        const int lt = MESH == 2 ? 0 : indmtr(z, i, j, k);
+        const bool last = k == k1 + 1;
+        if (cell) {
+            face_flux<MESH, FLOW, SCHEME, SLOPE, 2>(z, v, ls, l, lt, f);
+            if (k > k0) {
+#pragma unroll
+                for (int e = 0; e < NEQ; e++) acc[e] -= f[e];
+                rhs_finish<MESH, FLOW, IMPL>(z, a, v, ls + v.kdn, l - z.inck, coe1p, acc);
+            }
+        }
+        if (last) break;      // uniform; no TMA is in flight any more (plane k1+2 was waited for above)
+        double coe1 = 0.;
+        if (cell) {
+            if (IMPL || a.nitcfg == 1) {
+#pragma unroll
+                for (int e = 0; e < NEQ; e++) acc[e] = 0.;
+            } else {
+#pragma unroll
+                for (int e = 0; e < NEQ; e++) acc[e] = z.drodm[l + e * nd] * a.coefH;
+            }
+            if (IMPL) coe1 = z.coe[l];
+            else coe1 = MESH == 2 ? z.dtc / z.vol0 : z.dtc / __ldg(z.vol + lt);
+            if (FLOW == 3) sa_source<MESH, IMPL>(z, v, ls, l, lt, a.nitcfg, coe1, acc);
+#pragma unroll
+            for (int e = 0; e < NEQ; e++) acc[e] += f[e];
+        }
+        coe1p = coe1;
+        if (fj) {
+            face_flux<MESH, FLOW, SCHEME, SLOPE, 1>(z, v, ls, l, lt, f);
+#pragma unroll
+            for (int e = 0; e < NEQ; e++) sFj[k & 1][m][e][li] = f[e];
+            if (cell) {
+#pragma unroll
+                for (int e = 0; e < NEQ; e++) acc[e] += f[e];
+            }
+        }
+        if (fi) face_flux<MESH, FLOW, SCHEME, SLOPE, 0>(z, v, ls, l, lt, f);
+        else {
+#pragma unroll
+            for (int e = 0; e < NEQ; e++) f[e] = 0.;
+        }
+#pragma unroll
+        for (int e = 0; e < NEQ; e++) {
+            const double up = __shfl_down_sync(0xffffffffu, f[e], 1);
+            if (cell) acc[e] = (acc[e] + f[e]) - up;
+        }
+        // plane k-1 becomes plane k-2 of the next iteration
+#pragma unroll
+        for (int e = 0; e < NEQ; e++) km2[e] = v.q(e, ls + v.kdn);
+        __syncthreads();
+        // every thread is done with plane k-1: its slot takes plane k+3
+        if (leader && k + NS - 1 <= plast) issue(k + NS - 1);
+        if (cell) {
+#pragma unroll
+            for (int e = 0; e < NEQ; e++) acc[e] -= sFj[k & 1][m + 1][e][li];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ launchers
+// tensor maps of rop(ni,nj,nk,neq) / xmut(ni,nj,nk,naux) with a (36, rows, 1, nvar) box; nullptr when the strides
+// cannot be encoded (odd ni or NDIMDX) or the driver entry point is missing (fb_tma.cu)
+const CUtensorMap *fb_tma_map(const double *base, int ni, int nj, int nk, long long var_stride, int nvar_total, int box_rows, int box_vars);
+
 template <int MESH, int FLOW, int SCHEME, int SLOPE>
 static void launch_rhs2_t(const ZoneDev &z, const RhsArgs &a, bool impl, cudaStream_t st)
 {
@@ -231,14 +330,33 @@ static void launch_rhs2_t(const ZoneDev &z, const RhsArgs &a, bool impl, cudaStr
 }
 
 template <int MESH, int FLOW, int SCHEME, int SLOPE>
+static bool launch_rhs3_t(const ZoneDev &z, const RhsArgs &a, bool impl, cudaStream_t st)
+{
+    constexpr int RJ = FLOW == 3 ? RHS3_RJ_SA : RHS3_RJ_NS;
+    using C = Rhs3Cfg<FLOW, RJ>;
+    if (z.nf != 2 || z.nfk != 2) return false;
+    const CUtensorMap *tr = fb_tma_map(a.rop, z.ni, z.nj, z.nk, z.nd, C::NEQ, C::ROWS, C::NEQ);
+    const CUtensorMap *tm = FLOW >= 2 ? fb_tma_map(z.xmut, z.ni, z.nj, z.nk, z.nd, FLOW == 3 ? 2 : 1, C::ROWS, 1) : tr;
+    if (!tr || !tm) return false;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_rhs3<MESH, FLOW, SCHEME, SLOPE, true, RJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        cudaFuncSetAttribute(k_rhs3<MESH, FLOW, SCHEME, SLOPE, false, RJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        attr = true;
+    }
+    dim3 b(32, RJ + 1, 1);
+    dim3 g((z.iv + 30) / 31, (z.jv + RJ - 1) / RJ, (z.kv + RHS3_KC - 1) / RHS3_KC);
+    if (impl) k_rhs3<MESH, FLOW, SCHEME, SLOPE, true, RJ><<<g, b, C::SMEM, st>>>(*tr, *tm, z, a);
+    else k_rhs3<MESH, FLOW, SCHEME, SLOPE, false, RJ><<<g, b, C::SMEM, st>>>(*tr, *tm, z, a);
+    return true;
+}
+
+template <int MESH, int FLOW, int SCHEME, int SLOPE>
 static void launch_rhs_t(const ZoneDev &z, const RhsArgs &a, bool impl, cudaStream_t st)
 {
-    static const bool gather = [] { const char *e = getenv("FAST_B200_RHS"); return e && e[0] == 'g'; }();
-    if (!gather) { launch_rhs2_t<MESH, FLOW, SCHEME, SLOPE>(z, a, impl, st); return; }
-    dim3 b(64, 2, 1);
-    dim3 g = grid3r(z.iv, z.jv, z.kv, b);
-    if (impl) k_rhs<MESH, FLOW, SCHEME, SLOPE, true><<<g, b, 0, st>>>(z, a);
-    else k_rhs<MESH, FLOW, SCHEME, SLOPE, false><<<g, b, 0, st>>>(z, a);
+    static const bool l1path = [] { const char *e = getenv("FAST_B200_RHS"); return e && e[0] == '2'; }();   // A/B switch
+    if (!l1path && launch_rhs3_t<MESH, FLOW, SCHEME, SLOPE>(z, a, impl, st)) return;
+    launch_rhs2_t<MESH, FLOW, SCHEME, SLOPE>(z, a, impl, st);
 }
 template <int MESH, int FLOW, int SCHEME>
 static void launch_rhs_s(const ZoneDev &z, const RhsArgs &a, bool impl, cudaStream_t st)

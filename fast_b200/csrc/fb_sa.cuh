@@ -2,28 +2,26 @@
 #pragma once
 
 // AUSM / SENSOR: nutilde reconstructed with the scheme's slope times the MUSCL densities, same u / tdu as the mean flow
-template <int SLOPE>
-__device__ __forceinline__ double ausm_sa_flux(const ZoneDev &z, const double *__restrict__ rop, int l, int inc,
+template <int SLOPE, int DIR, class V>
+__device__ __forceinline__ double ausm_sa_flux(const ZoneDev &z, const V &v, int l, int nm, int np,
                                                double T0, double u, double tdu, double r1, double r2)
 {
-    const double *q = rop + 5 * z.nd;
     double qL, qR;
-    muscl<SLOPE>(z, q[l - 2 * inc], q[l - inc], q[l], q[l + inc], T0, qL, qR);
+    muscl<SLOPE>(z, v.template qm2<DIR>(5, l), v.q(5, nm), v.q(5, l), v.q(5, np), T0, qL, qR);
     const double qm6 = qR * r2, qp6 = qL * r1;
     return u * (qm6 + qp6) - tdu * (qm6 - qp6);
 }
 
 // Roe: first-order states, Roe-averaged normal velocity as dissipation speed (ROE/fluFaceSA.for:2-34)
-__device__ __forceinline__ double roe_sa_flux(const ZoneDev &z, const double *__restrict__ rop, int l, int inc,
-                                              const double tc[3], double s_1)
+template <class V>
+__device__ __forceinline__ double roe_sa_flux(const ZoneDev &z, const V &v, int l, int nm, const double tc[3], double s_1)
 {
-    const int nd = z.nd, nm = l - inc;
-    double p2 = rop[nm + nd], p3 = rop[nm + 2 * nd], p4 = rop[nm + 3 * nd];
-    const double m2 = rop[l + nd], m3 = rop[l + 2 * nd], m4 = rop[l + 3 * nd];
+    double p2 = v.q(1, nm), p3 = v.q(2, nm), p4 = v.q(3, nm);
+    const double m2 = v.q(1, l), m3 = v.q(2, l), m4 = v.q(3, l);
     double n1 = p2 * tc[0] + p3 * tc[1] + p4 * tc[2];
     const double n2 = m2 * tc[0] + m3 * tc[1] + m4 * tc[2];
-    double rp1 = rop[nm], rm1 = rop[l];
-    const double nul = rop[l + 5 * nd], num = rop[nm + 5 * nd];
+    double rp1 = v.q(0, nm), rm1 = v.q(0, l);
+    const double nul = v.q(5, l), num = v.q(5, nm);
     const double qm6 = nul * rm1 * n2, qp6 = num * rp1 * n1;
     const double d6 = nul * rm1 - num * rp1;
     rp1 = sqrt(rp1); rm1 = sqrt(rm1);

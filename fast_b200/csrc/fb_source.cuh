@@ -3,6 +3,7 @@
 // Newton residual assembly (core3as2.for).
 #pragma once
 #include "fb_common.cuh"
+#include "fb_view.cuh"
 
 __device__ __forceinline__ double mulam(const ZoneDev &z, double T)
 {   // S/Compute/mulam.for
@@ -24,12 +25,13 @@ __device__ __forceinline__ double vispalart_cell(const ZoneDev &z, const double 
 }
 
 // SA source of cell l: returns vol*tsource; when STORE the LU diagonal coe(:,6) is updated (nitcfg<=1, implicit)
-template <int MESH>
-__device__ __forceinline__ double sa_source_cell(const ZoneDev &z, const double *__restrict__ rop, int l, int lt,
-                                                 bool store, double coe1)
+// l: cell index in the view, lg: global cell index (wall distance, coe store)
+template <int MESH, class V>
+__device__ __forceinline__ double sa_source_cell(const ZoneDev &z, const V &v, int l, int lg, int lt, bool store, double coe1)
 {
     const int nd = z.nd, nm = z.nm;
-    const int l1 = l + 1, l2 = l - 1, l3 = l + z.incj, l4 = l - z.incj, l5 = l + z.inck, l6 = l - z.inck;
+    const int l1 = v.template up<0>(l), l2 = v.template dn<0>(l), l3 = v.template up<1>(l), l4 = v.template dn<1>(l),
+              l5 = v.template up<2>(l), l6 = v.template dn<2>(l);
     const double c1 = SA_CB2 / SA_SIGMA;
     const double cw1 = (SA_CB1 / SA_CKARM / SA_CKARM) + (1. + SA_CB2) / SA_SIGMA;
     double g[4][3];      // u,v,w,nutilde gradients (x 2 vol)
@@ -40,15 +42,14 @@ __device__ __forceinline__ double sa_source_cell(const ZoneDev &z, const double 
         const double tix = z.tc0[0], tjy = z.tc0[1], tkz = z.tc0[2];
 #pragma unroll
         for (int c = 0; c < 4; c++) {
-            const double *q = rop + (c < 3 ? c + 1 : 5) * nd;
-            const double q0 = q[l];
-            const double u1 = q0 + q[l2], u2 = q0 + q[l3], u3 = q0 + q[l1], u4 = q0 + q[l4], u5 = q0 + q[l5], u6 = q0 + q[l6];
+            const int e_ = c < 3 ? c + 1 : 5;
+            const double q0 = v.q(e_, l);
+            const double u1 = q0 + v.q(e_, l2), u2 = q0 + v.q(e_, l3), u3 = q0 + v.q(e_, l1), u4 = q0 + v.q(e_, l4), u5 = q0 + v.q(e_, l5), u6 = q0 + v.q(e_, l6);
             g[c][0] = (u3 - u1) * tix; g[c][1] = (u2 - u4) * tjy; g[c][2] = (u5 - u6) * tkz;
         }
-        const double *q = rop + 5 * nd;
-        const double q0 = q[l] * rop[l];
-        const double u1 = q0 + q[l2] * rop[l2], u2 = q0 + q[l3] * rop[l3], u3 = q0 + q[l1] * rop[l1],
-                     u4 = q0 + q[l4] * rop[l4], u5 = q0 + q[l5] * rop[l5], u6 = q0 + q[l6] * rop[l6];
+        const double q0 = v.q(5, l) * v.q(0, l);
+        const double u1 = q0 + v.q(5, l2) * v.q(0, l2), u2 = q0 + v.q(5, l3) * v.q(0, l3), u3 = q0 + v.q(5, l1) * v.q(0, l1),
+                     u4 = q0 + v.q(5, l4) * v.q(0, l4), u5 = q0 + v.q(5, l5) * v.q(0, l5), u6 = q0 + v.q(5, l6) * v.q(0, l6);
         h[0] = g[3][0] * (u3 - u1) * tix; h[1] = g[3][1] * (u2 - u4) * tjy; h[2] = g[3][2] * (u5 - u6) * tkz;
     } else if (MESH == 1) {
         vol = __ldg(z.vol + lt);
@@ -57,17 +58,16 @@ __device__ __forceinline__ double sa_source_cell(const ZoneDev &z, const double 
         const double tkz = __ldg(z.tk + lt);
 #pragma unroll
         for (int c = 0; c < 4; c++) {
-            const double *q = rop + (c < 3 ? c + 1 : 5) * nd;
-            const double q0 = q[l];
-            const double u1 = q0 + q[l2], u2 = q0 + q[l3], u3 = q0 + q[l1], u4 = q0 + q[l4], u5 = q0 + q[l5], u6 = q0 + q[l6];
+            const int e_ = c < 3 ? c + 1 : 5;
+            const double q0 = v.q(e_, l);
+            const double u1 = q0 + v.q(e_, l2), u2 = q0 + v.q(e_, l3), u3 = q0 + v.q(e_, l1), u4 = q0 + v.q(e_, l4), u5 = q0 + v.q(e_, l5), u6 = q0 + v.q(e_, l6);
             g[c][0] = (u3 * tix1 - u1 * tix + u2 * tjx1 - u4 * tjx);
             g[c][1] = (u3 * tiy1 - u1 * tiy + u2 * tjy1 - u4 * tjy);
             g[c][2] = (u5 - u6) * tkz;
         }
-        const double *q = rop + 5 * nd;
-        const double q0 = q[l] * rop[l];
-        const double u1 = q0 + q[l2] * rop[l2], u2 = q0 + q[l3] * rop[l3], u3 = q0 + q[l1] * rop[l1],
-                     u4 = q0 + q[l4] * rop[l4], u5 = q0 + q[l5] * rop[l5], u6 = q0 + q[l6] * rop[l6];
+        const double q0 = v.q(5, l) * v.q(0, l);
+        const double u1 = q0 + v.q(5, l2) * v.q(0, l2), u2 = q0 + v.q(5, l3) * v.q(0, l3), u3 = q0 + v.q(5, l1) * v.q(0, l1),
+                     u4 = q0 + v.q(5, l4) * v.q(0, l4), u5 = q0 + v.q(5, l5) * v.q(0, l5), u6 = q0 + v.q(5, l6) * v.q(0, l6);
         h[0] = g[3][0] * (u3 * tix1 - u1 * tix + u2 * tjx1 - u4 * tjx);
         h[1] = g[3][1] * (u3 * tiy1 - u1 * tiy + u2 * tjy1 - u4 * tjy);
         h[2] = g[3][2] * (u5 - u6) * tkz;
@@ -82,17 +82,16 @@ __device__ __forceinline__ double sa_source_cell(const ZoneDev &z, const double 
         }
 #pragma unroll
         for (int c = 0; c < 4; c++) {
-            const double *q = rop + (c < 3 ? c + 1 : 5) * nd;
-            const double q0 = q[l];
-            const double u1 = q0 + q[l2], u2 = q0 + q[l3], u3 = q0 + q[l1], u4 = q0 + q[l4], u5 = q0 + q[l5], u6 = q0 + q[l6];
+            const int e_ = c < 3 ? c + 1 : 5;
+            const double q0 = v.q(e_, l);
+            const double u1 = q0 + v.q(e_, l2), u2 = q0 + v.q(e_, l3), u3 = q0 + v.q(e_, l1), u4 = q0 + v.q(e_, l4), u5 = q0 + v.q(e_, l5), u6 = q0 + v.q(e_, l6);
 #pragma unroll
             for (int e = 0; e < 3; e++)
                 g[c][e] = (u3 * ti1[e] - u1 * ti0[e] + u2 * tj1[e] - u4 * tj0[e] + u5 * tk1[e] - u6 * tk0[e]);
         }
-        const double *q = rop + 5 * nd;
-        const double q0 = q[l] * rop[l];
-        const double u1 = q0 + q[l2] * rop[l2], u2 = q0 + q[l3] * rop[l3], u3 = q0 + q[l1] * rop[l1],
-                     u4 = q0 + q[l4] * rop[l4], u5 = q0 + q[l5] * rop[l5], u6 = q0 + q[l6] * rop[l6];
+        const double q0 = v.q(5, l) * v.q(0, l);
+        const double u1 = q0 + v.q(5, l2) * v.q(0, l2), u2 = q0 + v.q(5, l3) * v.q(0, l3), u3 = q0 + v.q(5, l1) * v.q(0, l1),
+                     u4 = q0 + v.q(5, l4) * v.q(0, l4), u5 = q0 + v.q(5, l5) * v.q(0, l5), u6 = q0 + v.q(5, l6) * v.q(0, l6);
 #pragma unroll
         for (int e = 0; e < 3; e++)
             h[e] = g[3][e] * (u3 * ti1[e] - u1 * ti0[e] + u2 * tj1[e] - u4 * tj0[e] + u5 * tk1[e] - u6 * tk0[e]);
@@ -102,15 +101,16 @@ __device__ __forceinline__ double sa_source_cell(const ZoneDev &z, const double 
     const double rot = sqrt(rotx * rotx + roty * roty + rotz * rotz) * xvol;
     const double anvisc = c1 * (h[0] + h[1] + h[2]) * xvol * xvol;
     // sourceSA_prod_dest.for
-    const double amulam = mulam(z, rop[l + 4 * nd]);
-    const double anulam = rop[l] / amulam;
-    const double anutild = fmax(rop[l + 5 * nd], 1.e-27);
+    const double rho = v.q(0, l);
+    const double amulam = mulam(z, v.q(4, l));
+    const double anulam = rho / amulam;
+    const double anutild = fmax(v.q(5, l), 1.e-27);
     const double chi = fmax(anutild * anulam, 1.e-7);
     const double f1 = 1. / (1. + SA_CV1 / (chi * chi * chi));
     const double f2 = 1. - chi / (1. + chi * f1);
-    const double dist = fmax(z.xmut[l + nd], 1.e-27);
+    const double dist = fmax(z.xmut[lg + nd], 1.e-27);
     double stild = rot + (anutild * f2) / (SA_CKARM * SA_CKARM * dist * dist);
-    const double prod = rop[l] * SA_CB1 * stild * anutild;
+    const double prod = rho * SA_CB1 * stild * anutild;
     stild = fmax(stild, 0.00000000000000000001);
     double r = anutild / (stild * SA_CKARM * SA_CKARM * dist * dist);
     r = fmin(r, 10.);
@@ -118,29 +118,28 @@ __device__ __forceinline__ double sa_source_cell(const ZoneDev &z, const double 
     const double gg = r * (1. + SA_CW2 * r5);
     const double g2 = gg * gg, g6 = g2 * g2 * g2;
     const double fwg = gg * pow((1. + SA_CW3) / (g6 + SA_CW3), 1. / 6.);
-    const double destruc = rop[l] * cw1 * fwg * (anutild / dist) * (anutild / dist);
+    const double destruc = rho * cw1 * fwg * (anutild / dist) * (anutild / dist);
     const double tsource = (prod + anvisc - destruc);
     if (store) {   // sourceSA_LU.for
         const double tsourceb = prod - destruc;
-        double amutild = anutild * rop[l];
+        double amutild = anutild * rho;
         amutild = fmax(amutild, 0.0000000000000001);
         const double tsourcenu = vol * tsourceb / amutild;
-        z.coe[l + 5 * nd] = z.coe[l + 4 * nd] - fmin(tsourcenu, 0.) * coe1;
+        z.coe[lg + 5 * nd] = z.coe[lg + 4 * nd] - fmin(tsourcenu, 0.) * coe1;
     }
     return vol * tsource;
 }
 
-template <int MESH, bool IMPL>
-__device__ __forceinline__ void sa_source(const ZoneDev &z, const double *__restrict__ rop, int l, int lt, int i, int j,
-                                          int k, int nitcfg, double coe1, double *acc)
+template <int MESH, bool IMPL, class V>
+__device__ __forceinline__ void sa_source(const ZoneDev &z, const V &v, int l, int lg, int lt, int nitcfg, double coe1, double *acc)
 {
-    (void)i; (void)j; (void)k;
-    acc[5] += sa_source_cell<MESH>(z, rop, l, lt, IMPL && nitcfg <= 1, coe1);
+    acc[5] += sa_source_cell<MESH>(z, v, l, lg, lt, IMPL && nitcfg <= 1, coe1);
 }
 
 // core3as2.for:37-195: Newton residual from the flux balance and the BDF time terms (conservative variables)
-template <int NEQ>
-__device__ __forceinline__ void implicit_assemble(const ZoneDev &z, const double *__restrict__ r0,
+// r0 (= rop_ssiter) is read through the view v at cell lv; rn / rm at the global cell l
+template <int NEQ, class V>
+__device__ __forceinline__ void implicit_assemble(const ZoneDev &z, const V &v, int lv, const double *r0,
                                                   const double *__restrict__ rn, const double *__restrict__ rm, int l,
                                                   double coe1, double c1, double c2, double c3, double *acc)
 {
@@ -151,7 +150,7 @@ __device__ __forceinline__ void implicit_assemble(const ZoneDev &z, const double
         for (int e = 0; e < NEQ; e++) acc[e] = coe1 * acc[e];
         return;
     }
-    const double a0 = r0[l], a1 = r0[l + nd], a2 = r0[l + 2 * nd], a3 = r0[l + 3 * nd], a4 = r0[l + 4 * nd];
+    const double a0 = v.q(0, lv), a1 = v.q(1, lv), a2 = v.q(2, lv), a3 = v.q(3, lv), a4 = v.q(4, lv);
     const double m0 = rm[l], m1 = rm[l + nd], m2 = rm[l + 2 * nd], m3 = rm[l + 3 * nd], m4 = rm[l + 4 * nd];
     const double roe = a0 * (cv * a4 + 0.5 * (a1 * a1 + a2 * a2 + a3 * a3));
     const double roe_n1 = m0 * (cv * m4 + 0.5 * (m1 * m1 + m2 * m2 + m3 * m3));
@@ -162,7 +161,7 @@ __device__ __forceinline__ void implicit_assemble(const ZoneDev &z, const double
         acc[2] = coe1 * acc[2] + c4 * a2 * a0 + c3 * m2 * m0;
         acc[3] = coe1 * acc[3] + c4 * a3 * a0 + c3 * m3 * m0;
         acc[4] = coe1 * acc[4] + c4 * roe + c3 * roe_n1;
-        if (NEQ == 6) acc[NEQ - 1] = coe1 * acc[NEQ - 1] + c4 * r0[l + 5 * nd] * a0 + c3 * rm[l + 5 * nd] * m0;
+        if (NEQ == 6) acc[NEQ - 1] = coe1 * acc[NEQ - 1] + c4 * v.q(5, lv) * a0 + c3 * rm[l + 5 * nd] * m0;
     } else {
         const double n0 = rn[l], n1 = rn[l + nd], n2 = rn[l + 2 * nd], n3 = rn[l + 3 * nd], n4 = rn[l + 4 * nd];
         const double roe_n = n0 * (cv * n4 + 0.5 * (n1 * n1 + n2 * n2 + n3 * n3));
@@ -172,6 +171,6 @@ __device__ __forceinline__ void implicit_assemble(const ZoneDev &z, const double
         acc[3] = coe1 * acc[3] + c1 * a3 * a0 + c2 * n3 * n0 + c3 * m3 * m0;
         acc[4] = coe1 * acc[4] + c1 * roe + c2 * roe_n + c3 * roe_n1;
         if (NEQ == 6)
-            acc[NEQ - 1] = coe1 * acc[NEQ - 1] + c1 * r0[l + 5 * nd] * a0 + c2 * rn[l + 5 * nd] * n0 + c3 * rm[l + 5 * nd] * m0;
+            acc[NEQ - 1] = coe1 * acc[NEQ - 1] + c1 * v.q(5, lv) * a0 + c2 * rn[l + 5 * nd] * n0 + c3 * rm[l + 5 * nd] * m0;
     }
 }

@@ -1,0 +1,60 @@
+// fb_tma.cu -- TMA tensor maps of the per-zone SoA arrays (rop levels, xmut) for the k-marching rhs kernel k_rhs3.
+//
+// An array a(ni,nj,nk,nvar) (i fastest, variable stride = NDIMDX doubles) is described as a rank-4 FP64 tensor; the box
+// is (36, rows, 1, box_vars): one k plane of a 31 x RJ tile with its 2-cell halo, all variables at once.  Out-of-range
+// box elements are zero-filled by the hardware.  Maps are cached per (pointer, shape): the three time levels rotate
+// by pointer swap, so each zone ends up with three rop maps + one xmut map.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <tuple>
+#include <memory>
+
+typedef CUresult (*EncodeTiled_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiled_t encode_fn()
+{
+    static EncodeTiled_t fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (EncodeTiled_t)p;
+    }();
+    return fn;
+}
+
+const CUtensorMap *fb_tma_map(const double *base, int ni, int nj, int nk, long long var_stride, int nvar_total, int box_rows, int box_vars)
+{
+    typedef std::tuple<const double *, int, int, int, long long, int, int, int> Key;
+    static std::map<Key, std::unique_ptr<CUtensorMap>> cache;
+    const Key key(base, ni, nj, nk, var_stride, nvar_total, box_rows, box_vars);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second.get();
+    std::unique_ptr<CUtensorMap> m;
+    EncodeTiled_t enc = encode_fn();
+    // global strides must be multiples of 16 bytes, the base 16-byte aligned
+    if (enc && base && (ni % 2) == 0 && (var_stride % 2) == 0 && ((uintptr_t)base % 16) == 0) {
+        m.reset(new CUtensorMap);
+        const cuuint64_t dims[4] = {(cuuint64_t)ni, (cuuint64_t)nj, (cuuint64_t)nk, (cuuint64_t)nvar_total};
+        const cuuint64_t strides[3] = {(cuuint64_t)ni * 8, (cuuint64_t)ni * nj * 8, (cuuint64_t)var_stride * 8};
+        const cuuint32_t box[4] = {36, (cuuint32_t)box_rows, 1, (cuuint32_t)box_vars};
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        // a 64-bit element type of the right size; the data are moved, never interpreted
+        const CUresult r = enc(m.get(), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, (void *)base, dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            static bool warned = false;
+            if (!warned) { fprintf(stderr, "fast_b200: cuTensorMapEncodeTiled failed (%d): rhs falls back to the L1 path\n", (int)r); warned = true; }
+            m.reset();
+        }
+    }
+    const CUtensorMap *out = m.get();
+    cache[key] = std::move(m);
+    return out;
+}
