@@ -2,7 +2,8 @@
 import ctypes, os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_PATH = os.path.join(_HERE, 'libfastb200.so')
+# FAST_B200_LIB: another build of the same library (kernel-configuration A/B runs, fast_b200/csrc/Makefile VAR=)
+_PATH = os.environ.get('FAST_B200_LIB') or os.path.join(_HERE, 'libfastb200.so')
 _lib = None
 
 c_dp = ctypes.POINTER(ctypes.c_double)

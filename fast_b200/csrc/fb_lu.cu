@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(LU_NT, 1) k_lu_tile(ZoneDev z, LuTileArgs a)
     for (int i = tid; i < 2 * 3 * L * EX + 6 * 16 * EX; i += LU_NT) exb[i] = 0.;
     __syncthreads();
     const int J = s_tile & 0xffff, K = s_tile >> 16;
-    if (a.dbg && tid == 0) { a.dbg[4 * (K * a.NJ + J)] = gtime(); a.dbg[4 * (K * a.NJ + J) + 3] = smid(); }
+    if (a.dbg && tid == 0) { a.dbg[8 * (K * a.NJ + J)] = gtime(); a.dbg[8 * (K * a.NJ + J) + 3] = smid(); }
     const int bi = a.bi, bj = a.bj, bk = a.bk;
     const int nst = bi + TJ + TK - 2;
     const int nd = z.nd;
@@ -300,9 +300,10 @@ __global__ void __launch_bounds__(LU_NT, 1) k_lu_tile(ZoneDev z, LuTileArgs a)
     // relative to the buffer of the step parity
     const int offj = jj > 0 ? ((lam - 1) * 3 + 1) * EX : -1, offk = kk > 0 ? ((lam - TJ) * 3 + 2) * EX : -1;
     const int mofj = kk * EX, mofk = (8 + jj) * EX;
-    if (a.dbg && tid == 0) a.dbg[4 * (K * a.NJ + J) + 1] = gtime();
+    if (a.dbg && tid == 0) a.dbg[8 * (K * a.NJ + J) + 1] = gtime();
     for (int s = 0; s < nst; s++) {
         __syncthreads();
+        if (a.dbg && tid == 0 && (s == 16 || s == 128 || s == 256 || s == 384)) a.dbg[8 * (K * a.NJ + J) + 4 + (s >> 7)] = gtime();
         const int ii = s - sigma;
         if (!(lvalid && ii >= 0 && ii < bi)) continue;
         const int c = ii / CI, slot = ii % CI;
@@ -388,7 +389,7 @@ __global__ void __launch_bounds__(LU_NT, 1) k_lu_tile(ZoneDev z, LuTileArgs a)
 #undef RING
     }
     __syncthreads();
-    if (a.dbg && tid == 0) a.dbg[4 * (K * a.NJ + J) + 2] = gtime();
+    if (a.dbg && tid == 0) a.dbg[8 * (K * a.NJ + J) + 2] = gtime();
 }
 
 // cell-centred mean normals 0.5*(t_d(l) + t_d(l + d)) of every cell (lu_{i,j,k}_*.for build them on the fly)
@@ -492,25 +493,26 @@ static int run_lu_tiles(const ZoneDev &z, const LuPlan &p, const double *rop, do
     static const bool dbg = getenv("FAST_B200_LU_DEBUG") != nullptr;
     static unsigned long long *d_dbg = nullptr; static int dbg_calls = 0;
     a.dbg = nullptr;
-    if (dbg && dbg_calls < 3) { if (!d_dbg) cudaMalloc(&d_dbg, 2 * 4 * 65536 * sizeof(unsigned long long)); a.dbg = d_dbg; }
+    if (dbg && dbg_calls < 3) { if (!d_dbg) cudaMalloc(&d_dbg, 2 * 8 * 65536 * sizeof(unsigned long long)); a.dbg = d_dbg; }
     a.ticket = p.d_ctl; a.order_mode = lu_match ? 1 : (MESH == 2 ? 2 : 0);
     k_lu_tile<MESH, NEQ, false><<<ntiles, LU_NT, LuCfg<MESH, NEQ, false>::SMEM, st>>>(z, a);
     a.ticket = p.d_ctl + 1; a.order_mode = lu_match ? 1 : 0;
-    if (a.dbg) a.dbg += 4 * 65536;
+    if (a.dbg) a.dbg += 8 * 65536;
     k_lu_tile<MESH, NEQ, true><<<ntiles, LU_NT, LuCfg<MESH, NEQ, true>::SMEM, st>>>(z, a);
     if (a.dbg) {
         cudaStreamSynchronize(st);
-        std::vector<unsigned long long> h(2 * 4 * 65536);
+        std::vector<unsigned long long> h(2 * 8 * 65536);
         cudaMemcpy(h.data(), d_dbg, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
         for (int sw = 0; sw < 2; sw++) {
-            const unsigned long long *q = h.data() + sw * 4 * 65536; unsigned long long t0 = ~0ULL, t1 = 0;
-            for (int t = 0; t < ntiles; t++) { t0 = std::min(t0, q[4 * t]); t1 = std::max(t1, q[4 * t + 2]); }
+            const unsigned long long *q = h.data() + sw * 8 * 65536; unsigned long long t0 = ~0ULL, t1 = 0;
+            for (int t = 0; t < ntiles; t++) { t0 = std::min(t0, q[8 * t]); t1 = std::max(t1, q[8 * t + 2]); }
             fprintf(stderr, "LUDBG sweep %d call %d: NJ %d NK %d tiles %d bi %d total %.1f us\n", sw, dbg_calls, p.NJ, p.NK, ntiles, a.bi, (t1 - t0) * 1e-3);
             for (int t = 0; t < ntiles; t++) {
                 const int J = t % p.NJ, K = t / p.NJ;
                 if (dbg_calls == 1 && (J % 4 == 0) && (K % 2 == 0 || K == p.NK - 1))
-                    fprintf(stderr, "LUDBG   tile J %2d K %2d sm %3llu start %8.1f first %8.1f end %8.1f dur %8.1f\n", J, K, q[4 * t + 3],
-                            (q[4 * t] - t0) * 1e-3, (q[4 * t + 1] - t0) * 1e-3, (q[4 * t + 2] - t0) * 1e-3, (q[4 * t + 2] - q[4 * t]) * 1e-3);
+                    fprintf(stderr, "LUDBG   tile J %2d K %2d sm %3llu start %8.1f s16 %8.1f s128 %8.1f s256 %8.1f s384 %8.1f end %8.1f dur %8.1f\n", J, K, q[8 * t + 3],
+                            (q[8 * t] - t0) * 1e-3, (q[8 * t + 4] - t0) * 1e-3, (q[8 * t + 5] - t0) * 1e-3, (q[8 * t + 6] - t0) * 1e-3, (q[8 * t + 7] - t0) * 1e-3,
+                            (q[8 * t + 2] - t0) * 1e-3, (q[8 * t + 2] - q[8 * t]) * 1e-3);
             }
         }
         dbg_calls++;

@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(32 * (RHS2_RJ + 1)) k_rhs2(ZoneDev z, RhsArgs 
 #define RHS3_MINB 2         // resident CTAs per SM the register allocation aims at
 #endif
 #ifndef RHS3_KC
-#define RHS3_KC 64          // k planes per CTA
+#define RHS3_KC 32          // k planes per CTA (measured: 32 < 64 < 128 on TGV 256^3 and the plate)
 #endif
 
 template <int FLOW, int RJ>
@@ -198,8 +198,11 @@ __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *tm, in
                    "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
 
+// register budget: two resident CTAs per SM where the flux fits 96-128 registers; Roe and the 3dfull metrics need more
+template <int MESH, int SCHEME> struct Rhs3MinB { static constexpr int V = (SCHEME == 5 || MESH == 0) ? 1 : RHS3_MINB; };
+
 template <int MESH, int FLOW, int SCHEME, int SLOPE, bool IMPL, int RJ>
-__global__ void __launch_bounds__(32 * (RJ + 1), RHS3_MINB)
+__global__ void __launch_bounds__(32 * (RJ + 1), Rhs3MinB<MESH, SCHEME>::V)
 k_rhs3(const __grid_constant__ CUtensorMap tm_rop, const __grid_constant__ CUtensorMap tm_mu, ZoneDev z, RhsArgs a)
 {
     using C = Rhs3Cfg<FLOW, RJ>;
