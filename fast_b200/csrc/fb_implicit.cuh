@@ -11,7 +11,7 @@ struct LuPlan {
     int ndefault_rhs = 0;             // leading default-extrapolation windows of the rhs BC table
     int modulo_verif = 0;
     // tile-pipelined wavefront (fb_lu.cu)
-    int tk = 8, NJ = 0, NK = 0;       // tile height in k, tiles per direction of the (j,k) cross-section
+    int tj = 8, tk = 8, NJ = 0, NK = 0;   // tile size in j and k (lines), tiles per direction of the (j,k) cross-section
     int *d_order = nullptr;           // ticket -> tile, i+j+k order
     int *d_ctl = nullptr;             // [ticket lower, ticket upper, error flag, pad]
     double *d_mb = nullptr;           // inter-tile mailboxes: j interfaces then k interfaces
@@ -23,6 +23,9 @@ int  lu_plan_build(LuPlan &p, const ZoneDev &z, const int box[6]);
 void lu_plan_free(LuPlan &p);
 void lu_plan_metrics(LuPlan &p, const ZoneDev &z, cudaStream_t st);   // after the metrics exist
 int  lu_plan_error(const LuPlan &p);
+bool lu_use_lines();                                                  // fb_lu2.cu (default) or fb_lu.cu (FAST_B200_LU=tile)
+void lu2_tile_dims(int mesh, int neq, int &tj, int &tk);
+int  launch_lu_lines(const ZoneDev &z, const LuPlan &p, const double *rop_ssiter, double *rop_out, int lu_match, cudaStream_t st);
 int  launch_lu_tiles(const ZoneDev &z, const LuPlan &p, const double *rop_ssiter, double *rop_out, int lu_match, cudaStream_t st);
 void launch_coe(const ZoneDev &z, const double *rop, int first_it, int lssiter_verif, double *cfl, cudaStream_t st);
 void launch_sa_ring(const ZoneDev &z, const double *rop, cudaStream_t st);

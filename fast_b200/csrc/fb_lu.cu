@@ -85,27 +85,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 // mailbox accesses: strong (volatile) 8-byte accesses served by L2; an entry validates itself word by word
 __device__ __forceinline__ bool mb_empty(unsigned long long v) { return v == LU_EMPTY; }
 
-// B_d(l) . dW(l) with the cell-centred mean normal (tcx,tcy,tcz) of cell l (lu_{i,j,k}_*.for; signe folded into cd).
-// The reference spells out the 5x5 flux Jacobian; the product is evaluated here in its factored form
-//   theta = n.dm - qn drho,  dp = (g-1)(q2 drho - q.dm + dE),  A dW = [n.dm, qn dm + q theta + n dp, qn (dE + dp) + h theta]
-// (identical algebra, ~4x fewer FP64 operations, differences at round-off level).
-template <int NEQ>
-__device__ __forceinline__ void lu_prod(double tcx, double tcy, double tcz, double u, double v, double w, double t,
-                                        double cd, double gam, double cp, const double *d, double *b)
-{
-    const double gamm1 = gam - 1.;
-    const double q2 = .5 * (u * u + v * v + w * w), h = cp * t + q2;
-    const double qn = tcx * u + tcy * v + tcz * w;
-    const double ndm = tcx * d[1] + tcy * d[2] + tcz * d[3];
-    const double theta = ndm - qn * d[0];
-    const double dp = gamm1 * ((q2 * d[0] - (u * d[1] + v * d[2] + w * d[3])) + d[4]);
-    b[0] = ndm + cd * d[0];
-    b[1] = (qn * d[1] + u * theta) + (tcx * dp + cd * d[1]);
-    b[2] = (qn * d[2] + v * theta) + (tcy * dp + cd * d[2]);
-    b[3] = (qn * d[3] + w * theta) + (tcz * dp + cd * d[3]);
-    b[4] = (qn * (d[4] + dp) + h * theta) + cd * d[4];
-    if (NEQ == 6) b[NEQ - 1] = (qn + cd) * d[NEQ - 1];
-}
+#include "fb_lu_prod.cuh"
 
 template <int MESH, int NEQ, bool UPPER>
 __global__ void __launch_bounds__(LU_NT, 1) k_lu_tile(ZoneDev z, LuTileArgs a)
@@ -432,12 +412,14 @@ int lu_plan_build(LuPlan &p, const ZoneDev &z, const int box[6])
     for (int i = 0; i < 6; i++) p.box[i] = box[i];
     const int bi = box[1] - box[0] + 1, bj = box[3] - box[2] + 1, bk = box[5] - box[4] + 1;
     p.nplanes = bi + bj + bk - 2;
-    p.tk = lu_tile_tk(z.typ, z.neq);
-    p.NJ = (bj + LU_TJ - 1) / LU_TJ; p.NK = (bk + p.tk - 1) / p.tk;
+    if (lu_use_lines()) lu2_tile_dims(z.typ, z.neq, p.tj, p.tk);
+    else { p.tj = LU_TJ; p.tk = lu_tile_tk(z.typ, z.neq); }
+    p.NJ = (bj + p.tj - 1) / p.tj; p.NK = (bk + p.tk - 1) / p.tk;
     std::vector<int> ord;
     for (int K = 0; K < p.NK; K++) for (int J = 0; J < p.NJ; J++) ord.push_back(J | (K << 16));
     std::stable_sort(ord.begin(), ord.end(), [](int a, int b) { return (a & 0xffff) + (a >> 16) < (b & 0xffff) + (b >> 16); });
-    if (cudaMalloc(&p.d_order, ord.size() * sizeof(int)) != cudaSuccess) return 1;
+    if (cudaMalloc(&p.d_order, (ord.size() + 16) * sizeof(int)) != cudaSuccess) return 1;   // + padding: idle mailbox threads read it as a dummy
+    cudaMemset(p.d_order, 0, (ord.size() + 16) * sizeof(int));
     cudaMemcpy(p.d_order, ord.data(), ord.size() * sizeof(int), cudaMemcpyHostToDevice);
     if (cudaMalloc(&p.d_ctl, 4 * sizeof(int)) != cudaSuccess) return 1;
     cudaMemset(p.d_ctl, 0, 4 * sizeof(int));
@@ -520,8 +502,17 @@ static int run_lu_tiles(const ZoneDev &z, const LuPlan &p, const double *rop, do
     return 3;
 }
 
+bool lu_use_lines()
+{   // default: the 4-lanes-per-line tile kernel of this file; FAST_B200_LU=line selects the one-thread-per-line kernel
+    // (fb_lu2.cu: 5x fewer instructions per cell, parity-green, but its 8-byte cp.async refill of 128 lines saturates the
+    // LSU -- measured 3.6 ms per sweep on C3 against 1.0 ms here; it waits for a TMA-staged ring)
+    static const bool lines = [] { const char *e = getenv("FAST_B200_LU"); return e && e[0] == 'l'; }();
+    return lines;
+}
+
 int launch_lu_tiles(const ZoneDev &z, const LuPlan &p, const double *rop, double *rop_out, int lu_match, cudaStream_t st)
 {
+    if (lu_use_lines()) return launch_lu_lines(z, p, rop, rop_out, lu_match, st);
     if (z.neq == 6) {
         if (z.typ == 0) return run_lu_tiles<0, 6>(z, p, rop, rop_out, lu_match, st);
         if (z.typ == 1) return run_lu_tiles<1, 6>(z, p, rop, rop_out, lu_match, st);

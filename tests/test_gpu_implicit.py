@@ -23,6 +23,10 @@ CASES = {
     'sa_plate_full': lambda: synth.case_flatplate(n=(20, 12, 6), sheared=True),
     'sa_plate_roe': lambda: synth.case_flatplate(n=(16, 12, 4), scheme='roe'),
     'sa_plate_blocks': lambda: synth.case_flatplate(n=(24, 16, 8), nblocks=(2, 2, 2)),
+    # larger than one LU tile (16 x 8 lines, 16 x 6 for 3dfull SA) in both j and k: inter-tile mailboxes, ragged last tiles
+    'sa_plate_homo_tiles': lambda: synth.case_flatplate(n=(20, 20, 20)),
+    'sa_plate_full_tiles': lambda: synth.case_flatplate(n=(18, 20, 16), sheared=True),
+    'lamin_full_roe_tiles': _box(n=8, n3=(14, 22, 20), scheme='roe', model='NSLaminar', ReInf=1000., deform_amp=0.02, temporal='implicit'),
     'multiblock_roe_lumatch': lambda: synth.case_multiblock(nblk=(2, 2, 1), n=8),
     'multiblock_explicit': lambda: synth.case_multiblock(nblk=(2, 1, 2), n=8, temporal='explicit', scheme='senseur'),
 }
