@@ -27,6 +27,16 @@ def peaks():
     return 6650., 'fallback'
 
 
+def measured_traffic(workload, kernel):
+    """DRAM bytes per launch of `kernel` on `workload` from the committed ncu --set full capture (profiles/traffic.json,
+    written by tools/ncu_traffic.py from dram__bytes_read.sum + dram__bytes_write.sum); None when no capture exists."""
+    p = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if not os.path.exists(p): return None
+    with open(p) as f: t = json.load(f)
+    e = t.get(workload, {}).get(kernel)
+    return None if e is None else e['bytes_per_launch']
+
+
 def make_case(workload, n=None, rank=0, world=1):
     from fast_b200 import synth
     if workload == 'tgv256':
@@ -41,6 +51,14 @@ def make_case(workload, n=None, rank=0, world=1):
         t, j = synth.case_multiblock(nblk=(2, 2, 2), n=n, modulo_verif=1000)
         return t, j, '8 x %d^3 blocks, match joins, Roe o3, implicit LU-SGS 3 sub-iterations, lu_match (BASELINE configs[3])' % n
     raise ValueError(workload)
+
+
+def _desc_only(workload):
+    d = {'tgv256': 'laminar TGV 256^3, SENSOR o3, explicit RK3 (BASELINE configs[1])',
+         'plate': 'RANS-SA flat plate 512x256x64 (3dhomo), AUSM o3, implicit LU-SGS 5 sub-iterations, local dt (BASELINE configs[2])',
+         'multiblock': '8 x 128^3 blocks, match joins, Roe o3, implicit LU-SGS 3 sub-iterations, lu_match (BASELINE configs[3])'}
+    return None, None, d[workload]
+make_case.__wrapped_desc__ = _desc_only
 
 
 def algorithmic_bytes(pi):
@@ -103,10 +121,13 @@ def run_reference(args):
         r, nth, sample, nss = cpu_oracle_rate(args.workload, seconds=max(2., 60. / (args.warmup + args.steps)))
         if s >= args.warmup: rates.append(r)
     v = float(numpy.mean(rates))
+    _, _, full_desc = make_case.__wrapped_desc__(args.workload)
     out = {'impl': 'reference', 'metric': 'FP64 cell-updates/sec', 'value': v, 'unit': 'Mcell.it/s', 'n_gpus': args.gpus,
            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': None, 'higher_is_better': True, 'scaling': 'weak',
            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-           'config': {'workload': sample, 'note': 'CPU oracle (port of the reference Fortran; the reference itself cannot be built here)'},
+           'config': {'workload': full_desc, 'sample': sample,
+                      'note': 'CPU oracle (port of the reference Fortran; the reference itself cannot be built here: no Fortran compiler, no '
+                              'Cassiopee), all host threads, bounded sample of the workload (same scheme, smaller mesh)'},
            'cpu_baseline': {'value': v, 'unit': 'Mcell.it/s', 'cores': nth, 'kind': 'port', 'sample': sample},
            'e2e': {'value': v, 'unit': 'Mcell.it/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(out))
@@ -180,14 +201,20 @@ def run_gpu(args):
     b_sub, b_rhs = algorithmic_bytes(pi0)
     peak, pk = peaks()
     cz = cells / len(zones)
+    cnt = {}
+    for name in ('rhs_tma', 'rhs_l1', 'lu_line'):
+        v = ctypes.c_longlong(0); _lib.check(L.fb_counter(name.encode(), ctypes.byref(v))); cnt[name] = int(v.value)
     if tm['lu'] > tm['rhs']:
-        kern, nl, bpl = 'k_lu_tile', 2 * args.steps * nsub * len(zones), (b_sub - b_rhs) / 2.   # lower + upper launch
+        kern = 'k_lu_line' if cnt['lu_line'] else 'k_lu_tile'
+        nl, bpl = 2 * args.steps * nsub * len(zones), (b_sub - b_rhs) / 2.   # lower + upper launch
         avg_ms = tm['lu'] / nl
     else:
-        kern, nl, bpl = 'k_rhs2', args.steps * nsub * len(zones), b_rhs
+        kern = 'k_rhs3' if cnt['rhs_tma'] >= cnt['rhs_l1'] else 'k_rhs2'
+        nl, bpl = args.steps * nsub * len(zones), b_rhs
         avg_ms = tm['rhs'] / nl
     ach = cz * bpl / (avg_ms * 1e-3) / 1e9
-    roof = {'bound': 'hbm', 'kernel': kern, 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'traffic': None,
+    roof = {'bound': 'hbm', 'kernel': kern, 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
+            'traffic': measured_traffic(args.workload, kern) if world == 1 else None,
             'peak_source': pk + ' (MEASURED_PEAKS.json hbm_gbs)' if pk == 'measured' else pk, 'bytes_per_cell_per_launch': bpl,
             'avg_launch_ms': avg_ms,
             'whole_subiteration': {'bytes_per_cell_update': b_sub, 'GBs': cells_total * b_sub * nsub * args.steps / (ms * 1e-3) / 1e9,

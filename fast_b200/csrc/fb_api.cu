@@ -576,6 +576,15 @@ int fb_timing_get(fb_solver *s, const char *name, double *ms, long long *launche
     for (int i = 0; i < 6; i++) if (!strcmp(name, TNAMES[i])) { if (ms) *ms = s->tm[i].ms; if (launches) *launches = s->launches; return FB_OK; }
     return fail(FB_EINVAL, "unknown timer name");
 }
+extern long long g_fb_rhs_launches[2];
+int fb_counter(const char *name, long long *out)
+{
+    if (!name || !out) return fail(FB_EINVAL, "null");
+    if (!strcmp(name, "rhs_tma")) { *out = g_fb_rhs_launches[0]; return FB_OK; }
+    if (!strcmp(name, "rhs_l1")) { *out = g_fb_rhs_launches[1]; return FB_OK; }
+    if (!strcmp(name, "lu_line")) { *out = lu_use_lines() ? 1 : 0; return FB_OK; }
+    return fail(FB_EINVAL, "unknown counter");
+}
 static int check_lu(fb_solver *s)
 {
     for (auto &z : s->z) if (z.d.itypcp <= 1 && lu_plan_error(z.lu))

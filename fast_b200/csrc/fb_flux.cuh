@@ -221,9 +221,10 @@ __device__ __forceinline__ double visc_face(const ZoneDev &z, const V &v, int l,
 
 #include "fb_sa.cuh"
 
-// l: cell index in the view v; lg: the reference's global cell index (SENSOR switch, stores); lt: metric index
+// l: cell index in the view v; wigb: SENSOR switch byte of the cell (bit d = lower face in direction d; only read
+// for SCHEME == 2, loaded once per cell by the caller, early, so that its latency is hidden); lt: metric index
 template <int MESH, int FLOW, int SCHEME, int SLOPE, int DIR, class V>
-__device__ __forceinline__ void face_flux(const ZoneDev &z, const V &vw, int l, int lg, int lt, double *flu)
+__device__ __forceinline__ void face_flux(const ZoneDev &z, const V &vw, int l, unsigned wigb, int lt, double *flu)
 {
     constexpr int NEQ = FLOW == 3 ? 6 : 5;
     double tc[3], s;
@@ -296,7 +297,7 @@ __device__ __forceinline__ void face_flux(const ZoneDev &z, const V &vw, int l, 
             u = 0.25 * (qn1 + qn2) - tam1 * (p2 - p1);
             tdu = fmax(fabs(u), z.c1 * s) * z.wig_cte;
         } else {
-            const double wg = (double)((z.wigb[lg] >> DIR) & 1);
+            const double wg = (double)((wigb >> DIR) & 1);
             u = 0.25 * (qn1 + qn2) - z.c2 * s * (p2 - p1) * (z.opt0 * wg + 1. - z.opt0);
             tdu = fmax(fabs(u), z.c1 * s) * wg;
         }

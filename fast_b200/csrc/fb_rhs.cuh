@@ -85,9 +85,22 @@ __global__ void __launch_bounds__(32 * (RHS2_RJ + 1)) k_rhs2(ZoneDev z, RhsArgs 
         const int l = inddm(z, i, j, k);
         const int lt = MESH == 2 ? 0 : indmtr(z, i, j, k);
         const bool last = k == k1 + 1;
+        // early global loads of the cell of plane k: consumed after the k-face flux, which hides their latency
+        double accn[NEQ], coe1 = 0.;
+#pragma unroll
+        for (int e = 0; e < NEQ; e++) accn[e] = 0.;
+        if (cell && !last) {
+            if (!(IMPL || a.nitcfg == 1)) {
+#pragma unroll
+                for (int e = 0; e < NEQ; e++) accn[e] = z.drodm[l + e * nd];
+            }
+            if (IMPL) coe1 = z.coe[l];
+            else coe1 = MESH == 2 ? z.dtc / z.vol0 : z.dtc / __ldg(z.vol + lt);
+        }
+        const unsigned wg = (SCHEME == 2 && (cell || fi || fj)) ? z.wigb[l] : 0u;
         // lower k face: finishes the cell of plane k-1, starts the cell of plane k
         if (cell) {
-            face_flux<MESH, FLOW, SCHEME, SLOPE, 2>(z, v, l, l, lt, f);
+            face_flux<MESH, FLOW, SCHEME, SLOPE, 2>(z, v, l, wg, lt, f);
             if (k > k0) {
 #pragma unroll
                 for (int e = 0; e < NEQ; e++) acc[e] -= f[e];
@@ -95,18 +108,10 @@ __global__ void __launch_bounds__(32 * (RHS2_RJ + 1)) k_rhs2(ZoneDev z, RhsArgs 
             }
         }
         if (last) break;      // uniform
-        double coe1 = 0.;
         if (cell) {
             // init_rhs.for:85-129
-            if (IMPL || a.nitcfg == 1) {
 #pragma unroll
-                for (int e = 0; e < NEQ; e++) acc[e] = 0.;
-            } else {
-#pragma unroll
-                for (int e = 0; e < NEQ; e++) acc[e] = z.drodm[l + e * nd] * a.coefH;
-            }
-            if (IMPL) coe1 = z.coe[l];
-            else coe1 = MESH == 2 ? z.dtc / z.vol0 : z.dtc / __ldg(z.vol + lt);
+            for (int e = 0; e < NEQ; e++) acc[e] = (IMPL || a.nitcfg == 1) ? 0. : accn[e] * a.coefH;
             if (FLOW == 3) sa_source<MESH, IMPL>(z, v, l, l, lt, a.nitcfg, coe1, acc);
 #pragma unroll
             for (int e = 0; e < NEQ; e++) acc[e] += f[e];
@@ -114,7 +119,7 @@ __global__ void __launch_bounds__(32 * (RHS2_RJ + 1)) k_rhs2(ZoneDev z, RhsArgs 
         coe1p = coe1;
         // lower j face -> shared memory
         if (fj) {
-            face_flux<MESH, FLOW, SCHEME, SLOPE, 1>(z, v, l, l, lt, f);
+            face_flux<MESH, FLOW, SCHEME, SLOPE, 1>(z, v, l, wg, lt, f);
 #pragma unroll
             for (int e = 0; e < NEQ; e++) sFj[k & 1][m][e][li] = f[e];
             if (cell) {
@@ -123,7 +128,7 @@ __global__ void __launch_bounds__(32 * (RHS2_RJ + 1)) k_rhs2(ZoneDev z, RhsArgs 
             }
         }
         // lower i face; the upper one comes from the next lane
-        if (fi) face_flux<MESH, FLOW, SCHEME, SLOPE, 0>(z, v, l, l, lt, f);
+        if (fi) face_flux<MESH, FLOW, SCHEME, SLOPE, 0>(z, v, l, wg, lt, f);
         else {
 #pragma unroll
             for (int e = 0; e < NEQ; e++) f[e] = 0.;
@@ -170,8 +175,8 @@ struct Rhs3Cfg {
     static constexpr int NV = NEQ + (FLOW >= 2 ? 1 : 0);
     static constexpr int BI = 36, ROWS = RJ + 4;          // box: 2 halo columns / rows on each side (+1 face lane, +1 pad)
     static constexpr int RS = BI, VS = RS * ROWS;
-    static constexpr int PS = (NV * VS + 15) / 16 * 16;   // slot stride: TMA destinations must be 128-byte aligned
-    static_assert((NEQ * VS) % 16 == 0, "the mu box lands behind the rop box: NEQ*VS must be a multiple of 16 doubles");
+    static constexpr int MUOFF = (NEQ * VS + 15) / 16 * 16;                    // TMA destinations must be 128-byte aligned
+    static constexpr int PS = (MUOFF + (NV - NEQ) * VS + 15) / 16 * 16;       // slot stride
     static constexpr int NT = 32 * (RJ + 1);
     static constexpr unsigned TX = (unsigned)(NV * VS * sizeof(double));   // bytes one plane brings in
     static constexpr size_t SMEM = (size_t)(RHS3_NS * PS + 2 * (RJ + 1) * NEQ * 32) * sizeof(double) + RHS3_NS * sizeof(unsigned long long);
@@ -228,7 +233,7 @@ k_rhs3(const __grid_constant__ CUtensorMap tm_rop, const __grid_constant__ CUten
         const int slot = (p - pfirst) % NS;
         mbar_expect_tx(bar + slot, C::TX);
         tma_load_4d(ring + slot * PS, &tm_rop, ca, cb, p + z.nfk - 1, 0, bar + slot);
-        if (FLOW >= 2) tma_load_4d(ring + slot * PS + NEQ * VS, &tm_mu, ca, cb, p + z.nfk - 1, 0, bar + slot);
+        if (FLOW >= 2) tma_load_4d(ring + slot * PS + C::MUOFF, &tm_mu, ca, cb, p + z.nfk - 1, 0, bar + slot);
     };
     if (leader) {
         for (int s = 0; s < NS; s++) mbar_init(bar + s, 1);
@@ -254,15 +259,32 @@ k_rhs3(const __grid_constant__ CUtensorMap tm_rop, const __grid_constant__ CUten
     for (int k = k0; k <= k1 + 1; k++) {
         const int pk = k - pfirst;                       // >= 1
         const int sk = pk % NS, su = (pk + 1) % NS, sd = (pk - 1) % NS;
+        // early global loads of the cell of plane k (old rhs for the RK accumulation, dt/vol, SENSOR byte): issued
+        // before the wait and the k-face flux, which hide their latency
+        double accn[NEQ], coe1 = 0.;
+#pragma unroll
+        for (int e = 0; e < NEQ; e++) accn[e] = 0.;
+        {
+            const int lg = inddm(z, i, j, k);
+            if (cell && k <= k1) {
+                if (!(IMPL || a.nitcfg == 1)) {
+#pragma unroll
+                    for (int e = 0; e < NEQ; e++) accn[e] = z.drodm[lg + e * nd];
+                }
+                if (IMPL) coe1 = z.coe[lg];
+                else coe1 = MESH == 2 ? z.dtc / z.vol0 : z.dtc / __ldg(z.vol + indmtr(z, i, j, k));
+            }
+        }
+        const unsigned wg = (SCHEME == 2 && (cell || fi || fj)) ? z.wigb[inddm(z, i, j, k)] : 0u;
         mbar_wait(bar + su, ((pk + 1) / NS) & 1);        // plane k+1 has landed
-        SView<RS, VS, NEQ> v;
+        SView<RS, VS, NEQ, C::MUOFF> v;
         v.s = ring; v.kup = (su - sk) * PS; v.kdn = (sd - sk) * PS; v.km2 = km2;
         const int ls = sk * PS + lcol;
         const int l = inddm(z, i, j, k);
         const int lt = MESH == 2 ? 0 : indmtr(z, i, j, k);
         const bool last = k == k1 + 1;
         if (cell) {
-            face_flux<MESH, FLOW, SCHEME, SLOPE, 2>(z, v, ls, l, lt, f);
+            face_flux<MESH, FLOW, SCHEME, SLOPE, 2>(z, v, ls, wg, lt, f);
             if (k > k0) {
 #pragma unroll
                 for (int e = 0; e < NEQ; e++) acc[e] -= f[e];
@@ -270,24 +292,16 @@ k_rhs3(const __grid_constant__ CUtensorMap tm_rop, const __grid_constant__ CUten
             }
         }
         if (last) break;      // uniform; no TMA is in flight any more (plane k1+2 was waited for above)
-        double coe1 = 0.;
         if (cell) {
-            if (IMPL || a.nitcfg == 1) {
 #pragma unroll
-                for (int e = 0; e < NEQ; e++) acc[e] = 0.;
-            } else {
-#pragma unroll
-                for (int e = 0; e < NEQ; e++) acc[e] = z.drodm[l + e * nd] * a.coefH;
-            }
-            if (IMPL) coe1 = z.coe[l];
-            else coe1 = MESH == 2 ? z.dtc / z.vol0 : z.dtc / __ldg(z.vol + lt);
+            for (int e = 0; e < NEQ; e++) acc[e] = (IMPL || a.nitcfg == 1) ? 0. : accn[e] * a.coefH;
             if (FLOW == 3) sa_source<MESH, IMPL>(z, v, ls, l, lt, a.nitcfg, coe1, acc);
 #pragma unroll
             for (int e = 0; e < NEQ; e++) acc[e] += f[e];
         }
         coe1p = coe1;
         if (fj) {
-            face_flux<MESH, FLOW, SCHEME, SLOPE, 1>(z, v, ls, l, lt, f);
+            face_flux<MESH, FLOW, SCHEME, SLOPE, 1>(z, v, ls, wg, lt, f);
 #pragma unroll
             for (int e = 0; e < NEQ; e++) sFj[k & 1][m][e][li] = f[e];
             if (cell) {
@@ -295,7 +309,7 @@ k_rhs3(const __grid_constant__ CUtensorMap tm_rop, const __grid_constant__ CUten
                 for (int e = 0; e < NEQ; e++) acc[e] += f[e];
             }
         }
-        if (fi) face_flux<MESH, FLOW, SCHEME, SLOPE, 0>(z, v, ls, l, lt, f);
+        if (fi) face_flux<MESH, FLOW, SCHEME, SLOPE, 0>(z, v, ls, wg, lt, f);
         else {
 #pragma unroll
             for (int e = 0; e < NEQ; e++) f[e] = 0.;
@@ -354,12 +368,15 @@ static bool launch_rhs3_t(const ZoneDev &z, const RhsArgs &a, bool impl, cudaStr
     return true;
 }
 
+extern long long g_fb_rhs_launches[2];
+
 template <int MESH, int FLOW, int SCHEME, int SLOPE>
 static void launch_rhs_t(const ZoneDev &z, const RhsArgs &a, bool impl, cudaStream_t st)
 {
     static const bool l1path = [] { const char *e = getenv("FAST_B200_RHS"); return e && e[0] == '2'; }();   // A/B switch
-    if (!l1path && launch_rhs3_t<MESH, FLOW, SCHEME, SLOPE>(z, a, impl, st)) return;
+    if (!l1path && launch_rhs3_t<MESH, FLOW, SCHEME, SLOPE>(z, a, impl, st)) { g_fb_rhs_launches[0]++; return; }
     launch_rhs2_t<MESH, FLOW, SCHEME, SLOPE>(z, a, impl, st);
+    g_fb_rhs_launches[1]++;
 }
 template <int MESH, int FLOW, int SCHEME>
 static void launch_rhs_s(const ZoneDev &z, const RhsArgs &a, bool impl, cudaStream_t st)

@@ -151,7 +151,12 @@ __device__ __forceinline__ void implicit_assemble(const ZoneDev &z, const V &v, 
         return;
     }
     const double a0 = v.q(0, lv), a1 = v.q(1, lv), a2 = v.q(2, lv), a3 = v.q(3, lv), a4 = v.q(4, lv);
-    const double m0 = rm[l], m1 = rm[l + nd], m2 = rm[l + 2 * nd], m3 = rm[l + 3 * nd], m4 = rm[l + 4 * nd];
+    // level n-1 only enters with BDF2 (c3 != 0): first-order / local time stepping skips its loads (0 * W(n-1) = 0)
+    double m0 = 0., m1 = 0., m2 = 0., m3 = 0., m4 = 0., m5 = 0.;
+    if (c3 != 0.) {
+        m0 = rm[l]; m1 = rm[l + nd]; m2 = rm[l + 2 * nd]; m3 = rm[l + 3 * nd]; m4 = rm[l + 4 * nd];
+        if (NEQ == 6) m5 = rm[l + 5 * nd];
+    }
     const double roe = a0 * (cv * a4 + 0.5 * (a1 * a1 + a2 * a2 + a3 * a3));
     const double roe_n1 = m0 * (cv * m4 + 0.5 * (m1 * m1 + m2 * m2 + m3 * m3));
     if (first) {
@@ -161,7 +166,7 @@ __device__ __forceinline__ void implicit_assemble(const ZoneDev &z, const V &v, 
         acc[2] = coe1 * acc[2] + c4 * a2 * a0 + c3 * m2 * m0;
         acc[3] = coe1 * acc[3] + c4 * a3 * a0 + c3 * m3 * m0;
         acc[4] = coe1 * acc[4] + c4 * roe + c3 * roe_n1;
-        if (NEQ == 6) acc[NEQ - 1] = coe1 * acc[NEQ - 1] + c4 * v.q(5, lv) * a0 + c3 * rm[l + 5 * nd] * m0;
+        if (NEQ == 6) acc[NEQ - 1] = coe1 * acc[NEQ - 1] + c4 * v.q(5, lv) * a0 + c3 * m5 * m0;
     } else {
         const double n0 = rn[l], n1 = rn[l + nd], n2 = rn[l + 2 * nd], n3 = rn[l + 3 * nd], n4 = rn[l + 4 * nd];
         const double roe_n = n0 * (cv * n4 + 0.5 * (n1 * n1 + n2 * n2 + n3 * n3));
@@ -171,6 +176,6 @@ __device__ __forceinline__ void implicit_assemble(const ZoneDev &z, const V &v, 
         acc[3] = coe1 * acc[3] + c1 * a3 * a0 + c2 * n3 * n0 + c3 * m3 * m0;
         acc[4] = coe1 * acc[4] + c1 * roe + c2 * roe_n + c3 * roe_n1;
         if (NEQ == 6)
-            acc[NEQ - 1] = coe1 * acc[NEQ - 1] + c1 * v.q(5, lv) * a0 + c2 * rn[l + 5 * nd] * n0 + c3 * rm[l + 5 * nd] * m0;
+            acc[NEQ - 1] = coe1 * acc[NEQ - 1] + c1 * v.q(5, lv) * a0 + c2 * rn[l + 5 * nd] * n0 + c3 * m5 * m0;
     }
 }

@@ -58,3 +58,6 @@ const CUtensorMap *fb_tma_map(const double *base, int ni, int nj, int nk, long l
     cache[key] = std::move(m);
     return out;
 }
+
+// launch counters of the two rhs paths (fb_counter in the C ABI; bench.py names the kernel it times from them)
+long long g_fb_rhs_launches[2] = {0, 0};   // [0] k_rhs3 (TMA ring), [1] k_rhs2 (L1 path)

@@ -20,13 +20,13 @@ struct GView {
     template <int D> __device__ __forceinline__ double qm2(int e, int l) const { return rop[l - 2 * (D == 0 ? 1 : (D == 1 ? incj : inck)) + e * nd]; }
 };
 
-template <int RS, int VS, int NEQ>
+template <int RS, int VS, int NEQ, int MUOFF>
 struct SView {
     const double *s;          // shared-memory ring
     int kup, kdn;             // offset (doubles) from the slot of plane k to the slots of planes k+1 / k-1
     const double *km2;        // register array: own column at plane k-2
     __device__ __forceinline__ double q(int e, int l) const { return s[l + e * VS]; }
-    __device__ __forceinline__ double mu(int l) const { return s[l + NEQ * VS]; }
+    __device__ __forceinline__ double mu(int l) const { return s[l + MUOFF]; }
     template <int D> __device__ __forceinline__ int up(int l) const { return l + (D == 0 ? 1 : (D == 1 ? RS : kup)); }
     template <int D> __device__ __forceinline__ int dn(int l) const { return l - (D == 0 ? 1 : (D == 1 ? RS : -kdn)); }
     template <int D> __device__ __forceinline__ double qm2(int e, int l) const { return D == 2 ? km2[e] : s[l - 2 * (D == 0 ? 1 : RS) + e * VS]; }

@@ -85,6 +85,10 @@ int fb_timing_enable(fb_solver *s, int on);
 int fb_timing_reset(fb_solver *s);
 int fb_timing_get(fb_solver *s, const char *name, double *ms, long long *launches);
 int fb_sync(fb_solver *s);
+/* Which kernels ran (process-wide): "rhs_tma" / "rhs_l1" = launches of the TMA-staged (k_rhs3) and of the L1-path
+ * (k_rhs2) residual kernel, "lu_line" = 1 when the one-thread-per-line LU kernel is selected.  New with this library
+ * (no reference counterpart); bench.py names the kernel it reports a roofline for from it. */
+int fb_counter(const char *name, long long *out);
 /* Device pointer of a zone's state block (uintptr) so the Python host can hand halo buffers to
  * torch.distributed/NCCL without a host copy. */
 unsigned long long fb_zone_device_ptr(fb_solver *s, int nd, int level);
