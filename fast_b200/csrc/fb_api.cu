@@ -435,7 +435,8 @@ static int gsdr3(fb_solver *s, int nitcfg, int nssiter, int nitrun, int first_it
                 Scope c(s, 4);
                 if (z.d.iflow >= 2) { launch_invist(z.d, ssiter, implicit || z.d.iflow == 3 ? z.d.nf : 1, s->st); s->launches++; }
                 if (implicit) { launch_coe(z.d, ssiter, first_it, lssiter_verif, z.cflv, s->st); s->launches++; }
-                if (z.d.kflu == 2) { launch_sensor(z.d, ssiter, s->st); s->launches++; }
+                // SENSOR switch (wiggle2001.for) at nstep 1 (src_term.for:258-266)
+                if (z.d.kflu == 2 && !fb_sensor_fused()) { launch_sensor(z.d, ssiter, s->st); s->launches++; }
             }
             {
                 Scope r(s, 0);

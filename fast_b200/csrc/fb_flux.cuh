@@ -223,8 +223,11 @@ __device__ __forceinline__ double visc_face(const ZoneDev &z, const V &v, int l,
 
 // l: cell index in the view v; wigb: SENSOR switch byte of the cell (bit d = lower face in direction d; only read
 // for SCHEME == 2, loaded once per cell by the caller, early, so that its latency is hidden); lt: metric index
+// wcomp (SCHEME == 2, first sub-iteration): the switch of this face is evaluated here from the MUSCL stencil that is
+// already in registers (SENSOR/wiggle2001.for + wiggle.for: 1 when some primitive variable has two consecutive sign
+// changes of its differences across the face) and OR-ed into wigb; the caller stores the byte for the later stages.
 template <int MESH, int FLOW, int SCHEME, int SLOPE, int DIR, class V>
-__device__ __forceinline__ void face_flux(const ZoneDev &z, const V &vw, int l, unsigned wigb, int lt, double *flu)
+__device__ __forceinline__ void face_flux(const ZoneDev &z, const V &vw, int l, unsigned &wigb, bool wcomp, int lt, double *flu)
 {
     constexpr int NEQ = FLOW == 3 ? 6 : 5;
     double tc[3], s;
@@ -232,9 +235,20 @@ __device__ __forceinline__ void face_flux(const ZoneDev &z, const V &vw, int l, 
     const int nm = vw.template dn<DIR>(l), np = vw.template up<DIR>(l);
     const double T0 = vw.q(4, l);
     double qL[NEQ], qR[NEQ];
+    // wiggle.for: test = min over the variables of sign(1,qm) + sign(1,qp), switch on when test < -1e-12, i.e. when for
+    // some variable BOTH products carry the sign bit (sign() copies the sign bit, -0 included): an AND of sign bits
+    int wsign = 0;
 #pragma unroll
-    for (int e = 0; e < 5; e++)
-        muscl<SLOPE>(z, vw.template qm2<DIR>(e, l), vw.q(e, nm), vw.q(e, l), vw.q(e, np), T0, qL[e], qR[e]);
+    for (int e = 0; e < 5; e++) {
+        const double s0 = vw.template qm2<DIR>(e, l), s1 = vw.q(e, nm), s2 = vw.q(e, l), s3 = vw.q(e, np);
+        muscl<SLOPE>(z, s0, s1, s2, s3, T0, qL[e], qR[e]);
+        if (SCHEME == 2 && wcomp) {
+            const double dc = s2 - s1;
+            const double qm = (s1 - s0) * dc, qp = dc * (s3 - s2);
+            wsign |= __double2hiint(qm) & __double2hiint(qp);
+        }
+    }
+    if (SCHEME == 2 && wcomp) wigb |= ((unsigned)wsign >> 31) << DIR;
     const double rgp = z.rgp, gam1 = z.gam1;
     double qn1 = qL[1] * tc[0] + qL[2] * tc[1] + qL[3] * tc[2];
     double qn2 = qR[1] * tc[0] + qR[2] * tc[1] + qR[3] * tc[2];

@@ -10,6 +10,7 @@ struct BcWin {          // one BC window, ghost range already resolved (C/BC/ind
 void launch_metric(const ZoneDev &z, cudaStream_t st);
 void launch_invist(const ZoneDev &z, const double *rop, int ext, cudaStream_t st);
 void launch_sensor(const ZoneDev &z, const double *rop, cudaStream_t st);
+bool fb_sensor_fused();
 // explicit stage (init_rhs + flux balance + core3ark3) or implicit rhs (src + flux balance + core3as2)
 void launch_rhs(const ZoneDev &z, const double *rop, double *rop_out, const double *ro_n, const double *ro_n1,
                 int nitcfg, int first_it, cudaStream_t st);

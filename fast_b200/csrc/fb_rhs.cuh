@@ -16,6 +16,10 @@
 
 static inline dim3 grid3r(int ni, int nj, int nk, dim3 b) { return dim3((ni + b.x - 1) / b.x, (nj + b.y - 1) / b.y, nk); }
 
+// SENSOR byte store.  Written as PTX without a memory clobber: a C++ store through unsigned char* may alias everything,
+// which makes the compiler re-load the staged state around it.
+__device__ __forceinline__ void st_wig(unsigned char *p, unsigned v) { asm("st.global.u8 [%0], %1;" ::"l"(p), "r"(v)); }
+
 // ------------------------------------------------------------------------------------------------ cell epilogue
 // explicit: core3ark3.for:108-154 (+203-236 for nutilde) -- the stage is updated from its own input
 // (navier_stokes_struct.for:477-483); implicit: core3as2.for:70-100.  l: cell in the view, lg: global cell index.
@@ -64,7 +68,7 @@ __device__ __forceinline__ void rhs_finish(const ZoneDev &z, const RhsArgs &a, c
 #define RHS2_RJ 8
 #define RHS2_KC 32
 
-template <int MESH, int FLOW, int SCHEME, int SLOPE, bool IMPL>
+template <int MESH, int FLOW, int SCHEME, int SLOPE, bool IMPL, bool WC>
 __global__ void __launch_bounds__(32 * (RHS2_RJ + 1)) k_rhs2(ZoneDev z, RhsArgs a)
 {
     constexpr int NEQ = FLOW == 3 ? 6 : 5, RJ = RHS2_RJ;
@@ -76,6 +80,7 @@ __global__ void __launch_bounds__(32 * (RHS2_RJ + 1)) k_rhs2(ZoneDev z, RhsArgs 
     const bool fi = m < RJ && j <= z.jv && i <= z.iv + 1;               // owns a lower i face that somebody needs
     const bool fj = li < 31 && i <= z.iv && j <= z.jv + 1;              // owns a lower j face that somebody needs
     const int nd = z.nd;
+    constexpr bool wcomp = WC;   // first sub-iteration: the SENSOR switch is evaluated in the flux and stored
     const GView v(z, a.rop);
     double acc[NEQ], f[NEQ];
 #pragma unroll
@@ -97,17 +102,20 @@ __global__ void __launch_bounds__(32 * (RHS2_RJ + 1)) k_rhs2(ZoneDev z, RhsArgs 
             if (IMPL) coe1 = z.coe[l];
             else coe1 = MESH == 2 ? z.dtc / z.vol0 : z.dtc / __ldg(z.vol + lt);
         }
-        const unsigned wg = (SCHEME == 2 && (cell || fi || fj)) ? z.wigb[l] : 0u;
+        unsigned wg = (SCHEME == 2 && !wcomp && (cell || fi || fj)) ? z.wigb[l] : 0u;
         // lower k face: finishes the cell of plane k-1, starts the cell of plane k
         if (cell) {
-            face_flux<MESH, FLOW, SCHEME, SLOPE, 2>(z, v, l, wg, lt, f);
+            face_flux<MESH, FLOW, SCHEME, SLOPE, 2>(z, v, l, wg, wcomp, lt, f);
             if (k > k0) {
 #pragma unroll
                 for (int e = 0; e < NEQ; e++) acc[e] -= f[e];
                 rhs_finish<MESH, FLOW, IMPL>(z, a, v, l - z.inck, l - z.inck, coe1p, acc);
             }
         }
-        if (last) break;      // uniform
+        if (last) {           // uniform
+            if (wcomp && cell && k == z.kv + 1) st_wig(z.wigb + l, wg);   // k faces of the plane behind the last cells
+            break;
+        }
         if (cell) {
             // init_rhs.for:85-129
 #pragma unroll
@@ -119,7 +127,7 @@ __global__ void __launch_bounds__(32 * (RHS2_RJ + 1)) k_rhs2(ZoneDev z, RhsArgs 
         coe1p = coe1;
         // lower j face -> shared memory
         if (fj) {
-            face_flux<MESH, FLOW, SCHEME, SLOPE, 1>(z, v, l, wg, lt, f);
+            face_flux<MESH, FLOW, SCHEME, SLOPE, 1>(z, v, l, wg, wcomp, lt, f);
 #pragma unroll
             for (int e = 0; e < NEQ; e++) sFj[k & 1][m][e][li] = f[e];
             if (cell) {
@@ -128,7 +136,7 @@ __global__ void __launch_bounds__(32 * (RHS2_RJ + 1)) k_rhs2(ZoneDev z, RhsArgs 
             }
         }
         // lower i face; the upper one comes from the next lane
-        if (fi) face_flux<MESH, FLOW, SCHEME, SLOPE, 0>(z, v, l, wg, lt, f);
+        if (fi) face_flux<MESH, FLOW, SCHEME, SLOPE, 0>(z, v, l, wg, wcomp, lt, f);
         else {
 #pragma unroll
             for (int e = 0; e < NEQ; e++) f[e] = 0.;
@@ -138,6 +146,8 @@ __global__ void __launch_bounds__(32 * (RHS2_RJ + 1)) k_rhs2(ZoneDev z, RhsArgs 
             const double up = __shfl_down_sync(0xffffffffu, f[e], 1);
             if (cell) acc[e] = (acc[e] + f[e]) - up;
         }
+        // SENSOR byte of the cell for the later stages; face-only threads store where no tile owns the cell
+        if (wcomp && (cell || (fi && i == z.iv + 1) || (fj && j == z.jv + 1))) st_wig(z.wigb + l, wg);
         __syncthreads();
         if (cell) {
 #pragma unroll
@@ -206,7 +216,7 @@ __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *tm, in
 // register budget: two resident CTAs per SM where the flux fits 96-128 registers; Roe and the 3dfull metrics need more
 template <int MESH, int SCHEME> struct Rhs3MinB { static constexpr int V = (SCHEME == 5 || MESH == 0) ? 1 : RHS3_MINB; };
 
-template <int MESH, int FLOW, int SCHEME, int SLOPE, bool IMPL, int RJ>
+template <int MESH, int FLOW, int SCHEME, int SLOPE, bool IMPL, int RJ, bool WC>
 __global__ void __launch_bounds__(32 * (RJ + 1), Rhs3MinB<MESH, SCHEME>::V)
 k_rhs3(const __grid_constant__ CUtensorMap tm_rop, const __grid_constant__ CUtensorMap tm_mu, ZoneDev z, RhsArgs a)
 {
@@ -223,6 +233,7 @@ k_rhs3(const __grid_constant__ CUtensorMap tm_rop, const __grid_constant__ CUten
     const bool fi = m < RJ && j <= z.jv && i <= z.iv + 1;
     const bool fj = li < 31 && i <= z.iv && j <= z.jv + 1;
     const int nd = z.nd;
+    constexpr bool wcomp = WC;   // first sub-iteration: the SENSOR switch is evaluated in the flux and stored
     // array coordinates of the box origin (cell i0-2, j0-2) and planes k0-1 .. k1+2
     // (TMA needs a 16-byte aligned global start: an odd first column is shifted one to the left -- the 36-wide box
     // still covers the 35 columns i0-2 .. i0+32 the tile reads)
@@ -275,7 +286,7 @@ k_rhs3(const __grid_constant__ CUtensorMap tm_rop, const __grid_constant__ CUten
                 else coe1 = MESH == 2 ? z.dtc / z.vol0 : z.dtc / __ldg(z.vol + indmtr(z, i, j, k));
             }
         }
-        const unsigned wg = (SCHEME == 2 && (cell || fi || fj)) ? z.wigb[inddm(z, i, j, k)] : 0u;
+        unsigned wg = (SCHEME == 2 && !wcomp && (cell || fi || fj)) ? z.wigb[inddm(z, i, j, k)] : 0u;
         mbar_wait(bar + su, ((pk + 1) / NS) & 1);        // plane k+1 has landed
         SView<RS, VS, NEQ, C::MUOFF> v;
         v.s = ring; v.kup = (su - sk) * PS; v.kdn = (sd - sk) * PS; v.km2 = km2;
@@ -284,14 +295,17 @@ k_rhs3(const __grid_constant__ CUtensorMap tm_rop, const __grid_constant__ CUten
         const int lt = MESH == 2 ? 0 : indmtr(z, i, j, k);
         const bool last = k == k1 + 1;
         if (cell) {
-            face_flux<MESH, FLOW, SCHEME, SLOPE, 2>(z, v, ls, wg, lt, f);
+            face_flux<MESH, FLOW, SCHEME, SLOPE, 2>(z, v, ls, wg, wcomp, lt, f);
             if (k > k0) {
 #pragma unroll
                 for (int e = 0; e < NEQ; e++) acc[e] -= f[e];
                 rhs_finish<MESH, FLOW, IMPL>(z, a, v, ls + v.kdn, l - z.inck, coe1p, acc);
             }
         }
-        if (last) break;      // uniform; no TMA is in flight any more (plane k1+2 was waited for above)
+        if (last) {           // uniform; no TMA is in flight any more (plane k1+2 was waited for above)
+            if (wcomp && cell && k == z.kv + 1) st_wig(z.wigb + l, wg);
+            break;
+        }
         if (cell) {
 #pragma unroll
             for (int e = 0; e < NEQ; e++) acc[e] = (IMPL || a.nitcfg == 1) ? 0. : accn[e] * a.coefH;
@@ -301,7 +315,7 @@ k_rhs3(const __grid_constant__ CUtensorMap tm_rop, const __grid_constant__ CUten
         }
         coe1p = coe1;
         if (fj) {
-            face_flux<MESH, FLOW, SCHEME, SLOPE, 1>(z, v, ls, wg, lt, f);
+            face_flux<MESH, FLOW, SCHEME, SLOPE, 1>(z, v, ls, wg, wcomp, lt, f);
 #pragma unroll
             for (int e = 0; e < NEQ; e++) sFj[k & 1][m][e][li] = f[e];
             if (cell) {
@@ -309,7 +323,7 @@ k_rhs3(const __grid_constant__ CUtensorMap tm_rop, const __grid_constant__ CUten
                 for (int e = 0; e < NEQ; e++) acc[e] += f[e];
             }
         }
-        if (fi) face_flux<MESH, FLOW, SCHEME, SLOPE, 0>(z, v, ls, wg, lt, f);
+        if (fi) face_flux<MESH, FLOW, SCHEME, SLOPE, 0>(z, v, ls, wg, wcomp, lt, f);
         else {
 #pragma unroll
             for (int e = 0; e < NEQ; e++) f[e] = 0.;
@@ -319,6 +333,7 @@ k_rhs3(const __grid_constant__ CUtensorMap tm_rop, const __grid_constant__ CUten
             const double up = __shfl_down_sync(0xffffffffu, f[e], 1);
             if (cell) acc[e] = (acc[e] + f[e]) - up;
         }
+        if (wcomp && (cell || (fi && i == z.iv + 1) || (fj && j == z.jv + 1))) st_wig(z.wigb + l, wg);
         // plane k-1 becomes plane k-2 of the next iteration
 #pragma unroll
         for (int e = 0; e < NEQ; e++) km2[e] = v.q(e, ls + v.kdn);
@@ -342,8 +357,14 @@ static void launch_rhs2_t(const ZoneDev &z, const RhsArgs &a, bool impl, cudaStr
 {
     dim3 b(32, RHS2_RJ + 1, 1);
     dim3 g((z.iv + 30) / 31, (z.jv + RHS2_RJ - 1) / RHS2_RJ, (z.kv + RHS2_KC - 1) / RHS2_KC);
-    if (impl) k_rhs2<MESH, FLOW, SCHEME, SLOPE, true><<<g, b, 0, st>>>(z, a);
-    else k_rhs2<MESH, FLOW, SCHEME, SLOPE, false><<<g, b, 0, st>>>(z, a);
+    // WC: first sub-iteration of a SENSOR zone -- the switch is evaluated inside the flux and stored
+    if (SCHEME == 2 && a.nitcfg == 1 && a.wfuse) {
+        if (impl) k_rhs2<MESH, FLOW, SCHEME, SLOPE, true, SCHEME == 2><<<g, b, 0, st>>>(z, a);
+        else k_rhs2<MESH, FLOW, SCHEME, SLOPE, false, SCHEME == 2><<<g, b, 0, st>>>(z, a);
+    } else {
+        if (impl) k_rhs2<MESH, FLOW, SCHEME, SLOPE, true, false><<<g, b, 0, st>>>(z, a);
+        else k_rhs2<MESH, FLOW, SCHEME, SLOPE, false, false><<<g, b, 0, st>>>(z, a);
+    }
 }
 
 template <int MESH, int FLOW, int SCHEME, int SLOPE>
@@ -357,14 +378,21 @@ static bool launch_rhs3_t(const ZoneDev &z, const RhsArgs &a, bool impl, cudaStr
     if (!tr || !tm) return false;
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(k_rhs3<MESH, FLOW, SCHEME, SLOPE, true, RJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-        cudaFuncSetAttribute(k_rhs3<MESH, FLOW, SCHEME, SLOPE, false, RJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        cudaFuncSetAttribute(k_rhs3<MESH, FLOW, SCHEME, SLOPE, true, RJ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        cudaFuncSetAttribute(k_rhs3<MESH, FLOW, SCHEME, SLOPE, false, RJ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        cudaFuncSetAttribute(k_rhs3<MESH, FLOW, SCHEME, SLOPE, true, RJ, SCHEME == 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        cudaFuncSetAttribute(k_rhs3<MESH, FLOW, SCHEME, SLOPE, false, RJ, SCHEME == 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
         attr = true;
     }
     dim3 b(32, RJ + 1, 1);
     dim3 g((z.iv + 30) / 31, (z.jv + RJ - 1) / RJ, (z.kv + RHS3_KC - 1) / RHS3_KC);
-    if (impl) k_rhs3<MESH, FLOW, SCHEME, SLOPE, true, RJ><<<g, b, C::SMEM, st>>>(*tr, *tm, z, a);
-    else k_rhs3<MESH, FLOW, SCHEME, SLOPE, false, RJ><<<g, b, C::SMEM, st>>>(*tr, *tm, z, a);
+    if (SCHEME == 2 && a.nitcfg == 1 && a.wfuse) {   // first sub-iteration of a SENSOR zone: the switch is evaluated in the flux
+        if (impl) k_rhs3<MESH, FLOW, SCHEME, SLOPE, true, RJ, SCHEME == 2><<<g, b, C::SMEM, st>>>(*tr, *tm, z, a);
+        else k_rhs3<MESH, FLOW, SCHEME, SLOPE, false, RJ, SCHEME == 2><<<g, b, C::SMEM, st>>>(*tr, *tm, z, a);
+    } else {
+        if (impl) k_rhs3<MESH, FLOW, SCHEME, SLOPE, true, RJ, false><<<g, b, C::SMEM, st>>>(*tr, *tm, z, a);
+        else k_rhs3<MESH, FLOW, SCHEME, SLOPE, false, RJ, false><<<g, b, C::SMEM, st>>>(*tr, *tm, z, a);
+    }
     return true;
 }
 

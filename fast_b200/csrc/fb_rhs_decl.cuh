@@ -9,6 +9,7 @@ struct RhsArgs {
     double coefH, coefW;    // low-storage RK (init_rhs.for:31-33, core3ark3.for:22-25)
     double c1, c2, c3;      // BDF weights (core3as2.for:37-46)
     int nitcfg;
+    int wfuse;              // SENSOR switch evaluated inside the first-sub-iteration kernel (default) instead of k_sensor
 };
 
 template <int MESH, int FLOW>

@@ -27,6 +27,7 @@ CASES = {
     'sa_plate_homo_tiles': lambda: synth.case_flatplate(n=(20, 20, 20)),
     'sa_plate_full_tiles': lambda: synth.case_flatplate(n=(18, 20, 16), sheared=True),
     'lamin_full_roe_tiles': _box(n=8, n3=(14, 22, 20), scheme='roe', model='NSLaminar', ReInf=1000., deform_amp=0.02, temporal='implicit'),
+    'sa_plate_medium': lambda: synth.case_flatplate(n=(64, 40, 24)),      # several rhs CTAs and LU tiles in every direction
     'multiblock_roe_lumatch': lambda: synth.case_multiblock(nblk=(2, 2, 1), n=8),
     'multiblock_explicit': lambda: synth.case_multiblock(nblk=(2, 1, 2), n=8, temporal='explicit', scheme='senseur'),
 }
