@@ -159,6 +159,19 @@ static int build_bc_tables(Zone &z)
         const int base = (p % 2) ? ijkv[p / 2] : 1;
         z.lu_box[p] = base + ((p % 2) ? 1 : -1) * (1 - lskip[p]) * ificmax[p];
     }
+    // Roe + wall windows: faces whose interior Euler flux is replaced by the wall pressure flux (correct_flux.for:60-131)
+    z.d.ncorr = 0;
+    if (pi[PI_KFLUDOM] == 5)
+        for (int b = 0; b < nb; b++) {
+            const int pb = pi[pt + 1 + b], ty = pi[pb + BC_TYPE], idir = pi[pb + BC_IDIR];
+            if (!(ty == 3 || ty == 4 || ty == 6)) continue;
+            CorrWin c; c.idir = idir; c.slip = ty == 3 ? 1 : 0;
+            if (!bc_window(pi, idir, pi + pb + BC_FEN, c.w)) continue;
+            const int d = (idir - 1) / 2;
+            if (idir % 2 == 1) { c.w[2 * d] = 1; c.w[2 * d + 1] = 1; } else c.w[2 * d + 1] = c.w[2 * d];
+            if (z.d.ncorr >= FB_MAXCORR) return fail(FB_EINVAL, "more than 8 wall windows on a Roe zone (flux correction table)");
+            z.d.corr[z.d.ncorr++] = c;
+        }
     for (int idir = 0; idir < 6; idir++) {      // default rhs extrapolation on the implicit-ed faces (BCzone.cpp:190-256)
         if (lskip[idir]) continue;
         int fen[6] = {1, ijkv[0], 1, ijkv[1], 1, ijkv[2]};

@@ -36,6 +36,10 @@ enum { BC_TYPE = 0, BC_IDIR = 1, BC_FEN = 2, BC_NBDATA = 8 };
 #define SA_CW3 64.
 #define SA_SIGMA (2. / 3.)
 
+// wall faces whose flux is corrected when the zone runs the Roe scheme (S/BC/correct_flux.for, lapply = 4)
+#define FB_MAXCORR 8
+struct CorrWin { int idir, slip; int w[6]; };   // face-cell range: the cell whose LOWER face is the wall face
+
 struct ZoneDev {
     int ni, nj, nk, nf, nfk, iv, jv, kv, nd;
     int incj, inck;
@@ -50,6 +54,7 @@ struct ZoneDev {
     double c1, c2, opt0, wig_cte, psiroe, tmin_1, cv, dtc, ratiom, cfl, roinf, xmul0, prandt;
     double tc0[3], vol0;
     double vinf[3], pinf, ronutildeinf;   // DEFAULT_STATE of the BCs (S/BC/BCzone.cpp:26-40)
+    int ncorr; CorrWin corr[FB_MAXCORR];
 };
 
 __device__ __forceinline__ int inddm(const ZoneDev &z, int i, int j, int k)

@@ -20,6 +20,65 @@ static inline dim3 grid3r(int ni, int nj, int nk, dim3 b) { return dim3((ni + b.
 // which makes the compiler re-load the staged state around it.
 __device__ __forceinline__ void st_wig(unsigned char *p, unsigned v) { asm("st.global.u8 [%0], %1;" ::"l"(p), "r"(v)); }
 
+// ------------------------------------------------------------------------------------------------ wall flux correction
+// S/BC/correct_flux.for:6-190 (lapply = 4: Roe scheme + wall windows), between the flux balance and the update
+// (navier_stokes_struct.for:376-383): the interior Euler flux of a wall face is taken back out of the balance
+// (template_correction.for:252-300, assemble_drodm_corrflu.for; only the five Euler components, iflow = 1) and the wall
+// pressure flux put in (CL_correction_flu.for -> bflwall.for:96-131, bflwallslip.for:104-190; non-ALE: qen = 0).
+// Only cells that touch a wall window do any work; they read the state through global memory.
+template <int MESH, int SLOPE, int NEQ, int D>
+__device__ __forceinline__ void wall_corr_dir(const ZoneDev &z, const GView &g, const CorrWin &c, int fi, int fj, int fk, double *acc)
+{
+    const int nd = z.nd;
+    const int l = inddm(z, fi, fj, fk), lt = MESH == 2 ? 0 : indmtr(z, fi, fj, fk);
+    const int ia = g.template dn<D>(l);
+    const bool up = (c.idir % 2) == 0;
+    double flu[5]; unsigned wg = 0;
+    face_flux<MESH, 1, 5, SLOPE, D>(z, g, l, wg, false, lt, flu);
+    const double sens_c = up ? 1. : -1., sens_b = up ? -1. : 1.;
+#pragma unroll
+    for (int e = 0; e < 5; e++) acc[e] += flu[e] * sens_c;
+    double tc[3], s;
+    face_normal<MESH, D>(z, lt, tc, s);
+    const double *rop = g.rop;
+    double r = 0.5 * (rop[l] + rop[ia]), u = 0.5 * (rop[l + nd] + rop[ia + nd]);
+    double v = 0.5 * (rop[l + 2 * nd] + rop[ia + 2 * nd]), w = 0.5 * (rop[l + 3 * nd] + rop[ia + 3 * nd]);
+    const double u_int = tc[0] * u + tc[1] * v + tc[2] * w;
+    double f[NEQ];
+#pragma unroll
+    for (int e = 0; e < NEQ; e++) f[e] = 0.;
+    if (!c.slip) {
+        const double p = 0.5 * (rop[l + 4 * nd] * rop[l] + rop[ia + 4 * nd] * rop[ia]) * z.rgp;
+        f[1] = tc[0] * p + u_int * u * r; f[2] = tc[1] * p + u_int * v * r; f[3] = tc[2] * p + u_int * w * r;
+    } else {
+        if (NEQ == 6) { r = rop[ia]; u = rop[ia + nd]; v = rop[ia + 2 * nd]; w = rop[ia + 3 * nd]; }
+        double p = rop[ia + 4 * nd] * rop[ia] * z.rgp;
+        const double h = z.gam1 * p + r * (u * u + v * v + w * w) * 0.5;
+        p = 0.5 * (rop[l + 4 * nd] * rop[l] + rop[ia + 4 * nd] * rop[ia]) * z.rgp;
+        f[0] = u_int * r;
+        f[1] = tc[0] * p + u_int * r * u; f[2] = tc[1] * p + u_int * r * v; f[3] = tc[2] * p + u_int * r * w;
+        f[4] = u_int * h;
+        if (NEQ == 6) f[NEQ - 1] = u_int * r * rop[ia + 5 * nd];
+    }
+#pragma unroll
+    for (int e = 0; e < NEQ; e++) acc[e] += f[e] * sens_b;
+}
+
+template <int MESH, int SLOPE, int NEQ>
+__device__ __noinline__ void wall_corr(const ZoneDev &z, const double *rop, int i, int j, int k, double *acc)
+{
+    const GView g(z, rop);
+    for (int n = 0; n < z.ncorr; n++) {
+        const CorrWin &c = z.corr[n];
+        const int d = (c.idir - 1) / 2, up = (c.idir % 2) == 0 ? 1 : 0;
+        const int fi = i + (d == 0 ? up : 0), fj = j + (d == 1 ? up : 0), fk = k + (d == 2 ? up : 0);   // cell whose lower face is the wall face
+        if (fi < c.w[0] || fi > c.w[1] || fj < c.w[2] || fj > c.w[3] || fk < c.w[4] || fk > c.w[5]) continue;
+        if (d == 0) wall_corr_dir<MESH, SLOPE, NEQ, 0>(z, g, c, fi, fj, fk, acc);
+        else if (d == 1) wall_corr_dir<MESH, SLOPE, NEQ, 1>(z, g, c, fi, fj, fk, acc);
+        else wall_corr_dir<MESH, SLOPE, NEQ, 2>(z, g, c, fi, fj, fk, acc);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ cell epilogue
 // explicit: core3ark3.for:108-154 (+203-236 for nutilde) -- the stage is updated from its own input
 // (navier_stokes_struct.for:477-483); implicit: core3as2.for:70-100.  l: cell in the view, lg: global cell index.
@@ -109,6 +168,7 @@ __global__ void __launch_bounds__(32 * (RHS2_RJ + 1)) k_rhs2(ZoneDev z, RhsArgs 
             if (k > k0) {
 #pragma unroll
                 for (int e = 0; e < NEQ; e++) acc[e] -= f[e];
+                if (SCHEME == 5 && z.ncorr) wall_corr<MESH, SLOPE, NEQ>(z, a.rop, i, j, k - 1, acc);
                 rhs_finish<MESH, FLOW, IMPL>(z, a, v, l - z.inck, l - z.inck, coe1p, acc);
             }
         }
@@ -299,6 +359,7 @@ k_rhs3(const __grid_constant__ CUtensorMap tm_rop, const __grid_constant__ CUten
             if (k > k0) {
 #pragma unroll
                 for (int e = 0; e < NEQ; e++) acc[e] -= f[e];
+                if (SCHEME == 5 && z.ncorr) wall_corr<MESH, SLOPE, NEQ>(z, a.rop, i, j, k - 1, acc);
                 rhs_finish<MESH, FLOW, IMPL>(z, a, v, ls + v.kdn, l - z.inck, coe1p, acc);
             }
         }

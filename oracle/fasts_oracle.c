@@ -657,6 +657,68 @@ void fo_flux_balance(const int *pi, const double *pr, const int ind[6], int mask
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* Wall flux correction of the Roe scheme. FastS/BC/correct_flux.for:6-190 (lapply = 4),  */
+/* FastS/Compute/template_correction.for:252-300 + assemble_drodm_corrflu.for (the interior */
+/* Euler flux of the wall face is taken back out of the balance), FastS/BC/                 */
+/* CL_correction_flu.for -> bflwall.for:96-131 / bflwallslip.for:104-190 (wall pressure     */
+/* flux put in).  Non-ALE (qen = 0), npass = 0, whole-zone sub-domain.                      */
+/* ------------------------------------------------------------------------------------ */
+static int bc_window(const int *pi, int idir, const int *fen, const int ind_sdm[6], int out[6]);
+
+void fo_correct_flux(const int *pi, const double *pr, const double *rop, double *drodm, const double *wig,
+                     const double *ti, const double *tj, const double *tk, const double *vol, const double *xmut)
+{
+    if (pi[FO_KFLUDOM] != 5) return;
+    fctx c; fctx_init(&c, pi, pr, rop, wig, ti, tj, tk, vol, xmut);
+    c.iflow = 1;                                   /* iflow = 1: only the Euler flux is corrected (correct_flux.for:136) */
+    const int nd = c.nd, neq = pi[FO_NEQ];
+    const int pt_bcs = pi[FO_PT_BC], nb_bc = pi[pt_bcs];
+    const int ind_sdm[6] = {1, pi[FO_IJKV], 1, pi[FO_IJKV + 1], 1, pi[FO_IJKV + 2]};
+    const double gam2 = pr[FO_GAMMA] / (pr[FO_GAMMA] - 1.);
+    for (int ndf = 0; ndf < nb_bc; ndf++) {
+        const int pt_bc = pi[pt_bcs + 1 + ndf];
+        const int ty = pi[pt_bc + FO_BC_TYPE], idir = pi[pt_bc + FO_BC_IDIR];
+        const int wall = (ty == 4 || ty == 6 || ty == 7 || ty == 12), slip = (ty == 3);
+        if (!wall && !slip) continue;
+        int w[6];
+        if (bc_window(pi, idir, pi + pt_bc + FO_BC_FEN, ind_sdm, w)) continue;
+        const int d = (idir - 1) / 2, inc = c.inc[d];
+        if (idir % 2 == 1) { w[2 * d] = 1; w[2 * d + 1] = 1; } else w[2 * d + 1] = w[2 * d];   /* correct_flux.for:116-131 */
+        const double sens_c = (idir % 2 == 0) ? 1. : -1.;      /* template_correction.for:196-201 */
+        const double sens_b = (idir % 2 == 0) ? -1. : 1.;      /* bflwall.for:81-86 */
+        const int shift = (idir % 2 == 0) ? inc : 0;
+        for (int k = w[4]; k <= w[5]; k++) for (int j = w[2]; j <= w[3]; j++) for (int i = w[0]; i <= w[1]; i++) {
+            const int l = fo_inddm(pi, i, j, k), lt = c.typ == 2 ? 0 : fo_indmtr(pi, i, j, k), l0 = l - shift, ia = l - inc;
+            double flu[6];
+            face_flux(&c, d, l, lt, flu);
+            for (int e = 0; e < 5; e++) drodm[l0 + e * nd] += flu[e] * sens_c;
+            double tc[3] = {0., 0., 0.};
+            if (c.typ == 0) { const double *T = c.t[d]; tc[0] = T[lt]; tc[1] = T[lt + c.nm]; tc[2] = T[lt + 2 * c.nm]; }
+            else if (c.typ == 1) { if (d < 2) { const double *T = c.t[d]; tc[0] = T[lt]; tc[1] = T[lt + c.nm]; } else tc[2] = c.t[2][lt]; }
+            else tc[d] = c.tc0[d];
+            double r = 0.5 * (rop[l] + rop[ia]), u = 0.5 * (rop[l + nd] + rop[ia + nd]);
+            double v = 0.5 * (rop[l + 2 * nd] + rop[ia + 2 * nd]), ww = 0.5 * (rop[l + 3 * nd] + rop[ia + 3 * nd]);
+            const double u_int = tc[0] * u + tc[1] * v + tc[2] * ww;
+            double f[6] = {0., 0., 0., 0., 0., 0.};
+            if (wall) {
+                const double p = 0.5 * (rop[l + 4 * nd] * rop[l] + rop[ia + 4 * nd] * rop[ia]) * c.rgp;
+                f[1] = tc[0] * p + u_int * u * r; f[2] = tc[1] * p + u_int * v * r; f[3] = tc[2] * p + u_int * ww * r;
+            } else {
+                if (neq == 6) { r = rop[ia]; u = rop[ia + nd]; v = rop[ia + 2 * nd]; ww = rop[ia + 3 * nd]; }
+                double p = rop[ia + 4 * nd] * rop[ia] * c.rgp;
+                const double h = gam2 * p + r * (u * u + v * v + ww * ww) * 0.5;
+                p = 0.5 * (rop[l + 4 * nd] * rop[l] + rop[ia + 4 * nd] * rop[ia]) * c.rgp;
+                f[0] = u_int * r;
+                f[1] = tc[0] * p + u_int * r * u; f[2] = tc[1] * p + u_int * r * v; f[3] = tc[2] * p + u_int * r * ww;
+                f[4] = u_int * h;
+                if (neq == 6) f[5] = u_int * r * rop[ia + 5 * nd];
+            }
+            for (int e = 0; e < neq; e++) drodm[l0 + e * nd] += f[e] * sens_b;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* FastS/Compute/core3ark3.for:22-25,65-86,108-154,203-236 (EXPLOC=0)                     */
 /* ------------------------------------------------------------------------------------ */
 void fo_core3ark3(const int *pi, const double *pr, int nitcfg, const int ind[6],

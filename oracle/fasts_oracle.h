@@ -64,6 +64,8 @@ void fo_flux_balance(const int *pi, const double *pr, const int ind[6], int mask
                      const double *rop, double *drodm, const double *wig,
                      const double *ti, const double *tj, const double *tk,
                      const double *vol, const double *xmut);
+void fo_correct_flux(const int *pi, const double *pr, const double *rop, double *drodm, const double *wig,
+                     const double *ti, const double *tj, const double *tk, const double *vol, const double *xmut);
 void fo_core3ark3(const int *pi, const double *pr, int nitcfg, const int ind[6],
                   double *rop_1, const double *rop, const double *drodm, const double *coe);
 void fo_core3as2(const int *pi, const double *pr, int nitcfg, int first_it, const int ind[6],

@@ -89,6 +89,9 @@ static void rhs_zone(fo_zone *z, int nitcfg, int nssiter, int nitrun, int first_
             fo_flux_balance(pi, pr, s_sdm, mask, rop_ssiter, z->drodm, z->wig, z->ti, z->tj, z->tk, z->vol, z->xmut);
         }
 #pragma omp barrier
+        /* navier_stokes_struct.for:376-383: wall flux correction (Roe) between the balance and the update */
+#pragma omp single
+        fo_correct_flux(pi, pr, rop_ssiter, z->drodm, z->wig, z->ti, z->tj, z->tk, z->vol, z->xmut);
         if (implicit) fo_core3as2(pi, pr, nitcfg, first_it, s_sdm, rop_ssiter, z->ro, z->ro_m1, z->drodm, z->coe);
         else if (nitcfg % 2 == 1) fo_core3ark3(pi, pr, nitcfg, s_sdm, z->ro_p1, z->ro, z->drodm, z->coe);
         else fo_core3ark3(pi, pr, nitcfg, s_sdm, z->ro, z->ro_p1, z->drodm, z->coe);

@@ -15,6 +15,9 @@ CASES = {
     'c2_lamin_cart_senseur_rk3': lambda: (synth.case_euler_box(n=12, scheme='senseur', model='NSLaminar', ReInf=1600.), None),
     'c3_sa_plate_homo_lu': lambda: synth.case_flatplate(n=(16, 12, 4)),
     'c4_blocks_roe_lu_match': lambda: synth.case_multiblock(nblk=(2, 1, 1), n=8),
+    'c5_lamin_roe_wall_flux': lambda: (synth.case_euler_box(n=10, scheme='roe', model='NSLaminar', ReInf=2000., deform_amp=0.02,
+                                                            bcs={'imin': 'BCWallInviscid', 'imax': 'BCFarfield', 'jmin': 'BCWallViscous',
+                                                                 'jmax': 'BCFarfield', 'kmin': 'BCFarfield', 'kmax': 'BCWall'}), None),
 }
 
 

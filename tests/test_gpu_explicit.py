@@ -15,6 +15,12 @@ CASES = {
     'lamin_full_roe_minmod': dict(n=12, scheme='roe', slope='minmod', model='NSLaminar', ReInf=2000., deform_amp=0.02),
     'euler_cart_roe_o1_rk2': dict(n=12, scheme='roe', slope='o1', rk=2),
     'euler_ragged_ausm': dict(n=8, n3=(19, 7, 10), scheme='ausmpred'),
+    # Roe + walls: wall flux correction (correct_flux.for) on slip walls (i faces), viscous walls (j faces), farfield in k
+    'lamin_roe_walls': dict(n=12, scheme='roe', model='NSLaminar', ReInf=2000., deform_amp=0.02,
+                            bcs={'imin': 'BCWallInviscid', 'imax': 'BCWallInviscid', 'jmin': 'BCWallViscous', 'jmax': 'BCWallViscous',
+                                 'kmin': 'BCFarfield', 'kmax': 'BCFarfield'}),
+    'euler_roe_slipwalls_cart': dict(n=10, scheme='roe', bcs={'imin': 'BCWallInviscid', 'imax': 'BCExtrapolate', 'jmin': 'BCFarfield',
+                                                            'jmax': 'BCWallInviscid', 'kmin': 'BCWallInviscid', 'kmax': 'BCWallInviscid'}),
 }
 
 

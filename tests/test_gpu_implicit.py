@@ -21,6 +21,9 @@ CASES = {
     'lamin_full_senseur_minmod': _box(n=10, scheme='senseur', model='NSLaminar', ReInf=500., deform_amp=0.02, temporal='implicit'),
     'sa_plate_homo': lambda: synth.case_flatplate(n=(24, 16, 6)),
     'sa_plate_full': lambda: synth.case_flatplate(n=(20, 12, 6), sheared=True),
+    'lamin_roe_walls_bdf': _box(n=10, scheme='roe', model='NSLaminar', ReInf=1000., deform_amp=0.02, temporal='implicit',
+                               bcs={'imin': 'BCWallInviscid', 'imax': 'BCFarfield', 'jmin': 'BCWallViscous', 'jmax': 'BCFarfield',
+                                    'kmin': 'BCFarfield', 'kmax': 'BCWall'}),
     'sa_plate_roe': lambda: synth.case_flatplate(n=(16, 12, 4), scheme='roe'),
     'sa_plate_blocks': lambda: synth.case_flatplate(n=(24, 16, 8), nblocks=(2, 2, 2)),
     # larger than one LU tile (16 x 8 lines, 16 x 6 for 3dfull SA) in both j and k: inter-tile mailboxes, ragged last tiles

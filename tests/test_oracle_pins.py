@@ -31,6 +31,22 @@ def test_free_stream_preserved(kw):
         assert numpy.abs(a[e] - v).max() < 5e-13
 
 
+@pytest.mark.parametrize('wall', ['BCWallInviscid', 'BCWallViscous'])
+def test_roe_wall_flux_correction_keeps_fluid_at_rest(wall):
+    """correct_flux.for (Roe + walls): in a closed box of walls a fluid at rest must stay at rest -- the corrected wall
+    flux is p*S and the pressure forces of a closed cell cancel.  Without the correction the Roe dissipation acting on
+    the mirrored ghost cells is also zero here, so the pin checks signs / addressing of the two corrections: a wrong sign
+    leaves +-2 p*S in the wall cells."""
+    faces = ('imin', 'imax', 'jmin', 'jmax', 'kmin', 'kmax')
+    t = synth.case_euler_box(n=8, scheme='roe', deform_amp=0.03, model='NSLaminar', ReInf=500., bcs={f: wall for f in faces})
+    _uniform(t, (1., 0., 0., 0., 1.))
+    o = oracle_from_tree(t); z = o.zones[0]
+    for it in (1, 2, 3): o.compute(it, 1, 3, 1)
+    a = interior(z.pi, z.lev[0])
+    for e, v in enumerate((1., 0., 0., 0., 1.)):
+        assert numpy.abs(a[e] - v).max() < 5e-13
+
+
 def test_conservation_periodic():
     """Telescoping fluxes: total mass, momentum and energy constant to round-off in a periodic Cartesian box (Euler:
     the viscous cross terms read the edge ghost cells, which correct_coins replaces by averages -- reference behaviour)."""
