@@ -37,6 +37,13 @@
 #define LU_NC 256          // compute threads: 4 lanes per line
 #define LU_NR 128          // refill threads (cp.async, lanes along i)
 #define LU_NT 448          // + 64 write-back / mailbox threads
+// per-role cycle counters of the FAST_B200_LU_DEBUG report (LUCLK lines) cost two clock reads per step and role: build
+// with -DLU_CLK to get them (make VAR=clk EXTRA=-DLU_CLK); otherwise they read as zero
+#ifdef LU_CLK
+#define LU_CLOCK() clock64()
+#else
+#define LU_CLOCK() 0LL
+#endif
 
 template <int MESH, int NEQ, bool UPPER>
 struct LuCfg {
@@ -104,7 +111,7 @@ __global__ void __launch_bounds__(LU_NT, 1) k_lu_tile(ZoneDev z, LuTileArgs a)
     for (int i = tid; i < 2 * 3 * L * EX + 6 * 16 * EX; i += LU_NT) exb[i] = 0.;
     __syncthreads();
     const int J = s_tile & 0xffff, K = s_tile >> 16;
-    if (a.dbg && tid == 0) { a.dbg[8 * (K * a.NJ + J)] = gtime(); a.dbg[8 * (K * a.NJ + J) + 3] = smid(); }
+    if (a.dbg && tid == 0) { a.dbg[16 * (K * a.NJ + J)] = gtime(); a.dbg[16 * (K * a.NJ + J) + 3] = smid(); }
     const int bi = a.bi, bj = a.bj, bk = a.bk;
     const int nst = bi + TJ + TK - 2;
     const int nd = z.nd;
@@ -157,12 +164,18 @@ __global__ void __launch_bounds__(LU_NT, 1) k_lu_tile(ZoneDev z, LuTileArgs a)
                 }
             };
             for (int t = -CI; t <= -3; t++) { refill(t); cp_async_commit(); }
+            long long tw = 0, tq = 0;
             for (int s = 0; s < nst; s++) {
+                const long long t0 = LU_CLOCK();
                 refill(s - 2);
                 cp_async_commit();
+                const long long t1 = LU_CLOCK();
                 cp_async_wait<CI - 2>();
+                const long long t2 = LU_CLOCK();
+                tw += t1 - t0; tq += t2 - t1;
                 __syncthreads();
             }
+            if (a.dbg && st == 0) { a.dbg[16 * (K * a.NJ + J) + 9] = tw; a.dbg[16 * (K * a.NJ + J) + 10] = tq; }
             __syncthreads();
             cp_async_wait<0>();
             return;
@@ -184,13 +197,13 @@ __global__ void __launch_bounds__(LU_NT, 1) k_lu_tile(ZoneDev z, LuTileArgs a)
                     const double ro = SRC(C::A_ST), u = SRC(C::A_ST + 1), v = SRC(C::A_ST + 2), w = SRC(C::A_ST + 3), t_ = SRC(C::A_ST + 4);
                     const double cvinv = 1. / z.cv, cvinv2 = 0.5 * cvinv;
                     const double rn = ro + SRC(C::A_DW);
-                    const double r_1 = 1. / rn;
+                    const double r_1 = lu_rcp(rn);
                     const double un = (ro * u + SRC(C::A_DW + 1)) * r_1, vn = (ro * v + SRC(C::A_DW + 2)) * r_1, wn = (ro * w + SRC(C::A_DW + 3)) * r_1;
                     const double roe_old = ro * (z.cv * t_ + 0.5 * (u * u + v * v + w * w));
                     const double tn = (roe_old + SRC(C::A_DW + 4)) * r_1 * cvinv - cvinv2 * (un * un + vn * vn + wn * wn);
                     a.rop_out[l] = rn; a.rop_out[l + nd] = un; a.rop_out[l + 2 * nd] = vn; a.rop_out[l + 3 * nd] = wn; a.rop_out[l + 4 * nd] = tn;
                     if (NEQ == 6) {
-                        double anulam = z.coesut * sqrt(tn * z.temp01) * tn / (tn + z.cmus1);   // = coesut sqrt(T/T0) / (1 + Cs/T)
+                        double anulam = z.coesut * sqrt(tn * z.temp01) * tn * lu_rcp(tn + z.cmus1);   // = coesut sqrt(T/T0) / (1 + Cs/T)
                         anulam = anulam * r_1 * z.ratiom;
                         double tt = (ro * SRC(C::A_ST + NEQ - 1) + SRC(C::A_DW + NEQ - 1)) * r_1;
                         tt = fmin(tt, anulam);
@@ -244,13 +257,20 @@ __global__ void __launch_bounds__(LU_NT, 1) k_lu_tile(ZoneDev z, LuTileArgs a)
         }
         unsigned long long w0, w1;
         { volatile unsigned long long *p = entry(2); w0 = p[0]; w1 = p[1]; }
+        long long twb = 0, tdl = 0, tpk = 0;
         for (int s = 0; s < nst; s++) {
+            const long long t0 = LU_CLOCK();
             if (mth) { unsigned long long *d = mpre + (size_t)((s + 2) & 3) * 16 * EX; d[0] = w0; d[1] = w1; }
             { volatile unsigned long long *p = entry(s + 3); w0 = p[0]; w1 = p[1]; }
+            const long long t1 = LU_CLOCK();
             writeback(s - 1);
+            const long long t2 = LU_CLOCK();
             deliver(s);
+            const long long t3 = LU_CLOCK();
+            tpk += t1 - t0; twb += t2 - t1; tdl += t3 - t2;
             __syncthreads();
         }
+        if (a.dbg && sw == 0) { a.dbg[16 * (K * a.NJ + J) + 11] = tpk; a.dbg[16 * (K * a.NJ + J) + 12] = twb; a.dbg[16 * (K * a.NJ + J) + 13] = tdl; }
         __syncthreads();
         for (int s = nst; s <= nst + CI; s++) writeback(s - 1);
         return;
@@ -280,12 +300,14 @@ __global__ void __launch_bounds__(LU_NT, 1) k_lu_tile(ZoneDev z, LuTileArgs a)
     // relative to the buffer of the step parity
     const int offj = jj > 0 ? ((lam - 1) * 3 + 1) * EX : -1, offk = kk > 0 ? ((lam - TJ) * 3 + 2) * EX : -1;
     const int mofj = kk * EX, mofk = (8 + jj) * EX;
-    if (a.dbg && tid == 0) a.dbg[8 * (K * a.NJ + J) + 1] = gtime();
+    if (a.dbg && tid == 0) a.dbg[16 * (K * a.NJ + J) + 1] = gtime();
+    long long tcomp = 0;
     for (int s = 0; s < nst; s++) {
         __syncthreads();
-        if (a.dbg && tid == 0 && (s == 16 || s == 128 || s == 256 || s == 384)) a.dbg[8 * (K * a.NJ + J) + 4 + (s >> 7)] = gtime();
+        if (a.dbg && tid == 0 && (s == 16 || s == 128 || s == 256 || s == 384)) a.dbg[16 * (K * a.NJ + J) + 4 + (s >> 7)] = gtime();
         const int ii = s - sigma;
         if (!(lvalid && ii >= 0 && ii < bi)) continue;
+        const long long tc0 = LU_CLOCK();
         const int c = ii / CI, slot = ii % CI;
         double *R = ring + ((size_t)((c & 1) * A) * L + lam) * CI + slot;
 #define RING(arr) R[(size_t)(arr) * L * CI]
@@ -332,11 +354,11 @@ __global__ void __launch_bounds__(LU_NT, 1) k_lu_tile(ZoneDev z, LuTileArgs a)
         acc[3] = ((acc[3] + k1.y * xk) + j1.y * xj) + i1.y * xi;
         acc[4] = ((acc[4] + k2.x * xk) + j2.x * xj) + i2.x * xi;
         if (NEQ == 6) acc[NEQ - 1] = ((acc[NEQ - 1] + k2.y * xk) + j2.y * xj) + i2.y * xi;
-        const double diag = 1. / coe5;
+        const double diag = lu_rcp(coe5);
         double dwn[NEQ];
 #pragma unroll
         for (int e = 0; e < 5; e++) dwn[e] = acc[e] * diag;
-        if (NEQ == 6) dwn[NEQ - 1] = acc[NEQ - 1] / coe6;
+        if (NEQ == 6) dwn[NEQ - 1] = acc[NEQ - 1] * lu_rcp(coe6);
         if (r == 3) {
 #pragma unroll
             for (int e = 0; e < NEQ; e++) RING(C::A_DW + e) = dwn[e];
@@ -347,7 +369,7 @@ __global__ void __launch_bounds__(LU_NT, 1) k_lu_tile(ZoneDev z, LuTileArgs a)
             const int ig = a.box[1] - ii;
             const bool in_nb = line_in_nb && ig >= a.nbx[0] && ig <= a.nbx[1] && rr == 2;
             const double cvinv = 1. / z.cv, cvinv2 = 0.5 * cvinv;
-            const double r_1 = 1. / (ro + dwn[0]);
+            const double r_1 = lu_rcp(ro + dwn[0]);
             const double un = (ro * u + dwn[1]) * r_1, vn = (ro * v + dwn[2]) * r_1, wn = (ro * w + dwn[3]) * r_1;
             const double roe_old = ro * (z.cv * t + 0.5 * (u * u + v * v + w * w));
             const double tn = (roe_old + dwn[4]) * r_1 * cvinv - cvinv2 * (un * un + vn * vn + wn * wn);
@@ -367,9 +389,11 @@ __global__ void __launch_bounds__(LU_NT, 1) k_lu_tile(ZoneDev z, LuTileArgs a)
             }
         }
 #undef RING
+        tcomp += LU_CLOCK() - tc0;
     }
     __syncthreads();
-    if (a.dbg && tid == 0) a.dbg[8 * (K * a.NJ + J) + 2] = gtime();
+    if (a.dbg && tid == 0) { a.dbg[16 * (K * a.NJ + J) + 2] = gtime(); a.dbg[16 * (K * a.NJ + J) + 8] = tcomp; }
+    if (a.dbg && tid == 252) a.dbg[16 * (K * a.NJ + J) + 14] = tcomp;
 }
 
 // cell-centred mean normals 0.5*(t_d(l) + t_d(l + d)) of every cell (lu_{i,j,k}_*.for build them on the fly)
@@ -475,26 +499,30 @@ static int run_lu_tiles(const ZoneDev &z, const LuPlan &p, const double *rop, do
     static const bool dbg = getenv("FAST_B200_LU_DEBUG") != nullptr;
     static unsigned long long *d_dbg = nullptr; static int dbg_calls = 0;
     a.dbg = nullptr;
-    if (dbg && dbg_calls < 3) { if (!d_dbg) cudaMalloc(&d_dbg, 2 * 8 * 65536 * sizeof(unsigned long long)); a.dbg = d_dbg; }
+    if (dbg && dbg_calls < 3) { if (!d_dbg) cudaMalloc(&d_dbg, 2 * 16 * 65536 * sizeof(unsigned long long)); a.dbg = d_dbg; }
     a.ticket = p.d_ctl; a.order_mode = lu_match ? 1 : (MESH == 2 ? 2 : 0);
     k_lu_tile<MESH, NEQ, false><<<ntiles, LU_NT, LuCfg<MESH, NEQ, false>::SMEM, st>>>(z, a);
     a.ticket = p.d_ctl + 1; a.order_mode = lu_match ? 1 : 0;
-    if (a.dbg) a.dbg += 8 * 65536;
+    if (a.dbg) a.dbg += 16 * 65536;
     k_lu_tile<MESH, NEQ, true><<<ntiles, LU_NT, LuCfg<MESH, NEQ, true>::SMEM, st>>>(z, a);
     if (a.dbg) {
         cudaStreamSynchronize(st);
-        std::vector<unsigned long long> h(2 * 8 * 65536);
+        std::vector<unsigned long long> h(2 * 16 * 65536);
         cudaMemcpy(h.data(), d_dbg, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
         for (int sw = 0; sw < 2; sw++) {
-            const unsigned long long *q = h.data() + sw * 8 * 65536; unsigned long long t0 = ~0ULL, t1 = 0;
-            for (int t = 0; t < ntiles; t++) { t0 = std::min(t0, q[8 * t]); t1 = std::max(t1, q[8 * t + 2]); }
+            const unsigned long long *q = h.data() + sw * 16 * 65536; unsigned long long t0 = ~0ULL, t1 = 0;
+            for (int t = 0; t < ntiles; t++) { t0 = std::min(t0, q[16 * t]); t1 = std::max(t1, q[16 * t + 2]); }
             fprintf(stderr, "LUDBG sweep %d call %d: NJ %d NK %d tiles %d bi %d total %.1f us\n", sw, dbg_calls, p.NJ, p.NK, ntiles, a.bi, (t1 - t0) * 1e-3);
             for (int t = 0; t < ntiles; t++) {
                 const int J = t % p.NJ, K = t / p.NJ;
                 if (dbg_calls == 1 && (J % 4 == 0) && (K % 2 == 0 || K == p.NK - 1))
-                    fprintf(stderr, "LUDBG   tile J %2d K %2d sm %3llu start %8.1f s16 %8.1f s128 %8.1f s256 %8.1f s384 %8.1f end %8.1f dur %8.1f\n", J, K, q[8 * t + 3],
-                            (q[8 * t] - t0) * 1e-3, (q[8 * t + 4] - t0) * 1e-3, (q[8 * t + 5] - t0) * 1e-3, (q[8 * t + 6] - t0) * 1e-3, (q[8 * t + 7] - t0) * 1e-3,
-                            (q[8 * t + 2] - t0) * 1e-3, (q[8 * t + 2] - q[8 * t]) * 1e-3);
+                    fprintf(stderr, "LUDBG   tile J %2d K %2d sm %3llu start %8.1f s16 %8.1f s128 %8.1f s256 %8.1f s384 %8.1f end %8.1f dur %8.1f\n", J, K, q[16 * t + 3],
+                            (q[16 * t] - t0) * 1e-3, (q[16 * t + 4] - t0) * 1e-3, (q[16 * t + 5] - t0) * 1e-3, (q[16 * t + 6] - t0) * 1e-3, (q[16 * t + 7] - t0) * 1e-3,
+                            (q[16 * t + 2] - t0) * 1e-3, (q[16 * t + 2] - q[16 * t]) * 1e-3);
+                if (dbg_calls == 1 && (J % 8 == 0) && (K % 4 == 0))
+                    fprintf(stderr, "LUCLK   tile J %2d K %2d cycles/step: compute(w0) %6.0f compute(w7) %6.0f | refill issue %6.0f wait %6.0f | wb: park %6.0f writeback %6.0f deliver %6.0f\n", J, K,
+                            (double)q[16 * t + 8] / a.bi, (double)q[16 * t + 14] / a.bi, (double)q[16 * t + 9] / (a.bi + 14), (double)q[16 * t + 10] / (a.bi + 14),
+                            (double)q[16 * t + 11] / (a.bi + 14), (double)q[16 * t + 12] / (a.bi + 14), (double)q[16 * t + 13] / (a.bi + 14));
             }
         }
         dbg_calls++;

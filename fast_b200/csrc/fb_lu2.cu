@@ -314,11 +314,11 @@ __global__ void __launch_bounds__((Lu2Cfg<MESH, NEQ, UPPER>::NTH), 1) k_lu_line(
         acc[3] = ((acc[3] + k1.y * xk) + j1.y * xj) + pi_[3] * xi;
         acc[4] = ((acc[4] + k2.x * xk) + j2.x * xj) + pi_[4] * xi;
         if (NEQ == 6) acc[NEQ - 1] = ((acc[NEQ - 1] + k2.y * xk) + j2.y * xj) + pi_[5] * xi;
-        const double diag = 1. / coe5;
+        const double diag = lu_rcp(coe5);
         double dwn[NEQ];
 #pragma unroll
         for (int e = 0; e < 5; e++) dwn[e] = acc[e] * diag;
-        if (NEQ == 6) dwn[NEQ - 1] = acc[NEQ - 1] / coe6;
+        if (NEQ == 6) dwn[NEQ - 1] = acc[NEQ - 1] * lu_rcp(coe6);
         double uk = u, vk = v, wk = w, tk_ = t;          // state the k product is evaluated with
         if (!UPPER) {
 #pragma unroll
@@ -326,13 +326,13 @@ __global__ void __launch_bounds__((Lu2Cfg<MESH, NEQ, UPPER>::NTH), 1) k_lu_line(
         } else {
             // mjr_newton[_SA].for: ro_P1 = prim(W(rop_ssiter) + dW); left in the ring for the write-back warps
             const double rn = ro + dwn[0];
-            const double r_1 = 1. / rn;
+            const double r_1 = lu_rcp(rn);
             const double un = (ro * u + dwn[1]) * r_1, vn = (ro * v + dwn[2]) * r_1, wn = (ro * w + dwn[3]) * r_1;
             const double roe_old = ro * (z.cv * t + 0.5 * (u * u + v * v + w * w));
             const double tn = (roe_old + dwn[4]) * r_1 * cvinv - cvinv2 * (un * un + vn * vn + wn * wn);
             RING(C::A_ST) = rn; RING(C::A_ST + 1) = un; RING(C::A_ST + 2) = vn; RING(C::A_ST + 3) = wn; RING(C::A_ST + 4) = tn;
             if (NEQ == 6) {
-                double anulam = z.coesut * sqrt(tn * z.temp01) * tn / (tn + z.cmus1);   // = coesut sqrt(T/T0) / (1 + Cs/T)
+                double anulam = z.coesut * sqrt(tn * z.temp01) * tn * lu_rcp(tn + z.cmus1);   // = coesut sqrt(T/T0) / (1 + Cs/T)
                 anulam = anulam * r_1 * z.ratiom;
                 double tt = (ro * nut + dwn[NEQ - 1]) * r_1;
                 tt = fmin(tt, anulam);
