@@ -18,8 +18,8 @@ __device__ __forceinline__ double avmin(double c, double r)
     return s * fmax(0., fmin(fabs(c), s * r));
 }
 
-template <int MESH, int DIR>
-__device__ __forceinline__ void face_normal(const ZoneDev &z, int lt, double tc[3], double &s)
+template <int MESH, int DIR, class M>
+__device__ __forceinline__ void face_normal(const ZoneDev &z, const M &mt, int lt, double tc[3], double &s)
 {
     tc[0] = tc[1] = tc[2] = 0.;
     if (MESH == 0) {
@@ -28,10 +28,9 @@ __device__ __forceinline__ void face_normal(const ZoneDev &z, int lt, double tc[
         s = sqrt(tc[0] * tc[0] + tc[1] * tc[1] + tc[2] * tc[2]);
     } else if (MESH == 1) {
         if (DIR < 2) {
-            const double *T = DIR == 0 ? z.ti : z.tj;
-            tc[0] = __ldg(T + lt); tc[1] = __ldg(T + lt + z.nm);
+            tc[0] = DIR == 0 ? mt.ti(0, lt) : mt.tj(0, lt); tc[1] = DIR == 0 ? mt.ti(1, lt) : mt.tj(1, lt);
             s = sqrt(tc[0] * tc[0] + tc[1] * tc[1]);
-        } else { tc[2] = __ldg(z.tk + lt); s = fabs(tc[2]); }
+        } else { tc[2] = mt.tk(lt); s = fabs(tc[2]); }
     } else { tc[DIR] = z.tc0[DIR]; s = fabs(tc[DIR]); }
 }
 
@@ -52,8 +51,8 @@ __device__ __forceinline__ void muscl(const ZoneDev &z, double qm2_, double qm1_
 }
 
 // laminar viscous flux of one face, added into flu[1..4]; returns volinv (needed by the SA diffusion flux)
-template <int MESH, int FLOW, int DIR, class V>
-__device__ __forceinline__ double visc_face(const ZoneDev &z, const V &v, int l, int lt, const double tc[3], double *flu)
+template <int MESH, int FLOW, int DIR, class V, class M>
+__device__ __forceinline__ double visc_face(const ZoneDev &z, const V &v, const M &mt, int l, int lt, const double tc[3], double *flu)
 {
     constexpr int D1 = (DIR + 1) % 3, D2 = (DIR + 2) % 3;
     const int il = v.template dn<DIR>(l), ir = l;
@@ -114,25 +113,23 @@ __device__ __forceinline__ double visc_face(const ZoneDev &z, const V &v, int l,
         }
         volinv = 1. / (__ldg(z.vol + lt) + __ldg(z.vol + lt - m0));
     } else {   // 3dhomo
-        const int nm = z.nm;
         if (DIR < 2) {
             constexpr int DP = 1 - (DIR < 2 ? DIR : 0);
             // DP is D1 for DIR = 0 and D2 for DIR = 1; k is the other tangential direction
             const int ilmp = DIR == 0 ? ilm1 : ilm2, irmp = DIR == 0 ? irm1 : irm2, ilpp = DIR == 0 ? ilp1 : ilp2, irpp = DIR == 0 ? irp1 : irp2;
             const int ilmk = DIR == 0 ? ilm2 : ilm1, irmk = DIR == 0 ? irm2 : irm1, ilpk = DIR == 0 ? ilp2 : ilp1, irpk = DIR == 0 ? irp2 : irp1;
-            const int m0 = DIR == 0 ? z.mi : z.mj, mp = DP == 0 ? z.mi : z.mj;
-            const double *T0 = DIR == 0 ? z.ti : z.tj, *Tp = DP == 0 ? z.ti : z.tj;
+            // metric neighbours: one cell back / forward in the face direction, one forward in the in-plane tangential one
+            const int ltm = mt.template dn<DIR>(lt), ltp = mt.template up<DIR>(lt), ltq = mt.template up<DP>(lt), ltqm = mt.template dn<DIR>(ltq);
             double tn[2], tn1[2], tp[2], tp1[2];
 #pragma unroll
             for (int e = 0; e < 2; e++) {
-                const int o = e * nm;
-                const double t00 = __ldg(T0 + lt + o);
-                tn[e] = .5 * (t00 + __ldg(T0 + lt - m0 + o));
-                tn1[e] = .5 * (t00 + __ldg(T0 + lt + m0 + o));
-                tp[e] = .125 * (__ldg(Tp + lt + o) + __ldg(Tp + lt - m0 + o));
-                tp1[e] = .125 * (__ldg(Tp + lt + mp + o) + __ldg(Tp + lt + mp - m0 + o));
+                const double t00 = DIR == 0 ? mt.ti(e, lt) : mt.tj(e, lt);
+                tn[e] = .5 * (t00 + (DIR == 0 ? mt.ti(e, ltm) : mt.tj(e, ltm)));
+                tn1[e] = .5 * (t00 + (DIR == 0 ? mt.ti(e, ltp) : mt.tj(e, ltp)));
+                tp[e] = .125 * ((DP == 0 ? mt.ti(e, lt) : mt.tj(e, lt)) + (DP == 0 ? mt.ti(e, ltm) : mt.tj(e, ltm)));
+                tp1[e] = .125 * ((DP == 0 ? mt.ti(e, ltq) : mt.tj(e, ltq)) + (DP == 0 ? mt.ti(e, ltqm) : mt.tj(e, ltqm)));
             }
-            const double tkz = .125 * (__ldg(z.tk + lt) + __ldg(z.tk + lt - m0));
+            const double tkz = .125 * (mt.tk(lt) + mt.tk(ltm));
 #pragma unroll
             for (int c = 0; c < NV; c++) {
                 const int e_ = c + 1;
@@ -145,13 +142,14 @@ __device__ __forceinline__ double visc_face(const ZoneDev &z, const V &v, int l,
                     G[c][2] = (fk1 - fk0) * tkz;
                 }
             }
-            volinv = 1. / (__ldg(z.vol + lt) + __ldg(z.vol + lt - m0));
+            volinv = 1. / (mt.vol(lt) + mt.vol(ltm));
         } else {
-            const double tiz = __ldg(z.tk + lt);
-            const double tjx = 0.25 * __ldg(z.ti + lt), tjy = 0.25 * __ldg(z.ti + lt + nm);
-            const double tjx1 = 0.25 * __ldg(z.ti + lt + z.mi), tjy1 = 0.25 * __ldg(z.ti + lt + z.mi + nm);
-            const double tkx = 0.25 * __ldg(z.tj + lt), tky = 0.25 * __ldg(z.tj + lt + nm);
-            const double tkx1 = 0.25 * __ldg(z.tj + lt + z.mj), tky1 = 0.25 * __ldg(z.tj + lt + z.mj + nm);
+            const double tiz = mt.tk(lt);
+            const int lti = mt.template up<0>(lt), ltj = mt.template up<1>(lt);
+            const double tjx = 0.25 * mt.ti(0, lt), tjy = 0.25 * mt.ti(1, lt);
+            const double tjx1 = 0.25 * mt.ti(0, lti), tjy1 = 0.25 * mt.ti(1, lti);
+            const double tkx = 0.25 * mt.tj(0, lt), tky = 0.25 * mt.tj(1, lt);
+            const double tkx1 = 0.25 * mt.tj(0, ltj), tky1 = 0.25 * mt.tj(1, ltj);
 #pragma unroll
             for (int c = 0; c < NV; c++) {
                 const int e_ = c + 1;
@@ -163,8 +161,8 @@ __device__ __forceinline__ double visc_face(const ZoneDev &z, const V &v, int l,
                 G[c][0] = ((f4 * tjx1 - f3 * tjx) + (f6 * tkx1 - f5 * tkx));
                 G[c][1] = ((f4 * tjy1 - f3 * tjy) + (f6 * tky1 - f5 * tky));
             }
-            const double v = __ldg(z.vol + lt);
-            volinv = 1. / (v + v);
+            const double vv = mt.vol(lt);
+            volinv = 1. / (vv + vv);
         }
     }
     const double div = (G[0][0] + G[1][1] + G[2][2]) * (1. / 3);
@@ -226,12 +224,13 @@ __device__ __forceinline__ double visc_face(const ZoneDev &z, const V &v, int l,
 // wcomp (SCHEME == 2, first sub-iteration): the switch of this face is evaluated here from the MUSCL stencil that is
 // already in registers (SENSOR/wiggle2001.for + wiggle.for: 1 when some primitive variable has two consecutive sign
 // changes of its differences across the face) and OR-ed into wigb; the caller stores the byte for the later stages.
-template <int MESH, int FLOW, int SCHEME, int SLOPE, int DIR, class V>
-__device__ __forceinline__ void face_flux(const ZoneDev &z, const V &vw, int l, unsigned &wigb, bool wcomp, int lt, double *flu)
+// mt / lt: metric accessor of 3dhomo zones and the cell's index in it (MESH 0 / 2 read z.ti.. / constants with the global lt)
+template <int MESH, int FLOW, int SCHEME, int SLOPE, int DIR, class V, class M>
+__device__ __forceinline__ void face_flux(const ZoneDev &z, const V &vw, const M &mt, int l, unsigned &wigb, bool wcomp, int lt, double *flu)
 {
     constexpr int NEQ = FLOW == 3 ? 6 : 5;
     double tc[3], s;
-    face_normal<MESH, DIR>(z, lt, tc, s);
+    face_normal<MESH, DIR>(z, mt, lt, tc, s);
     const int nm = vw.template dn<DIR>(l), np = vw.template up<DIR>(l);
     const double T0 = vw.q(4, l);
     double qL[NEQ], qR[NEQ];
@@ -323,5 +322,5 @@ __device__ __forceinline__ void face_flux(const ZoneDev &z, const V &vw, int l, 
         flu[4] = u * (h1 + h2) - tdu * (h2 - h1);
         if (FLOW == 3) flu[5] = ausm_sa_flux<SLOPE, DIR>(z, vw, l, nm, np, T0, u, tdu, r1, r2);
     }
-    if (FLOW >= 2) visc_face<MESH, FLOW, DIR>(z, vw, l, lt, tc, flu);
+    if (FLOW >= 2) visc_face<MESH, FLOW, DIR>(z, vw, mt, l, lt, tc, flu);
 }

@@ -109,7 +109,7 @@ __global__ void k_sa_ring(ZoneDev z, const double *__restrict__ rop)
     const bool inner = i >= 1 && i <= z.iv && j >= 1 && j <= z.jv && k >= 1 && k <= z.kv;
     if (inner) return;
     const int l = inddm(z, i, j, k), lt = MESH == 2 ? 0 : indmtr(z, i, j, k);
-    sa_source_cell<MESH>(z, GView(z, rop), l, l, lt, true, z.coe[l]);
+    sa_source_cell<MESH>(z, GView(z, rop), GMet1(z), l, l, lt, true, z.coe[l]);
 }
 
 void launch_sa_ring(const ZoneDev &z, const double *rop, cudaStream_t st)

@@ -7,6 +7,7 @@
 // +F_k +F_j +F_i -F_i(i+1) -F_j(j+1) -F_k(k+1) (template_FluxAndBalance.for:192-271), so they agree bit for bit.
 #pragma once
 #include <cstdlib>
+#include <type_traits>
 #include <cuda.h>
 #include "fb_kernels.cuh"
 #include "fb_flux.cuh"
@@ -34,12 +35,13 @@ __device__ __forceinline__ void wall_corr_dir(const ZoneDev &z, const GView &g, 
     const int ia = g.template dn<D>(l);
     const bool up = (c.idir % 2) == 0;
     double flu[5]; unsigned wg = 0;
-    face_flux<MESH, 1, 5, SLOPE, D>(z, g, l, wg, false, lt, flu);
+    const GMet1 mt(z);
+    face_flux<MESH, 1, 5, SLOPE, D>(z, g, mt, l, wg, false, lt, flu);
     const double sens_c = up ? 1. : -1., sens_b = up ? -1. : 1.;
 #pragma unroll
     for (int e = 0; e < 5; e++) acc[e] += flu[e] * sens_c;
     double tc[3], s;
-    face_normal<MESH, D>(z, lt, tc, s);
+    face_normal<MESH, D>(z, mt, lt, tc, s);
     const double *rop = g.rop;
     double r = 0.5 * (rop[l] + rop[ia]), u = 0.5 * (rop[l + nd] + rop[ia + nd]);
     double v = 0.5 * (rop[l + 2 * nd] + rop[ia + 2 * nd]), w = 0.5 * (rop[l + 3 * nd] + rop[ia + 3 * nd]);
@@ -141,6 +143,7 @@ __global__ void __launch_bounds__(32 * (RHS2_RJ + 1)) k_rhs2(ZoneDev z, RhsArgs 
     const int nd = z.nd;
     constexpr bool wcomp = WC;   // first sub-iteration: the SENSOR switch is evaluated in the flux and stored
     const GView v(z, a.rop);
+    const GMet1 mt(z);
     double acc[NEQ], f[NEQ];
 #pragma unroll
     for (int e = 0; e < NEQ; e++) acc[e] = 0.;
@@ -164,7 +167,7 @@ __global__ void __launch_bounds__(32 * (RHS2_RJ + 1)) k_rhs2(ZoneDev z, RhsArgs 
         unsigned wg = (SCHEME == 2 && !wcomp && (cell || fi || fj)) ? z.wigb[l] : 0u;
         // lower k face: finishes the cell of plane k-1, starts the cell of plane k
         if (cell) {
-            face_flux<MESH, FLOW, SCHEME, SLOPE, 2>(z, v, l, wg, wcomp, lt, f);
+            face_flux<MESH, FLOW, SCHEME, SLOPE, 2>(z, v, mt, l, wg, wcomp, lt, f);
             if (k > k0) {
 #pragma unroll
                 for (int e = 0; e < NEQ; e++) acc[e] -= f[e];
@@ -180,14 +183,14 @@ __global__ void __launch_bounds__(32 * (RHS2_RJ + 1)) k_rhs2(ZoneDev z, RhsArgs 
             // init_rhs.for:85-129
 #pragma unroll
             for (int e = 0; e < NEQ; e++) acc[e] = (IMPL || a.nitcfg == 1) ? 0. : accn[e] * a.coefH;
-            if (FLOW == 3) sa_source<MESH, IMPL>(z, v, l, l, lt, a.nitcfg, coe1, acc);
+            if (FLOW == 3) sa_source<MESH, IMPL>(z, v, mt, l, l, lt, a.nitcfg, coe1, acc);
 #pragma unroll
             for (int e = 0; e < NEQ; e++) acc[e] += f[e];
         }
         coe1p = coe1;
         // lower j face -> shared memory
         if (fj) {
-            face_flux<MESH, FLOW, SCHEME, SLOPE, 1>(z, v, l, wg, wcomp, lt, f);
+            face_flux<MESH, FLOW, SCHEME, SLOPE, 1>(z, v, mt, l, wg, wcomp, lt, f);
 #pragma unroll
             for (int e = 0; e < NEQ; e++) sFj[k & 1][m][e][li] = f[e];
             if (cell) {
@@ -196,7 +199,7 @@ __global__ void __launch_bounds__(32 * (RHS2_RJ + 1)) k_rhs2(ZoneDev z, RhsArgs 
             }
         }
         // lower i face; the upper one comes from the next lane
-        if (fi) face_flux<MESH, FLOW, SCHEME, SLOPE, 0>(z, v, l, wg, wcomp, lt, f);
+        if (fi) face_flux<MESH, FLOW, SCHEME, SLOPE, 0>(z, v, mt, l, wg, wcomp, lt, f);
         else {
 #pragma unroll
             for (int e = 0; e < NEQ; e++) f[e] = 0.;
@@ -239,6 +242,13 @@ __global__ void __launch_bounds__(32 * (RHS2_RJ + 1)) k_rhs2(ZoneDev z, RhsArgs 
 #define RHS3_KC 32          // k planes per CTA (measured: 32 < 64 < 128 on TGV 256^3 and the plate)
 #endif
 
+template <int MESH, int RS, int VS>
+__device__ __forceinline__ typename std::conditional<MESH == 1, SMet1<RS, VS>, GMet1>::type make_met(const ZoneDev &z, const double *smet)
+{
+    if constexpr (MESH == 1) { SMet1<RS, VS> m; m.s = smet; return m; }
+    else return GMet1(z);
+}
+
 template <int FLOW, int RJ>
 struct Rhs3Cfg {
     static constexpr int NEQ = FLOW == 3 ? 6 : 5;
@@ -249,7 +259,12 @@ struct Rhs3Cfg {
     static constexpr int PS = (MUOFF + (NV - NEQ) * VS + 15) / 16 * 16;       // slot stride
     static constexpr int NT = 32 * (RJ + 1);
     static constexpr unsigned TX = (unsigned)(NV * VS * sizeof(double));   // bytes one plane brings in
-    static constexpr size_t SMEM = (size_t)(RHS3_NS * PS + 2 * (RJ + 1) * NEQ * 32) * sizeof(double) + RHS3_NS * sizeof(unsigned long long);
+    // F_j exchange: double-buffered by plane parity (one barrier per plane); 3dhomo SA keeps a single buffer and pays a
+    // second barrier per plane so that ring + metric tile leave room for two CTAs per SM
+    template <int MESH> __host__ __device__ static constexpr int nsf() { return (MESH == 1 && FLOW == 3) ? 1 : 2; }
+    template <int MESH> __host__ __device__ static constexpr int sfj() { return nsf<MESH>() * (RJ + 1) * NEQ * 32; }
+    template <int MESH> __host__ __device__ static constexpr int met() { return MESH == 1 ? 6 * VS : 0; }   // 3dhomo: metric tile (k-invariant)
+    template <int MESH> __host__ __device__ static constexpr size_t smem() { return (size_t)(RHS3_NS * PS + sfj<MESH>() + met<MESH>()) * sizeof(double) + RHS3_NS * sizeof(unsigned long long); }
 };
 
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
@@ -284,7 +299,9 @@ k_rhs3(const __grid_constant__ CUtensorMap tm_rop, const __grid_constant__ CUten
     constexpr int NEQ = C::NEQ, NS = RHS3_NS, PS = C::PS, RS = C::RS, VS = C::VS;
     extern __shared__ __align__(128) double ring[];
     double (*sFj)[RJ + 1][NEQ][32] = (double (*)[RJ + 1][NEQ][32])(ring + NS * PS);
-    unsigned long long *bar = (unsigned long long *)(ring + NS * PS + 2 * (RJ + 1) * NEQ * 32);
+    constexpr int NSF = C::template nsf<MESH>();
+    double *smet = ring + NS * PS + C::template sfj<MESH>();   // 3dhomo: [ti.x, ti.y, tj.x, tj.y, tk, vol][rows][36]
+    unsigned long long *bar = (unsigned long long *)(smet + C::template met<MESH>());
     const int li = threadIdx.x, m = threadIdx.y;
     const bool leader = li == 0 && m == 0;
     const int i = 1 + blockIdx.x * 31 + li, j = 1 + blockIdx.y * RJ + m;
@@ -310,6 +327,17 @@ k_rhs3(const __grid_constant__ CUtensorMap tm_rop, const __grid_constant__ CUten
         for (int s = 0; s < NS; s++) mbar_init(bar + s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (MESH == 1) {
+        // the metrics of a 3dhomo zone do not depend on k: the tile's neighbourhood is copied once and serves every plane
+        const int tid = m * 32 + li, mlast = z.nm - 1;
+        for (int n = tid; n < 6 * VS; n += C::NT) {
+            const int arr = n / VS, r = (n % VS) / RS, c = n % RS;
+            int lt = indmtr(z, 1 + blockIdx.x * 31 - 2 - sh + c, 1 + blockIdx.y * RJ - 2 + r, 1);
+            lt = lt < 0 ? 0 : (lt > mlast ? mlast : lt);        // outside the arrays: never used, any finite value will do
+            const double *src = arr < 2 ? z.ti + arr * z.nm : (arr < 4 ? z.tj + (arr - 2) * z.nm : (arr == 4 ? z.tk : z.vol));
+            smet[n] = __ldg(src + lt);
+        }
+    }
     __syncthreads();
     if (leader)
         for (int p = pfirst; p < pfirst + NS && p <= plast; p++) issue(p);
@@ -327,6 +355,7 @@ k_rhs3(const __grid_constant__ CUtensorMap tm_rop, const __grid_constant__ CUten
     mbar_wait(bar + 0, 0);
     mbar_wait(bar + 1, 0);
     const int lcol = (m + 2) * RS + li + 2 + sh;
+    typename std::conditional<MESH == 1, SMet1<RS, VS>, GMet1>::type mt = make_met<MESH, RS, VS>(z, smet);
     for (int k = k0; k <= k1 + 1; k++) {
         const int pk = k - pfirst;                       // >= 1
         const int sk = pk % NS, su = (pk + 1) % NS, sd = (pk - 1) % NS;
@@ -352,10 +381,10 @@ k_rhs3(const __grid_constant__ CUtensorMap tm_rop, const __grid_constant__ CUten
         v.s = ring; v.kup = (su - sk) * PS; v.kdn = (sd - sk) * PS; v.km2 = km2;
         const int ls = sk * PS + lcol;
         const int l = inddm(z, i, j, k);
-        const int lt = MESH == 2 ? 0 : indmtr(z, i, j, k);
+        const int lt = MESH == 2 ? 0 : (MESH == 1 ? lcol : indmtr(z, i, j, k));   // 3dhomo: index in the shared metric tile
         const bool last = k == k1 + 1;
         if (cell) {
-            face_flux<MESH, FLOW, SCHEME, SLOPE, 2>(z, v, ls, wg, wcomp, lt, f);
+            face_flux<MESH, FLOW, SCHEME, SLOPE, 2>(z, v, mt, ls, wg, wcomp, lt, f);
             if (k > k0) {
 #pragma unroll
                 for (int e = 0; e < NEQ; e++) acc[e] -= f[e];
@@ -370,21 +399,21 @@ k_rhs3(const __grid_constant__ CUtensorMap tm_rop, const __grid_constant__ CUten
         if (cell) {
 #pragma unroll
             for (int e = 0; e < NEQ; e++) acc[e] = (IMPL || a.nitcfg == 1) ? 0. : accn[e] * a.coefH;
-            if (FLOW == 3) sa_source<MESH, IMPL>(z, v, ls, l, lt, a.nitcfg, coe1, acc);
+            if (FLOW == 3) sa_source<MESH, IMPL>(z, v, mt, ls, l, lt, a.nitcfg, coe1, acc);
 #pragma unroll
             for (int e = 0; e < NEQ; e++) acc[e] += f[e];
         }
         coe1p = coe1;
         if (fj) {
-            face_flux<MESH, FLOW, SCHEME, SLOPE, 1>(z, v, ls, wg, wcomp, lt, f);
+            face_flux<MESH, FLOW, SCHEME, SLOPE, 1>(z, v, mt, ls, wg, wcomp, lt, f);
 #pragma unroll
-            for (int e = 0; e < NEQ; e++) sFj[k & 1][m][e][li] = f[e];
+            for (int e = 0; e < NEQ; e++) sFj[NSF == 2 ? (k & 1) : 0][m][e][li] = f[e];
             if (cell) {
 #pragma unroll
                 for (int e = 0; e < NEQ; e++) acc[e] += f[e];
             }
         }
-        if (fi) face_flux<MESH, FLOW, SCHEME, SLOPE, 0>(z, v, ls, wg, wcomp, lt, f);
+        if (fi) face_flux<MESH, FLOW, SCHEME, SLOPE, 0>(z, v, mt, ls, wg, wcomp, lt, f);
         else {
 #pragma unroll
             for (int e = 0; e < NEQ; e++) f[e] = 0.;
@@ -403,8 +432,9 @@ k_rhs3(const __grid_constant__ CUtensorMap tm_rop, const __grid_constant__ CUten
         if (leader && k + NS - 1 <= plast) issue(k + NS - 1);
         if (cell) {
 #pragma unroll
-            for (int e = 0; e < NEQ; e++) acc[e] -= sFj[k & 1][m + 1][e][li];
+            for (int e = 0; e < NEQ; e++) acc[e] -= sFj[NSF == 2 ? (k & 1) : 0][m + 1][e][li];
         }
+        if (NSF == 1) __syncthreads();      // single F_j buffer: everybody has read it before the next plane overwrites it
     }
 }
 
@@ -439,20 +469,20 @@ static bool launch_rhs3_t(const ZoneDev &z, const RhsArgs &a, bool impl, cudaStr
     if (!tr || !tm) return false;
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(k_rhs3<MESH, FLOW, SCHEME, SLOPE, true, RJ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-        cudaFuncSetAttribute(k_rhs3<MESH, FLOW, SCHEME, SLOPE, false, RJ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-        cudaFuncSetAttribute(k_rhs3<MESH, FLOW, SCHEME, SLOPE, true, RJ, SCHEME == 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-        cudaFuncSetAttribute(k_rhs3<MESH, FLOW, SCHEME, SLOPE, false, RJ, SCHEME == 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        cudaFuncSetAttribute(k_rhs3<MESH, FLOW, SCHEME, SLOPE, true, RJ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::template smem<MESH>());
+        cudaFuncSetAttribute(k_rhs3<MESH, FLOW, SCHEME, SLOPE, false, RJ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::template smem<MESH>());
+        cudaFuncSetAttribute(k_rhs3<MESH, FLOW, SCHEME, SLOPE, true, RJ, SCHEME == 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::template smem<MESH>());
+        cudaFuncSetAttribute(k_rhs3<MESH, FLOW, SCHEME, SLOPE, false, RJ, SCHEME == 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::template smem<MESH>());
         attr = true;
     }
     dim3 b(32, RJ + 1, 1);
     dim3 g((z.iv + 30) / 31, (z.jv + RJ - 1) / RJ, (z.kv + RHS3_KC - 1) / RHS3_KC);
     if (SCHEME == 2 && a.nitcfg == 1 && a.wfuse) {   // first sub-iteration of a SENSOR zone: the switch is evaluated in the flux
-        if (impl) k_rhs3<MESH, FLOW, SCHEME, SLOPE, true, RJ, SCHEME == 2><<<g, b, C::SMEM, st>>>(*tr, *tm, z, a);
-        else k_rhs3<MESH, FLOW, SCHEME, SLOPE, false, RJ, SCHEME == 2><<<g, b, C::SMEM, st>>>(*tr, *tm, z, a);
+        if (impl) k_rhs3<MESH, FLOW, SCHEME, SLOPE, true, RJ, SCHEME == 2><<<g, b, C::template smem<MESH>(), st>>>(*tr, *tm, z, a);
+        else k_rhs3<MESH, FLOW, SCHEME, SLOPE, false, RJ, SCHEME == 2><<<g, b, C::template smem<MESH>(), st>>>(*tr, *tm, z, a);
     } else {
-        if (impl) k_rhs3<MESH, FLOW, SCHEME, SLOPE, true, RJ, false><<<g, b, C::SMEM, st>>>(*tr, *tm, z, a);
-        else k_rhs3<MESH, FLOW, SCHEME, SLOPE, false, RJ, false><<<g, b, C::SMEM, st>>>(*tr, *tm, z, a);
+        if (impl) k_rhs3<MESH, FLOW, SCHEME, SLOPE, true, RJ, false><<<g, b, C::template smem<MESH>(), st>>>(*tr, *tm, z, a);
+        else k_rhs3<MESH, FLOW, SCHEME, SLOPE, false, RJ, false><<<g, b, C::template smem<MESH>(), st>>>(*tr, *tm, z, a);
     }
     return true;
 }

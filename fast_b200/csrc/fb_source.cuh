@@ -26,8 +26,8 @@ __device__ __forceinline__ double vispalart_cell(const ZoneDev &z, const double 
 
 // SA source of cell l: returns vol*tsource; when STORE the LU diagonal coe(:,6) is updated (nitcfg<=1, implicit)
 // l: cell index in the view, lg: global cell index (wall distance, coe store)
-template <int MESH, class V>
-__device__ __forceinline__ double sa_source_cell(const ZoneDev &z, const V &v, int l, int lg, int lt, bool store, double coe1)
+template <int MESH, class V, class M>
+__device__ __forceinline__ double sa_source_cell(const ZoneDev &z, const V &v, const M &mt, int l, int lg, int lt, bool store, double coe1)
 {
     const int nd = z.nd, nm = z.nm;
     const int l1 = v.template up<0>(l), l2 = v.template dn<0>(l), l3 = v.template up<1>(l), l4 = v.template dn<1>(l),
@@ -52,10 +52,11 @@ __device__ __forceinline__ double sa_source_cell(const ZoneDev &z, const V &v, i
                      u4 = q0 + v.q(5, l4) * v.q(0, l4), u5 = q0 + v.q(5, l5) * v.q(0, l5), u6 = q0 + v.q(5, l6) * v.q(0, l6);
         h[0] = g[3][0] * (u3 - u1) * tix; h[1] = g[3][1] * (u2 - u4) * tjy; h[2] = g[3][2] * (u5 - u6) * tkz;
     } else if (MESH == 1) {
-        vol = __ldg(z.vol + lt);
-        const double tix = __ldg(z.ti + lt), tiy = __ldg(z.ti + lt + nm), tix1 = __ldg(z.ti + lt + z.mi), tiy1 = __ldg(z.ti + lt + z.mi + nm);
-        const double tjx = __ldg(z.tj + lt), tjy = __ldg(z.tj + lt + nm), tjx1 = __ldg(z.tj + lt + z.mj), tjy1 = __ldg(z.tj + lt + z.mj + nm);
-        const double tkz = __ldg(z.tk + lt);
+        vol = mt.vol(lt);
+        const int lti = mt.template up<0>(lt), ltj = mt.template up<1>(lt);
+        const double tix = mt.ti(0, lt), tiy = mt.ti(1, lt), tix1 = mt.ti(0, lti), tiy1 = mt.ti(1, lti);
+        const double tjx = mt.tj(0, lt), tjy = mt.tj(1, lt), tjx1 = mt.tj(0, ltj), tjy1 = mt.tj(1, ltj);
+        const double tkz = mt.tk(lt);
 #pragma unroll
         for (int c = 0; c < 4; c++) {
             const int e_ = c < 3 ? c + 1 : 5;
@@ -130,10 +131,10 @@ __device__ __forceinline__ double sa_source_cell(const ZoneDev &z, const V &v, i
     return vol * tsource;
 }
 
-template <int MESH, bool IMPL, class V>
-__device__ __forceinline__ void sa_source(const ZoneDev &z, const V &v, int l, int lg, int lt, int nitcfg, double coe1, double *acc)
+template <int MESH, bool IMPL, class V, class M>
+__device__ __forceinline__ void sa_source(const ZoneDev &z, const V &v, const M &mt, int l, int lg, int lt, int nitcfg, double coe1, double *acc)
 {
-    acc[5] += sa_source_cell<MESH>(z, v, l, lg, lt, IMPL && nitcfg <= 1, coe1);
+    acc[5] += sa_source_cell<MESH>(z, v, mt, l, lg, lt, IMPL && nitcfg <= 1, coe1);
 }
 
 // core3as2.for:37-195: Newton residual from the flux balance and the BDF time terms (conservative variables)

@@ -31,3 +31,27 @@ struct SView {
     template <int D> __device__ __forceinline__ int dn(int l) const { return l - (D == 0 ? 1 : (D == 1 ? RS : -kdn)); }
     template <int D> __device__ __forceinline__ double qm2(int e, int l) const { return D == 2 ? km2[e] : s[l - 2 * (D == 0 ? 1 : RS) + e * VS]; }
 };
+
+// 3dhomo metrics (ti, tj: two components; tk, vol: one; all independent of k).  GMet1 reads the node-strided plane
+// arrays through L1; SMet1 is the copy of the tile's (36 x rows) neighbourhood that k_rhs3 keeps in shared memory for
+// the whole k march (same in-plane index as the state window, immediate offsets).  lt = metric index of the cell.
+struct GMet1 {
+    const double *pti, *ptj, *ptk, *pvol; int nm, mi, mj;
+    __device__ __forceinline__ GMet1(const ZoneDev &z) : pti(z.ti), ptj(z.tj), ptk(z.tk), pvol(z.vol), nm(z.nm), mi(z.mi), mj(z.mj) {}
+    __device__ __forceinline__ double ti(int e, int lt) const { return __ldg(pti + lt + e * nm); }
+    __device__ __forceinline__ double tj(int e, int lt) const { return __ldg(ptj + lt + e * nm); }
+    __device__ __forceinline__ double tk(int lt) const { return __ldg(ptk + lt); }
+    __device__ __forceinline__ double vol(int lt) const { return __ldg(pvol + lt); }
+    template <int D> __device__ __forceinline__ int up(int lt) const { return lt + (D == 0 ? mi : mj); }
+    template <int D> __device__ __forceinline__ int dn(int lt) const { return lt - (D == 0 ? mi : mj); }
+};
+template <int RS, int VS>
+struct SMet1 {
+    const double *s;          // [ti.x, ti.y, tj.x, tj.y, tk, vol][rows][RS]
+    __device__ __forceinline__ double ti(int e, int lt) const { return s[lt + e * VS]; }
+    __device__ __forceinline__ double tj(int e, int lt) const { return s[lt + (2 + e) * VS]; }
+    __device__ __forceinline__ double tk(int lt) const { return s[lt + 4 * VS]; }
+    __device__ __forceinline__ double vol(int lt) const { return s[lt + 5 * VS]; }
+    template <int D> __device__ __forceinline__ int up(int lt) const { return lt + (D == 0 ? 1 : RS); }
+    template <int D> __device__ __forceinline__ int dn(int lt) const { return lt - (D == 0 ? 1 : RS); }
+};
