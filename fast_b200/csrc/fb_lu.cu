@@ -532,8 +532,9 @@ static int run_lu_tiles(const ZoneDev &z, const LuPlan &p, const double *rop, do
 
 bool lu_use_lines()
 {   // default: the 4-lanes-per-line tile kernel of this file; FAST_B200_LU=line selects the one-thread-per-line kernel
-    // (fb_lu2.cu: 5x fewer instructions per cell, parity-green, but its 8-byte cp.async refill of 128 lines saturates the
-    // LSU -- measured 3.6 ms per sweep on C3 against 1.0 ms here; it waits for a TMA-staged ring)
+    // (fb_lu2.cu: 5x fewer instructions per cell, two tiles per SM, parity-green, but a single warp evaluating the three
+    // products in sequence needs 2.0 us per step against 0.69 us here -- measured 3.4 ms per sweep on C3 against 1.0 ms,
+    // see DESIGN.md 3.4)
     static const bool lines = [] { const char *e = getenv("FAST_B200_LU"); return e && e[0] == 'l'; }();
     return lines;
 }

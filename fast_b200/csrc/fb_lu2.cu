@@ -1,18 +1,18 @@
-// fb_lu2.cu -- LU-SGS lower / upper sweeps + Newton update, tile-pipelined wavefront, ONE THREAD PER GRID LINE.
+// fb_lu2.cu -- LU-SGS lower / upper sweeps + Newton update, tile-pipelined wavefront, ONE THREAD PER GRID LINE,
+// TWO TILES PER SM.
 //
 // Reference: S/Compute/LU/invlu.for:6-344 -> invlu_l[_SA].for:79-215, invlu_u[_SA].for:60-215, lu_{i,j,k}_*.for,
 // mjr_newton[_SA].for.  Same dependency-preserving reordering, mailboxes and staging ring as k_lu_tile (fb_lu.cu, which
-// stays selectable with FAST_B200_LU=tile), but re-balanced after measuring that kernel (profiles/r01_*lu*): it spent
-// 1200 thread instructions per cell (4 lanes per line redo dW*, 14 warps synchronise every step on 64 cells) and ran
-// at 1360 cycles per step, and its 264 tiles needed two waves of CTAs.  Here
-//   * a tile is TJ x TK = 16 x 8 lines (16 x 6 for 3dfull SA) and thread lam = jj + TJ*kk owns line (jj,kk): it keeps
-//     dW*, the state and its i product in registers, evaluates all three products B_d(l).dW(l) itself (common
-//     sub-expressions shared) and applies the Newton update of the upper sweep in place -- ~250 instructions per cell;
-//   * 4 compute warps (one per scheduler) + 4 refill warps + 4 write-back warps + 3 mailbox warps, one __syncthreads per
-//     step on 128 cells;
-//   * the staging ring holds NB = 4 chunks of CI = 2 cells per line and array: a chunk that retires at step t is
-//     written back at t+1 and its buffer refilled at t+2, (NB-1)*CI-2 = 4 steps before its first use;
-//   * C3 (257 x 64 lines) becomes 17 x 8 = 136 tiles: one wave on 148 SMs, 23 tile hops instead of 39.
+// stays selectable with FAST_B200_LU=tile), re-balanced after measuring that kernel (profiles/r01_summary.md): its
+// compute warps -- 4 lanes per line, every lane redoing dW* -- are busy 1130 / 2070 cycles per step on a chain of
+// dependent FP64 instructions, memory is idle, one 172-KB tile fits per SM and 264 tiles need two waves.  Here
+//   * thread lam = jj + TJ*kk owns line (jj,kk) of a TJ x TK = 8 x 8 tile (8 x 6 for 3dfull SA): it keeps dW*, the state
+//     and its i product in registers, evaluates the three products B_d(l).dW(l) itself (three independent chains,
+//     common sub-expressions shared) and applies the Newton update of the upper sweep in place;
+//   * 2 compute warps + 4 refill / write-back warps + 2 mailbox warps = 256 threads, one __syncthreads per step;
+//   * the staging ring holds NB = 2 chunks of CI = 4 cells per line and array (half of k_lu_tile's), so that TWO CTAs
+//     are resident per SM: 296 tile slots for the 264 tiles of C3 (one wave), and the second tile's warps fill the
+//     issue slots the first one leaves idle while it waits on its dependent chain.
 // HBM traffic per cell is unchanged: lower reads rhs+coe+(u,v,w,T)+normals, writes dW*; upper reads dW*+coe+state+
 // normals and writes ro_P1 (dW itself is never stored).
 #include <cstdio>
@@ -22,23 +22,23 @@
 #include "fb_implicit.cuh"
 #include "fb_lu_prod.cuh"
 
-#define L2_CI 2
-#define L2_NB 4
-#define L2_TJ 16
+#define L2_CI 4
+#define L2_NB 2
+#define L2_TJ 8
 #define L2_MB 6
 #define L2_EMPTY 0xFFF7DEADBEEF5A5AULL   // signalling NaN: never produced by arithmetic
 #define L2_SPIN_MAX (1 << 21)
-#define L2_NRT 128         // refill threads
-#define L2_NWT 128         // write-back threads
-#define L2_NMT 96          // mailbox threads (3 per interface line)
+#define L2_NCT 64          // compute threads (one per line)
+#define L2_NIO 128         // refill + write-back threads (two halves sharing the staged arrays)
+#define L2_NMT 64          // mailbox threads (3 per interface line)
 
 template <int MESH, int NEQ, bool UPPER>
 struct Lu2Cfg {
     static constexpr int TJ = L2_TJ;
     static constexpr int TK = (MESH == 0 && NEQ == 6) ? 6 : 8;
     static constexpr int L = TJ * TK;
-    static constexpr int NCT = (L + 31) / 32 * 32;         // compute threads
-    static constexpr int NTH = NCT + L2_NRT + L2_NWT + L2_NMT;
+    static constexpr int NCT = L2_NCT;
+    static constexpr int NTH = L2_NCT + L2_NIO + L2_NMT;
     static constexpr int NC = NEQ == 6 ? 6 : 5;            // coe columns staged
     static constexpr int NS = UPPER ? NEQ : 4;             // state variables staged (upper: all, lower: u,v,w,T)
     static constexpr int S0 = UPPER ? 0 : 1;
@@ -48,6 +48,7 @@ struct Lu2Cfg {
     static constexpr int NIL = TJ + TK;                    // interface lines: TK on the j side, TJ on the k side
     static constexpr int RING = L2_NB * A * L * L2_CI, EXB = 2 * 2 * L * L2_MB, MBS = 4 * NIL * L2_MB, MBX = 2 * NIL * L2_MB;
     static constexpr size_t SMEM = (size_t)(RING + EXB + MBS + MBX) * sizeof(double);
+    static_assert(L <= L2_NCT && (L / L2_CI) * L2_CI <= L2_NIO / 2 && 3 * NIL <= L2_NMT, "thread roles too small for the tile");
 };
 
 void lu2_tile_dims(int mesh, int neq, int &tj, int &tk) { tj = L2_TJ; tk = (mesh == 0 && neq == 6) ? 6 : 8; }
@@ -79,16 +80,17 @@ __device__ __forceinline__ void l2_commit() { asm volatile("cp.async.commit_grou
 template <int N> __device__ __forceinline__ void l2_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 __device__ __forceinline__ unsigned long long l2_gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 
-// ring address of (chunk buffer, array, line, cell slot); the slot is XOR-swizzled with bit 3 of the line so that the
-// 32 lines of a warp (whose slots alternate with the line skew) spread over all banks: 2 wavefronts per LDS.64
+// ring address of (chunk buffer, array, line, cell slot).  The line's block of CI cells is XOR-permuted inside its kk row
+// (jj ^ 2kk): the 32 lines of a compute warp, whose slots follow the line skew, then hit every 8-byte bank exactly twice
+// (2 wavefronts per LDS.64, the minimum), and the 8 lines a refill warp fills at once spread over two bank groups.
 template <int A, int L>
 __device__ __forceinline__ int ring_at(int buf, int arr, int lam, int slot)
 {
-    return ((buf * A + arr) * L + lam) * L2_CI + (slot ^ ((lam >> 3) & 1));
+    return ((buf * A + arr) * L + (lam ^ ((lam >> 2) & 6))) * L2_CI + slot;
 }
 
 template <int MESH, int NEQ, bool UPPER>
-__global__ void __launch_bounds__((Lu2Cfg<MESH, NEQ, UPPER>::NTH), 1) k_lu_line(ZoneDev z, Lu2Args a)
+__global__ void __launch_bounds__((Lu2Cfg<MESH, NEQ, UPPER>::NTH), 2) k_lu_line(ZoneDev z, Lu2Args a)
 {
     using C = Lu2Cfg<MESH, NEQ, UPPER>;
     constexpr int TJ = C::TJ, TK = C::TK, L = C::L, A = C::A, CI = L2_CI, NB = L2_NB, EX = L2_MB, NIL = C::NIL;
@@ -115,57 +117,46 @@ __global__ void __launch_bounds__((Lu2Cfg<MESH, NEQ, UPPER>::NTH), 1) k_lu_line(
 
     if (tid >= C::NCT) {
         // ------------------------------------------------------------------------------------ service warps
-        // rule(t): the lines with (t - sigma) % CI == 0 finished chunk m-1 at step t-1 (m = (t - sigma) / CI).  That
-        // chunk is written back one iteration later (t = s-1: the barrier of iteration s-1 orders it after the compute
-        // step that produced it) and its buffer refilled with chunk m-1+NB two iterations later (t = s-2).
-        const int st = (tid - C::NCT) % 128;
-        const int q = st / CI, cell = st % CI;
-        const int kk = q / LPK, kkg = K * TK + kk;
-        struct Ln { int lam, lrow, m, jjg; bool ok; };
-        auto line_of = [&](int t) {
-            Ln o;
-            const int jj = ((t - kk) % CI + CI) % CI + CI * (q % LPK);
-            o.jjg = J * TJ + jj;
-            o.ok = kk < TK && o.jjg < bj && kkg < bk;
-            o.m = (t - (jj + kk)) / CI;                         // exact: a multiple of CI (may be < 0)
-            o.lam = kk * TJ + jj;
-            o.lrow = l0 + sg * (o.jjg * z.incj + kkg * z.inck);
-            return o;
-        };
-        const int role = (tid - C::NCT) / 128;
-        if (role == 0) {
-            // ---- refill: lanes along i inside a chunk, then across lines
+        if (tid < C::NCT + L2_NIO) {
+            // ---- refill + write-back: 2 x 64 threads, lanes along i inside a chunk, then across the 16 lines whose chunk
+            // turns over at this step; the two halves share the staged arrays
+            const int st = tid - C::NCT, half = st / 64, s2 = st % 64;
+            const int q = s2 / CI, cell = s2 % CI;
+            const int kk = q / LPK, kkg = K * TK + kk;
+            struct Ln { int lam, lrow, m, jjg; bool ok; };
+            auto line_of = [&](int t) {
+                Ln o;
+                const int jj = ((t - kk) % CI + CI) % CI + CI * (q % LPK);
+                o.jjg = J * TJ + jj;
+                o.ok = kk < TK && o.jjg < bj && kkg < bk;
+                o.m = (t - (jj + kk)) / CI;                         // exact: a multiple of CI (may be < 0)
+                o.lam = kk * TJ + jj;
+                o.lrow = l0 + sg * (o.jjg * z.incj + kkg * z.inck);
+                return o;
+            };
             auto refill = [&](int t) {
                 const Ln o = line_of(t);
                 const int c = o.m - 1 + NB, ii = c * CI + cell;
                 if (!(o.ok && c >= 0 && ii < bi)) return;
                 const int l = o.lrow + sg * ii;
                 double *dst = ring + ring_at<A, L>(c % NB, 0, o.lam, cell);
+                if (half == 0) {
 #pragma unroll
-                for (int e = 0; e < NEQ; e++) l2_cp_async8(dst + (size_t)(C::A_DW + e) * L * CI, a.dw + l + e * nd);
+                    for (int e = 0; e < NEQ; e++) l2_cp_async8(dst + (size_t)(C::A_DW + e) * L * CI, a.dw + l + e * nd);
 #pragma unroll
-                for (int e = 0; e < C::NC; e++) l2_cp_async8(dst + (size_t)(C::A_COE + e) * L * CI, a.coe + l + e * nd);
+                    for (int e = 0; e < C::NC; e++) l2_cp_async8(dst + (size_t)(C::A_COE + e) * L * CI, a.coe + l + e * nd);
+                } else {
 #pragma unroll
-                for (int e = 0; e < C::NS; e++) l2_cp_async8(dst + (size_t)(C::A_ST + e) * L * CI, a.rop + l + (C::S0 + e) * nd);
-                if (MESH != 2) {
-                    const int lt = MESH == 1 ? l % a.plane : l;
+                    for (int e = 0; e < C::NS; e++) l2_cp_async8(dst + (size_t)(C::A_ST + e) * L * CI, a.rop + l + (C::S0 + e) * nd);
+                    if (MESH != 2) {
+                        const int lt = MESH == 1 ? l % a.plane : l;
 #pragma unroll
-                    for (int e = 0; e < C::NT; e++) l2_cp_async8(dst + (size_t)(C::A_T + e) * L * CI, a.tcm + lt + e * a.tstride);
+                        for (int e = 0; e < C::NT; e++) l2_cp_async8(dst + (size_t)(C::A_T + e) * L * CI, a.tcm + lt + e * a.tstride);
+                    }
                 }
             };
-            for (int t = (1 - NB) * CI; t <= -3; t++) { refill(t); l2_commit(); }
-            for (int s = 0; s < nst; s++) {
-                refill(s - 2);
-                l2_commit();
-                l2_wait<(NB - 1) * CI - 2>();
-                __syncthreads();
-            }
-            __syncthreads();
-            l2_wait<0>();
-            return;
-        }
-        if (role == 1) {
-            // ---- write-back: dW* (lower) or the Newton-updated state the compute thread left in the ring (upper)
+            // write-back: dW* (lower) or the Newton-updated state the compute thread left in the ring (upper); each half
+            // takes every other variable
             auto writeback = [&](int t) {
                 const Ln o = line_of(t);
                 const int c = o.m - 1, ii = c * CI + cell;
@@ -174,20 +165,28 @@ __global__ void __launch_bounds__((Lu2Cfg<MESH, NEQ, UPPER>::NTH), 1) k_lu_line(
                 const double *src = ring + ring_at<A, L>(c % NB, 0, o.lam, cell);
                 if (!UPPER) {
 #pragma unroll
-                    for (int e = 0; e < NEQ; e++) a.dw[l + e * nd] = src[(size_t)(C::A_DW + e) * L * CI];
+                    for (int e = 0; e < NEQ; e++) if ((e & 1) == half) a.dw[l + e * nd] = src[(size_t)(C::A_DW + e) * L * CI];
                 } else {
                     const int i = a.box[1] - ii, j = a.box[3] - o.jjg, k = a.box[5] - kkg;
                     if (i >= a.nbx[0] && i <= a.nbx[1] && j >= a.nbx[2] && j <= a.nbx[3] && k >= a.nbx[4] && k <= a.nbx[5]) {
 #pragma unroll
-                        for (int e = 0; e < NEQ; e++) a.rop_out[l + e * nd] = src[(size_t)(C::A_ST + e) * L * CI];
+                        for (int e = 0; e < NEQ; e++) if ((e & 1) == half) a.rop_out[l + e * nd] = src[(size_t)(C::A_ST + e) * L * CI];
                     }
                 }
             };
+            // rule(t): the lines with (t - sigma) % CI == 0 finished chunk m-1 at step t-1 (m = (t - sigma) / CI).  That
+            // chunk is written back one iteration later (t = s-1: the barrier of iteration s-1 orders it after the compute
+            // step that produced it) and its buffer refilled with chunk m-1+NB two iterations later (t = s-2).
+            for (int t = (1 - NB) * CI; t <= -3; t++) { refill(t); l2_commit(); }
             for (int s = 0; s < nst; s++) {
+                refill(s - 2);
+                l2_commit();
                 writeback(s - 1);
+                l2_wait<(NB - 1) * CI - 2>();
                 __syncthreads();
             }
             __syncthreads();
+            l2_wait<0>();
             for (int s = nst; s <= nst + CI; s++) writeback(s - 1);
             return;
         }
@@ -195,7 +194,7 @@ __global__ void __launch_bounds__((Lu2Cfg<MESH, NEQ, UPPER>::NTH), 1) k_lu_line(
         // otherwise k interface, column jj = il - TK).  Words needed at step X are loaded at iteration X-3 (registers
         // carried over the loop edge), parked in shared memory at X-2 and, before the barrier of step X, delivered
         // validated into mbx (polling global memory while the producer tile has not delivered); the entry is re-armed.
-        const int sw = tid - C::NCT - 256;
+        const int sw = tid - C::NCT - L2_NIO;
         const int il = sw / 3, part = sw % 3;
         const bool isj = il < TK;
         const int mjj = isj ? 0 : il - TK, mkk = isj ? il : 0;
@@ -389,6 +388,8 @@ static int run_lu_lines(const ZoneDev &z, const LuPlan &p, const double *rop, do
     if (!attr_done) {
         cudaFuncSetAttribute(k_lu_line<MESH, NEQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CL::SMEM);
         cudaFuncSetAttribute(k_lu_line<MESH, NEQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CU::SMEM);
+        cudaFuncSetAttribute(k_lu_line<MESH, NEQ, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(k_lu_line<MESH, NEQ, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         attr_done = true;
     }
     cudaMemsetAsync(p.d_ctl, 0, 2 * sizeof(int), st);
