@@ -16,7 +16,7 @@ SYMBOLS = ['fb_version', 'fb_last_error', 'fb_device_count', 'fb_solver_create',
            'fb_zone_download_work', 'fb_set_joins', 'fb_compute', 'fb_apply_bc', 'fb_transfers', 'fb_compute_mut',
            'fb_zone_get_residuals', 'fb_zone_get_cfl', 'fb_compute_host', 'fb_timing_enable', 'fb_timing_reset',
            'fb_timing_get', 'fb_sync', 'fb_zone_device_ptr', 'fb_halo_pack', 'fb_halo_unpack', 'fb_set_modulo_verif',
-           'fb_stream', 'fb_halo_sizes', 'fb_set_exchange_cb', 'fb_halo_buffers', 'fb_counter']
+           'fb_stream', 'fb_halo_sizes', 'fb_set_exchange_cb', 'fb_halo_buffers', 'fb_counter', 'fb_exchange_stream']
 
 
 def lib():
@@ -29,6 +29,7 @@ def lib():
         L.fb_last_error.restype = ctypes.c_char_p
         L.fb_zone_device_ptr.restype = ctypes.c_ulonglong
         L.fb_stream.restype = ctypes.c_ulonglong
+        L.fb_exchange_stream.restype = ctypes.c_ulonglong
         L.fb_halo_pack.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_ulonglong, ctypes.c_longlong]
         L.fb_halo_unpack.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_ulonglong, ctypes.c_longlong]
         for n in SYMBOLS:

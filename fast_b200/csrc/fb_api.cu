@@ -42,6 +42,9 @@ struct Timer { cudaEvent_t a, b; double ms = 0; long long n = 0; std::vector<std
 struct fb_solver {
     int dev = 0, nz = 0;
     cudaStream_t st = nullptr;
+    cudaStream_t st2 = nullptr;       // cross-rank halo exchange (pack, host transport, unpack): overlaps the interior tiles
+    cudaEvent_t ev1 = nullptr, ev2 = nullptr;
+    int *d_done = nullptr;            // face tiles finished (RhsArgs::done), device counter
     std::vector<Zone> z;
     bool metric_done = false;
     JoinSet joins;
@@ -90,6 +93,9 @@ int fb_solver_create(int device, int nzones, fb_solver **out)
     fb_solver *s = new fb_solver();
     s->dev = device; s->nz = nzones; s->z.resize(nzones);
     CK(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&s->st2, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&s->ev1, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&s->ev2, cudaEventDisableTiming));
+    CK(cudaMalloc(&s->d_done, 2 * sizeof(int))); CK(cudaMemset(s->d_done, 0, 2 * sizeof(int)));
     *out = s;
     return FB_OK;
 }
@@ -107,6 +113,10 @@ void fb_solver_destroy(fb_solver *s)
     joins_free(s->joins);
     cudaFree(s->halo_send); cudaFree(s->halo_recv);
     if (s->st) cudaStreamDestroy(s->st);
+    if (s->st2) cudaStreamDestroy(s->st2);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->ev2) cudaEventDestroy(s->ev2);
+    cudaFree(s->d_done);
     delete s;
 }
 
@@ -410,29 +420,64 @@ static void apply_bc_zone(fb_solver *s, Zone &z, double *rop, int lrhs)
     }
 }
 
-static void transfers(fb_solver *s, int which, int level_ssiter_dummy, double **target)
+// Match-join transfers.  Cross-rank joins (C/Com/setInterpTransfersFast.cpp:962 setInterpTransfersInter) run on the exchange
+// stream st2: pack the donor cells (ordered after everything queued on st so far), let the host transport move the send
+// buffer to the peers' receive buffers (fb_exchange_stream), unpack into the ghost cells.  transfers_begin returns at once;
+// whatever the caller queues on st before transfers_end overlaps the exchange.  Local joins run on st in transfers_end.
+static bool cross_rank(fb_solver *s) { return s->xcb && (s->joins.send_doubles || s->joins.recv_doubles); }
+
+// exchange stream: wait until `target` face tiles of the running rhs kernels have signalled (RhsArgs::done), then re-arm
+// the counter.  Bounded: after ~4 s without progress it gives up and raises cnt[1] (reported by fb_sync).
+__global__ void k_wait_count(int *cnt, int target)
 {
-    (void)level_ssiter_dummy;
+    if (threadIdx.x != 0) return;
+    long long spins = 0;
+    while (atomicAdd(cnt, 0) < target) {
+        __nanosleep(200);
+        if (++spins > 20000000LL) { cnt[1] = 1; break; }
+    }
+    cnt[0] = 0;
+    __threadfence();
+}
+
+// wait_count > 0: the donor cells are produced by the face tiles of rhs kernels already queued on st (gsdr3 overlap);
+// otherwise the exchange simply waits for everything queued on st so far
+static void transfers_begin(fb_solver *s, int which, double **target, int wait_count = -1)
+{
+    if (s->joins.njoin == 0 || !cross_rank(s)) return;
+    std::vector<double *> ptr(s->nz);
+    for (int i = 0; i < s->nz; i++) ptr[i] = which == 1 ? s->z[i].drodm : target[i];
+    if (wait_count > 0) { k_wait_count<<<1, 32, 0, s->st2>>>(s->d_done, wait_count); s->launches++; }
+    else { cudaEventRecord(s->ev1, s->st); cudaStreamWaitEvent(s->st2, s->ev1, 0); cudaMemsetAsync(s->d_done, 0, sizeof(int), s->st2); }
+    if (s->joins.send_doubles) { joins_pack(s->joins, ptr.data(), s->halo_send, s->joins.send_doubles * 8, s->st2); s->launches++; }
+    s->xcb(s->xuser, which);
+    if (s->joins.recv_doubles) { joins_unpack(s->joins, ptr.data(), s->halo_recv, s->joins.recv_doubles * 8, s->st2); s->launches++; }
+    cudaEventRecord(s->ev2, s->st2);
+}
+static void transfers_end(fb_solver *s, int which, double **target)
+{
     if (s->joins.njoin == 0) return;
     Scope t(s, 3);
     std::vector<double *> ptr(s->nz);
     for (int i = 0; i < s->nz; i++) ptr[i] = which == 1 ? s->z[i].drodm : target[i];
-    // cross-rank joins (C/Com/setInterpTransfersFast.cpp:962 setInterpTransfersInter): pack the donor cells, let the host
-    // transport exchange the two device buffers on this stream, unpack into the ghost cells; local joins in between
-    const bool cross = s->xcb && (s->joins.send_doubles || s->joins.recv_doubles);
-    if (cross && s->joins.send_doubles) { joins_pack(s->joins, ptr.data(), s->halo_send, s->joins.send_doubles * 8, s->st); s->launches++; }
     s->launches += joins_apply(s->joins, ptr.data(), s->nz, s->st);
-    if (cross) {
-        s->xcb(s->xuser, which);
-        if (s->joins.recv_doubles) { joins_unpack(s->joins, ptr.data(), s->halo_recv, s->joins.recv_doubles * 8, s->st); s->launches++; }
-    }
+    if (cross_rank(s)) cudaStreamWaitEvent(s->st, s->ev2, 0);
+}
+static void transfers(fb_solver *s, int which, int level_ssiter_dummy, double **target)
+{
+    (void)level_ssiter_dummy;
+    transfers_begin(s, which, target);
+    transfers_end(s, which, target);
 }
 
 static int gsdr3(fb_solver *s, int nitcfg, int nssiter, int nitrun, int first_it, int lssiter_verif, int lexit_lu)
 {
     (void)nitrun; (void)nssiter;
     const bool implicit = s->z[0].d.itypcp <= 1;
+    static const bool no_overlap = [] { const char *e = getenv("FAST_B200_OVERLAP"); return e && e[0] == '0'; }();   // A/B switch
+    const bool overlap = !implicit && lexit_lu == 0 && cross_rank(s) && !no_overlap;
     std::vector<double *> cl(s->nz);
+    int face_tiles = 0; bool face_ok = true;
     {
         Scope all(s, 5);
         for (int n = 0; n < s->nz; n++) {
@@ -455,9 +500,15 @@ static int gsdr3(fb_solver *s, int nitcfg, int nssiter, int nitrun, int first_it
                 Scope r(s, 0);
                 if (implicit && z.d.iflow == 3 && nitcfg == 1) { launch_sa_ring(z.d, ssiter, s->st); s->launches++; }
                 double *out = implicit ? nullptr : clp;   // explicit: the stage writes the array that then gets the BCs
-                launch_rhs(z.d, ssiter, out, z.rop[0], z.rop[1], nitcfg, first_it, s->st); s->launches++;
+                // explicit + cross-rank joins: the CTAs take the tiles that touch a zone face first (their cells are the
+                // donors of the exchange) and count them off; the exchange stream starts when they are all in memory and
+                // runs while the interior tiles are still being computed
+                const int nb = launch_rhs(z.d, ssiter, out, z.rop[0], z.rop[1], nitcfg, first_it, s->st, overlap ? s->d_done : nullptr);
+                s->launches++;
+                if (nb > 0) face_tiles += nb; else face_ok = false;
             }
         }
+        if (overlap) transfers_begin(s, 0, cl.data(), face_ok ? face_tiles : -1);
         if (implicit) {
             if (s->z[0].pi[PI_LU_MATCH] == 1) transfers(s, 1, 0, nullptr);   // lhs.cpp:1-15
             for (int n = 0; n < s->nz; n++) {
@@ -472,7 +523,8 @@ static int gsdr3(fb_solver *s, int nitcfg, int nssiter, int nitrun, int first_it
             }
         }
         if (lexit_lu == 0) {
-            transfers(s, 0, 0, cl.data());                                     // transfert_multiblock.cpp
+            if (overlap) transfers_end(s, 0, cl.data());
+            else transfers(s, 0, 0, cl.data());                                // transfert_multiblock.cpp
             Scope b(s, 2);
             for (int n = 0; n < s->nz; n++) apply_bc_zone(s, s->z[n], cl[n], 0);   // bcs.cpp:32-40
         }
@@ -601,6 +653,10 @@ int fb_counter(const char *name, long long *out)
 }
 static int check_lu(fb_solver *s)
 {
+    if (s->d_done) {
+        int flag = 0; cudaMemcpy(&flag, s->d_done + 1, sizeof(int), cudaMemcpyDeviceToHost);
+        if (flag) return fail(FB_ECUDA, "halo exchange: the face tiles of the rhs kernel never signalled (results invalid)");
+    }
     for (auto &z : s->z) if (z.d.itypcp <= 1 && lu_plan_error(z.lu))
         return fail(FB_ECUDA, "LU wavefront: a tile timed out waiting for its neighbour (results invalid)");
     return FB_OK;
@@ -630,6 +686,7 @@ int fb_halo_unpack(fb_solver *s, int which, unsigned long long buf, long long nb
     return FB_OK;
 }
 unsigned long long fb_stream(fb_solver *s) { return s ? (unsigned long long)s->st : 0; }
+unsigned long long fb_exchange_stream(fb_solver *s) { return s ? (unsigned long long)s->st2 : 0; }
 int fb_set_exchange_cb(fb_solver *s, fb_exchange_fn cb, void *user)
 {
     if (!s) return fail(FB_EINVAL, "null");

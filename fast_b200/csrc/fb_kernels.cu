@@ -267,7 +267,7 @@ void launch_sensor(const ZoneDev &z, const double *rop, cudaStream_t st)
 }
 
 template <int MESH>
-static void launch_rhs_f(const ZoneDev &z, const RhsArgs &a, bool impl, cudaStream_t st)
+static void launch_rhs_f(const ZoneDev &z, RhsArgs &a, bool impl, cudaStream_t st)
 {
     switch (z.iflow) {
     case 1: launch_rhs_k<MESH, 1>(z, a, impl, st); break;
@@ -276,10 +276,10 @@ static void launch_rhs_f(const ZoneDev &z, const RhsArgs &a, bool impl, cudaStre
     }
 }
 
-void launch_rhs(const ZoneDev &z, const double *rop, double *rop_out, const double *ro_n, const double *ro_n1,
-                int nitcfg, int first_it, cudaStream_t st)
+int launch_rhs(const ZoneDev &z, const double *rop, double *rop_out, const double *ro_n, const double *ro_n1,
+               int nitcfg, int first_it, cudaStream_t st, int *done)
 {
-    RhsArgs a;
+    RhsArgs a; a.order = nullptr; a.nbnd = 0; a.done = done;
     a.rop = rop; a.rop_out = rop_out; a.ro_n = ro_n; a.ro_n1 = ro_n1; a.nitcfg = nitcfg; a.wfuse = fb_sensor_fused() ? 1 : 0;
     const bool impl = z.itypcp <= 1;
     a.coefH = 0.; a.coefW = 1.;
@@ -295,6 +295,7 @@ void launch_rhs(const ZoneDev &z, const double *rop, double *rop_out, const doub
     case 1: launch_rhs_f<1>(z, a, impl, st); break;
     default: launch_rhs_f<2>(z, a, impl, st); break;
     }
+    return a.order ? a.nbnd : 0;
 }
 
 #include "fb_bc.cuh"

@@ -21,6 +21,15 @@ static inline dim3 grid3r(int ni, int nj, int nk, dim3 b) { return dim3((ni + b.
 // which makes the compiler re-load the staged state around it.
 __device__ __forceinline__ void st_wig(unsigned char *p, unsigned v) { asm("st.global.u8 [%0], %1;" ::"l"(p), "r"(v)); }
 
+// a face tile tells the exchange stream that its cells are in memory (see RhsArgs::order)
+__device__ __forceinline__ void rhs_signal_done(const RhsArgs &a, int clin, bool leader)
+{
+    if (a.order && clin < a.nbnd) {        // uniform per CTA
+        __syncthreads();
+        if (leader) { __threadfence(); atomicAdd(a.done, 1); }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ wall flux correction
 // S/BC/correct_flux.for:6-190 (lapply = 4: Roe scheme + wall windows), between the flux balance and the update
 // (navier_stokes_struct.for:376-383): the interior Euler flux of a wall face is taken back out of the balance
@@ -133,10 +142,12 @@ template <int MESH, int FLOW, int SCHEME, int SLOPE, bool IMPL, bool WC>
 __global__ void __launch_bounds__(32 * (RHS2_RJ + 1)) k_rhs2(ZoneDev z, RhsArgs a)
 {
     constexpr int NEQ = FLOW == 3 ? 6 : 5, RJ = RHS2_RJ;
+    int bx = blockIdx.x, by = blockIdx.y, bz = blockIdx.z, clin = 0;
+    if (a.order) { clin = bx + gridDim.x * (by + gridDim.y * bz); const int t = a.order[clin]; bx = t & 1023; by = (t >> 10) & 1023; bz = t >> 20; }
     __shared__ double sFj[2][RJ + 1][NEQ][32];
     const int li = threadIdx.x, m = threadIdx.y;
-    const int i = 1 + blockIdx.x * 31 + li, j = 1 + blockIdx.y * RJ + m;
-    const int k0 = 1 + blockIdx.z * RHS2_KC, k1 = min(k0 + RHS2_KC - 1, z.kv);
+    const int i = 1 + bx * 31 + li, j = 1 + by * RJ + m;
+    const int k0 = 1 + bz * RHS2_KC, k1 = min(k0 + RHS2_KC - 1, z.kv);
     const bool cell = li < 31 && m < RJ && i <= z.iv && j <= z.jv;      // owns a cell
     const bool fi = m < RJ && j <= z.jv && i <= z.iv + 1;               // owns a lower i face that somebody needs
     const bool fj = li < 31 && i <= z.iv && j <= z.jv + 1;              // owns a lower j face that somebody needs
@@ -217,6 +228,7 @@ __global__ void __launch_bounds__(32 * (RHS2_RJ + 1)) k_rhs2(ZoneDev z, RhsArgs 
             for (int e = 0; e < NEQ; e++) acc[e] -= sFj[k & 1][m + 1][e][li];
         }
     }
+    rhs_signal_done(a, clin, li == 0 && m == 0);
 }
 
 // ------------------------------------------------------------------------------------------------ fused rhs, TMA path
@@ -297,6 +309,8 @@ k_rhs3(const __grid_constant__ CUtensorMap tm_rop, const __grid_constant__ CUten
 {
     using C = Rhs3Cfg<FLOW, RJ>;
     constexpr int NEQ = C::NEQ, NS = RHS3_NS, PS = C::PS, RS = C::RS, VS = C::VS;
+    int bx = blockIdx.x, by = blockIdx.y, bz = blockIdx.z, clin = 0;
+    if (a.order) { clin = bx + gridDim.x * (by + gridDim.y * bz); const int t = a.order[clin]; bx = t & 1023; by = (t >> 10) & 1023; bz = t >> 20; }
     extern __shared__ __align__(128) double ring[];
     double (*sFj)[RJ + 1][NEQ][32] = (double (*)[RJ + 1][NEQ][32])(ring + NS * PS);
     constexpr int NSF = C::template nsf<MESH>();
@@ -304,8 +318,8 @@ k_rhs3(const __grid_constant__ CUtensorMap tm_rop, const __grid_constant__ CUten
     unsigned long long *bar = (unsigned long long *)(smet + C::template met<MESH>());
     const int li = threadIdx.x, m = threadIdx.y;
     const bool leader = li == 0 && m == 0;
-    const int i = 1 + blockIdx.x * 31 + li, j = 1 + blockIdx.y * RJ + m;
-    const int k0 = 1 + blockIdx.z * RHS3_KC, k1 = min(k0 + RHS3_KC - 1, z.kv);
+    const int i = 1 + bx * 31 + li, j = 1 + by * RJ + m;
+    const int k0 = 1 + bz * RHS3_KC, k1 = min(k0 + RHS3_KC - 1, z.kv);
     const bool cell = li < 31 && m < RJ && i <= z.iv && j <= z.jv;
     const bool fi = m < RJ && j <= z.jv && i <= z.iv + 1;
     const bool fj = li < 31 && i <= z.iv && j <= z.jv + 1;
@@ -314,7 +328,7 @@ k_rhs3(const __grid_constant__ CUtensorMap tm_rop, const __grid_constant__ CUten
     // array coordinates of the box origin (cell i0-2, j0-2) and planes k0-1 .. k1+2
     // (TMA needs a 16-byte aligned global start: an odd first column is shifted one to the left -- the 36-wide box
     // still covers the 35 columns i0-2 .. i0+32 the tile reads)
-    const int ca0 = blockIdx.x * 31 + z.nf - 2, cb = blockIdx.y * RJ + z.nf - 2;
+    const int ca0 = bx * 31 + z.nf - 2, cb = by * RJ + z.nf - 2;
     const int sh = ca0 & 1, ca = ca0 - sh;
     const int pfirst = k0 - 1, plast = k1 + 2;
     auto issue = [&](int p) {
@@ -332,7 +346,7 @@ k_rhs3(const __grid_constant__ CUtensorMap tm_rop, const __grid_constant__ CUten
         const int tid = m * 32 + li, mlast = z.nm - 1;
         for (int n = tid; n < 6 * VS; n += C::NT) {
             const int arr = n / VS, r = (n % VS) / RS, c = n % RS;
-            int lt = indmtr(z, 1 + blockIdx.x * 31 - 2 - sh + c, 1 + blockIdx.y * RJ - 2 + r, 1);
+            int lt = indmtr(z, 1 + bx * 31 - 2 - sh + c, 1 + by * RJ - 2 + r, 1);
             lt = lt < 0 ? 0 : (lt > mlast ? mlast : lt);        // outside the arrays: never used, any finite value will do
             const double *src = arr < 2 ? z.ti + arr * z.nm : (arr < 4 ? z.tj + (arr - 2) * z.nm : (arr == 4 ? z.tk : z.vol));
             smet[n] = __ldg(src + lt);
@@ -436,18 +450,22 @@ k_rhs3(const __grid_constant__ CUtensorMap tm_rop, const __grid_constant__ CUten
         }
         if (NSF == 1) __syncthreads();      // single F_j buffer: everybody has read it before the next plane overwrites it
     }
+    rhs_signal_done(a, clin, leader);
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
 // tensor maps of rop(ni,nj,nk,neq) / xmut(ni,nj,nk,naux) with a (36, rows, 1, nvar) box; nullptr when the strides
 // cannot be encoded (odd ni or NDIMDX) or the driver entry point is missing (fb_tma.cu)
 const CUtensorMap *fb_tma_map(const double *base, int ni, int nj, int nk, long long var_stride, int nvar_total, int box_rows, int box_vars);
+// tile order of a gx x gy x gz launch with the tiles that touch a zone face first (cached device table); *nbnd = their number
+const int *fb_tile_order(int gx, int gy, int gz, int *nbnd);
 
 template <int MESH, int FLOW, int SCHEME, int SLOPE>
-static void launch_rhs2_t(const ZoneDev &z, const RhsArgs &a, bool impl, cudaStream_t st)
+static void launch_rhs2_t(const ZoneDev &z, RhsArgs &a, bool impl, cudaStream_t st)
 {
     dim3 b(32, RHS2_RJ + 1, 1);
     dim3 g((z.iv + 30) / 31, (z.jv + RHS2_RJ - 1) / RHS2_RJ, (z.kv + RHS2_KC - 1) / RHS2_KC);
+    a.order = a.done ? fb_tile_order(g.x, g.y, g.z, &a.nbnd) : nullptr;
     // WC: first sub-iteration of a SENSOR zone -- the switch is evaluated inside the flux and stored
     if (SCHEME == 2 && a.nitcfg == 1 && a.wfuse) {
         if (impl) k_rhs2<MESH, FLOW, SCHEME, SLOPE, true, SCHEME == 2><<<g, b, 0, st>>>(z, a);
@@ -459,7 +477,7 @@ static void launch_rhs2_t(const ZoneDev &z, const RhsArgs &a, bool impl, cudaStr
 }
 
 template <int MESH, int FLOW, int SCHEME, int SLOPE>
-static bool launch_rhs3_t(const ZoneDev &z, const RhsArgs &a, bool impl, cudaStream_t st)
+static bool launch_rhs3_t(const ZoneDev &z, RhsArgs &a, bool impl, cudaStream_t st)
 {
     constexpr int RJ = FLOW == 3 ? RHS3_RJ_SA : RHS3_RJ_NS;
     using C = Rhs3Cfg<FLOW, RJ>;
@@ -477,6 +495,7 @@ static bool launch_rhs3_t(const ZoneDev &z, const RhsArgs &a, bool impl, cudaStr
     }
     dim3 b(32, RJ + 1, 1);
     dim3 g((z.iv + 30) / 31, (z.jv + RJ - 1) / RJ, (z.kv + RHS3_KC - 1) / RHS3_KC);
+    a.order = a.done ? fb_tile_order(g.x, g.y, g.z, &a.nbnd) : nullptr;
     if (SCHEME == 2 && a.nitcfg == 1 && a.wfuse) {   // first sub-iteration of a SENSOR zone: the switch is evaluated in the flux
         if (impl) k_rhs3<MESH, FLOW, SCHEME, SLOPE, true, RJ, SCHEME == 2><<<g, b, C::template smem<MESH>(), st>>>(*tr, *tm, z, a);
         else k_rhs3<MESH, FLOW, SCHEME, SLOPE, false, RJ, SCHEME == 2><<<g, b, C::template smem<MESH>(), st>>>(*tr, *tm, z, a);
@@ -490,7 +509,7 @@ static bool launch_rhs3_t(const ZoneDev &z, const RhsArgs &a, bool impl, cudaStr
 extern long long g_fb_rhs_launches[2];
 
 template <int MESH, int FLOW, int SCHEME, int SLOPE>
-static void launch_rhs_t(const ZoneDev &z, const RhsArgs &a, bool impl, cudaStream_t st)
+static void launch_rhs_t(const ZoneDev &z, RhsArgs &a, bool impl, cudaStream_t st)
 {
     static const bool l1path = [] { const char *e = getenv("FAST_B200_RHS"); return e && e[0] == '2'; }();   // A/B switch
     if (!l1path && launch_rhs3_t<MESH, FLOW, SCHEME, SLOPE>(z, a, impl, st)) { g_fb_rhs_launches[0]++; return; }
@@ -498,7 +517,7 @@ static void launch_rhs_t(const ZoneDev &z, const RhsArgs &a, bool impl, cudaStre
     g_fb_rhs_launches[1]++;
 }
 template <int MESH, int FLOW, int SCHEME>
-static void launch_rhs_s(const ZoneDev &z, const RhsArgs &a, bool impl, cudaStream_t st)
+static void launch_rhs_s(const ZoneDev &z, RhsArgs &a, bool impl, cudaStream_t st)
 {
     switch (z.slope) {
     case 2: launch_rhs_t<MESH, FLOW, SCHEME, 2>(z, a, impl, st); break;
@@ -507,7 +526,7 @@ static void launch_rhs_s(const ZoneDev &z, const RhsArgs &a, bool impl, cudaStre
     }
 }
 template <int MESH, int FLOW>
-void launch_rhs_k(const ZoneDev &z, const RhsArgs &a, bool impl, cudaStream_t st)
+void launch_rhs_k(const ZoneDev &z, RhsArgs &a, bool impl, cudaStream_t st)
 {
     switch (z.kflu) {
     case 1: launch_rhs_s<MESH, FLOW, 1>(z, a, impl, st); break;

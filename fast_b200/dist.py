@@ -38,7 +38,7 @@ class _DevArray:
 
 
 class HaloExchange:
-    """Transport behind fb_set_exchange_cb: torch.distributed point-to-point on the solver's stream."""
+    """Transport behind fb_set_exchange_cb: torch.distributed point-to-point on the library's exchange stream."""
 
     def __init__(self, solver, peers, device, group=None):
         import torch
@@ -53,7 +53,7 @@ class HaloExchange:
         self.send = torch.as_tensor(_DevArray(ps.value, ns.value), device=dev) if ns.value else None
         self.recv = torch.as_tensor(_DevArray(pr.value, nr.value), device=dev) if nr.value else None
         self.peers = dict(peers)
-        self.stream = torch.cuda.ExternalStream(L.fb_stream(solver), device=dev)
+        self.stream = torch.cuda.ExternalStream(L.fb_exchange_stream(solver), device=dev)   # the library's exchange stream
         self.bytes_per_exchange = 8 * (ns.value + nr.value)
         self.calls = 0
         self._cb = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_int)(self._exchange)

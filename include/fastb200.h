@@ -102,7 +102,7 @@ int fb_halo_sizes(fb_solver *s, long long *send_doubles, long long *recv_doubles
  * reference exchanges MPI messages (drodm before the LU sweep when lu_match=1, S/Compute/lhs.cpp:1-15; rop_CL after
  * it, S/Compute/gsdr3.cpp:362 -> C/Com/setInterpTransfersFast.cpp:962), the library packs on its stream, calls
  * cb(user, which) (which: 0 state, 1 drodm) -- the host transport moves fb_halo_buffers() send -> peers' recv, ordered
- * on fb_stream() -- and unpacks.  Without a callback cross-rank entries are ignored. */
+ * on fb_exchange_stream() -- and unpacks.  Without a callback cross-rank entries are ignored. */
 typedef void (*fb_exchange_fn)(void *user, int which);
 int fb_set_exchange_cb(fb_solver *s, fb_exchange_fn cb, void *user);
 int fb_halo_buffers(fb_solver *s, unsigned long long *send_ptr, unsigned long long *recv_ptr);
@@ -110,6 +110,10 @@ int fb_halo_buffers(fb_solver *s, unsigned long long *send_ptr, unsigned long lo
 int fb_set_modulo_verif(fb_solver *s, int modulo_verif);
 /* cudaStream_t of the solver (uintptr) so that torch/NCCL work can be ordered against it. */
 unsigned long long fb_stream(fb_solver *s);
+/* cudaStream_t (uintptr) the library runs the cross-rank halo exchange on: the exchange callback must order its transfers
+ * on THIS stream (pack precedes, unpack follows on it); the solver stream only waits for it where the ghost cells are
+ * needed, so the exchange overlaps the interior tiles of an explicit stage. */
+unsigned long long fb_exchange_stream(fb_solver *s);
 
 #ifdef __cplusplus
 }
