@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the FastS residual-and-update hot path on B200.
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload tgv256|plate|multiblock]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload tgv256|plate|multiblock|c5]
 
 A "step" is one full time iteration of the hot path (all sub-iterations: 3 RK stages, or ss_iteration Newton
 sub-iterations incl. LU sweeps, plus match-join transfers and BC fill) over one synthetic case.  Default workload at
@@ -50,13 +50,18 @@ def make_case(workload, n=None, rank=0, world=1):
         n = n or 128
         t, j = synth.case_multiblock(nblk=(2, 2, 2), n=n, modulo_verif=1000)
         return t, j, '8 x %d^3 blocks, match joins, Roe o3, implicit LU-SGS 3 sub-iterations, lu_match (BASELINE configs[3])' % n
+    if workload == 'c5':     # one GPU's share of BASELINE configs[4]: a 2x2x2 brick of 256x256x64 blocks
+        from fast_b200 import dist as fdist
+        t, table, peers, desc, _ = fdist.local_case('c5', 0, 1, n=n)
+        return t, table, desc
     raise ValueError(workload)
 
 
 def _desc_only(workload):
     d = {'tgv256': 'laminar TGV 256^3, SENSOR o3, explicit RK3 (BASELINE configs[1])',
          'plate': 'RANS-SA flat plate 512x256x64 (3dhomo), AUSM o3, implicit LU-SGS 5 sub-iterations, local dt (BASELINE configs[2])',
-         'multiblock': '8 x 128^3 blocks, match joins, Roe o3, implicit LU-SGS 3 sub-iterations, lu_match (BASELINE configs[3])'}
+         'multiblock': '8 x 128^3 blocks, match joins, Roe o3, implicit LU-SGS 3 sub-iterations, lu_match (BASELINE configs[3])',
+         'c5': 'RANS-SA flat plate in blocks of 256x256x64 (3dhomo), 8 blocks per GPU, implicit LU-SGS 5 sub-iterations (BASELINE configs[4])'}
     return None, None, d[workload]
 make_case.__wrapped_desc__ = _desc_only
 
@@ -98,7 +103,7 @@ def cpu_oracle_rate(workload, seconds=15., threads=None):
     """Mcell.it/s of the CPU oracle (OpenMP: k slabs for the rhs, one zone per thread for the LU) on a bounded sample."""
     sys.path.insert(0, os.path.join(ROOT, 'tests')); sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     from helpers import oracle_from_tree, V
-    sample_n = {'tgv256': 96, 'plate': (128, 64, 16), 'multiblock': 32}[workload]
+    sample_n = {'tgv256': 96, 'plate': (128, 64, 16), 'multiblock': 32, 'c5': (32, 32, 8)}[workload]
     t, j, desc = make_case(workload, n=sample_n)
     o = oracle_from_tree(t, joins=j, fast=True)
     nthreads = threads or o.L.fo_max_threads()
@@ -202,11 +207,13 @@ def run_gpu(args):
     peak, pk = peaks()
     cz = cells / len(zones)
     cnt = {}
-    for name in ('rhs_tma', 'rhs_l1', 'lu_line'):
+    for name in ('rhs_tma', 'rhs_l1', 'lu_line', 'lu_batch'):
         v = ctypes.c_longlong(0); _lib.check(L.fb_counter(name.encode(), ctypes.byref(v))); cnt[name] = int(v.value)
     if tm['lu'] > tm['rhs']:
         kern = 'k_lu_line' if cnt['lu_line'] else 'k_lu_tile'
         nl, bpl = 2 * args.steps * nsub * len(zones), (b_sub - b_rhs) / 2.   # lower + upper launch
+        if cnt['lu_batch']:      # one lower + one upper launch sweep ALL zones of the rank (k_lu_tile_b)
+            kern, nl, cz = 'k_lu_tile_b', 2 * args.steps * nsub, cells
         avg_ms = tm['lu'] / nl
     else:
         kern = 'k_rhs3' if cnt['rhs_tma'] >= cnt['rhs_l1'] else 'k_rhs2'

@@ -53,6 +53,7 @@ struct fb_solver {
     bool timing = false;
     Timer tm[6];     // rhs, lu, bc, transfer, coe, all
     long long launches = 0;
+    LuBatch *lub = nullptr; bool lub_tried = false;   // multi-zone LU launch (fb_lu.cu: k_lu_tile_b), built on first use
 };
 
 static const char *TNAMES[6] = {"rhs", "lu", "bc", "transfer", "coe", "all"};
@@ -117,6 +118,7 @@ void fb_solver_destroy(fb_solver *s)
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->ev2) cudaEventDestroy(s->ev2);
     cudaFree(s->d_done);
+    lu_batch_free(s->lub);
     delete s;
 }
 
@@ -284,6 +286,7 @@ int fb_zone_set_params(fb_solver *s, int nd, const int *pi, int n_int, const dou
     d.xmut = z.aux; d.drodm = z.drodm; d.coe = z.coe; d.wigb = z.wigb;
     cudaFree(z.wins); cudaFree(z.wins_rhs); z.wins = z.wins_rhs = nullptr;
     int rc = build_bc_tables(z); if (rc) return rc;
+    lu_batch_free(s->lub); s->lub = nullptr; s->lub_tried = false;
     if (d.itypcp <= 1) { rc = lu_plan_build(z.lu, d, z.lu_box); if (rc) return fail(FB_ECUDA, "lu_plan_build failed"); }
     z.has_params = true; s->metric_done = false;
     return FB_OK;
@@ -470,6 +473,7 @@ static void transfers(fb_solver *s, int which, int level_ssiter_dummy, double **
     transfers_end(s, which, target);
 }
 
+static long long g_lu_batch_launches = 0;   // multi-zone LU sweeps (lower + upper pairs), fb_counter("lu_batch")
 static int gsdr3(fb_solver *s, int nitcfg, int nssiter, int nitrun, int first_it, int lssiter_verif, int lexit_lu)
 {
     (void)nitrun; (void)nssiter;
@@ -511,15 +515,36 @@ static int gsdr3(fb_solver *s, int nitcfg, int nssiter, int nitrun, int first_it
         if (overlap) transfers_begin(s, 0, cl.data(), face_ok ? face_tiles : -1);
         if (implicit) {
             if (s->z[0].pi[PI_LU_MATCH] == 1) transfers(s, 1, 0, nullptr);   // lhs.cpp:1-15
+            // several zones: one pair of launches sweeps them all, tiles of the zones interleaved (k_lu_tile_b)
+            static const bool no_batch = [] { const char *e = getenv("FAST_B200_LU_BATCH"); return e && e[0] == '0'; }();   // A/B switch
+            if (s->nz > 1 && !s->lub_tried && !no_batch && lexit_lu == 0) {
+                std::vector<const ZoneDev *> zs(s->nz); std::vector<const LuPlan *> ps(s->nz);
+                for (int n = 0; n < s->nz; n++) { zs[n] = &s->z[n].d; ps[n] = &s->z[n].lu; }
+                bool same = true;
+                for (int n = 1; n < s->nz; n++) same = same && s->z[n].pi[PI_LU_MATCH] == s->z[0].pi[PI_LU_MATCH];
+                s->lub = same ? lu_batch_create(s->nz, zs.data(), ps.data()) : nullptr; s->lub_tried = true;
+            }
+            const bool batch = s->lub && lexit_lu == 0;
             for (int n = 0; n < s->nz; n++) {
                 Zone &z = s->z[n];
                 { Scope b(s, 2); apply_bc_zone(s, z, z.drodm, 1); }           // lhs.cpp:57-67
                 if (lssiter_verif == 1) { launch_resid(z.d, z.rdm, nitcfg, z.pi[PI_NSSITER], s->st); s->launches += 2; }   // cprdu3s1
-                if (lexit_lu == 0) {
+                if (lexit_lu == 0 && !batch) {
                     Scope l(s, 1);
                     double *ssiter = nitcfg == 1 ? z.rop[0] : z.rop[2];
                     s->launches += launch_lu(z.d, z.lu, ssiter, z.rop[2], z.pi[PI_LU_MATCH] == 1, s->st);   // invlu_ + mjr_newton
                 }
+            }
+            if (batch) {
+                Scope l(s, 1);
+                std::vector<const ZoneDev *> zs(s->nz); std::vector<const LuPlan *> ps(s->nz);
+                std::vector<const double *> rin(s->nz); std::vector<double *> rout(s->nz);
+                for (int n = 0; n < s->nz; n++) {
+                    zs[n] = &s->z[n].d; ps[n] = &s->z[n].lu; rin[n] = nitcfg == 1 ? s->z[n].rop[0] : s->z[n].rop[2]; rout[n] = s->z[n].rop[2];
+                }
+                const int nl = lu_batch_launch(s->lub, zs.data(), ps.data(), rin.data(), rout.data(), s->z[0].pi[PI_LU_MATCH] == 1, s->st);
+                if (nl < 0) return fail(FB_ECUDA, "lu_batch_launch: out of device memory");
+                s->launches += nl; g_lu_batch_launches++;
             }
         }
         if (lexit_lu == 0) {
@@ -649,6 +674,7 @@ int fb_counter(const char *name, long long *out)
     if (!strcmp(name, "rhs_tma")) { *out = g_fb_rhs_launches[0]; return FB_OK; }
     if (!strcmp(name, "rhs_l1")) { *out = g_fb_rhs_launches[1]; return FB_OK; }
     if (!strcmp(name, "lu_line")) { *out = lu_use_lines() ? 1 : 0; return FB_OK; }
+    if (!strcmp(name, "lu_batch")) { *out = g_lu_batch_launches; return FB_OK; }
     return fail(FB_EINVAL, "unknown counter");
 }
 static int check_lu(fb_solver *s)

@@ -27,6 +27,13 @@ bool lu_use_lines();                                                  // fb_lu2.
 void lu2_tile_dims(int mesh, int neq, int &tj, int &tk);
 int  launch_lu_lines(const ZoneDev &z, const LuPlan &p, const double *rop_ssiter, double *rop_out, int lu_match, cudaStream_t st);
 int  launch_lu_tiles(const ZoneDev &z, const LuPlan &p, const double *rop_ssiter, double *rop_out, int lu_match, cudaStream_t st);
+// all zones of a multi-zone solver swept by one pair of launches (fb_lu.cu: k_lu_tile_b); nullptr when the zones cannot share
+// a launch (different mesh family / number of equations, line kernel selected)
+struct LuBatch;
+LuBatch *lu_batch_create(int nz, const ZoneDev *const *zs, const LuPlan *const *plans);
+void lu_batch_free(LuBatch *b);
+int  lu_batch_launch(LuBatch *b, const ZoneDev *const *zs, const LuPlan *const *plans, const double *const *rop_ssiter,
+                     double *const *rop_out, int lu_match, cudaStream_t st);
 void launch_coe(const ZoneDev &z, const double *rop, int first_it, int lssiter_verif, double *cfl, cudaStream_t st);
 void launch_sa_ring(const ZoneDev &z, const double *rop, cudaStream_t st);
 void launch_resid(const ZoneDev &z, double *rdm, int nitcfg, int nss, cudaStream_t st);

@@ -27,6 +27,8 @@
 #include <vector>
 #include <algorithm>
 #include <type_traits>
+#include <map>
+#include <cstring>
 #include "fb_implicit.cuh"
 
 #define LU_CI 8            // cells per line per staged chunk
@@ -94,23 +96,22 @@ __device__ __forceinline__ bool mb_empty(unsigned long long v) { return v == LU_
 
 #include "fb_lu_prod.cuh"
 
+// one tile (J | K << 16 = tile) of zone z for the whole length of the sweep box; z and a live in the constant bank
+// (k_lu_tile: one zone per launch) or in shared memory (k_lu_tile_b: all zones of a solver in one launch)
 template <int MESH, int NEQ, bool UPPER>
-__global__ void __launch_bounds__(LU_NT, 1) k_lu_tile(ZoneDev z, LuTileArgs a)
+__device__ __forceinline__ void lu_tile_body(const ZoneDev &z, const LuTileArgs &a, const int tile, double *smem)
 {
     using C = LuCfg<MESH, NEQ, UPPER>;
     constexpr int TJ = C::TJ, TK = C::TK, L = C::L, A = C::A, CI = LU_CI, EX = LU_MB;
-    extern __shared__ double smem[];
     double *ring = smem;                              // [2][A][L][CI]
     double *exb = smem + 2 * A * L * CI;              // [2][L][3][EX] products handed to (ii+1), (jj+1), (kk+1)
     unsigned long long *mbs = (unsigned long long *)(exb + 2 * 3 * L * EX);   // [4][16][EX] prefetched mailbox words
     double *mbx = (double *)(mbs + 4 * 16 * EX);      // [2][16][EX] validated products of the neighbour tiles
-    __shared__ int s_tile;
     const int tid = threadIdx.x;
-    if (tid == 0) s_tile = a.order[atomicAdd(a.ticket, 1)];
     // exchange buffers start at zero: products that are multiplied by a zero weight (box boundary) must be finite
     for (int i = tid; i < 2 * 3 * L * EX + 6 * 16 * EX; i += LU_NT) exb[i] = 0.;
     __syncthreads();
-    const int J = s_tile & 0xffff, K = s_tile >> 16;
+    const int J = tile & 0xffff, K = tile >> 16;
     if (a.dbg && tid == 0) { a.dbg[16 * (K * a.NJ + J)] = gtime(); a.dbg[16 * (K * a.NJ + J) + 3] = smid(); }
     const int bi = a.bi, bj = a.bj, bk = a.bk;
     const int nst = bi + TJ + TK - 2;
@@ -396,6 +397,38 @@ __global__ void __launch_bounds__(LU_NT, 1) k_lu_tile(ZoneDev z, LuTileArgs a)
     if (a.dbg && tid == 252) a.dbg[16 * (K * a.NJ + J) + 14] = tcomp;
 }
 
+template <int MESH, int NEQ, bool UPPER>
+__global__ void __launch_bounds__(LU_NT, 1) k_lu_tile(ZoneDev z, LuTileArgs a)
+{
+    extern __shared__ double smem[];
+    __shared__ int s_tile;
+    if (threadIdx.x == 0) s_tile = a.order[atomicAdd(a.ticket, 1)];
+    __syncthreads();
+    lu_tile_body<MESH, NEQ, UPPER>(z, a, s_tile, smem);
+}
+
+// Multi-zone solvers (C4 / C5: several blocks per GPU): the sweeps of all zones in ONE launch.  A zone on its own leaves
+// most SMs idle -- its tiles trail each other by ~12 steps per (J,K) hop, so a 128^3 block (256 tiles of 144 steps) spends
+// most of a sweep ramping up and down -- and, with one CTA per SM, tiles of a second launch cannot become resident while
+// the first launch's tiles sit waiting.  Here tickets run over the tiles of ALL zones ordered by J+K, zones interleaved,
+// so that every zone's wavefront advances on its share of the SMs; the zone descriptor and the sweep arguments of the
+// tile's zone are copied from a device table into shared memory.  Dependencies stay inside a zone (invlu_l.for:79-96).
+struct LuBatchItem { ZoneDev z; LuTileArgs a; };
+template <int MESH, int NEQ, bool UPPER>
+__global__ void __launch_bounds__(LU_NT, 1) k_lu_tile_b(const LuBatchItem *items, const int2 *order, int *ticket)
+{
+    extern __shared__ double smem[];
+    __shared__ int2 s_t;
+    __shared__ __align__(16) LuBatchItem s_it;
+    if (threadIdx.x == 0) s_t = order[atomicAdd(ticket, 1)];
+    __syncthreads();
+    static_assert(sizeof(LuBatchItem) % 8 == 0, "LuBatchItem is copied in 8-byte words");
+    const unsigned long long *src = (const unsigned long long *)(items + s_t.x);
+    for (int i = threadIdx.x; i < (int)(sizeof(LuBatchItem) / 8); i += LU_NT) ((unsigned long long *)&s_it)[i] = src[i];
+    __syncthreads();
+    lu_tile_body<MESH, NEQ, UPPER>(s_it.z, s_it.a, s_t.y, smem);
+}
+
 // cell-centred mean normals 0.5*(t_d(l) + t_d(l + d)) of every cell (lu_{i,j,k}_*.for build them on the fly)
 template <int MESH>
 __global__ void k_lunorm(ZoneDev z, double *tcm, long long tstride)
@@ -477,10 +510,9 @@ void lu_plan_metrics(LuPlan &p, const ZoneDev &z, cudaStream_t st)
     else k_lunorm<1><<<g, b, 0, st>>>(z, p.d_tcm, p.tstride);
 }
 
-template <int MESH, int NEQ>
-static int run_lu_tiles(const ZoneDev &z, const LuPlan &p, const double *rop, double *rop_out, int lu_match, cudaStream_t st)
+static void lu_fill_args(LuTileArgs &a, const ZoneDev &z, const LuPlan &p, const double *rop, double *rop_out, int lu_match)
 {
-    LuTileArgs a;
+    memset(&a, 0, sizeof(a));
     a.rop = rop; a.rop_out = rop_out; a.dw = z.drodm; a.coe = z.coe; a.tcm = p.d_tcm; a.tstride = p.tstride;
     a.ifj = p.d_mb; a.ifk = p.d_mb ? p.d_mb + p.n_ifj : nullptr;
     a.order = p.d_order; a.err = p.d_ctl + 2;
@@ -488,6 +520,90 @@ static int run_lu_tiles(const ZoneDev &z, const LuPlan &p, const double *rop, do
     if (lu_match) { a.nbx[0] = 1; a.nbx[1] = z.iv; a.nbx[2] = 1; a.nbx[3] = z.jv; a.nbx[4] = 1; a.nbx[5] = z.kv; }
     a.bi = p.box[1] - p.box[0] + 1; a.bj = p.box[3] - p.box[2] + 1; a.bk = p.box[5] - p.box[4] + 1;
     a.NJ = p.NJ; a.NK = p.NK; a.alias = (rop == rop_out) ? 1 : 0; a.plane = z.ni * z.nj;
+}
+
+// ------------------------------------------------------------------------------------------------ multi-zone launch
+struct LuBatch {
+    int nz = 0, typ = 0, neq = 0, ntiles = 0;
+    int2 *d_order = nullptr;          // ticket -> (zone, J | K << 16), ordered by J + K with the zones interleaved
+    int *d_ticket = nullptr;          // [lower, upper]
+    // device tables of {ZoneDev, LuTileArgs} per zone, one per combination of state pointers the time-level rotation and
+    // the sub-iteration number produce (six in a run), built on first use
+    std::map<std::vector<const void *>, LuBatchItem *> tables;
+};
+
+LuBatch *lu_batch_create(int nz, const ZoneDev *const *zs, const LuPlan *const *plans)
+{
+    if (nz < 2 || getenv("FAST_B200_LU")) return nullptr;        // the A/B kernels (plane, line) keep one launch per zone
+    for (int n = 0; n < nz; n++)
+        if (zs[n]->typ != zs[0]->typ || zs[n]->neq != zs[0]->neq || zs[n]->itypcp > 1 || !plans[n]->d_order) return nullptr;
+    LuBatch *b = new LuBatch();
+    b->nz = nz; b->typ = zs[0]->typ; b->neq = zs[0]->neq;
+    std::vector<std::pair<int, int2>> ord;     // (J + K, (zone, tile))
+    for (int n = 0; n < nz; n++)
+        for (int K = 0; K < plans[n]->NK; K++) for (int J = 0; J < plans[n]->NJ; J++) ord.push_back({J + K, make_int2(n, J | (K << 16))});
+    std::stable_sort(ord.begin(), ord.end(), [](const std::pair<int, int2> &x, const std::pair<int, int2> &y) { return x.first < y.first; });
+    std::vector<int2> o2(ord.size());
+    for (size_t i = 0; i < ord.size(); i++) o2[i] = ord[i].second;
+    b->ntiles = (int)o2.size();
+    if (cudaMalloc(&b->d_order, o2.size() * sizeof(int2)) != cudaSuccess || cudaMalloc(&b->d_ticket, 2 * sizeof(int)) != cudaSuccess) {
+        cudaGetLastError(); lu_batch_free(b); return nullptr;
+    }
+    cudaMemcpy(b->d_order, o2.data(), o2.size() * sizeof(int2), cudaMemcpyHostToDevice);
+    return b;
+}
+
+void lu_batch_free(LuBatch *b)
+{
+    if (!b) return;
+    for (auto &t : b->tables) cudaFree(t.second);
+    cudaFree(b->d_order); cudaFree(b->d_ticket);
+    delete b;
+}
+
+template <int MESH, int NEQ>
+static void run_lu_batch(const LuBatch *b, const LuBatchItem *items, cudaStream_t st)
+{
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_lu_tile_b<MESH, NEQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LuCfg<MESH, NEQ, false>::SMEM);
+        cudaFuncSetAttribute(k_lu_tile_b<MESH, NEQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LuCfg<MESH, NEQ, true>::SMEM);
+        attr_done = true;
+    }
+    cudaMemsetAsync(b->d_ticket, 0, 2 * sizeof(int), st);
+    k_lu_tile_b<MESH, NEQ, false><<<b->ntiles, LU_NT, LuCfg<MESH, NEQ, false>::SMEM, st>>>(items, b->d_order, b->d_ticket);
+    k_lu_tile_b<MESH, NEQ, true><<<b->ntiles, LU_NT, LuCfg<MESH, NEQ, true>::SMEM, st>>>(items, b->d_order, b->d_ticket + 1);
+}
+
+int lu_batch_launch(LuBatch *b, const ZoneDev *const *zs, const LuPlan *const *plans, const double *const *rop, double *const *rop_out,
+                    int lu_match, cudaStream_t st)
+{
+    std::vector<const void *> key;
+    for (int n = 0; n < b->nz; n++) { key.push_back(rop[n]); key.push_back(rop_out[n]); }
+    key.push_back((const void *)(size_t)lu_match);
+    auto it = b->tables.find(key);
+    if (it == b->tables.end()) {
+        std::vector<LuBatchItem> h(b->nz);
+        for (int n = 0; n < b->nz; n++) { h[n].z = *zs[n]; lu_fill_args(h[n].a, *zs[n], *plans[n], rop[n], rop_out[n], lu_match); }
+        LuBatchItem *d = nullptr;
+        if (cudaMalloc(&d, h.size() * sizeof(LuBatchItem)) != cudaSuccess) { cudaGetLastError(); return -1; }
+        cudaMemcpy(d, h.data(), h.size() * sizeof(LuBatchItem), cudaMemcpyHostToDevice);   // blocking, six times in a run
+        it = b->tables.emplace(key, d).first;
+    }
+    const LuBatchItem *items = it->second;
+    if (b->neq == 6) {
+        if (b->typ == 0) run_lu_batch<0, 6>(b, items, st); else if (b->typ == 1) run_lu_batch<1, 6>(b, items, st); else run_lu_batch<2, 6>(b, items, st);
+    } else {
+        if (b->typ == 0) run_lu_batch<0, 5>(b, items, st); else if (b->typ == 1) run_lu_batch<1, 5>(b, items, st); else run_lu_batch<2, 5>(b, items, st);
+    }
+    return 3;
+}
+
+template <int MESH, int NEQ>
+static int run_lu_tiles(const ZoneDev &z, const LuPlan &p, const double *rop, double *rop_out, int lu_match, cudaStream_t st)
+{
+    LuTileArgs a;
+    lu_fill_args(a, z, p, rop, rop_out, lu_match);
     static bool attr_done = false;
     if (!attr_done) {
         cudaFuncSetAttribute(k_lu_tile<MESH, NEQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LuCfg<MESH, NEQ, false>::SMEM);

@@ -22,9 +22,10 @@ static inline dim3 grid3r(int ni, int nj, int nk, dim3 b) { return dim3((ni + b.
 __device__ __forceinline__ void st_wig(unsigned char *p, unsigned v) { asm("st.global.u8 [%0], %1;" ::"l"(p), "r"(v)); }
 
 // a face tile tells the exchange stream that its cells are in memory (see RhsArgs::order)
-__device__ __forceinline__ void rhs_signal_done(const RhsArgs &a, int clin, bool leader)
+__device__ __forceinline__ unsigned rhs_cta_linear() { return blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z); }
+__device__ __forceinline__ void rhs_signal_done(const RhsArgs &a, bool leader)
 {
-    if (a.order && clin < a.nbnd) {        // uniform per CTA
+    if (a.order && rhs_cta_linear() < (unsigned)a.nbnd) {        // uniform per CTA
         __syncthreads();
         if (leader) { __threadfence(); atomicAdd(a.done, 1); }
     }
@@ -142,8 +143,9 @@ template <int MESH, int FLOW, int SCHEME, int SLOPE, bool IMPL, bool WC>
 __global__ void __launch_bounds__(32 * (RHS2_RJ + 1)) k_rhs2(ZoneDev z, RhsArgs a)
 {
     constexpr int NEQ = FLOW == 3 ? 6 : 5, RJ = RHS2_RJ;
-    int bx = blockIdx.x, by = blockIdx.y, bz = blockIdx.z, clin = 0;
-    if (a.order) { clin = bx + gridDim.x * (by + gridDim.y * bz); const int t = a.order[clin]; bx = t & 1023; by = (t >> 10) & 1023; bz = t >> 20; }
+    // (unsigned on purpose, like blockIdx: with signed tile coordinates the address arithmetic of the whole kernel grows by a quarter)
+    unsigned bx = blockIdx.x, by = blockIdx.y, bz = blockIdx.z;
+    if (!IMPL && a.order) { const unsigned t = a.order[rhs_cta_linear()]; bx = t & 1023u; by = (t >> 10) & 1023u; bz = t >> 20; }   // explicit stages only
     __shared__ double sFj[2][RJ + 1][NEQ][32];
     const int li = threadIdx.x, m = threadIdx.y;
     const int i = 1 + bx * 31 + li, j = 1 + by * RJ + m;
@@ -228,7 +230,7 @@ __global__ void __launch_bounds__(32 * (RHS2_RJ + 1)) k_rhs2(ZoneDev z, RhsArgs 
             for (int e = 0; e < NEQ; e++) acc[e] -= sFj[k & 1][m + 1][e][li];
         }
     }
-    rhs_signal_done(a, clin, li == 0 && m == 0);
+    if (!IMPL) rhs_signal_done(a, li == 0 && m == 0);
 }
 
 // ------------------------------------------------------------------------------------------------ fused rhs, TMA path
@@ -309,8 +311,9 @@ k_rhs3(const __grid_constant__ CUtensorMap tm_rop, const __grid_constant__ CUten
 {
     using C = Rhs3Cfg<FLOW, RJ>;
     constexpr int NEQ = C::NEQ, NS = RHS3_NS, PS = C::PS, RS = C::RS, VS = C::VS;
-    int bx = blockIdx.x, by = blockIdx.y, bz = blockIdx.z, clin = 0;
-    if (a.order) { clin = bx + gridDim.x * (by + gridDim.y * bz); const int t = a.order[clin]; bx = t & 1023; by = (t >> 10) & 1023; bz = t >> 20; }
+    // (unsigned on purpose, like blockIdx: with signed tile coordinates the address arithmetic of the whole kernel grows by a quarter)
+    unsigned bx = blockIdx.x, by = blockIdx.y, bz = blockIdx.z;
+    if (!IMPL && a.order) { const unsigned t = a.order[rhs_cta_linear()]; bx = t & 1023u; by = (t >> 10) & 1023u; bz = t >> 20; }   // explicit stages only
     extern __shared__ __align__(128) double ring[];
     double (*sFj)[RJ + 1][NEQ][32] = (double (*)[RJ + 1][NEQ][32])(ring + NS * PS);
     constexpr int NSF = C::template nsf<MESH>();
@@ -450,7 +453,7 @@ k_rhs3(const __grid_constant__ CUtensorMap tm_rop, const __grid_constant__ CUten
         }
         if (NSF == 1) __syncthreads();      // single F_j buffer: everybody has read it before the next plane overwrites it
     }
-    rhs_signal_done(a, clin, leader);
+    if (!IMPL) rhs_signal_done(a, leader);
 }
 
 // ------------------------------------------------------------------------------------------------ launchers

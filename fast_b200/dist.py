@@ -98,6 +98,24 @@ def local_case(workload, rank, world, n=None):
         desc = '8 x %d^3 blocks over %d GPUs, match joins, Roe o3, implicit LU-SGS 3 sub-iterations, lu_match ' \
                '(BASELINE configs[3])' % (n, world)
         return t, table, peers, desc, 8 * n ** 3
+    if workload == 'c5':
+        # BASELINE configs[4]: RANS-SA plate in blocks of 256x256x64, 8 blocks (a 2x2x2 brick) per GPU; at 8 GPUs this is
+        # the 1024x1024x256 mesh (268 M cells) in 64 blocks.  Weak scaling: the plate grows with the number of GPUs.
+        nloc = n or (256, 256, 64)
+        g = grid_for(world)
+        nb = (2 * g[0], 2 * g[1], 2 * g[2])
+        rank_of, zid = {}, 0
+        for bk in range(nb[2]):
+            for bj in range(nb[1]):
+                for bi in range(nb[0]):
+                    rank_of[zid] = (bi // 2) + g[0] * ((bj // 2) + g[1] * (bk // 2)); zid += 1
+        mine = {z for z, r in rank_of.items() if r == rank}
+        nglob = tuple(nloc[d] * nb[d] for d in range(3))
+        t, layout = synth.case_flatplate(n=nglob, nblocks=nb, modulo_verif=1000, only=mine, return_layout=True)
+        table, peers = synth.build_joins(layout, nb, tuple(nloc), periodic=(False, False, True), rank_of=rank_of, rank=rank, neq=6)
+        desc = 'RANS-SA flat plate %dx%dx%d in %d blocks of %dx%dx%d (3dhomo), 8 blocks per GPU, match joins, AUSM o3, implicit ' \
+               'LU-SGS 5 sub-iterations, local dt (BASELINE configs[4]%s)' % (nglob + (len(rank_of),) + tuple(nloc) + ('' if world == 8 else ', weak-scaling member',))
+        return t, table, peers, desc, nglob[0] * nglob[1] * nglob[2]
     raise ValueError("fast_b200.dist: workload %r has no multi-GPU decomposition" % workload)
 
 

@@ -224,10 +224,12 @@ def case_tgv_blocks(n=256, nblk=(2, 1, 1), only=None, scheme='senseur', Re=1600.
 
 
 def case_flatplate(n=(64, 48, 8), seed=2025, MInf=0.2, ReInf=25.e6, ss_iteration=5, cfl=7., sheared=False,
-                   scheme='ausmpred', modulo_verif=1, nblocks=(1, 1, 1)):
+                   scheme='ausmpred', modulo_verif=1, nblocks=(1, 1, 1), only=None, return_layout=False):
     """C3 / C5-style RANS-SA flat plate: x geometric stretch, y tanh clustering toward the wall (jmin = viscous wall),
     z uniform => typezone 1 (3dhomo); `sheared=True` adds a smooth 3-D shear => typezone 0 (3dfull).
-    Farfield on imin/imax/jmax, autoperiodic in k.  nblocks splits the plate into match-joined blocks."""
+    Farfield on imin/imax/jmax, autoperiodic in k.  nblocks splits the plate into match-joined blocks; `only` (a set of
+    global block ids, k-major numbering) builds just those blocks -- the per-rank share of a sharded case, every block
+    drawing from its own random stream -- and `return_layout` returns (tree, layout) for dist.local_case."""
     from .FastC import PyTree as FastC
     rng = numpy.random.default_rng(seed)
     state = adim1(MInf=MInf, ReInf=ReInf, MutSMuInf=15.)
@@ -245,6 +247,11 @@ def case_flatplate(n=(64, 48, 8), seed=2025, MInf=0.2, ReInf=25.e6, ss_iteration
     for bk in range(nb[2]):
         for bj in range(nb[1]):
             for bi in range(nb[0]):
+                zid = len(layout)
+                if only is not None:
+                    layout[(bi, bj, bk)] = zid
+                    if zid not in only: continue
+                    rng = numpy.random.default_rng(seed + 7919 * zid)
                 name = 'plate' if nb == (1, 1, 1) else 'plate_%d_%d_%d' % (bi, bj, bk)
                 z = make_block(name, tuple(nloc), L=(Lx, H, Lz), stretch=(sx, sy, None), deform=deform,
                                index_offset=(bi * nloc[0], bj * nloc[1], bk * nloc[2]), nglob=n)
@@ -260,7 +267,7 @@ def case_flatplate(n=(64, 48, 8), seed=2025, MInf=0.2, ReInf=25.e6, ss_iteration
                 nut = state['TurbulentSANuTildeDensity'] * (0.1 + 3. * prof * numpy.exp(-numpy.abs(yc) / (4 * delta))) \
                     * (1. + 1e-2 * rng.random(xc.shape))
                 set_fields(z, ro, u, v, w, T, nutilde=nut, dist=d)
-                layout[(bi, bj, bk)] = len(zones)
+                if only is None: layout[(bi, bj, bk)] = len(zones)
                 zones.append(z)
                 if bi == 0: add_bc(z, 'imin', 'BCFarfield', 'imin')
                 if bi == nb[0] - 1: add_bc(z, 'imax', 'BCFarfield', 'imax')
@@ -271,6 +278,7 @@ def case_flatplate(n=(64, 48, 8), seed=2025, MInf=0.2, ReInf=25.e6, ss_iteration
     t = new_tree(zones, state, 'NSTurbulent')
     FastC._setNum2Zones(t, {'scheme': scheme, 'slope': 'o3', 'time_step_nature': 'local', 'cfl': cfl, 'nb_relax': 1})
     FastC._setNum2Base(t, {'temporal_scheme': 'implicit', 'ss_iteration': ss_iteration, 'modulo_verif': modulo_verif})
+    if return_layout: return t, layout
     joins = build_joins(layout, nb, tuple(nloc), periodic=(False, False, nb[2] > 1))
     return t, joins
 

@@ -67,7 +67,7 @@ def main_gpu(workload):
     rank = int(os.environ['RANK']); world = int(os.environ['WORLD_SIZE']); local = int(os.environ['LOCAL_RANK'])
     torch.cuda.set_device(local)
     dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-    n = 16
+    n = 16 if workload != 'c5' else (16, 24, 8)
     t, table, peers, desc, cells = fdist.local_case(workload, rank, world, n=n)
     t, metrics, hx = fdist.warmup_rank(t, table, peers, local)
     for it in range(1, 4): FastS._compute(t, metrics, it)
@@ -75,7 +75,12 @@ def main_gpu(workload):
     mine = [(z[0], FastC.block_of(z, '').copy()) for z in Internal.getZones(t)]
     calls = hx.calls
     # the whole case on this GPU alone
-    if workload == 'multiblock':
+    if workload == 'c5':
+        g = fdist.grid_for(world); nb = (2 * g[0], 2 * g[1], 2 * g[2])
+        nglob = tuple(n[d] * nb[d] for d in range(3))
+        t2, layout = synth.case_flatplate(n=nglob, nblocks=nb, modulo_verif=1000, only=set(range(nb[0] * nb[1] * nb[2])), return_layout=True)
+        j2 = synth.build_joins(layout, nb, n, periodic=(False, False, True))
+    elif workload == 'multiblock':
         t2, layout = synth.case_multiblock(nblk=(2, 2, 2), n=n, modulo_verif=1000, only=set(range(8)), return_layout=True)
         j2 = synth.build_joins(layout, (2, 2, 2), (n, n, n))
     else:

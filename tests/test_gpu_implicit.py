@@ -32,6 +32,9 @@ CASES = {
     'lamin_full_roe_tiles': _box(n=8, n3=(14, 22, 20), scheme='roe', model='NSLaminar', ReInf=1000., deform_amp=0.02, temporal='implicit'),
     'sa_plate_medium': lambda: synth.case_flatplate(n=(64, 40, 24)),      # several rhs CTAs and LU tiles in every direction
     'multiblock_roe_lumatch': lambda: synth.case_multiblock(nblk=(2, 2, 1), n=8),
+    # several zones with several LU tiles each: the multi-zone launch (k_lu_tile_b) interleaves the tiles of all zones
+    'sa_plate_blocks_tiles': lambda: synth.case_flatplate(n=(24, 40, 40), nblocks=(1, 2, 2)),
+    'multiblock_roe_lumatch_tiles': lambda: synth.case_multiblock(nblk=(2, 1, 2), n=18),
     'multiblock_explicit': lambda: synth.case_multiblock(nblk=(2, 1, 2), n=8, temporal='explicit', scheme='senseur'),
 }
 

@@ -31,8 +31,26 @@ def test_partition_and_tables():
     assert int(t0[0]) == 4 and sorted(t0[2:2 + 28:7]) == [1, 1, 2, 2]
 
 
+@pytest.mark.parametrize('world', [1, 2, 8])
+def test_c5_bricks(world):
+    """BASELINE configs[4] family: every rank owns a 2x2x2 brick of blocks; what a rank sends to a peer is what the peer expects."""
+    sys.path.insert(0, ROOT)
+    from fast_b200 import dist as fdist
+    from fast_b200.FastC.PyTree import Internal
+    n = (4, 4, 4)
+    per = {}
+    for rank in range(world):
+        t, table, peers, desc, cells = fdist.local_case('c5', rank, world, n=n)
+        assert len(Internal.getZones(t)) == 8 and cells == 8 * world * 64
+        per[rank] = peers
+    for r, peers in per.items():
+        for p, (so, sn, ro, rn) in peers.items():
+            assert per[p][r][3] == sn and per[p][r][1] == rn
+    if world == 8: assert '1024' not in desc and 'configs[4]' in desc
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize('workload', ['tgv', 'multiblock'])
+@pytest.mark.parametrize('workload', ['tgv', 'multiblock', 'c5'])
 def test_sharded_solve_nccl(workload):
     import torch
     if torch.cuda.device_count() < 2: pytest.skip("needs 2 GPUs (run: gpurun --gpus 2 -- python -m pytest tests -m gpu -k nccl)")
