@@ -45,6 +45,10 @@ struct fb_solver {
     cudaStream_t st2 = nullptr;       // cross-rank halo exchange (pack, host transport, unpack): overlaps the interior tiles
     cudaEvent_t ev1 = nullptr, ev2 = nullptr;
     int *d_done = nullptr;            // face tiles finished (RhsArgs::done), device counter
+    // multi-zone solvers: the per-zone kernels of a phase fan out over st + 3 lanes so that the tail of one zone's grid
+    // (a 128^3 block is 1.08 waves of rhs CTAs) is filled by the next zone's CTAs; the phase joins back on st
+    cudaStream_t lane[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_lane[3] = {nullptr, nullptr, nullptr};
     std::vector<Zone> z;
     bool metric_done = false;
     JoinSet joins;
@@ -96,6 +100,8 @@ int fb_solver_create(int device, int nzones, fb_solver **out)
     CK(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&s->st2, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&s->ev1, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&s->ev2, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+    for (int q = 0; q < 3; q++) { CK(cudaStreamCreateWithFlags(&s->lane[q], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&s->ev_lane[q], cudaEventDisableTiming)); }
     CK(cudaMalloc(&s->d_done, 2 * sizeof(int))); CK(cudaMemset(s->d_done, 0, 2 * sizeof(int)));
     *out = s;
     return FB_OK;
@@ -118,6 +124,8 @@ void fb_solver_destroy(fb_solver *s)
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->ev2) cudaEventDestroy(s->ev2);
     cudaFree(s->d_done);
+    for (int q = 0; q < 3; q++) { if (s->lane[q]) cudaStreamDestroy(s->lane[q]); if (s->ev_lane[q]) cudaEventDestroy(s->ev_lane[q]); }
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
     lu_batch_free(s->lub);
     delete s;
 }
@@ -247,7 +255,8 @@ int fb_zone_set_params(fb_solver *s, int nd, const int *pi, int n_int, const dou
     if (pi[PI_LALE] != 0 || pi[PI_EXPLOC] != 0 || pi[PI_ILES] != 0 || pi[PI_IMPLICITSOLVER] != 0 || pi[PI_NB_RELAX] != 1)
         return fail(FB_EINVAL, "ALE / local explicit / LES / GMRES / nb_relax>1 are outside the hot-path scope");
     if (d.nf != 2) return fail(FB_EINVAL, "only 2 ghost layers are supported");
-    if (pi[PI_LU_MATCH] == 1 && d.iflow == 3) return fail(FB_EINVAL, "lu_match with SA (extrap_coe) is not built");
+    // lu_match with SA (invlu_overlap_{l,u}_SA.for): same sweeps with six equations; extrap_coe.for only acts where the sweep
+    // box reaches the second ghost row, which needs a BC of type 18 / 30 -- rejected above -- so it is a no-op here
     if (d.dtloc == 1 && d.iflow == 1) return fail(FB_EINVAL, "local time step needs a viscous model (dtloc.for divides by mu)");
     if (d.dtloc == 1 && d.itypcp == 2) return fail(FB_EINVAL, "explicit local time step (tstb3_expli) is not built");
     // constants of template_FluxAndBalance.for:121-153
@@ -473,6 +482,21 @@ static void transfers(fb_solver *s, int which, int level_ssiter_dummy, double **
     transfers_end(s, which, target);
 }
 
+// fork / join of a phase whose per-zone kernels are independent (fb_solver::lane)
+struct Fan {
+    fb_solver *s; bool on;
+    Fan(fb_solver *s_, bool on_) : s(s_), on(on_) {
+        if (!on) return;
+        cudaEventRecord(s->ev_fork, s->st);
+        for (int q = 0; q < 3; q++) cudaStreamWaitEvent(s->lane[q], s->ev_fork, 0);
+    }
+    cudaStream_t stream(int n) const { return on && (n & 3) ? s->lane[(n & 3) - 1] : s->st; }
+    ~Fan() {
+        if (!on) return;
+        for (int q = 0; q < 3; q++) { cudaEventRecord(s->ev_lane[q], s->lane[q]); cudaStreamWaitEvent(s->st, s->ev_lane[q], 0); }
+    }
+};
+
 static long long g_lu_batch_launches = 0;   // multi-zone LU sweeps (lower + upper pairs), fb_counter("lu_batch")
 static int gsdr3(fb_solver *s, int nitcfg, int nssiter, int nitrun, int first_it, int lssiter_verif, int lexit_lu)
 {
@@ -482,8 +506,11 @@ static int gsdr3(fb_solver *s, int nitcfg, int nssiter, int nitrun, int first_it
     const bool overlap = !implicit && lexit_lu == 0 && cross_rank(s) && !no_overlap;
     std::vector<double *> cl(s->nz);
     int face_tiles = 0; bool face_ok = true;
+    static const bool no_fan = [] { const char *e = getenv("FAST_B200_FAN"); return e && e[0] == '0'; }();   // A/B switch
+    const bool fan = s->nz > 1 && !no_fan;
     {
         Scope all(s, 5);
+        std::vector<double *> ss(s->nz);
         for (int n = 0; n < s->nz; n++) {
             Zone &z = s->z[n];
             // gsdr3.cpp:162-173: flux input and array receiving transfers + BC
@@ -492,22 +519,30 @@ static int gsdr3(fb_solver *s, int nitcfg, int nssiter, int nitrun, int first_it
             else if (implicit) { ssiter = z.rop[2]; clp = z.rop[2]; }
             else if (nitcfg % 2 == 0) { ssiter = z.rop[2]; clp = z.rop[0]; }
             else { ssiter = z.rop[0]; clp = z.rop[2]; }
-            cl[n] = clp;
-            if (nitcfg == 1) {   // navier_stokes_struct.for:216-301
-                Scope c(s, 4);
-                if (z.d.iflow >= 2) { launch_invist(z.d, ssiter, implicit || z.d.iflow == 3 ? z.d.nf : 1, s->st); s->launches++; }
-                if (implicit) { launch_coe(z.d, ssiter, first_it, lssiter_verif, z.cflv, s->st); s->launches++; }
+            cl[n] = clp; ss[n] = ssiter;
+        }
+        if (nitcfg == 1) {   // navier_stokes_struct.for:216-301
+            Scope c(s, 4);
+            Fan f(s, fan);
+            for (int n = 0; n < s->nz; n++) {
+                Zone &z = s->z[n]; double *ssiter = ss[n]; cudaStream_t zst = f.stream(n);
+                if (z.d.iflow >= 2) { launch_invist(z.d, ssiter, implicit || z.d.iflow == 3 ? z.d.nf : 1, zst); s->launches++; }
+                if (implicit) { launch_coe(z.d, ssiter, first_it, lssiter_verif, z.cflv, zst); s->launches++; }
                 // SENSOR switch (wiggle2001.for) at nstep 1 (src_term.for:258-266)
-                if (z.d.kflu == 2 && !fb_sensor_fused()) { launch_sensor(z.d, ssiter, s->st); s->launches++; }
+                if (z.d.kflu == 2 && !fb_sensor_fused()) { launch_sensor(z.d, ssiter, zst); s->launches++; }
             }
-            {
-                Scope r(s, 0);
-                if (implicit && z.d.iflow == 3 && nitcfg == 1) { launch_sa_ring(z.d, ssiter, s->st); s->launches++; }
+        }
+        {
+            Scope r(s, 0);
+            Fan f(s, fan);
+            for (int n = 0; n < s->nz; n++) {
+                Zone &z = s->z[n]; double *ssiter = ss[n], *clp = cl[n]; cudaStream_t zst = f.stream(n);
+                if (implicit && z.d.iflow == 3 && nitcfg == 1) { launch_sa_ring(z.d, ssiter, zst); s->launches++; }
                 double *out = implicit ? nullptr : clp;   // explicit: the stage writes the array that then gets the BCs
                 // explicit + cross-rank joins: the CTAs take the tiles that touch a zone face first (their cells are the
                 // donors of the exchange) and count them off; the exchange stream starts when they are all in memory and
                 // runs while the interior tiles are still being computed
-                const int nb = launch_rhs(z.d, ssiter, out, z.rop[0], z.rop[1], nitcfg, first_it, s->st, overlap ? s->d_done : nullptr);
+                const int nb = launch_rhs(z.d, ssiter, out, z.rop[0], z.rop[1], nitcfg, first_it, zst, overlap ? s->d_done : nullptr);
                 s->launches++;
                 if (nb > 0) face_tiles += nb; else face_ok = false;
             }

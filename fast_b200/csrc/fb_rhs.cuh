@@ -21,14 +21,50 @@ static inline dim3 grid3r(int ni, int nj, int nk, dim3 b) { return dim3((ni + b.
 // which makes the compiler re-load the staged state around it.
 __device__ __forceinline__ void st_wig(unsigned char *p, unsigned v) { asm("st.global.u8 [%0], %1;" ::"l"(p), "r"(v)); }
 
-// a face tile tells the exchange stream that its cells are in memory (see RhsArgs::order)
+#ifndef RHS_VAR
+#define RHS_VAR 0      // A/B builds: 1 = no completion signal, 2 = no signal and no tile reordering
+#endif
+// Halo-exchange overlap (RhsArgs::done): CTA c works on tile rhs_face_first(c) -- a bijection of the launch grid that puts
+// the tiles touching a zone face first (their cells are the donors of the exchange).  It is pure arithmetic on blockIdx /
+// gridDim so that the tile coordinates stay provably warp-uniform: reading them from a table made the compiler treat the
+// k loop bound as divergent (WARPSYNC around every shuffle, duplicated loop tails; the TGV stage went from 1.0 to 1.4 ms).
 __device__ __forceinline__ unsigned rhs_cta_linear() { return blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z); }
-__device__ __forceinline__ void rhs_signal_done(const RhsArgs &a, bool leader)
+__device__ __forceinline__ void rhs_face_first(unsigned c, unsigned &x, unsigned &y, unsigned &z)
 {
-    if (a.order && rhs_cta_linear() < (unsigned)a.nbnd) {        // uniform per CTA
-        __syncthreads();
-        if (leader) { __threadfence(); atomicAdd(a.done, 1); }
-    }
+    const unsigned gx = gridDim.x, gy = gridDim.y, gz = gridDim.z;
+    const unsigned sxy = gx * gy;
+    if (c < sxy) { z = 0; y = c / gx; x = c - y * gx; return; }                              // slab z = 0
+    c -= sxy;
+    if (c < sxy) { z = gz - 1; y = c / gx; x = c - y * gx; return; }                         // slab z = gz-1 (gz >= 2 here)
+    c -= sxy;
+    const unsigned nzm = gz - 2, sxz = gx * nzm;                                             // layers z = 1 .. gz-2 (gz >= 3 here)
+    if (c < sxz) { y = 0; z = 1 + c / gx; x = c % gx; return; }                              // rows y = 0
+    c -= sxz;
+    if (c < sxz) { y = gy - 1; z = 1 + c / gx; x = c % gx; return; }                         // rows y = gy-1 (gy >= 2 here)
+    c -= sxz;
+    const unsigned nym = gy - 2, syz = nym * nzm;                                            // y = 1 .. gy-2 (gy >= 3 here)
+    if (c < syz) { x = 0; z = 1 + c / nym; y = 1 + c % nym; return; }                        // columns x = 0
+    c -= syz;
+    if (c < syz) { x = gx - 1; z = 1 + c / nym; y = 1 + c % nym; return; }                   // columns x = gx-1 (gx >= 2 here)
+    c -= syz;
+    const unsigned nxm = gx - 2;                                                             // interior (gx >= 3 here)
+    x = 1 + c % nxm; c /= nxm; y = 1 + c % nym; z = 1 + c / nym;
+}
+// number of face tiles of a gx x gy x gz launch (host)
+static inline int rhs_face_tiles(unsigned gx, unsigned gy, unsigned gz)
+{
+    const unsigned ix = gx > 2 ? gx - 2 : 0, iy = gy > 2 ? gy - 2 : 0, iz = gz > 2 ? gz - 2 : 0;
+    return (int)(gx * gy * gz - ix * iy * iz);
+}
+// a face tile tells the exchange stream that its cells are in memory: every thread fences its own stores and counts itself.
+// Predicated PTX, no C++ branch and no CTA barrier, on purpose: with an `if` (or a __syncthreads) in this tail the compiler
+// restructured the k loop in front of it (a second copy of the F_i shuffle block, WARPSYNC before every shuffle) and the
+// TGV stage went from 1.0 to 1.4 ms even with the overlap switched off.
+__device__ __forceinline__ void rhs_signal_done(const RhsArgs &a)
+{
+    const unsigned on = (a.done != nullptr && rhs_cta_linear() < (unsigned)a.nbnd) ? 1u : 0u;      // uniform per CTA
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p membar.gl;\n\t@p red.global.add.s32 [%0], 1;\n\t}"
+                 :: "l"(a.done), "r"(on) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------ wall flux correction
@@ -145,7 +181,9 @@ __global__ void __launch_bounds__(32 * (RHS2_RJ + 1)) k_rhs2(ZoneDev z, RhsArgs 
     constexpr int NEQ = FLOW == 3 ? 6 : 5, RJ = RHS2_RJ;
     // (unsigned on purpose, like blockIdx: with signed tile coordinates the address arithmetic of the whole kernel grows by a quarter)
     unsigned bx = blockIdx.x, by = blockIdx.y, bz = blockIdx.z;
-    if (!IMPL && a.order) { const unsigned t = a.order[rhs_cta_linear()]; bx = t & 1023u; by = (t >> 10) & 1023u; bz = t >> 20; }   // explicit stages only
+#if RHS_VAR < 2
+    if (!IMPL && a.done) rhs_face_first(rhs_cta_linear(), bx, by, bz);   // explicit stages only
+#endif
     __shared__ double sFj[2][RJ + 1][NEQ][32];
     const int li = threadIdx.x, m = threadIdx.y;
     const int i = 1 + bx * 31 + li, j = 1 + by * RJ + m;
@@ -190,6 +228,9 @@ __global__ void __launch_bounds__(32 * (RHS2_RJ + 1)) k_rhs2(ZoneDev z, RhsArgs 
         }
         if (last) {           // uniform
             if (wcomp && cell && k == z.kv + 1) st_wig(z.wigb + l, wg);   // k faces of the plane behind the last cells
+#if RHS_VAR < 1
+            if (!IMPL) rhs_signal_done(a);      // here, not behind the loop: the loop's only exit stays a plain thread exit
+#endif
             break;
         }
         if (cell) {
@@ -230,7 +271,6 @@ __global__ void __launch_bounds__(32 * (RHS2_RJ + 1)) k_rhs2(ZoneDev z, RhsArgs 
             for (int e = 0; e < NEQ; e++) acc[e] -= sFj[k & 1][m + 1][e][li];
         }
     }
-    if (!IMPL) rhs_signal_done(a, li == 0 && m == 0);
 }
 
 // ------------------------------------------------------------------------------------------------ fused rhs, TMA path
@@ -313,7 +353,9 @@ k_rhs3(const __grid_constant__ CUtensorMap tm_rop, const __grid_constant__ CUten
     constexpr int NEQ = C::NEQ, NS = RHS3_NS, PS = C::PS, RS = C::RS, VS = C::VS;
     // (unsigned on purpose, like blockIdx: with signed tile coordinates the address arithmetic of the whole kernel grows by a quarter)
     unsigned bx = blockIdx.x, by = blockIdx.y, bz = blockIdx.z;
-    if (!IMPL && a.order) { const unsigned t = a.order[rhs_cta_linear()]; bx = t & 1023u; by = (t >> 10) & 1023u; bz = t >> 20; }   // explicit stages only
+#if RHS_VAR < 2
+    if (!IMPL && a.done) rhs_face_first(rhs_cta_linear(), bx, by, bz);   // explicit stages only
+#endif
     extern __shared__ __align__(128) double ring[];
     double (*sFj)[RJ + 1][NEQ][32] = (double (*)[RJ + 1][NEQ][32])(ring + NS * PS);
     constexpr int NSF = C::template nsf<MESH>();
@@ -411,6 +453,9 @@ k_rhs3(const __grid_constant__ CUtensorMap tm_rop, const __grid_constant__ CUten
         }
         if (last) {           // uniform; no TMA is in flight any more (plane k1+2 was waited for above)
             if (wcomp && cell && k == z.kv + 1) st_wig(z.wigb + l, wg);
+#if RHS_VAR < 1
+            if (!IMPL) rhs_signal_done(a);      // here, not behind the loop: the loop's only exit stays a plain thread exit
+#endif
             break;
         }
         if (cell) {
@@ -453,22 +498,19 @@ k_rhs3(const __grid_constant__ CUtensorMap tm_rop, const __grid_constant__ CUten
         }
         if (NSF == 1) __syncthreads();      // single F_j buffer: everybody has read it before the next plane overwrites it
     }
-    if (!IMPL) rhs_signal_done(a, leader);
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
 // tensor maps of rop(ni,nj,nk,neq) / xmut(ni,nj,nk,naux) with a (36, rows, 1, nvar) box; nullptr when the strides
 // cannot be encoded (odd ni or NDIMDX) or the driver entry point is missing (fb_tma.cu)
 const CUtensorMap *fb_tma_map(const double *base, int ni, int nj, int nk, long long var_stride, int nvar_total, int box_rows, int box_vars);
-// tile order of a gx x gy x gz launch with the tiles that touch a zone face first (cached device table); *nbnd = their number
-const int *fb_tile_order(int gx, int gy, int gz, int *nbnd);
 
 template <int MESH, int FLOW, int SCHEME, int SLOPE>
 static void launch_rhs2_t(const ZoneDev &z, RhsArgs &a, bool impl, cudaStream_t st)
 {
     dim3 b(32, RHS2_RJ + 1, 1);
     dim3 g((z.iv + 30) / 31, (z.jv + RHS2_RJ - 1) / RHS2_RJ, (z.kv + RHS2_KC - 1) / RHS2_KC);
-    a.order = a.done ? fb_tile_order(g.x, g.y, g.z, &a.nbnd) : nullptr;
+    a.nbnd = a.done ? rhs_face_tiles(g.x, g.y, g.z) : 0; a.nsig = a.nbnd * (int)(b.x * b.y);
     // WC: first sub-iteration of a SENSOR zone -- the switch is evaluated inside the flux and stored
     if (SCHEME == 2 && a.nitcfg == 1 && a.wfuse) {
         if (impl) k_rhs2<MESH, FLOW, SCHEME, SLOPE, true, SCHEME == 2><<<g, b, 0, st>>>(z, a);
@@ -498,7 +540,7 @@ static bool launch_rhs3_t(const ZoneDev &z, RhsArgs &a, bool impl, cudaStream_t 
     }
     dim3 b(32, RJ + 1, 1);
     dim3 g((z.iv + 30) / 31, (z.jv + RJ - 1) / RJ, (z.kv + RHS3_KC - 1) / RHS3_KC);
-    a.order = a.done ? fb_tile_order(g.x, g.y, g.z, &a.nbnd) : nullptr;
+    a.nbnd = a.done ? rhs_face_tiles(g.x, g.y, g.z) : 0; a.nsig = a.nbnd * (int)(b.x * b.y);
     if (SCHEME == 2 && a.nitcfg == 1 && a.wfuse) {   // first sub-iteration of a SENSOR zone: the switch is evaluated in the flux
         if (impl) k_rhs3<MESH, FLOW, SCHEME, SLOPE, true, RJ, SCHEME == 2><<<g, b, C::template smem<MESH>(), st>>>(*tr, *tm, z, a);
         else k_rhs3<MESH, FLOW, SCHEME, SLOPE, false, RJ, SCHEME == 2><<<g, b, C::template smem<MESH>(), st>>>(*tr, *tm, z, a);

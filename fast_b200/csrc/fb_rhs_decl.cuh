@@ -9,10 +9,11 @@ struct RhsArgs {
     double coefH, coefW;    // low-storage RK (init_rhs.for:31-33, core3ark3.for:22-25)
     double c1, c2, c3;      // BDF weights (core3as2.for:37-46)
     int nitcfg;
-    // halo-exchange overlap (fb_api.cu: gsdr3, explicit stages with cross-rank joins): CTA c works on tile order[c] -- the
-    // tiles that touch a zone face come first (their cells are the donors of the exchange) -- and the first nbnd CTAs add
-    // 1 to *done when their results are in memory; the exchange stream waits for that count while the interior tiles run
-    const int *order; int nbnd; int *done;
+    // halo-exchange overlap (fb_api.cu: gsdr3, explicit stages with cross-rank joins): with done != nullptr the CTAs take the
+    // tiles that touch a zone face first (fb_rhs.cuh: rhs_face_first; their cells are the donors of the exchange) and the first
+    // nbnd CTAs count their threads into *done when their results are in memory; the exchange stream waits for that count
+    // (nsig = nbnd x threads per CTA, set by the launcher) while the interior tiles run
+    int nbnd, nsig; int *done;
     int wfuse;              // SENSOR switch evaluated inside the first-sub-iteration kernel (default) instead of k_sensor
 };
 

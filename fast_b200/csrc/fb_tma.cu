@@ -61,29 +61,3 @@ const CUtensorMap *fb_tma_map(const double *base, int ni, int nj, int nk, long l
 
 // launch counters of the two rhs paths (fb_counter in the C ABI; bench.py names the kernel it times from them)
 long long g_fb_rhs_launches[2] = {0, 0};   // [0] k_rhs3 (TMA ring), [1] k_rhs2 (L1 path)
-
-// tile order table for the halo-exchange overlap: tiles on a zone face first, then the interior, each packed as
-// bx | by << 10 | bz << 20
-#include <vector>
-const int *fb_tile_order(int gx, int gy, int gz, int *nbnd)
-{
-    typedef std::tuple<int, int, int> Key;
-    static std::map<Key, std::pair<int *, int>> cache;
-    const Key key(gx, gy, gz);
-    auto it = cache.find(key);
-    if (it == cache.end()) {
-        std::vector<int> face, inner;
-        for (int z = 0; z < gz; z++) for (int y = 0; y < gy; y++) for (int x = 0; x < gx; x++) {
-            const bool f = x == 0 || x == gx - 1 || y == 0 || y == gy - 1 || z == 0 || z == gz - 1;
-            (f ? face : inner).push_back(x | (y << 10) | (z << 20));
-        }
-        const int nb = (int)face.size();
-        face.insert(face.end(), inner.begin(), inner.end());
-        int *d = nullptr;
-        if (gx > 1023 || gy > 1023 || gz > 1023 || cudaMalloc(&d, face.size() * sizeof(int)) != cudaSuccess) d = nullptr;
-        else cudaMemcpy(d, face.data(), face.size() * sizeof(int), cudaMemcpyHostToDevice);
-        it = cache.emplace(key, std::make_pair(d, nb)).first;
-    }
-    if (nbnd) *nbnd = it->second.second;
-    return it->second.first;
-}

@@ -224,7 +224,7 @@ def case_tgv_blocks(n=256, nblk=(2, 1, 1), only=None, scheme='senseur', Re=1600.
 
 
 def case_flatplate(n=(64, 48, 8), seed=2025, MInf=0.2, ReInf=25.e6, ss_iteration=5, cfl=7., sheared=False,
-                   scheme='ausmpred', modulo_verif=1, nblocks=(1, 1, 1), only=None, return_layout=False):
+                   scheme='ausmpred', modulo_verif=1, nblocks=(1, 1, 1), only=None, return_layout=False, lu_match=0):
     """C3 / C5-style RANS-SA flat plate: x geometric stretch, y tanh clustering toward the wall (jmin = viscous wall),
     z uniform => typezone 1 (3dhomo); `sheared=True` adds a smooth 3-D shear => typezone 0 (3dfull).
     Farfield on imin/imax/jmax, autoperiodic in k.  nblocks splits the plate into match-joined blocks; `only` (a set of
@@ -276,7 +276,7 @@ def case_flatplate(n=(64, 48, 8), seed=2025, MInf=0.2, ReInf=25.e6, ss_iteration
                 if nb[2] == 1:
                     add_bc(z, 'kmin', 'BCautoperiod', 'kmin'); add_bc(z, 'kmax', 'BCautoperiod', 'kmax')
     t = new_tree(zones, state, 'NSTurbulent')
-    FastC._setNum2Zones(t, {'scheme': scheme, 'slope': 'o3', 'time_step_nature': 'local', 'cfl': cfl, 'nb_relax': 1})
+    FastC._setNum2Zones(t, {'scheme': scheme, 'slope': 'o3', 'time_step_nature': 'local', 'cfl': cfl, 'nb_relax': 1, 'lu_match': lu_match})
     FastC._setNum2Base(t, {'temporal_scheme': 'implicit', 'ss_iteration': ss_iteration, 'modulo_verif': modulo_verif})
     if return_layout: return t, layout
     joins = build_joins(layout, nb, tuple(nloc), periodic=(False, False, nb[2] > 1))

@@ -231,7 +231,10 @@ void fo_invlu(const int *pi, const double *pr, const int box[6], const double *r
     c.gam1 = pr[FO_GAMMA]; c.gamm1 = c.gam1 - 1.; c.cp = pr[FO_GAMMA] * pr[FO_CVINF]; c.gam2 = c.gamm1 - 1.;
     c.tc0[0] = ti[0]; c.tc0[1] = tj[0]; c.tc0[2] = tk[0];
     const int nd = c.nd, neq = c.neq, overlap = pi[FO_LU_MATCH] == 1;
-    if (overlap && neq == 6) { fprintf(stderr, "oracle: lu_match with SA (extrap_coe) is not restated\n"); abort(); }
+    /* SA + lu_match (invlu.for:32-49): invlu_overlap_{l,u}_SA.for are the 6-equation copies of the overlap variants
+       (same includes with the _SA bodies).  extrap_coe.for:24-25,39,52,66 only acts on a face where the sweep box reaches
+       the second ghost row (ind_loop = 1 - nfic), which for a whole-zone box needs a BC of type 18 / 30 (BCzone.cpp:117-127);
+       with the BC families restated here the box stops at row 0, so extrap_coe is a no-op. */
     const int ideb = box[0], ifin = box[1], jdeb = box[2], jfin = box[3], kdeb = box[4], kfin = box[5];
     double b[6];
     /* ---- lower sweep (invlu_l.for:79-215): normals 0.5*(t(lt)+t(lt-m)) of the cell l-d */

@@ -35,6 +35,7 @@ CASES = {
     # several zones with several LU tiles each: the multi-zone launch (k_lu_tile_b) interleaves the tiles of all zones
     'sa_plate_blocks_tiles': lambda: synth.case_flatplate(n=(24, 40, 40), nblocks=(1, 2, 2)),
     'multiblock_roe_lumatch_tiles': lambda: synth.case_multiblock(nblk=(2, 1, 2), n=18),
+    'sa_plate_blocks_lumatch': lambda: synth.case_flatplate(n=(24, 16, 8), nblocks=(2, 2, 2), lu_match=1),   # invlu_overlap_*_SA
     'multiblock_explicit': lambda: synth.case_multiblock(nblk=(2, 1, 2), n=8, temporal='explicit', scheme='senseur'),
 }
 
