@@ -33,6 +33,7 @@ struct Zone {
     int lu_box[6];                  // ishift_lu (BCzone.cpp:136-143)
     int lcorner = 1;
     LuPlan lu;                      // hyperplane bookkeeping (fb_implicit.cu)
+    int xfaces = 0;                 // faces whose interior cells are donors of cross-rank joins (bit 0..5 = imin .. kmax)
     bool has_params = false, has_xyz = false;
     size_t n_state = 0, n_aux = 0;
 };
@@ -44,7 +45,6 @@ struct fb_solver {
     cudaStream_t st = nullptr;
     cudaStream_t st2 = nullptr;       // cross-rank halo exchange (pack, host transport, unpack): overlaps the interior tiles
     cudaEvent_t ev1 = nullptr, ev2 = nullptr;
-    int *d_done = nullptr;            // face tiles finished (RhsArgs::done), device counter
     // multi-zone solvers: the per-zone kernels of a phase fan out over st + 3 lanes so that the tail of one zone's grid
     // (a 128^3 block is 1.08 waves of rhs CTAs) is filled by the next zone's CTAs; the phase joins back on st
     cudaStream_t lane[3] = {nullptr, nullptr, nullptr};
@@ -98,11 +98,13 @@ int fb_solver_create(int device, int nzones, fb_solver **out)
     fb_solver *s = new fb_solver();
     s->dev = device; s->nz = nzones; s->z.resize(nzones);
     CK(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&s->st2, cudaStreamNonBlocking));
+    {   // the exchange stream outranks the others: its pack / unpack CTAs go ahead of the interior tiles still queued
+        int lo = 0, hi = 0; CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(cudaStreamCreateWithPriority(&s->st2, cudaStreamNonBlocking, hi));
+    }
     CK(cudaEventCreateWithFlags(&s->ev1, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&s->ev2, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
     for (int q = 0; q < 3; q++) { CK(cudaStreamCreateWithFlags(&s->lane[q], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&s->ev_lane[q], cudaEventDisableTiming)); }
-    CK(cudaMalloc(&s->d_done, 2 * sizeof(int))); CK(cudaMemset(s->d_done, 0, 2 * sizeof(int)));
     *out = s;
     return FB_OK;
 }
@@ -123,7 +125,6 @@ void fb_solver_destroy(fb_solver *s)
     if (s->st2) cudaStreamDestroy(s->st2);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->ev2) cudaEventDestroy(s->ev2);
-    cudaFree(s->d_done);
     for (int q = 0; q < 3; q++) { if (s->lane[q]) cudaStreamDestroy(s->lane[q]); if (s->ev_lane[q]) cudaEventDestroy(s->ev_lane[q]); }
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
     lu_batch_free(s->lub);
@@ -411,6 +412,31 @@ int fb_set_joins(fb_solver *s, const int *ji, int n)
     for (int i = 0; i < s->nz; i++) { nds[i] = s->z[i].d.nd; neqs[i] = s->z[i].d.neq; }
     std::string err;
     if (joins_build(s->joins, ji, n, s->nz, nds.data(), neqs.data(), err)) return fail(FB_EINVAL, "fb_set_joins: " + err);
+    // which faces of each zone feed cross-rank joins (kind 1 = pack): the explicit stages compute the tiles on those faces first
+    for (auto &z : s->z) z.xfaces = 0;
+    {
+        const int nj = ji[0]; const int *idx = ji + 2 + 7 * nj;
+        for (int q = 0; q < nj; q++) {
+            const int *d = ji + 2 + 7 * q;
+            if (d[0] != 1 || d[3] <= 0) continue;
+            Zone &z = s->z[d[1]]; const ZoneDev &zd = z.d;
+            int lo[3] = {1 << 30, 1 << 30, 1 << 30}, hi[3] = {-(1 << 30), -(1 << 30), -(1 << 30)};
+            for (int p = 0; p < d[3]; p++) {
+                const int l = idx[d[4] + p];
+                const int c[3] = {l % zd.ni - zd.nf + 1, (l / zd.ni) % zd.nj - zd.nf + 1, l / (zd.ni * zd.nj) - zd.nfk + 1};
+                for (int e = 0; e < 3; e++) { lo[e] = std::min(lo[e], c[e]); hi[e] = std::max(hi[e], c[e]); }
+            }
+            const int nv[3] = {zd.iv, zd.jv, zd.kv};
+            int flags = 0;
+            for (int e = 0; e < 3; e++) {
+                if (hi[e] - lo[e] + 1 >= nv[e]) continue;                   // spans the direction: not a face in it
+                if (hi[e] <= 2) flags |= 1 << (2 * e);                         // two layers behind the lower face
+                else if (lo[e] >= nv[e] - 1) flags |= 2 << (2 * e);            // ... the upper face
+                else flags = 63;                                               // not a face window: all faces first
+            }
+            z.xfaces |= flags ? flags : 63;
+        }
+    }
     cudaFree(s->halo_send); cudaFree(s->halo_recv); s->halo_send = s->halo_recv = nullptr;
     if (s->joins.send_doubles) CK(cudaMalloc(&s->halo_send, s->joins.send_doubles * sizeof(double)));
     if (s->joins.recv_doubles) CK(cudaMalloc(&s->halo_recv, s->joins.recv_doubles * sizeof(double)));
@@ -438,29 +464,15 @@ static void apply_bc_zone(fb_solver *s, Zone &z, double *rop, int lrhs)
 // whatever the caller queues on st before transfers_end overlaps the exchange.  Local joins run on st in transfers_end.
 static bool cross_rank(fb_solver *s) { return s->xcb && (s->joins.send_doubles || s->joins.recv_doubles); }
 
-// exchange stream: wait until `target` face tiles of the running rhs kernels have signalled (RhsArgs::done), then re-arm
-// the counter.  Bounded: after ~4 s without progress it gives up and raises cnt[1] (reported by fb_sync).
-__global__ void k_wait_count(int *cnt, int target)
-{
-    if (threadIdx.x != 0) return;
-    long long spins = 0;
-    while (atomicAdd(cnt, 0) < target) {
-        __nanosleep(200);
-        if (++spins > 20000000LL) { cnt[1] = 1; break; }
-    }
-    cnt[0] = 0;
-    __threadfence();
-}
-
-// wait_count > 0: the donor cells are produced by the face tiles of rhs kernels already queued on st (gsdr3 overlap);
-// otherwise the exchange simply waits for everything queued on st so far
-static void transfers_begin(fb_solver *s, int which, double **target, int wait_count = -1)
+// ev1_recorded: the caller has already recorded ev1 on st behind the kernels that produce the donor cells (the face tiles of
+// an explicit stage, gsdr3) and may have queued more work since; otherwise the exchange waits for everything queued on st so far
+static void transfers_begin(fb_solver *s, int which, double **target, bool ev1_recorded = false)
 {
     if (s->joins.njoin == 0 || !cross_rank(s)) return;
     std::vector<double *> ptr(s->nz);
     for (int i = 0; i < s->nz; i++) ptr[i] = which == 1 ? s->z[i].drodm : target[i];
-    if (wait_count > 0) { k_wait_count<<<1, 32, 0, s->st2>>>(s->d_done, wait_count); s->launches++; }
-    else { cudaEventRecord(s->ev1, s->st); cudaStreamWaitEvent(s->st2, s->ev1, 0); cudaMemsetAsync(s->d_done, 0, sizeof(int), s->st2); }
+    if (!ev1_recorded) cudaEventRecord(s->ev1, s->st);
+    cudaStreamWaitEvent(s->st2, s->ev1, 0);
     if (s->joins.send_doubles) { joins_pack(s->joins, ptr.data(), s->halo_send, s->joins.send_doubles * 8, s->st2); s->launches++; }
     s->xcb(s->xuser, which);
     if (s->joins.recv_doubles) { joins_unpack(s->joins, ptr.data(), s->halo_recv, s->joins.recv_doubles * 8, s->st2); s->launches++; }
@@ -505,7 +517,6 @@ static int gsdr3(fb_solver *s, int nitcfg, int nssiter, int nitrun, int first_it
     static const bool no_overlap = [] { const char *e = getenv("FAST_B200_OVERLAP"); return e && e[0] == '0'; }();   // A/B switch
     const bool overlap = !implicit && lexit_lu == 0 && cross_rank(s) && !no_overlap;
     std::vector<double *> cl(s->nz);
-    int face_tiles = 0; bool face_ok = true;
     static const bool no_fan = [] { const char *e = getenv("FAST_B200_FAN"); return e && e[0] == '0'; }();   // A/B switch
     const bool fan = s->nz > 1 && !no_fan;
     {
@@ -532,22 +543,33 @@ static int gsdr3(fb_solver *s, int nitcfg, int nssiter, int nitrun, int first_it
                 if (z.d.kflu == 2 && !fb_sensor_fused()) { launch_sensor(z.d, ssiter, zst); s->launches++; }
             }
         }
-        {
+        if (!overlap) {
             Scope r(s, 0);
             Fan f(s, fan);
             for (int n = 0; n < s->nz; n++) {
-                Zone &z = s->z[n]; double *ssiter = ss[n], *clp = cl[n]; cudaStream_t zst = f.stream(n);
-                if (implicit && z.d.iflow == 3 && nitcfg == 1) { launch_sa_ring(z.d, ssiter, zst); s->launches++; }
-                double *out = implicit ? nullptr : clp;   // explicit: the stage writes the array that then gets the BCs
-                // explicit + cross-rank joins: the CTAs take the tiles that touch a zone face first (their cells are the
-                // donors of the exchange) and count them off; the exchange stream starts when they are all in memory and
-                // runs while the interior tiles are still being computed
-                const int nb = launch_rhs(z.d, ssiter, out, z.rop[0], z.rop[1], nitcfg, first_it, zst, overlap ? s->d_done : nullptr);
-                s->launches++;
-                if (nb > 0) face_tiles += nb; else face_ok = false;
+                Zone &z = s->z[n]; cudaStream_t zst = f.stream(n);
+                if (implicit && z.d.iflow == 3 && nitcfg == 1) { launch_sa_ring(z.d, ss[n], zst); s->launches++; }
+                // explicit: the stage writes the array that then gets the BCs
+                launch_rhs(z.d, ss[n], implicit ? nullptr : cl[n], z.rop[0], z.rop[1], nitcfg, first_it, zst); s->launches++;
             }
+        } else {
+            // explicit stage + cross-rank joins: the tiles that touch a zone face (their cells are the donors of the exchange)
+            // run first on st; the exchange stream starts behind them (ev1) while the interior tiles, queued on a lane at the
+            // same time, fill the SMs as the face tiles drain.  Everything joins back on st before the local joins and BCs.
+            Scope r(s, 0);
+            cudaEventRecord(s->ev_fork, s->st); cudaStreamWaitEvent(s->lane[0], s->ev_fork, 0);
+            for (int n = 0; n < s->nz; n++) {
+                Zone &z = s->z[n];
+                launch_rhs(z.d, ss[n], cl[n], z.rop[0], z.rop[1], nitcfg, first_it, s->st, 1, z.xfaces); s->launches++;
+            }
+            cudaEventRecord(s->ev1, s->st);
+            for (int n = 0; n < s->nz; n++) {
+                Zone &z = s->z[n];
+                launch_rhs(z.d, ss[n], cl[n], z.rop[0], z.rop[1], nitcfg, first_it, s->lane[0], 2, z.xfaces); s->launches++;
+            }
+            transfers_begin(s, 0, cl.data(), true);
+            cudaEventRecord(s->ev_lane[0], s->lane[0]); cudaStreamWaitEvent(s->st, s->ev_lane[0], 0);
         }
-        if (overlap) transfers_begin(s, 0, cl.data(), face_ok ? face_tiles : -1);
         if (implicit) {
             if (s->z[0].pi[PI_LU_MATCH] == 1) transfers(s, 1, 0, nullptr);   // lhs.cpp:1-15
             // several zones: one pair of launches sweeps them all, tiles of the zones interleaved (k_lu_tile_b)
@@ -714,10 +736,6 @@ int fb_counter(const char *name, long long *out)
 }
 static int check_lu(fb_solver *s)
 {
-    if (s->d_done) {
-        int flag = 0; cudaMemcpy(&flag, s->d_done + 1, sizeof(int), cudaMemcpyDeviceToHost);
-        if (flag) return fail(FB_ECUDA, "halo exchange: the face tiles of the rhs kernel never signalled (results invalid)");
-    }
     for (auto &z : s->z) if (z.d.itypcp <= 1 && lu_plan_error(z.lu))
         return fail(FB_ECUDA, "LU wavefront: a tile timed out waiting for its neighbour (results invalid)");
     return FB_OK;

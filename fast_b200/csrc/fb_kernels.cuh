@@ -12,9 +12,9 @@ void launch_invist(const ZoneDev &z, const double *rop, int ext, cudaStream_t st
 void launch_sensor(const ZoneDev &z, const double *rop, cudaStream_t st);
 bool fb_sensor_fused();
 // explicit stage (init_rhs + flux balance + core3ark3) or implicit rhs (src + flux balance + core3as2)
-// done != nullptr: face tiles first, their threads count themselves into *done when finished (halo-exchange overlap);
-// returns the count the exchange stream has to wait for
-int launch_rhs(const ZoneDev &z, const double *rop, double *rop_out, const double *ro_n, const double *ro_n1,
-               int nitcfg, int first_it, cudaStream_t st, int *done = nullptr);
+// part: 0 the whole zone, 1 only the tiles that touch a zone face, 2 only the interior tiles (halo-exchange overlap of the
+// explicit stages; implicit zones always run whole); faces: bit 0..5 = imin .. kmax faces that carry cross-rank joins
+void launch_rhs(const ZoneDev &z, const double *rop, double *rop_out, const double *ro_n, const double *ro_n1,
+                int nitcfg, int first_it, cudaStream_t st, int part = 0, int faces = 63);
 void launch_bc(const ZoneDev &z, const BcWin *d_wins, int nwin, int maxcells, double *rop, int lrhs, cudaStream_t st);
 void launch_corners(const ZoneDev &z, double *rop, const int box[6], cudaStream_t st);

@@ -21,50 +21,65 @@ static inline dim3 grid3r(int ni, int nj, int nk, dim3 b) { return dim3((ni + b.
 // which makes the compiler re-load the staged state around it.
 __device__ __forceinline__ void st_wig(unsigned char *p, unsigned v) { asm("st.global.u8 [%0], %1;" ::"l"(p), "r"(v)); }
 
-#ifndef RHS_VAR
-#define RHS_VAR 0      // A/B builds: 1 = no completion signal, 2 = no signal and no tile reordering
-#endif
-// Halo-exchange overlap (RhsArgs::done): CTA c works on tile rhs_face_first(c) -- a bijection of the launch grid that puts
-// the tiles touching a zone face first (their cells are the donors of the exchange).  It is pure arithmetic on blockIdx /
-// gridDim so that the tile coordinates stay provably warp-uniform: reading them from a table made the compiler treat the
-// k loop bound as divergent (WARPSYNC around every shuffle, duplicated loop tails; the TGV stage went from 1.0 to 1.4 ms).
-__device__ __forceinline__ unsigned rhs_cta_linear() { return blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z); }
-__device__ __forceinline__ void rhs_face_first(unsigned c, unsigned &x, unsigned &y, unsigned &z)
+// Halo-exchange overlap (RhsArgs::gx != 0): the stage is launched in two parts with 1-D grids, CTA c of a part working on
+// tile rhs_face_first(tile0 + c) -- a bijection of the gx x gy x gz tile grid that puts the tiles touching a zone face with
+// cross-rank joins first (their cells are the donors of the exchange).  Part 1 = the face tiles, part 2 = the interior tiles on another
+// stream; the exchange starts behind an event recorded after part 1.  Pure arithmetic on kernel parameters, and nothing
+// in the kernel tells anybody that a tile is finished: two earlier variants -- tile coordinates read from a table, and a
+// per-tile completion count (fence + atomic, even predicated off) at the end of the kernel -- cost the TGV stage 40 %
+// (1.0 -> 1.43 ms, profiles/r01_rhs_overlap_variants.md) with the overlap switched OFF.
+// fl: which faces of the zone carry cross-rank joins, bit 0..5 = imin, imax, jmin, jmax, kmin, kmax (rhs_face_flags has
+// resolved degenerate tile grids, so that lo + hi <= g in every direction)
+__host__ __device__ __forceinline__ void rhs_face_first(unsigned c, unsigned gx, unsigned gy, unsigned gz, unsigned fl,
+                                                        unsigned &x, unsigned &y, unsigned &z)
 {
-    const unsigned gx = gridDim.x, gy = gridDim.y, gz = gridDim.z;
+    const unsigned xl = fl & 1u, xh = (fl >> 1) & 1u, yl = (fl >> 2) & 1u, yh = (fl >> 3) & 1u, zl = (fl >> 4) & 1u, zh = (fl >> 5) & 1u;
     const unsigned sxy = gx * gy;
-    if (c < sxy) { z = 0; y = c / gx; x = c - y * gx; return; }                              // slab z = 0
-    c -= sxy;
-    if (c < sxy) { z = gz - 1; y = c / gx; x = c - y * gx; return; }                         // slab z = gz-1 (gz >= 2 here)
-    c -= sxy;
-    const unsigned nzm = gz - 2, sxz = gx * nzm;                                             // layers z = 1 .. gz-2 (gz >= 3 here)
-    if (c < sxz) { y = 0; z = 1 + c / gx; x = c % gx; return; }                              // rows y = 0
-    c -= sxz;
-    if (c < sxz) { y = gy - 1; z = 1 + c / gx; x = c % gx; return; }                         // rows y = gy-1 (gy >= 2 here)
-    c -= sxz;
-    const unsigned nym = gy - 2, syz = nym * nzm;                                            // y = 1 .. gy-2 (gy >= 3 here)
-    if (c < syz) { x = 0; z = 1 + c / nym; y = 1 + c % nym; return; }                        // columns x = 0
-    c -= syz;
-    if (c < syz) { x = gx - 1; z = 1 + c / nym; y = 1 + c % nym; return; }                   // columns x = gx-1 (gx >= 2 here)
-    c -= syz;
-    const unsigned nxm = gx - 2;                                                             // interior (gx >= 3 here)
-    x = 1 + c % nxm; c /= nxm; y = 1 + c % nym; z = 1 + c / nym;
+    unsigned n = zl * sxy;
+    if (c < n) { z = 0; y = c / gx; x = c - y * gx; return; }                                // slab z = 0
+    c -= n; n = zh * sxy;
+    if (c < n) { z = gz - 1; y = c / gx; x = c - y * gx; return; }                           // slab z = gz-1
+    c -= n;
+    const unsigned nzm = gz - zl - zh, sxz = gx * nzm;                                       // layers z = zl .. zl+nzm-1
+    n = yl * sxz;
+    if (c < n) { y = 0; z = zl + c / gx; x = c % gx; return; }                               // rows y = 0
+    c -= n; n = yh * sxz;
+    if (c < n) { y = gy - 1; z = zl + c / gx; x = c % gx; return; }                          // rows y = gy-1
+    c -= n;
+    const unsigned nym = gy - yl - yh, syz = nym * nzm;                                      // y = yl .. yl+nym-1
+    n = xl * syz;
+    if (c < n) { x = 0; z = zl + c / nym; y = yl + c % nym; return; }                        // columns x = 0
+    c -= n; n = xh * syz;
+    if (c < n) { x = gx - 1; z = zl + c / nym; y = yl + c % nym; return; }                   // columns x = gx-1
+    c -= n;
+    const unsigned nxm = gx - xl - xh;                                                       // interior
+    x = xl + c % nxm; c /= nxm; y = yl + c % nym; z = zl + c / nym;
 }
-// number of face tiles of a gx x gy x gz launch (host)
-static inline int rhs_face_tiles(unsigned gx, unsigned gy, unsigned gz)
+// face flags usable on a gx x gy x gz tile grid: a direction with a single tile keeps one flag at most
+static inline unsigned rhs_face_flags(unsigned fl, unsigned gx, unsigned gy, unsigned gz)
 {
-    const unsigned ix = gx > 2 ? gx - 2 : 0, iy = gy > 2 ? gy - 2 : 0, iz = gz > 2 ? gz - 2 : 0;
-    return (int)(gx * gy * gz - ix * iy * iz);
+    const unsigned g[3] = {gx, gy, gz};
+    for (int d = 0; d < 3; d++) if (g[d] < 2 && ((fl >> (2 * d)) & 3u) == 3u) fl &= ~(2u << (2 * d));
+    return fl;
 }
-// a face tile tells the exchange stream that its cells are in memory: every thread fences its own stores and counts itself.
-// Predicated PTX, no C++ branch and no CTA barrier, on purpose: with an `if` (or a __syncthreads) in this tail the compiler
-// restructured the k loop in front of it (a second copy of the F_i shuffle block, WARPSYNC before every shuffle) and the
-// TGV stage went from 1.0 to 1.4 ms even with the overlap switched off.
-__device__ __forceinline__ void rhs_signal_done(const RhsArgs &a)
+// number of face tiles (host)
+static inline unsigned rhs_face_tiles(unsigned gx, unsigned gy, unsigned gz, unsigned fl)
 {
-    const unsigned on = (a.done != nullptr && rhs_cta_linear() < (unsigned)a.nbnd) ? 1u : 0u;      // uniform per CTA
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p membar.gl;\n\t@p red.global.add.s32 [%0], 1;\n\t}"
-                 :: "l"(a.done), "r"(on) : "memory");
+    const unsigned ix = gx - (fl & 1u) - ((fl >> 1) & 1u), iy = gy - ((fl >> 2) & 1u) - ((fl >> 3) & 1u), iz = gz - ((fl >> 4) & 1u) - ((fl >> 5) & 1u);
+    return gx * gy * gz - ix * iy * iz;
+}
+// launch grid of a part (RhsArgs::part: 0 whole zone as a 3-D grid, 1 face tiles, 2 interior tiles); false = nothing to launch
+static inline bool rhs_part_grid(RhsArgs &a, dim3 &g)
+{
+    a.gx = a.gy = a.gz = a.tile0 = 0;
+    if (a.part == 0) return true;
+    a.faces = (int)rhs_face_flags((unsigned)a.faces, g.x, g.y, g.z);
+    const unsigned nb = rhs_face_tiles(g.x, g.y, g.z, (unsigned)a.faces), total = g.x * g.y * g.z;
+    a.gx = (int)g.x; a.gy = (int)g.y; a.gz = (int)g.z;
+    a.tile0 = a.part == 1 ? 0 : (int)nb;
+    const unsigned n = a.part == 1 ? nb : total - nb;
+    g = dim3(n, 1, 1);
+    return n > 0;
 }
 
 // ------------------------------------------------------------------------------------------------ wall flux correction
@@ -181,9 +196,7 @@ __global__ void __launch_bounds__(32 * (RHS2_RJ + 1)) k_rhs2(ZoneDev z, RhsArgs 
     constexpr int NEQ = FLOW == 3 ? 6 : 5, RJ = RHS2_RJ;
     // (unsigned on purpose, like blockIdx: with signed tile coordinates the address arithmetic of the whole kernel grows by a quarter)
     unsigned bx = blockIdx.x, by = blockIdx.y, bz = blockIdx.z;
-#if RHS_VAR < 2
-    if (!IMPL && a.done) rhs_face_first(rhs_cta_linear(), bx, by, bz);   // explicit stages only
-#endif
+    if (!IMPL && a.gx) rhs_face_first(blockIdx.x + (unsigned)a.tile0, a.gx, a.gy, a.gz, a.faces, bx, by, bz);   // explicit stages only
     __shared__ double sFj[2][RJ + 1][NEQ][32];
     const int li = threadIdx.x, m = threadIdx.y;
     const int i = 1 + bx * 31 + li, j = 1 + by * RJ + m;
@@ -228,9 +241,6 @@ __global__ void __launch_bounds__(32 * (RHS2_RJ + 1)) k_rhs2(ZoneDev z, RhsArgs 
         }
         if (last) {           // uniform
             if (wcomp && cell && k == z.kv + 1) st_wig(z.wigb + l, wg);   // k faces of the plane behind the last cells
-#if RHS_VAR < 1
-            if (!IMPL) rhs_signal_done(a);      // here, not behind the loop: the loop's only exit stays a plain thread exit
-#endif
             break;
         }
         if (cell) {
@@ -353,9 +363,7 @@ k_rhs3(const __grid_constant__ CUtensorMap tm_rop, const __grid_constant__ CUten
     constexpr int NEQ = C::NEQ, NS = RHS3_NS, PS = C::PS, RS = C::RS, VS = C::VS;
     // (unsigned on purpose, like blockIdx: with signed tile coordinates the address arithmetic of the whole kernel grows by a quarter)
     unsigned bx = blockIdx.x, by = blockIdx.y, bz = blockIdx.z;
-#if RHS_VAR < 2
-    if (!IMPL && a.done) rhs_face_first(rhs_cta_linear(), bx, by, bz);   // explicit stages only
-#endif
+    if (!IMPL && a.gx) rhs_face_first(blockIdx.x + (unsigned)a.tile0, a.gx, a.gy, a.gz, a.faces, bx, by, bz);   // explicit stages only
     extern __shared__ __align__(128) double ring[];
     double (*sFj)[RJ + 1][NEQ][32] = (double (*)[RJ + 1][NEQ][32])(ring + NS * PS);
     constexpr int NSF = C::template nsf<MESH>();
@@ -453,9 +461,6 @@ k_rhs3(const __grid_constant__ CUtensorMap tm_rop, const __grid_constant__ CUten
         }
         if (last) {           // uniform; no TMA is in flight any more (plane k1+2 was waited for above)
             if (wcomp && cell && k == z.kv + 1) st_wig(z.wigb + l, wg);
-#if RHS_VAR < 1
-            if (!IMPL) rhs_signal_done(a);      // here, not behind the loop: the loop's only exit stays a plain thread exit
-#endif
             break;
         }
         if (cell) {
@@ -510,7 +515,7 @@ static void launch_rhs2_t(const ZoneDev &z, RhsArgs &a, bool impl, cudaStream_t 
 {
     dim3 b(32, RHS2_RJ + 1, 1);
     dim3 g((z.iv + 30) / 31, (z.jv + RHS2_RJ - 1) / RHS2_RJ, (z.kv + RHS2_KC - 1) / RHS2_KC);
-    a.nbnd = a.done ? rhs_face_tiles(g.x, g.y, g.z) : 0; a.nsig = a.nbnd * (int)(b.x * b.y);
+    if (!rhs_part_grid(a, g)) return;
     // WC: first sub-iteration of a SENSOR zone -- the switch is evaluated inside the flux and stored
     if (SCHEME == 2 && a.nitcfg == 1 && a.wfuse) {
         if (impl) k_rhs2<MESH, FLOW, SCHEME, SLOPE, true, SCHEME == 2><<<g, b, 0, st>>>(z, a);
@@ -540,7 +545,7 @@ static bool launch_rhs3_t(const ZoneDev &z, RhsArgs &a, bool impl, cudaStream_t 
     }
     dim3 b(32, RJ + 1, 1);
     dim3 g((z.iv + 30) / 31, (z.jv + RJ - 1) / RJ, (z.kv + RHS3_KC - 1) / RHS3_KC);
-    a.nbnd = a.done ? rhs_face_tiles(g.x, g.y, g.z) : 0; a.nsig = a.nbnd * (int)(b.x * b.y);
+    if (!rhs_part_grid(a, g)) return true;
     if (SCHEME == 2 && a.nitcfg == 1 && a.wfuse) {   // first sub-iteration of a SENSOR zone: the switch is evaluated in the flux
         if (impl) k_rhs3<MESH, FLOW, SCHEME, SLOPE, true, RJ, SCHEME == 2><<<g, b, C::template smem<MESH>(), st>>>(*tr, *tm, z, a);
         else k_rhs3<MESH, FLOW, SCHEME, SLOPE, false, RJ, SCHEME == 2><<<g, b, C::template smem<MESH>(), st>>>(*tr, *tm, z, a);

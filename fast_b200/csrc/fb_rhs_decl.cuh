@@ -9,11 +9,11 @@ struct RhsArgs {
     double coefH, coefW;    // low-storage RK (init_rhs.for:31-33, core3ark3.for:22-25)
     double c1, c2, c3;      // BDF weights (core3as2.for:37-46)
     int nitcfg;
-    // halo-exchange overlap (fb_api.cu: gsdr3, explicit stages with cross-rank joins): with done != nullptr the CTAs take the
-    // tiles that touch a zone face first (fb_rhs.cuh: rhs_face_first; their cells are the donors of the exchange) and the first
-    // nbnd CTAs count their threads into *done when their results are in memory; the exchange stream waits for that count
-    // (nsig = nbnd x threads per CTA, set by the launcher) while the interior tiles run
-    int nbnd, nsig; int *done;
+    // halo-exchange overlap (fb_api.cu: gsdr3, explicit stages with cross-rank joins): part 1 / 2 = only the tiles that touch
+    // a zone face / only the interior tiles, as a 1-D grid whose CTA c works on tile rhs_face_first(tile0 + c) of the
+    // gx x gy x gz tile grid (fb_rhs.cuh); part 0 = the whole zone as a 3-D grid (gx = 0)
+    int part, tile0, gx, gy, gz;
+    int faces;              // faces of the zone that carry cross-rank joins: bit 0..5 = imin, imax, jmin, jmax, kmin, kmax
     int wfuse;              // SENSOR switch evaluated inside the first-sub-iteration kernel (default) instead of k_sensor
 };
 
