@@ -229,7 +229,10 @@ def run_gpu(args):
             'step_share': {k: (v / tm['all'] if tm['all'] else None) for k, v in tm.items()}}
 
     # end to end through the C-ABI with host buffers (pinned): H2D inputs + D2H result every step
+    e2e = None
     nz = len(zones)
+    if args.no_e2e:      # auxiliary multi-GPU lines of the large cases (pinned copies of three time levels per rank)
+        return finish(args, rank, world, dist, desc, cells_total, nsub, ms, value, roof, None, nlaunch, clk, hx, implicit, pi0, V)
     hb = [[torch.empty(FastC.block_of(z, suf).size, dtype=torch.float64, pin_memory=True) for z in zones] for suf in ('', '_M1', '_P1')]
     FastS.sync_tree(t)
     for li, suf in enumerate(('', '_M1', '_P1')):
@@ -255,6 +258,10 @@ def run_gpu(args):
     a = hb[order[0]][0].numpy()
     assert numpy.isfinite(a).all(), "non-finite state after the benchmark"
 
+    return finish(args, rank, world, dist, desc, cells_total, nsub, ms, value, roof, e2e, nlaunch, clk, hx, implicit, pi0, V)
+
+
+def finish(args, rank, world, dist, desc, cells_total, nsub, ms, value, roof, e2e, nlaunch, clk, hx, implicit, pi0, V):
     cpu = None
     if not args.no_cpu and world == 1:
         r, nth, sample, _ = cpu_oracle_rate(args.workload, seconds=12.)
@@ -280,6 +287,7 @@ def main():
     ap.add_argument('--gpus', type=int, default=1); ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3); ap.add_argument('--impl', default='fast_b200')
     ap.add_argument('--workload', default=None); ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
     args = ap.parse_args()
     if args.workload is None: args.workload = 'tgv256'
     if args.impl == 'reference': run_reference(args)
