@@ -272,7 +272,8 @@ def finish(args, rank, world, dist, desc, cells_total, nsub, ms, value, roof, e2
     cfg = {'workload': desc, 'cells': cells_total, 'sub_iterations_per_step': nsub, 'l2': 'working set >> 126 MB L2 (no flush needed)',
            'cell_updates_per_s': cells_total * nsub * args.steps / (ms * 1e-3)}
     if hx is not None:
-        cfg['halo'] = {'transport': 'NCCL isend/irecv per neighbour on the exchange stream, overlapped with the interior tiles of the stage', 'bytes_per_exchange_per_rank': hx.bytes_per_exchange,
+        cfg['halo'] = {'transport': 'NCCL isend/irecv per neighbour on the exchange stream' + (', after the upper sweep' if implicit else ', overlapped with the interior tiles of the stage'),
+                       'bytes_per_exchange_per_rank': hx.bytes_per_exchange,
                        'exchanges_per_step': nsub * (2 if implicit and int(pi0[V.LU_MATCH]) else 1)}
     out = {'metric': 'FP64 cell-updates/sec', 'value': value, 'unit': 'Mcell.it/s', 'n_gpus': world, 'steps': args.steps,
            'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
