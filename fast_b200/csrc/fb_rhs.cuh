@@ -297,19 +297,25 @@ __global__ void __launch_bounds__(32 * (RHS2_RJ + 1)) k_rhs2(ZoneDev z, RhsArgs 
 #define RHS3_RJ_NS 8        // tile rows, Euler / laminar
 #endif
 #ifndef RHS3_RJ_SA
-#define RHS3_RJ_SA 6        // tile rows, Spalart-Allmaras (7 staged variables)
+#define RHS3_RJ_SA 7        // tile rows, Spalart-Allmaras (7 staged variables): 8 warps -- registers are allocated as if the
+                            // CTA had a multiple of 4 warps, so the 7-warp tile of RJ = 6 paid for a warp it did not have
 #endif
 #ifndef RHS3_MINB
 #define RHS3_MINB 2         // resident CTAs per SM the register allocation aims at
+#endif
+#ifndef RHS3_SMET_SA
+#define RHS3_SMET_SA 0      // 3dhomo SA zones: 1 = k-invariant metric tile in shared memory; 0 = read through L1, which frees the
+                            // 19 KB per CTA that let two CTAs of RJ = 7 stay resident (measured: C5 rhs 34.6 -> 31.9 ms)
 #endif
 #ifndef RHS3_KC
 #define RHS3_KC 32          // k planes per CTA (measured: 32 < 64 < 128 on TGV 256^3 and the plate)
 #endif
 
-template <int MESH, int RS, int VS>
-__device__ __forceinline__ typename std::conditional<MESH == 1, SMet1<RS, VS>, GMet1>::type make_met(const ZoneDev &z, const double *smet)
+template <int MESH, int FLOW> struct Rhs3SMet { static constexpr bool V = MESH == 1 && (FLOW != 3 || RHS3_SMET_SA != 0); };
+template <bool SM, int RS, int VS>
+__device__ __forceinline__ typename std::conditional<SM, SMet1<RS, VS>, GMet1>::type make_met(const ZoneDev &z, const double *smet)
 {
-    if constexpr (MESH == 1) { SMet1<RS, VS> m; m.s = smet; return m; }
+    if constexpr (SM) { SMet1<RS, VS> m; m.s = smet; return m; }
     else return GMet1(z);
 }
 
@@ -327,7 +333,7 @@ struct Rhs3Cfg {
     // second barrier per plane so that ring + metric tile leave room for two CTAs per SM
     template <int MESH> __host__ __device__ static constexpr int nsf() { return (MESH == 1 && FLOW == 3) ? 1 : 2; }
     template <int MESH> __host__ __device__ static constexpr int sfj() { return nsf<MESH>() * (RJ + 1) * NEQ * 32; }
-    template <int MESH> __host__ __device__ static constexpr int met() { return MESH == 1 ? 6 * VS : 0; }   // 3dhomo: metric tile (k-invariant)
+    template <int MESH> __host__ __device__ static constexpr int met() { return Rhs3SMet<MESH, FLOW>::V ? 6 * VS : 0; }   // 3dhomo: metric tile (k-invariant)
     template <int MESH> __host__ __device__ static constexpr size_t smem() { return (size_t)(RHS3_NS * PS + sfj<MESH>() + met<MESH>()) * sizeof(double) + RHS3_NS * sizeof(unsigned long long); }
 };
 
@@ -394,7 +400,7 @@ k_rhs3(const __grid_constant__ CUtensorMap tm_rop, const __grid_constant__ CUten
         for (int s = 0; s < NS; s++) mbar_init(bar + s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (MESH == 1) {
+    if (Rhs3SMet<MESH, FLOW>::V) {
         // the metrics of a 3dhomo zone do not depend on k: the tile's neighbourhood is copied once and serves every plane
         const int tid = m * 32 + li, mlast = z.nm - 1;
         for (int n = tid; n < 6 * VS; n += C::NT) {
@@ -422,7 +428,7 @@ k_rhs3(const __grid_constant__ CUtensorMap tm_rop, const __grid_constant__ CUten
     mbar_wait(bar + 0, 0);
     mbar_wait(bar + 1, 0);
     const int lcol = (m + 2) * RS + li + 2 + sh;
-    typename std::conditional<MESH == 1, SMet1<RS, VS>, GMet1>::type mt = make_met<MESH, RS, VS>(z, smet);
+    typename std::conditional<Rhs3SMet<MESH, FLOW>::V, SMet1<RS, VS>, GMet1>::type mt = make_met<Rhs3SMet<MESH, FLOW>::V, RS, VS>(z, smet);
     for (int k = k0; k <= k1 + 1; k++) {
         const int pk = k - pfirst;                       // >= 1
         const int sk = pk % NS, su = (pk + 1) % NS, sd = (pk - 1) % NS;
@@ -448,7 +454,7 @@ k_rhs3(const __grid_constant__ CUtensorMap tm_rop, const __grid_constant__ CUten
         v.s = ring; v.kup = (su - sk) * PS; v.kdn = (sd - sk) * PS; v.km2 = km2;
         const int ls = sk * PS + lcol;
         const int l = inddm(z, i, j, k);
-        const int lt = MESH == 2 ? 0 : (MESH == 1 ? lcol : indmtr(z, i, j, k));   // 3dhomo: index in the shared metric tile
+        const int lt = MESH == 2 ? 0 : (Rhs3SMet<MESH, FLOW>::V ? lcol : indmtr(z, i, j, k));   // 3dhomo: index in the shared metric tile
         const bool last = k == k1 + 1;
         if (cell) {
             face_flux<MESH, FLOW, SCHEME, SLOPE, 2>(z, v, mt, ls, wg, wcomp, lt, f);
