@@ -297,8 +297,8 @@ __global__ void __launch_bounds__(32 * (RHS2_RJ + 1)) k_rhs2(ZoneDev z, RhsArgs 
 #define RHS3_RJ_NS 8        // tile rows, Euler / laminar
 #endif
 #ifndef RHS3_RJ_SA
-#define RHS3_RJ_SA 7        // tile rows, Spalart-Allmaras (7 staged variables): 8 warps -- registers are allocated as if the
-                            // CTA had a multiple of 4 warps, so the 7-warp tile of RJ = 6 paid for a warp it did not have
+#define RHS3_RJ_SA 7        // tile rows, Spalart-Allmaras (7 staged variables): 8 warps of 128 registers, so that two CTAs fill the
+                            // four 16 K-register sub-partitions of an SM exactly (4 warps each); RJ = 6 left a warp slot empty
 #endif
 #ifndef RHS3_MINB
 #define RHS3_MINB 2         // resident CTAs per SM the register allocation aims at
