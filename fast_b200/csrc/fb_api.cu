@@ -14,6 +14,7 @@
 #include "../../include/fastb200.h"
 #include "fb_kernels.cuh"
 #include "fb_implicit.cuh"
+#include "fb_tiles.cuh"
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string &m) { g_err = m; return code; }
@@ -725,6 +726,20 @@ int fb_timing_get(fb_solver *s, const char *name, double *ms, long long *launche
     return fail(FB_EINVAL, "unknown timer name");
 }
 extern long long g_fb_rhs_launches[2];
+// test hook (tests/test_host_logic.py): the tile order of the two-part explicit stage on a gx x gy x gz tile grid, computed
+// by the very function the kernels use; out = 3 ints per tile in launch order, *nface = tiles of part 1
+int fb_debug_tile_order(int gx, int gy, int gz, int faces, int *out, int *nface)
+{
+    if (gx < 1 || gy < 1 || gz < 1 || !out || !nface) return fail(FB_EINVAL, "fb_debug_tile_order: bad arguments");
+    const unsigned fl = rhs_face_flags((unsigned)faces & 63u, gx, gy, gz);
+    *nface = (int)rhs_face_tiles(gx, gy, gz, fl);
+    for (unsigned c = 0; c < (unsigned)(gx * gy * gz); c++) {
+        unsigned x, y, z; rhs_face_first(c, gx, gy, gz, fl, x, y, z);
+        out[3 * c] = (int)x; out[3 * c + 1] = (int)y; out[3 * c + 2] = (int)z;
+    }
+    return FB_OK;
+}
+
 int fb_counter(const char *name, long long *out)
 {
     if (!name || !out) return fail(FB_EINVAL, "null");

@@ -86,9 +86,14 @@ int fb_timing_reset(fb_solver *s);
 int fb_timing_get(fb_solver *s, const char *name, double *ms, long long *launches);
 int fb_sync(fb_solver *s);
 /* Which kernels ran (process-wide): "rhs_tma" / "rhs_l1" = launches of the TMA-staged (k_rhs3) and of the L1-path
- * (k_rhs2) residual kernel, "lu_line" = 1 when the one-thread-per-line LU kernel is selected.  New with this library
+ * (k_rhs2) residual kernel, "lu_line" = 1 when the one-thread-per-line LU kernel is selected, "lu_batch" = multi-zone
+ * LU launch pairs (k_lu_tile_b).  New with this library
  * (no reference counterpart); bench.py names the kernel it reports a roofline for from it. */
 int fb_counter(const char *name, long long *out);
+/* Test hook, needs no device: the order in which the two-part explicit stage of the halo-exchange overlap visits a
+ * gx x gy x gz tile grid (tiles on the faces flagged in `faces` -- bit 0..5 = imin, imax, jmin, jmax, kmin, kmax -- first),
+ * computed by the function the kernels use.  out: 3 ints (x, y, z) per tile in launch order; *nface: tiles of part 1. */
+int fb_debug_tile_order(int gx, int gy, int gz, int faces, int *out, int *nface);
 /* Device pointer of a zone's state block (uintptr) so the Python host can hand halo buffers to
  * torch.distributed/NCCL without a host copy. */
 unsigned long long fb_zone_device_ptr(fb_solver *s, int nd, int level);

@@ -99,6 +99,26 @@ def test_abi_exports_every_declared_symbol():
     assert set(_lib.SYMBOLS) == set(names)
 
 
+def test_overlap_tile_order_is_a_face_first_bijection():
+    """Halo-exchange overlap (csrc/fb_tiles.cuh): part 1 of an explicit stage must cover exactly the tiles on the flagged faces,
+    part 2 the rest, every tile once -- for every face mask, including degenerate tile grids."""
+    import ctypes, itertools
+    L = _lib.lib()
+    for gx, gy, gz in itertools.product((1, 2, 3, 5), (1, 2, 4), (1, 2, 3)):
+        n = gx * gy * gz
+        for faces in range(64):
+            out = (ctypes.c_int * (3 * n))(); nf = ctypes.c_int(0)
+            assert L.fb_debug_tile_order(gx, gy, gz, faces, out, ctypes.byref(nf)) == 0
+            tiles = [(out[3 * c], out[3 * c + 1], out[3 * c + 2]) for c in range(n)]
+            assert len(set(tiles)) == n and all(0 <= x < gx and 0 <= y < gy and 0 <= z < gz for x, y, z in tiles)
+
+            def on_face(t):
+                g = (gx, gy, gz)
+                return any(((faces >> (2 * d)) & 1 and t[d] == 0) or ((faces >> (2 * d + 1)) & 1 and t[d] == g[d] - 1) for d in range(3))
+            assert all(on_face(t) for t in tiles[:nf.value]) and not any(on_face(t) for t in tiles[nf.value:]), (gx, gy, gz, faces)
+    assert L.fb_debug_tile_order(0, 1, 1, 0, None, None) != 0
+
+
 def test_no_cpu_fallback():
     """Without a GPU the product path must fail loudly (never route through the oracle)."""
     L = _lib.lib()
