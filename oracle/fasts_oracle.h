@@ -72,6 +72,11 @@ void fo_core3as2(const int *pi, const double *pr, int nitcfg, int first_it, cons
                  const double *rop_1, const double *rop_n, const double *rop_n1,
                  double *drodm, const double *coe);
 void fo_cprdu3s1(const int *pi, int nitcfg, const int ind[6], const double *drodm, double *rdm_blk);
+/* max |rhs - (D + L + U) dW| over the sweep box, with the operators of fo_invlu (pin of the nb_relax >= 2 relaxations) */
+double fo_lu_residual(const int *pi, const double *pr, const int box[6], const double *rop, const double *rhs, const double *dw,
+                      const double *coe, const double *ti, const double *tj, const double *tk);
+void fo_invlu_relax(const int *pi, const double *pr, const int box[6], const double *rop, double *rop_out, double *drodm,
+                    const double *coe, const double *ti, const double *tj, const double *tk, int nrelax);
 void fo_invlu(const int *pi, const double *pr, const int ind_lu[6], const double *rop,
               double *rop_out, double *drodm, const double *coe,
               const double *ti, const double *tj, const double *tk);

@@ -6,6 +6,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 #include "fo_internal.h"
 #include "fasts_oracle.h"
 
@@ -216,11 +217,91 @@ static void mjr_newton(const int *pi, const double *pr, int l, const double *rop
     }
 }
 
+/* LU/invlu.for:163-240 (nb_relax >= 2, fixed mesh): invlussor1_l / invlussor_l / invlussor_u[_SA].for, lussor_initssor.for,
+   mjr_drodm[_IO]_ssor.for, mjr_ssor.for -- symmetric Gauss-Seidel relaxations of (D + L + U) dW = rhs on the sweep box:
+     lower, relaxation m:  dW*_l = (rhs_l + U-sum of relaxation m-1 at l + sum over the lower neighbours B_d(l-d) dW*(l-d) xal) / coe5
+                           (invlussor_l.for: drodm_out enters as rhs + ssor, mjr_ssor.for of the previous upper sweep; the first
+                           relaxation invlussor1_l.for starts from the rhs alone, lu_dinv_IO.for / mjr_drodm_IO_ssor.for);
+                           the L-sum of the cell is kept in ssor (mjr_drodm_ssor.for) and one plane later the cell becomes
+                           rhs + L-sum (mjr_ssor.for at l - inck, invlussor1_l.for:158-160)
+     upper, relaxation m:  dW_l  = (rhs_l + L-sum_l + sum over the upper neighbours B_d(l+d) dW(l+d) xal) / coe5, the U-sum is
+                           kept in ssor for the next lower sweep (invlussor_u.for:111-228, 245-272)
+   Terms are added in i, j, k order (the include order of those files).  The Newton update runs plane by plane inside
+   the LAST upper sweep (lussor_end = 1, invlussor_u.for:155-170, 232-244) over the interior ind_loop_sdm, so with rop
+   aliased to rop_out the k term of plane k reads the updated state of plane k+1 exactly as in invlu_u.for.  The ssor
+   array of the reference also spans the ghost rows of an OpenMP sub-domain; for the whole-zone box restated here those
+   entries are never read.  The first relaxation equals LU-SGS: (D+U) dW = rhs + L-sum = D dW*. */
+static void fo_invlussor(const int *pi, const double *pr, const int box[6], luctx *c, double *rop_out, double *drodm, int nrelax)
+{
+    const int nd = c->nd, neq = c->neq;
+    const double *coe = c->coe;
+    const int ideb = box[0], ifin = box[1], jdeb = box[2], jfin = box[3], kdeb = box[4], kfin = box[5];
+    double *rhs = (double *)malloc(sizeof(double) * (size_t)nd * neq);
+    double *low = (double *)calloc((size_t)nd * neq, sizeof(double));
+    double *us = (double *)calloc((size_t)nd * neq, sizeof(double));     /* lussor_initssor.for: ssor = 0 */
+    memcpy(rhs, drodm, sizeof(double) * (size_t)nd * neq);
+    const int nb[6] = {1, pi[FO_IJKV], 1, pi[FO_IJKV + 1], 1, pi[FO_IJKV + 2]};
+    double b[6];
+    for (int m = 1; m <= nrelax; m++) {
+        for (int k = kdeb; k <= kfin; k++) for (int j = jdeb; j <= jfin; j++) for (int i = ideb; i <= ifin; i++) {
+            const int l = fo_inddm(pi, i, j, k), lt = c->typ == 2 ? 0 : fo_indmtr(pi, i, j, k);
+            const double xal = coe[l] * 0.5;
+            const int has[3] = {i > ideb, j > jdeb, k > kdeb};
+            double acc[6], s[6] = {0., 0., 0., 0., 0., 0.};
+            for (int e = 0; e < neq; e++) acc[e] = rhs[l + e * nd] + us[l + e * nd];
+            for (int d = 0; d < 3; d++) {
+                if (!has[d]) continue;
+                lu_term(c, d, l - c->inc[d], lt - c->incm[d], lt, 0.5, drodm, b);
+                for (int e = 0; e < neq; e++) { acc[e] = acc[e] + b[e] * xal; s[e] = s[e] + b[e] * xal; }
+            }
+            const double diag = 1. / coe[l + 4 * nd];
+            for (int e = 0; e < 5; e++) drodm[l + e * nd] = acc[e] * diag;
+            if (neq == 6) drodm[l + 5 * nd] = acc[5] / coe[l + 5 * nd];
+            for (int e = 0; e < neq; e++) low[l + e * nd] = s[e];
+        }
+        for (int k = kfin; k >= kdeb; k--) {
+            for (int j = jfin; j >= jdeb; j--) for (int i = ifin; i >= ideb; i--) {
+                const int l = fo_inddm(pi, i, j, k), lt = c->typ == 2 ? 0 : fo_indmtr(pi, i, j, k);
+                const double xal = coe[l] * -0.5;
+                const int has[3] = {i < ifin, j < jfin, k < kfin};
+                double acc[6], s[6] = {0., 0., 0., 0., 0., 0.};
+                for (int e = 0; e < neq; e++) acc[e] = rhs[l + e * nd] + low[l + e * nd];
+                for (int d = 0; d < 3; d++) {
+                    if (!has[d]) continue;
+                    lu_term(c, d, l + c->inc[d], lt + c->incm[d], c->typ == 1 && d == 2 ? lt : lt + 2 * c->incm[d], -0.5, drodm, b);
+                    for (int e = 0; e < neq; e++) { acc[e] = acc[e] + b[e] * xal; s[e] = s[e] + b[e] * xal; }
+                }
+                const double diag = 1. / coe[l + 4 * nd];
+                for (int e = 0; e < 5; e++) drodm[l + e * nd] = acc[e] * diag;
+                if (neq == 6) drodm[l + 5 * nd] = acc[5] / coe[l + 5 * nd];
+                for (int e = 0; e < neq; e++) us[l + e * nd] = s[e];
+            }
+            if (m == nrelax && k >= nb[4] && k <= nb[5])
+                for (int j = nb[2]; j <= nb[3]; j++) for (int i = nb[0]; i <= nb[1]; i++)
+                    mjr_newton(pi, pr, fo_inddm(pi, i, j, k), c->rop, rop_out, drodm);
+        }
+    }
+    free(rhs); free(low); free(us);
+}
+
 /* LU/invlu.for:6-344 (nb_relax = 1, fixed mesh): invlu_l[_SA] then invlu_u[_SA]; lu_match = 1 selects the "overlap"
    variants whose only effect for a whole-zone box is the i,j,k accumulation order and a Newton update restricted to
    the interior (invlu_overlap_u.for).  In place: drodm holds rhs -> dW* -> dW. */
+static void fo_invlu_impl(const int *pi, const double *pr, const int box[6], const double *rop, double *rop_out, double *drodm,
+                          const double *coe, const double *ti, const double *tj, const double *tk, int nrelax_forced);
 void fo_invlu(const int *pi, const double *pr, const int box[6], const double *rop, double *rop_out, double *drodm,
               const double *coe, const double *ti, const double *tj, const double *tk)
+{
+    fo_invlu_impl(pi, pr, box, rop, rop_out, drodm, coe, ti, tj, tk, 0);
+}
+/* test hook: the relaxation sweeps with a given number of relaxations (1 must reproduce the nb_relax = 1 path) */
+void fo_invlu_relax(const int *pi, const double *pr, const int box[6], const double *rop, double *rop_out, double *drodm,
+                    const double *coe, const double *ti, const double *tj, const double *tk, int nrelax)
+{
+    fo_invlu_impl(pi, pr, box, rop, rop_out, drodm, coe, ti, tj, tk, nrelax);
+}
+static void fo_invlu_impl(const int *pi, const double *pr, const int box[6], const double *rop, double *rop_out, double *drodm,
+                          const double *coe, const double *ti, const double *tj, const double *tk, int nrelax_forced)
 {
     if (box[1] < box[0]) return;
     luctx c;
@@ -231,6 +312,7 @@ void fo_invlu(const int *pi, const double *pr, const int box[6], const double *r
     c.gam1 = pr[FO_GAMMA]; c.gamm1 = c.gam1 - 1.; c.cp = pr[FO_GAMMA] * pr[FO_CVINF]; c.gam2 = c.gamm1 - 1.;
     c.tc0[0] = ti[0]; c.tc0[1] = tj[0]; c.tc0[2] = tk[0];
     const int nd = c.nd, neq = c.neq, overlap = pi[FO_LU_MATCH] == 1;
+    if (pi[FO_NB_RELAX] >= 2 || nrelax_forced > 0) { fo_invlussor(pi, pr, box, &c, rop_out, drodm, nrelax_forced > 0 ? nrelax_forced : pi[FO_NB_RELAX]); return; }
     /* SA + lu_match (invlu.for:32-49): invlu_overlap_{l,u}_SA.for are the 6-equation copies of the overlap variants
        (same includes with the _SA bodies).  extrap_coe.for:24-25,39,52,66 only acts on a face where the sweep box reaches
        the second ghost row (ind_loop = 1 - nfic), which for a whole-zone box needs a BC of type 18 / 30 (BCzone.cpp:117-127);
@@ -307,4 +389,36 @@ void fo_transfers(fo_zone *zones, int nz, const int *ji, const double *prtc, int
         for (int n = 0; n < s[3]; n++)
             for (int e = 0; e < neq; e++) dst[idx[s[5] + n] + e * ndr] = src[idx[s[4] + n] + e * ndd];
     }
+}
+
+/* test hook: max-norm of rhs - (D + L + U) dW over the box, with the operators of the sweeps above (tests/test_oracle_pins.py) */
+double fo_lu_residual(const int *pi, const double *pr, const int box[6], const double *rop, const double *rhs, const double *dw,
+                      const double *coe, const double *ti, const double *tj, const double *tk)
+{
+    luctx c;
+    c.pi = pi; c.rop = rop; c.coe = coe; c.t[0] = ti; c.t[1] = tj; c.t[2] = tk;
+    c.inc[0] = 1; c.inc[1] = pi[FO_NIJK]; c.inc[2] = pi[FO_NIJK] * pi[FO_NIJK + 1];
+    c.incm[0] = pi[FO_NIJK_MTR]; c.incm[1] = pi[FO_NIJK_MTR + 1]; c.incm[2] = pi[FO_NIJK_MTR + 2];
+    c.nd = pi[FO_NDIMDX]; c.nm = pi[FO_NDIMDX_MTR]; c.typ = pi[FO_ITYPZONE]; c.neq = pi[FO_NEQ];
+    c.gam1 = pr[FO_GAMMA]; c.gamm1 = c.gam1 - 1.; c.cp = pr[FO_GAMMA] * pr[FO_CVINF]; c.gam2 = c.gamm1 - 1.;
+    c.tc0[0] = ti[0]; c.tc0[1] = tj[0]; c.tc0[2] = tk[0];
+    const int nd = c.nd, neq = c.neq;
+    double worst = 0., b[6];
+    for (int k = box[4]; k <= box[5]; k++) for (int j = box[2]; j <= box[3]; j++) for (int i = box[0]; i <= box[1]; i++) {
+        const int l = fo_inddm(pi, i, j, k), lt = c.typ == 2 ? 0 : fo_indmtr(pi, i, j, k);
+        const int lo[3] = {i > box[0], j > box[2], k > box[4]}, hi[3] = {i < box[1], j < box[3], k < box[5]};
+        double acc[6];
+        for (int e = 0; e < neq; e++) acc[e] = rhs[l + e * nd];
+        for (int d = 0; d < 3; d++) {
+            if (lo[d]) { lu_term(&c, d, l - c.inc[d], lt - c.incm[d], lt, 0.5, dw, b); for (int e = 0; e < neq; e++) acc[e] += b[e] * coe[l] * 0.5; }
+            if (hi[d]) { lu_term(&c, d, l + c.inc[d], lt + c.incm[d], c.typ == 1 && d == 2 ? lt : lt + 2 * c.incm[d], -0.5, dw, b);
+                         for (int e = 0; e < neq; e++) acc[e] += b[e] * coe[l] * -0.5; }
+        }
+        for (int e = 0; e < neq; e++) {
+            const double r = fabs(acc[e] - dw[l + e * nd] * coe[l + (e < 5 ? 4 : 5) * nd]);
+            if (r > worst) worst = r;
+        }
+    }
+    (void)pr;
+    return worst;
 }

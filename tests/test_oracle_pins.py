@@ -115,6 +115,62 @@ def test_lu_sgs_reduces_to_diagonal():
     assert numpy.abs(interior(pi, out)[0] - (interior(pi, z.lev[0])[0] + a[0])).max() < 1e-14
 
 
+@pytest.mark.parametrize('case', ['lamin_full', 'sa_homo'])
+def test_lussor_relaxations(case):
+    """nb_relax >= 2 (LU/invlussor*.for) as symmetric Gauss-Seidel on (D + L + U) dW = rhs, pinned three ways: the first
+    relaxation IS LU-SGS (invlu.for nb_relax = 1 path, to round-off); every further relaxation lowers the linear residual
+    max |rhs - (D + L + U) dW| (operators of the sweeps, fo_lu_residual); and many relaxations reach the exact solve."""
+    if case == 'lamin_full': t = synth.case_euler_box(n=8, scheme='roe', model='NSLaminar', ReInf=1000., temporal='implicit', deform_amp=0.02)
+    else: t, _ = synth.case_flatplate(n=(12, 10, 6))
+    o = oracle_from_tree(t); z = o.zones[0]; L = o.L
+    nss = int(z.pi[V.NSSITER])
+    o.compute(1, 1, 1, 1)                      # one sub-iteration: coe, rhs and metrics of a real Newton step are in place
+    L.fo_lu_residual.restype = ctypes.c_double
+    nd = int(z.pi[V.NDIMDX]); neq = z.neq
+    box = (ctypes.c_int * 6)(1, int(z.pi[V.IJKV]), 1, int(z.pi[V.IJKV + 1]), 1, int(z.pi[V.IJKV + 2]))
+    rng = numpy.random.default_rng(3)
+    rhs = 1e-3 * rng.standard_normal(neq * nd)
+    state = z.lev[0].copy()
+
+    def solve(nrelax):
+        pi = z.pi.copy(); pi[V.NB_RELAX] = nrelax
+        dw = rhs.copy(); out = state.copy()
+        L.fo_invlu(pi.ctypes.data_as(_ip), z.pr.ctypes.data_as(_dp), box, state.ctypes.data_as(_dp), out.ctypes.data_as(_dp),
+                   dw.ctypes.data_as(_dp), z.coe.ctypes.data_as(_dp), z.ti.ctypes.data_as(_dp), z.tj.ctypes.data_as(_dp), z.tk.ctypes.data_as(_dp))
+        res = L.fo_lu_residual(pi.ctypes.data_as(_ip), z.pr.ctypes.data_as(_dp), box, state.ctypes.data_as(_dp), rhs.ctypes.data_as(_dp),
+                               dw.ctypes.data_as(_dp), z.coe.ctypes.data_as(_dp), z.ti.ctypes.data_as(_dp), z.tj.ctypes.data_as(_dp), z.tk.ctypes.data_as(_dp))
+        return dw, out, res
+    dw1, out1, r1 = solve(1)
+    dw2, out2, r2 = solve(2); dw4, out4, r4 = solve(4); dw30, out30, r30 = solve(30)
+    scale = numpy.abs(rhs).max()
+    assert r2 < r1 and r4 < r2 and r30 < 1e-9 * scale, (r1, r2, r4, r30)
+    assert numpy.isfinite(out4).all()
+    # Newton update of the last relaxation: rho_new = rho + dW1 on the interior
+    a = interior(z.pi, out4)[0]; b = interior(z.pi, state)[0] + interior(z.pi, dw4)[0]
+    assert numpy.abs(a - b).max() < 1e-14
+
+
+def test_lussor_first_relaxation_is_lu_sgs():
+    """One relaxation of the nb_relax >= 2 sweeps ((D+U) dW = rhs + L-sum) reproduces invlu_l / invlu_u ((D+U) dW = D dW*),
+    Newton update included, on an interior box and with the state aliased to the output (plane-by-plane update)."""
+    t = synth.case_euler_box(n=8, scheme='roe', model='NSLaminar', ReInf=1000., temporal='implicit', deform_amp=0.02)
+    o = oracle_from_tree(t); z = o.zones[0]; L = o.L
+    o.compute(1, 1, 1, 1)
+    nd = int(z.pi[V.NDIMDX]); neq = z.neq
+    box = (ctypes.c_int * 6)(1, int(z.pi[V.IJKV]), 1, int(z.pi[V.IJKV + 1]), 1, int(z.pi[V.IJKV + 2]))
+    rhs = 1e-3 * numpy.random.default_rng(4).standard_normal(neq * nd)
+    for alias in (False, True):
+        outs = []
+        for relax in (0, 1):
+            dw = rhs.copy(); st = z.lev[0].copy(); out = st if alias else st.copy()
+            args = [z.pi.ctypes.data_as(_ip), z.pr.ctypes.data_as(_dp), box, st.ctypes.data_as(_dp), out.ctypes.data_as(_dp), dw.ctypes.data_as(_dp),
+                    z.coe.ctypes.data_as(_dp), z.ti.ctypes.data_as(_dp), z.tj.ctypes.data_as(_dp), z.tk.ctypes.data_as(_dp)]
+            if relax: L.fo_invlu_relax(*args, ctypes.c_int(1))
+            else: L.fo_invlu(*args)
+            outs.append((interior(z.pi, dw).copy(), interior(z.pi, out).copy()))
+        assert relerr(outs[1][0], outs[0][0]) < 1e-12 and relerr(outs[1][1], outs[0][1]) < 1e-13
+
+
 def test_newton_converges_and_bdf_first_iteration():
     """Implicit dual time stepping: the Newton residual drops monotonically over the sub-iterations."""
     t = synth.case_euler_box(n=10, scheme='roe', temporal='implicit')
