@@ -159,8 +159,7 @@ def _buildOwnData(t, Padding=None):
             cb = [_get(dz, 'cache_blocking_I', 2048), _get(dz, 'cache_blocking_J', 2), _get(dz, 'cache_blocking_K', 7)]
             shiftvar = _get(dz, 'shiftvar', 0); io_th = _get(dz, 'io_thread', 0)
             extract_res = _get(dz, 'extract_res', 0)
-            if int(nbr_relax) != 1:
-                raise ValueError("fast_b200: nb_relax>=2 (LU-SSOR relaxations) is a 'next' row (SURVEY 8f-3), not built")
+            if int(nbr_relax) < 1: raise ValueError("fast_b200: nb_relax must be >= 1")
             iflow = {'Euler': 1, 'euler': 1, 'NSLaminar': 2, 'nslaminar': 2, 'NSTurbulent': 3, 'nsspalart': 3}.get(model)
             if iflow is None: raise ValueError("fast_b200: model %s is out of scope" % model)
             itypcp = 2 if temporal_scheme == "explicit" else 1

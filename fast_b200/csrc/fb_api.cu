@@ -254,8 +254,8 @@ int fb_zone_set_params(fb_solver *s, int nd, const int *pi, int n_int, const dou
     if (d.iflow < 1 || d.iflow > 3) return fail(FB_EINVAL, "IFLOW outside 1..3");
     if (!(d.kflu == 1 || d.kflu == 2 || d.kflu == 5)) return fail(FB_EINVAL, "scheme (KFLUDOM) outside ausmpred/senseur/roe");
     if (d.slope < 1 || d.slope > 3) return fail(FB_EINVAL, "slope outside o1/o3/minmod");
-    if (pi[PI_LALE] != 0 || pi[PI_EXPLOC] != 0 || pi[PI_ILES] != 0 || pi[PI_IMPLICITSOLVER] != 0 || pi[PI_NB_RELAX] != 1)
-        return fail(FB_EINVAL, "ALE / local explicit / LES / GMRES / nb_relax>1 are outside the hot-path scope");
+    if (pi[PI_LALE] != 0 || pi[PI_EXPLOC] != 0 || pi[PI_ILES] != 0 || pi[PI_IMPLICITSOLVER] != 0 || pi[PI_NB_RELAX] < 1)
+        return fail(FB_EINVAL, "ALE / local explicit / LES / GMRES are outside the hot-path scope");
     if (d.nf != 2) return fail(FB_EINVAL, "only 2 ghost layers are supported");
     // lu_match with SA (invlu_overlap_{l,u}_SA.for): same sweeps with six equations; extrap_coe.for only acts where the sweep
     // box reaches the second ghost row, which needs a BC of type 18 / 30 -- rejected above -- so it is a no-op here
@@ -298,6 +298,7 @@ int fb_zone_set_params(fb_solver *s, int nd, const int *pi, int n_int, const dou
     cudaFree(z.wins); cudaFree(z.wins_rhs); z.wins = z.wins_rhs = nullptr;
     int rc = build_bc_tables(z); if (rc) return rc;
     lu_batch_free(s->lub); s->lub = nullptr; s->lub_tried = false;
+    z.lu.nrelax = pi[PI_NB_RELAX];     // >= 2: LU-SSOR relaxations (invlussor*.for)
     if (d.itypcp <= 1) { rc = lu_plan_build(z.lu, d, z.lu_box); if (rc) return fail(FB_ECUDA, "lu_plan_build failed"); }
     z.has_params = true; s->metric_done = false;
     return FB_OK;

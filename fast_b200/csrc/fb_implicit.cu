@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include "fb_implicit.cuh"
+#include "fb_lu_prod.cuh"
 #include "fb_source.cuh"
 
 static inline dim3 grid3i(int ni, int nj, int nk, dim3 b) { return dim3((ni + b.x - 1) / b.x, (nj + b.y - 1) / b.y, nk); }
@@ -170,46 +171,6 @@ struct LuArgs {
     int order;              // 0: k,j,i (invlu_l/u)  1: i,j,k (overlap variants, lu_match)  2: 3dcart lower j,k,i
 };
 
-// B_d(l1) * dW(l1) with the cell-centred mean normal of the neighbour cell l1 (lu_{i,j,k}_*.for)
-template <int MESH, int NEQ>
-__device__ __forceinline__ void lu_term(const ZoneDev &z, const double *__restrict__ rop, int d, int l1, int lta, int ltb,
-                                        double signe, bool updated, double *b)
-{
-    const int nd = z.nd, nm = z.nm;
-    double tcx = 0., tcy = 0., tcz = 0.;
-    const double *T = d == 0 ? z.ti : (d == 1 ? z.tj : z.tk);
-    if (MESH == 0) { tcx = 0.5 * (T[ltb] + T[lta]); tcy = 0.5 * (T[ltb + nm] + T[lta + nm]); tcz = 0.5 * (T[ltb + 2 * nm] + T[lta + 2 * nm]); }
-    else if (MESH == 1) { if (d < 2) { tcx = 0.5 * (T[ltb] + T[lta]); tcy = 0.5 * (T[ltb + nm] + T[lta + nm]); } else tcz = T[ltb]; }
-    else { if (d == 0) tcx = z.tc0[0]; else if (d == 1) tcy = z.tc0[1]; else tcz = z.tc0[2]; }
-    const double *dw = z.drodm;
-    const double d1 = dw[l1], d2 = dw[l1 + nd], d3 = dw[l1 + 2 * nd], d4 = dw[l1 + 3 * nd], d5 = dw[l1 + 4 * nd];
-    double u = rop[l1 + nd], v = rop[l1 + 2 * nd], w = rop[l1 + 3 * nd], t = rop[l1 + 4 * nd];
-    if (updated) {   // mjr_newton.for applied on the fly to the k+1 neighbour
-        const double ro_old = rop[l1];
-        const double cvinv = 1. / z.cv, cvinv2 = 0.5 * cvinv;
-        const double r_1 = 1. / (ro_old + d1);
-        const double un = (ro_old * u + d2) * r_1, vn = (ro_old * v + d3) * r_1, wn = (ro_old * w + d4) * r_1;
-        const double roe_old = ro_old * (z.cv * t + 0.5 * (u * u + v * v + w * w));
-        t = (roe_old + d5) * r_1 * cvinv - cvinv2 * (un * un + vn * vn + wn * wn);
-        u = un; v = vn; w = wn;
-    }
-    const double gam1 = z.gam, gamm1 = gam1 - 1., gam2 = gamm1 - 1., cp = z.gam * z.cv;
-    const double q2 = .5 * (u * u + v * v + w * w), h = cp * t + q2, ph2 = gamm1 * q2;
-    const double qn = tcx * u + tcy * v + tcz * w;
-    const double cd = z.coe[l1 + (d + 1) * nd] * signe;
-    const double b11 = cd, b12 = tcx, b13 = tcy, b14 = tcz;
-    const double b21 = (tcx * ph2 - u * qn), b22 = (qn - tcx * gam2 * u) + cd, b23 = (tcy * u - tcx * gamm1 * v), b24 = (tcz * u - tcx * gamm1 * w), b25 = tcx * gamm1;
-    const double b31 = (tcy * ph2 - v * qn), b32 = (tcx * v - tcy * gamm1 * u), b33 = (qn - tcy * gam2 * v) + cd, b34 = (tcz * v - tcy * gamm1 * w), b35 = tcy * gamm1;
-    const double b41 = (tcz * ph2 - w * qn), b42 = (tcx * w - tcz * gamm1 * u), b43 = (tcy * w - tcz * gamm1 * v), b44 = (qn - tcz * gam2 * w) + cd, b45 = tcz * gamm1;
-    const double b51 = qn * (ph2 - h), b52 = (tcx * h - gamm1 * u * qn), b53 = (tcy * h - gamm1 * v * qn), b54 = (tcz * h - gamm1 * w * qn), b55 = (gam1 * qn) + cd;
-    b[0] = b11 * d1 + b12 * d2 + b13 * d3 + b14 * d4;
-    b[1] = b21 * d1 + b22 * d2 + b23 * d3 + b24 * d4 + b25 * d5;
-    b[2] = b31 * d1 + b32 * d2 + b33 * d3 + b34 * d4 + b35 * d5;
-    b[3] = b41 * d1 + b42 * d2 + b43 * d3 + b44 * d4 + b45 * d5;
-    b[4] = b51 * d1 + b52 * d2 + b53 * d3 + b54 * d4 + b55 * d5;
-    if (NEQ == 6) b[NEQ - 1] = (qn + cd) * dw[l1 + 5 * nd];
-}
-
 template <int MESH, int NEQ, bool UPPER>
 __global__ void k_lu(ZoneDev z, LuArgs a)
 {
@@ -316,7 +277,7 @@ int launch_lu(const ZoneDev &z, const LuPlan &p, const double *rop, double *rop_
 {
     // default: tile-pipelined wavefront (fb_lu.cu); FAST_B200_LU=plane keeps the one-launch-per-hyperplane kernels for A/B checks
     static const int use_plane = [] { const char *e = getenv("FAST_B200_LU"); return e && e[0] == 'p'; }();
-    if (!use_plane) return launch_lu_tiles(z, p, rop, rop_out, lu_match, st);
+    if (!use_plane || p.nrelax >= 2) return launch_lu_tiles(z, p, rop, rop_out, lu_match, st);   // relaxations: tile kernel only
     if (z.neq == 6) {
         if (z.typ == 0) return run_lu<0, 6>(z, p, rop, rop_out, lu_match, st);
         if (z.typ == 1) return run_lu<1, 6>(z, p, rop, rop_out, lu_match, st);

@@ -17,6 +17,8 @@ struct LuPlan {
     double *d_mb = nullptr;           // inter-tile mailboxes: j interfaces then k interfaces
     size_t n_ifj = 0, n_ifk = 0;
     double *d_tcm = nullptr;          // cell-centred mean normals (3dfull: 9 x NDIMDX, 3dhomo: 5 x ni*nj)
+    int nrelax = 1;                   // nb_relax (set before lu_plan_build); >= 2: LU-SSOR relaxations (fb_lu.cu: run_lu_ssor)
+    double *d_rhs = nullptr, *d_us = nullptr;   // nb_relax >= 2: rhs of the Newton step, U-sum of the previous relaxation
     long long tstride = 0;
 };
 int  lu_plan_build(LuPlan &p, const ZoneDev &z, const int box[6]);

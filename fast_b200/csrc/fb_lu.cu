@@ -77,6 +77,7 @@ struct LuTileArgs {
     int box[6], nbx[6];
     int bi, bj, bk, NJ, NK;
     int alias, order_mode;
+    int newton;             // upper sweep: 1 = Newton update written to rop_out (mjr_newton fused), 0 = dW stored back (nb_relax >= 2)
     int plane;              // ni*nj (3dhomo: tcm is a plane array)
     unsigned long long *dbg;   // FAST_B200_LU_DEBUG: per tile {start, first step, end, smid} (globaltimer ns)
 };
@@ -189,7 +190,7 @@ __device__ __forceinline__ void lu_tile_body(const ZoneDev &z, const LuTileArgs 
             const int l = o.lrow + sg * ii;
             const double *src = ring + ((size_t)((c & 1) * A) * L + o.lam) * CI + cell;
 #define SRC(arr) src[(size_t)(arr) * L * CI]
-            if (!UPPER) {
+            if (!UPPER || !a.newton) {
 #pragma unroll
                 for (int e = 0; e < NEQ; e++) a.dw[l + e * nd] = SRC(C::A_DW + e);
             } else {
@@ -487,6 +488,11 @@ int lu_plan_build(LuPlan &p, const ZoneDev &z, const int box[6])
         if (cudaMalloc(&p.d_mb, nmb * sizeof(double)) != cudaSuccess) return 1;
         k_fill_u64<<<592, 256>>>((unsigned long long *)p.d_mb, nmb, LU_EMPTY);
     }
+    if (p.nrelax >= 2) {      // rhs of the Newton step and U-sum of the previous relaxation (the reference's ssor arrays)
+        const size_t n = (size_t)z.nd * z.neq * sizeof(double);
+        if (cudaMalloc(&p.d_rhs, n) != cudaSuccess || cudaMalloc(&p.d_us, n) != cudaSuccess) return 1;
+        cudaMemset(p.d_us, 0, n);
+    }
     if (z.typ != 2) {
         p.tstride = z.typ == 0 ? (long long)z.nd : (long long)z.ni * z.nj;
         const int nt = z.typ == 0 ? 9 : 5;
@@ -498,8 +504,8 @@ int lu_plan_build(LuPlan &p, const ZoneDev &z, const int box[6])
 
 void lu_plan_free(LuPlan &p)
 {
-    cudaFree(p.d_order); cudaFree(p.d_ctl); cudaFree(p.d_mb); cudaFree(p.d_tcm);
-    p.d_order = nullptr; p.d_ctl = nullptr; p.d_mb = nullptr; p.d_tcm = nullptr;
+    cudaFree(p.d_order); cudaFree(p.d_ctl); cudaFree(p.d_mb); cudaFree(p.d_tcm); cudaFree(p.d_rhs); cudaFree(p.d_us);
+    p.d_order = nullptr; p.d_ctl = nullptr; p.d_mb = nullptr; p.d_tcm = nullptr; p.d_rhs = nullptr; p.d_us = nullptr;
 }
 
 void lu_plan_metrics(LuPlan &p, const ZoneDev &z, cudaStream_t st)
@@ -519,7 +525,7 @@ static void lu_fill_args(LuTileArgs &a, const ZoneDev &z, const LuPlan &p, const
     for (int i = 0; i < 6; i++) { a.box[i] = p.box[i]; a.nbx[i] = p.box[i]; }
     if (lu_match) { a.nbx[0] = 1; a.nbx[1] = z.iv; a.nbx[2] = 1; a.nbx[3] = z.jv; a.nbx[4] = 1; a.nbx[5] = z.kv; }
     a.bi = p.box[1] - p.box[0] + 1; a.bj = p.box[3] - p.box[2] + 1; a.bk = p.box[5] - p.box[4] + 1;
-    a.NJ = p.NJ; a.NK = p.NK; a.alias = (rop == rop_out) ? 1 : 0; a.plane = z.ni * z.nj;
+    a.NJ = p.NJ; a.NK = p.NK; a.alias = (rop == rop_out) ? 1 : 0; a.plane = z.ni * z.nj; a.newton = 1;
 }
 
 // ------------------------------------------------------------------------------------------------ multi-zone launch
@@ -536,7 +542,7 @@ LuBatch *lu_batch_create(int nz, const ZoneDev *const *zs, const LuPlan *const *
 {
     if (nz < 2 || getenv("FAST_B200_LU")) return nullptr;        // the A/B kernels (plane, line) keep one launch per zone
     for (int n = 0; n < nz; n++)
-        if (zs[n]->typ != zs[0]->typ || zs[n]->neq != zs[0]->neq || zs[n]->itypcp > 1 || !plans[n]->d_order) return nullptr;
+        if (zs[n]->typ != zs[0]->typ || zs[n]->neq != zs[0]->neq || zs[n]->itypcp > 1 || !plans[n]->d_order || plans[n]->nrelax >= 2) return nullptr;
     LuBatch *b = new LuBatch();
     b->nz = nz; b->typ = zs[0]->typ; b->neq = zs[0]->neq;
     std::vector<std::pair<int, int2>> ord;     // (J + K, (zone, tile))
@@ -646,6 +652,87 @@ static int run_lu_tiles(const ZoneDev &z, const LuPlan &p, const double *rop, do
     return 3;
 }
 
+// ------------------------------------------------------------------------------------------------ nb_relax >= 2
+// LU/invlu.for:163-240 -> invlussor1_l / invlussor_l / invlussor_u[_SA].for: symmetric Gauss-Seidel relaxations of
+// (D + L + U) dW = rhs.  Relaxation m >= 2 is run with the SAME sweep kernels by moving the coupling to the previous
+// relaxation into their inputs:
+//   lower:  (D + L) dW* = rhs + Usum(dW_prev)               -> input  rhs' = rhs + Usum                     (k_ssor_lower_in)
+//   upper:  (D + U) dW  = rhs + Lsum(dW*) = D dW* - Usum    -> input  dW*' = dW* - Usum / coe5 (coe6)        (k_ssor_upper_in)
+// with Usum(l) = xal(l) * sum_d B_d(l+d) dW_prev(l+d) over the upper neighbours inside the box (k_ssor_usum; the reference
+// accumulates the same sum in its ssor array while it sweeps, mjr_drodm_ssor.for).  Only the last upper sweep applies the
+// Newton update (lussor_end, invlussor_u.for:155-170), over the interior ind_loop_sdm; the others store dW.
+template <int MESH, int NEQ>
+__global__ void k_ssor_usum(ZoneDev z, const double *__restrict__ rop, int i0, int i1, int j0, int j1, int k0, int k1, double *__restrict__ us)
+{
+    const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x, j = j0 + blockIdx.y * blockDim.y + threadIdx.y, k = k0 + blockIdx.z;
+    if (i > i1 || j > j1) return;
+    const int nd = z.nd, l = inddm(z, i, j, k), lt = MESH == 2 ? 0 : indmtr(z, i, j, k);
+    const double xal = z.coe[l] * -0.5;
+    const int inc[3] = {1, z.incj, z.inck}, incm[3] = {z.mi, z.mj, z.mk};
+    const bool has[3] = {i < i1, j < j1, k < k1};
+    double s[NEQ], b[NEQ];
+#pragma unroll
+    for (int e = 0; e < NEQ; e++) s[e] = 0.;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        if (!has[d]) continue;
+        lu_term<MESH, NEQ>(z, rop, d, l + inc[d], lt + incm[d], (MESH == 1 && d == 2) ? lt : lt + 2 * incm[d], -0.5, false, b);
+#pragma unroll
+        for (int e = 0; e < NEQ; e++) s[e] = s[e] + b[e] * xal;
+    }
+#pragma unroll
+    for (int e = 0; e < NEQ; e++) us[l + e * nd] = s[e];
+}
+template <int NEQ, bool UPPER>
+__global__ void k_ssor_in(ZoneDev z, int i0, int i1, int j0, int j1, int k0, const double *__restrict__ rhs, const double *__restrict__ us)
+{
+    const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x, j = j0 + blockIdx.y * blockDim.y + threadIdx.y, k = k0 + blockIdx.z;
+    if (i > i1 || j > j1) return;
+    const int nd = z.nd, l = inddm(z, i, j, k);
+    if (!UPPER) {
+#pragma unroll
+        for (int e = 0; e < NEQ; e++) z.drodm[l + e * nd] = rhs[l + e * nd] + us[l + e * nd];
+    } else {
+        const double d5 = 1. / z.coe[l + 4 * nd];
+#pragma unroll
+        for (int e = 0; e < 5; e++) z.drodm[l + e * nd] = z.drodm[l + e * nd] - us[l + e * nd] * d5;
+        if (NEQ == 6) z.drodm[l + 5 * nd] = z.drodm[l + 5 * nd] - us[l + 5 * nd] / z.coe[l + 5 * nd];
+    }
+}
+
+template <int MESH, int NEQ>
+static int run_lu_ssor(const ZoneDev &z, const LuPlan &p, const double *rop, double *rop_out, cudaStream_t st)
+{
+    LuTileArgs a;
+    lu_fill_args(a, z, p, rop, rop_out, 1);       // Newton box = interior (ind_loop_sdm)
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_lu_tile<MESH, NEQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LuCfg<MESH, NEQ, false>::SMEM);
+        cudaFuncSetAttribute(k_lu_tile<MESH, NEQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LuCfg<MESH, NEQ, true>::SMEM);
+        attr_done = true;
+    }
+    const int ntiles = p.NJ * p.NK, alias = a.alias;
+    const int *bx = p.box;
+    dim3 b(64, 4, 1), g((bx[1] - bx[0] + 64) / 64, (bx[3] - bx[2] + 4) / 4, bx[5] - bx[4] + 1);
+    cudaMemcpyAsync(p.d_rhs, z.drodm, (size_t)z.nd * NEQ * sizeof(double), cudaMemcpyDeviceToDevice, st);
+    int launches = 1;
+    for (int m = 1; m <= p.nrelax; m++) {
+        if (m > 1) {
+            k_ssor_usum<MESH, NEQ><<<g, b, 0, st>>>(z, rop, bx[0], bx[1], bx[2], bx[3], bx[4], bx[5], p.d_us);
+            k_ssor_in<NEQ, false><<<g, b, 0, st>>>(z, bx[0], bx[1], bx[2], bx[3], bx[4], p.d_rhs, p.d_us);
+            launches += 2;
+        }
+        cudaMemsetAsync(p.d_ctl, 0, 2 * sizeof(int), st);
+        a.ticket = p.d_ctl; a.newton = 0; a.alias = 0;
+        k_lu_tile<MESH, NEQ, false><<<ntiles, LU_NT, LuCfg<MESH, NEQ, false>::SMEM, st>>>(z, a);
+        if (m > 1) { k_ssor_in<NEQ, true><<<g, b, 0, st>>>(z, bx[0], bx[1], bx[2], bx[3], bx[4], p.d_rhs, p.d_us); launches++; }
+        a.ticket = p.d_ctl + 1; a.newton = m == p.nrelax ? 1 : 0; a.alias = a.newton ? alias : 0;
+        k_lu_tile<MESH, NEQ, true><<<ntiles, LU_NT, LuCfg<MESH, NEQ, true>::SMEM, st>>>(z, a);
+        launches += 3;
+    }
+    return launches;
+}
+
 bool lu_use_lines()
 {   // default: the 4-lanes-per-line tile kernel of this file; FAST_B200_LU=line selects the one-thread-per-line kernel
     // (fb_lu2.cu: 5x fewer instructions per cell, two tiles per SM, parity-green, but a single warp evaluating the three
@@ -657,6 +744,10 @@ bool lu_use_lines()
 
 int launch_lu_tiles(const ZoneDev &z, const LuPlan &p, const double *rop, double *rop_out, int lu_match, cudaStream_t st)
 {
+    if (p.nrelax >= 2) {      // LU-SSOR relaxations: always the tile kernel
+        if (z.neq == 6) return z.typ == 0 ? run_lu_ssor<0, 6>(z, p, rop, rop_out, st) : (z.typ == 1 ? run_lu_ssor<1, 6>(z, p, rop, rop_out, st) : run_lu_ssor<2, 6>(z, p, rop, rop_out, st));
+        return z.typ == 0 ? run_lu_ssor<0, 5>(z, p, rop, rop_out, st) : (z.typ == 1 ? run_lu_ssor<1, 5>(z, p, rop, rop_out, st) : run_lu_ssor<2, 5>(z, p, rop, rop_out, st));
+    }
     if (lu_use_lines()) return launch_lu_lines(z, p, rop, rop_out, lu_match, st);
     if (z.neq == 6) {
         if (z.typ == 0) return run_lu_tiles<0, 6>(z, p, rop, rop_out, lu_match, st);

@@ -101,7 +101,8 @@ def _computePT_mut(zones, metrics, hook):
 
 
 def allocate_ssor(zones, metrics, hook):
-    """fasts.allocate_ssor (S/Compute/LU/allocate_ssor.cpp): only needed for nb_relax>1 (not built)."""
+    """fasts.allocate_ssor (S/Compute/LU/allocate_ssor.cpp): the reference's host-side ssor work arrays of nb_relax > 1; here the
+    two per-zone device arrays of the relaxations (rhs copy, U-sum) belong to the library's LU plan (csrc/fb_lu.cu: run_lu_ssor)."""
     return None
 
 

@@ -36,6 +36,12 @@ CASES = {
     'sa_plate_blocks_tiles': lambda: synth.case_flatplate(n=(24, 40, 40), nblocks=(1, 2, 2)),
     'multiblock_roe_lumatch_tiles': lambda: synth.case_multiblock(nblk=(2, 1, 2), n=18),
     'sa_plate_blocks_lumatch': lambda: synth.case_flatplate(n=(24, 16, 8), nblocks=(2, 2, 2), lu_match=1),   # invlu_overlap_*_SA
+    # nb_relax >= 2: LU-SSOR relaxations (invlussor*.for) around the same sweep kernels
+    'sa_plate_ssor2': lambda: synth.case_flatplate(n=(24, 16, 6), nb_relax=2),
+    'sa_plate_ssor2_tiles': lambda: synth.case_flatplate(n=(20, 20, 20), nb_relax=2),
+    'lamin_full_roe_ssor3': _box(n=12, scheme='roe', model='NSLaminar', ReInf=1000., deform_amp=0.02, temporal='implicit',
+                                 extra_numz={'nb_relax': 3}),
+    'multiblock_roe_lumatch_ssor2': lambda: synth.case_multiblock(nblk=(2, 1, 1), n=10, extra_numz={'nb_relax': 2}),
     'multiblock_explicit': lambda: synth.case_multiblock(nblk=(2, 1, 2), n=8, temporal='explicit', scheme='senseur'),
 }
 

@@ -84,7 +84,7 @@ def test_out_of_scope_options_fail_loudly():
     t = synth.case_euler_box(n=6)
     FastC._setNum2Zones(t, {'scheme': 'ausmpred', 'slope': 'o5'})
     with pytest.raises(ValueError): FastS._warmup_host(t)
-    t = synth.case_euler_box(n=6); FastC._setNum2Zones(t, {'scheme': 'ausmpred', 'nb_relax': 2, 'time_step': 1e-3})
+    t = synth.case_euler_box(n=6); FastC._setNum2Zones(t, {'scheme': 'ausmpred', 'nb_relax': 0, 'time_step': 1e-3})
     with pytest.raises(ValueError): FastS._warmup_host(t)
     t = synth.case_euler_box(n=6); FastC._setNum2Base(t, {'temporal_scheme': 'explicit_local'})
     with pytest.raises(ValueError): FastS._warmup_host(t)
