@@ -18,6 +18,9 @@ CASES = {
     'c5_lamin_roe_wall_flux': lambda: (synth.case_euler_box(n=10, scheme='roe', model='NSLaminar', ReInf=2000., deform_amp=0.02,
                                                             bcs={'imin': 'BCWallInviscid', 'imax': 'BCFarfield', 'jmin': 'BCWallViscous',
                                                                  'jmax': 'BCFarfield', 'kmin': 'BCFarfield', 'kmax': 'BCWall'}), None),
+    'c6_sa_plate_ssor2': lambda: synth.case_flatplate(n=(16, 12, 4), nb_relax=2),
+    'c7_lamin_full_roe_ssor3': lambda: (synth.case_euler_box(n=10, scheme='roe', model='NSLaminar', ReInf=1000., deform_amp=0.02,
+                                                              temporal='implicit', extra_numz={'nb_relax': 3}), None),
 }
 
 
