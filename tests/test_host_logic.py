@@ -46,6 +46,12 @@ def test_param_tables_implicit_sa_and_bcs():
     assert recs[3] == (6, [1, 12, 1, 1, 1, 4])        # jmin viscous wall, window in interior cell numbering
     assert recs[1] == (1, [1, 1, 1, 8, 1, 4]) and recs[2] == (1, [12, 12, 1, 8, 1, 4]) and recs[4][0] == 1
     assert recs[5][0] == 11 and recs[6] == (11, [1, 12, 1, 8, 4, 4])
+    assert pi[V.NB_RELAX] == 1 and pi[V.LU_MATCH] == 0
+    # nb_relax / lu_match travel in the reference's slots (S/param_solver.h: NB_RELAX 71, LU_MATCH 75)
+    t, j = synth.case_flatplate(n=(12, 8, 4), nb_relax=3, lu_match=1)
+    FastS._warmup_host(t)
+    pi, pr = _pi_pr(t)
+    assert pi[V.NB_RELAX] == 3 and pi[V.LU_MATCH] == 1 and V.NB_RELAX == 71 and V.LU_MATCH == 75
 
 
 def test_mesh_family_detection():
