@@ -106,7 +106,9 @@ def cpu_oracle_rate(workload, seconds=15., threads=None):
     sample_n = {'tgv256': 96, 'plate': (128, 64, 16), 'multiblock': 32, 'c5': (32, 32, 8)}[workload]
     t, j, desc = make_case(workload, n=sample_n)
     o = oracle_from_tree(t, joins=j, fast=True)
-    nthreads = threads or o.L.fo_max_threads()
+    # all host cores this process may use: torchrun exports OMP_NUM_THREADS=1 to its ranks, which would silently turn the
+    # reference arm at N > 1 into a one-thread run (the oracle passes the count in a num_threads clause, so it is honoured)
+    nthreads = threads or max(o.L.fo_max_threads(), len(os.sched_getaffinity(0)))
     nss = int(o.zones[0].pi[V.NSSITER])
     cells = sum(int(z.pi[V.IJKV]) * int(z.pi[V.IJKV + 1]) * int(z.pi[V.IJKV + 2]) for z in o.zones)
     o.compute(1, 1, nss, 1000, nthreads=nthreads)                     # warm-up / first touch
