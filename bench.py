@@ -209,10 +209,10 @@ def run_gpu(args):
     peak, pk = peaks()
     cz = cells / len(zones)
     cnt = {}
-    for name in ('rhs_tma', 'rhs_l1', 'lu_line', 'lu_batch'):
+    for name in ('rhs_tma', 'rhs_l1', 'lu_batch'):
         v = ctypes.c_longlong(0); _lib.check(L.fb_counter(name.encode(), ctypes.byref(v))); cnt[name] = int(v.value)
     if tm['lu'] > tm['rhs']:
-        kern = 'k_lu_line' if cnt['lu_line'] else 'k_lu_tile'
+        kern = 'k_lu_tile'
         nl, bpl = 2 * args.steps * nsub * len(zones), (b_sub - b_rhs) / 2.   # lower + upper launch
         if cnt['lu_batch']:      # one lower + one upper launch sweep ALL zones of the rank (k_lu_tile_b)
             kern, nl, cz = 'k_lu_tile_b', 2 * args.steps * nsub, cells

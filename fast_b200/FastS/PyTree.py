@@ -91,7 +91,11 @@ def _compute(t, metrics, nitrun, tc=None, graph=None, layer="c", NIT=1, ucData=N
     FastC.HOOK['FIRST_IT'] = FastC.FIRST_IT
     fasts._computePT(zones, metrics, nitrun, 1, nitmax, 1, NIT, FastC.HOOK)          # PyTree.py:219
     # time levels rotated on the device; rotate the tree's numpys the same way (PyTree.py:226-231)
-    for _ in range(NIT): FastC.switchPointers__(zones, 1, 3)
+    # -- switchPointers__(zones, case, nitmax%2+2) for explicit schemes: order 2 (RK2, an even number of stages) is a no-op,
+    # the last stage has written Density itself
+    itypcp = int(Internal.getNodeFromName1(Internal.getNodeFromName1(zones[0], '.Solver#ownData'), 'Parameter_int')[1][VSHARE.ITYPCP])
+    order = 3 if itypcp < 2 else nitmax % 2 + 2
+    for _ in range(NIT): FastC.switchPointers__(zones, 1, order)
     FastC.FIRST_IT = 1
     FastC.HOOK['FIRST_IT'] = 1
     return None
@@ -129,6 +133,7 @@ def display_temporal_criteria(t, metrics, nitrun, format=None, gmres=None, verbo
     out = fasts.display_ss_iteration(zones, metrics, nitrun, nssiter, 0, {'firstlast': 0, 'all': 1, 'none': 2}.get(verbose, 0))
     if stopAtNan:
         for zname, d in out.items():
-            if not numpy.all(numpy.isfinite(d['L2'])):
-                raise FloatingPointError("fast_b200: NaN in the Newton residual of zone %s" % zname)
+            if d['nonfinite'] or not numpy.all(numpy.isfinite(d['L2'])):
+                raise FloatingPointError("fast_b200: NaN in the state / Newton residual of zone %s (%d non-finite cells or norms seen "
+                                         "by the device checks)" % (zname, d['nonfinite']))
     return out

@@ -28,7 +28,7 @@ struct Zone {
     double *xyz = nullptr, *mtr = nullptr, *aux = nullptr, *drodm = nullptr, *coe = nullptr;
     unsigned char *wigb = nullptr;
     double *rdm = nullptr;          // device: nssiter*neq*2
-    double *cflv = nullptr;         // device: 3
+    double *cflv = nullptr;         // device: CFL max, min, sum (cpcfl3) + number of non-finite cells / residuals seen by the checks
     BcWin *wins = nullptr, *wins_rhs = nullptr;
     int nwin = 0, nwin_rhs = 0, maxc = 0, maxc_rhs = 0;
     int lu_box[6];                  // ishift_lu (BCzone.cpp:136-143)
@@ -293,7 +293,7 @@ int fb_zone_set_params(fb_solver *s, int nd, const int *pi, int n_int, const dou
     d.x = z.xyz; d.y = z.xyz + d.ndx; d.z = z.xyz + 2 * (size_t)d.ndx;
     const int nss = pi[PI_NSSITER] > 0 ? pi[PI_NSSITER] : 1;
     cudaFree(z.rdm); CK(cudaMalloc(&z.rdm, (size_t)nss * d.neq * 2 * sizeof(double))); CK(cudaMemset(z.rdm, 0, (size_t)nss * d.neq * 2 * sizeof(double)));
-    cudaFree(z.cflv); CK(cudaMalloc(&z.cflv, 3 * sizeof(double))); CK(cudaMemset(z.cflv, 0, 3 * sizeof(double)));
+    cudaFree(z.cflv); CK(cudaMalloc(&z.cflv, 4 * sizeof(double))); CK(cudaMemset(z.cflv, 0, 4 * sizeof(double)));
     d.xmut = z.aux; d.drodm = z.drodm; d.coe = z.coe; d.wigb = z.wigb;
     cudaFree(z.wins); cudaFree(z.wins_rhs); z.wins = z.wins_rhs = nullptr;
     int rc = build_bc_tables(z); if (rc) return rc;
@@ -540,7 +540,8 @@ static int gsdr3(fb_solver *s, int nitcfg, int nssiter, int nitrun, int first_it
             for (int n = 0; n < s->nz; n++) {
                 Zone &z = s->z[n]; double *ssiter = ss[n]; cudaStream_t zst = f.stream(n);
                 if (z.d.iflow >= 2) { launch_invist(z.d, ssiter, implicit || z.d.iflow == 3 ? z.d.nf : 1, zst); s->launches++; }
-                if (implicit) { launch_coe(z.d, ssiter, first_it, lssiter_verif, z.cflv, zst); s->launches++; }
+                if (implicit) { launch_coe(z.d, ssiter, first_it, zst); s->launches++; }
+                if (lssiter_verif) { launch_cfl(z.d, ssiter, z.cflv, zst); s->launches += 2; }   // cptst3.for:113-120 -> cpcfl3
                 // SENSOR switch (wiggle2001.for) at nstep 1 (src_term.for:258-266)
                 if (z.d.kflu == 2 && !fb_sensor_fused()) { launch_sensor(z.d, ssiter, zst); s->launches++; }
             }
@@ -587,7 +588,7 @@ static int gsdr3(fb_solver *s, int nitcfg, int nssiter, int nitrun, int first_it
             for (int n = 0; n < s->nz; n++) {
                 Zone &z = s->z[n];
                 { Scope b(s, 2); apply_bc_zone(s, z, z.drodm, 1); }           // lhs.cpp:57-67
-                if (lssiter_verif == 1) { launch_resid(z.d, z.rdm, nitcfg, z.pi[PI_NSSITER], s->st); s->launches += 2; }   // cprdu3s1
+                if (lssiter_verif == 1) { launch_resid(z.d, z.rdm, z.cflv, nitcfg, z.pi[PI_NSSITER], s->st); s->launches += 2; }   // cprdu3s1
                 if (lexit_lu == 0 && !batch) {
                     Scope l(s, 1);
                     double *ssiter = nitcfg == 1 ? z.rop[0] : z.rop[2];
@@ -635,7 +636,11 @@ int fb_compute(fb_solver *s, int nitrun, int nstep_deb, int nstep_fin, int nit_c
             int rc = gsdr3(s, nstep, nssiter, nitrun_loc, *first_it, verif, lexit); if (rc) return rc;
         }
         *first_it = 1;
-        for (auto &z : s->z) { double *sv = z.rop[1]; z.rop[1] = z.rop[0]; z.rop[0] = z.rop[2]; z.rop[2] = sv; }   // computePT.cpp:675-679
+        // computePT.cpp:675-679 swaps its local pointers; what persists is the rotation FastS._compute applies to the tree
+        // (S/PyTree.py:226-228): switchPointers__(zones, case, nitmax%2+2) is a no-op (order 2, C/PyTree.py:2299) for an explicit
+        // scheme with an even number of stages -- the last stage of RK2 has written `ro` itself (gsdr3.cpp:162-173)
+        if (!(itypcp == 2 && nssiter % 2 == 0))
+            for (auto &z : s->z) { double *sv = z.rop[1]; z.rop[1] = z.rop[0]; z.rop[0] = z.rop[2]; z.rop[2] = sv; }
     }
     return FB_OK;
 }
@@ -688,6 +693,16 @@ int fb_zone_get_cfl(fb_solver *s, int nd, double cfl[3])
     cfl[2] /= cells;   // computePT.cpp:645
     return FB_OK;
 }
+int fb_zone_isfinite(fb_solver *s, int nd, long long *bad)
+{
+    int rc = chk_zone(s, nd, 0); if (rc) return rc;
+    if (!bad) return fail(FB_EINVAL, "fb_zone_isfinite: null output");
+    CK(cudaSetDevice(s->dev)); CK(cudaStreamSynchronize(s->st));
+    double v = 0.;
+    CK(cudaMemcpy(&v, s->z[nd].cflv + 3, sizeof(double), cudaMemcpyDeviceToHost));
+    *bad = (long long)v;
+    return FB_OK;
+}
 
 int fb_compute_host(fb_solver *s, int nitrun, int nit_c, int *first_it, double **ro, double **ro_m1, double **ro_p1)
 {
@@ -704,10 +719,13 @@ int fb_compute_host(fb_solver *s, int nitrun, int nit_c, int *first_it, double *
     int rc = fb_compute(s, nitrun, 1, nssiter, 1, first_it); if (rc) return rc;
     // after the device-side rotation level 0 is the new solution: it lands in the caller's ro_P1 buffer, and the caller
     // rotates its three pointers exactly like FastC.switchPointers__ (ro_M1 <- ro <- ro_P1 <- old ro_M1)
+    // (explicit schemes with an even number of stages, i.e. RK2, do not rotate: the new solution is `ro` itself and goes back
+    // into the caller's ro buffers)
+    const bool norot = !implicit && nssiter % 2 == 0;
     for (int n = 0; n < s->nz; n++)
-        CK(cudaMemcpyAsync(ro_p1[n], s->z[n].rop[0], s->z[n].n_state * sizeof(double), cudaMemcpyDeviceToHost, s->st));
+        CK(cudaMemcpyAsync(norot ? ro[n] : ro_p1[n], s->z[n].rop[0], s->z[n].n_state * sizeof(double), cudaMemcpyDeviceToHost, s->st));
     CK(cudaStreamSynchronize(s->st));
-    return FB_OK;
+    return check_lu(s);
 }
 
 int fb_timing_enable(fb_solver *s, int on) { if (!s) return fail(FB_EINVAL, "null"); s->timing = on != 0; return FB_OK; }
@@ -729,10 +747,10 @@ int fb_timing_get(fb_solver *s, const char *name, double *ms, long long *launche
 extern long long g_fb_rhs_launches[2];
 // test hook (tests/test_host_logic.py): the tile order of the two-part explicit stage on a gx x gy x gz tile grid, computed
 // by the very function the kernels use; out = 3 ints per tile in launch order, *nface = tiles of part 1
-int fb_debug_tile_order(int gx, int gy, int gz, int faces, int *out, int *nface)
+int fb_debug_tile_order(int gx, int gy, int gz, int faces, int thin, int *out, int *nface)
 {
     if (gx < 1 || gy < 1 || gz < 1 || !out || !nface) return fail(FB_EINVAL, "fb_debug_tile_order: bad arguments");
-    const unsigned fl = rhs_face_flags((unsigned)faces & 63u, gx, gy, gz);
+    const unsigned fl = rhs_face_flags((unsigned)faces & 63u, (unsigned)thin & 7u, gx, gy, gz);
     *nface = (int)rhs_face_tiles(gx, gy, gz, fl);
     for (unsigned c = 0; c < (unsigned)(gx * gy * gz); c++) {
         unsigned x, y, z; rhs_face_first(c, gx, gy, gz, fl, x, y, z);
@@ -746,7 +764,6 @@ int fb_counter(const char *name, long long *out)
     if (!name || !out) return fail(FB_EINVAL, "null");
     if (!strcmp(name, "rhs_tma")) { *out = g_fb_rhs_launches[0]; return FB_OK; }
     if (!strcmp(name, "rhs_l1")) { *out = g_fb_rhs_launches[1]; return FB_OK; }
-    if (!strcmp(name, "lu_line")) { *out = lu_use_lines() ? 1 : 0; return FB_OK; }
     if (!strcmp(name, "lu_batch")) { *out = g_lu_batch_launches; return FB_OK; }
     return fail(FB_EINVAL, "unknown counter");
 }

@@ -87,14 +87,110 @@ __global__ void k_coe(ZoneDev z, const double *__restrict__ rop, int first_it)
     z.coe[l + 4 * nd] = xid + coe1 * (c2_ + c3_ + c4_) * 0.5;
 }
 
-void launch_coe(const ZoneDev &z, const double *rop, int first_it, int lssiter_verif, double *cfl, cudaStream_t st)
+void launch_coe(const ZoneDev &z, const double *rop, int first_it, cudaStream_t st)
 {
-    (void)lssiter_verif; (void)cfl;
     dim3 b(64, 4, 1);
     dim3 g = grid3i(z.iv + 2 * z.nf, z.jv + 2 * z.nf, z.kv + 2 * z.nfk, b);
     if (z.typ == 0) k_coe<0><<<g, b, 0, st>>>(z, rop, first_it);
     else if (z.typ == 1) k_coe<1><<<g, b, 0, st>>>(z, rop, first_it);
     else k_coe<2><<<g, b, 0, st>>>(z, rop, first_it);
+}
+
+// ------------------------------------------------------------------------------------------------ CFL statistics
+// S/Compute/cpcfl3.for (fixed meshes: viscous :276-440, Euler :635-790), called from cptst3.for:113-120 at the first
+// sub-iteration of a check iteration (lssiter_verif), explicit and implicit: per interior cell
+//   cfloc = dt / min(vis, conv),  conv = 2 vol surf / (|u| + c),  vis = 2 rho vol^2 surf^2 (gamma/Pr) / mu,
+//   surf = 1 / max_d(|t_d(l)| + |t_d(l+d)|)
+// reduced to [max, min, sum] over the zone (computePT.cpp:519-522 initial values, :619-645 gather) with warp shuffles, one
+// atomic per block and statistic.  cflv[3] counts cells whose state is not finite (the device side of stopAtNan).
+__device__ __forceinline__ void atomic_max_pos(double *addr, double v)
+{   // v >= 0: IEEE ordering of non-negative doubles == ordering of their bit patterns
+    atomicMax((unsigned long long *)addr, (unsigned long long)__double_as_longlong(v));
+}
+__device__ __forceinline__ void atomic_min_pos(double *addr, double v)
+{
+    atomicMin((unsigned long long *)addr, (unsigned long long)__double_as_longlong(v));
+}
+__global__ void k_cfl_init(double *cflv) { if (threadIdx.x == 0) { cflv[0] = 0.; cflv[1] = 100000000.; cflv[2] = 0.; cflv[3] = 0.; } }
+
+template <int MESH>
+__global__ void k_cfl(ZoneDev z, const double *__restrict__ rop, double *cflv)
+{
+    const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = 1 + blockIdx.z;
+    const bool ok = i <= z.iv && j <= z.jv;
+    double cmax = 0., cmin = 100000000., csum = 0., bad = 0.;
+    if (ok) {
+        const int nd = z.nd, nm = z.nm;
+        const int l = inddm(z, i, j, k), lt = MESH == 2 ? 0 : indmtr(z, i, j, k);
+        double surf, vol;
+        if (MESH == 0) {
+            const int li = lt + z.mi, lj = lt + z.mj, lk = lt + z.mk;
+            const double *ti = z.ti, *tj = z.tj, *tk = z.tk;
+            double ddi = sqrt(ti[li] * ti[li] + ti[li + nm] * ti[li + nm] + ti[li + 2 * nm] * ti[li + 2 * nm]);
+            ddi = ddi + sqrt(ti[lt] * ti[lt] + ti[lt + nm] * ti[lt + nm] + ti[lt + 2 * nm] * ti[lt + 2 * nm]);
+            double ddj = sqrt(tj[lj] * tj[lj] + tj[lj + nm] * tj[lj + nm] + tj[lj + 2 * nm] * tj[lj + 2 * nm]);
+            ddj = ddj + sqrt(tj[lt] * tj[lt] + tj[lt + nm] * tj[lt + nm] + tj[lt + 2 * nm] * tj[lt + 2 * nm]);
+            double ddk = sqrt(tk[lk] * tk[lk] + tk[lk + nm] * tk[lk + nm] + tk[lk + 2 * nm] * tk[lk + 2 * nm]);
+            ddk = ddk + sqrt(tk[lt] * tk[lt] + tk[lt + nm] * tk[lt + nm] + tk[lt + 2 * nm] * tk[lt + 2 * nm]);
+            surf = 1. / fmax(fmax(ddi, ddj), ddk); vol = z.vol[lt];
+        } else if (MESH == 1) {
+            const int li = lt + z.mi, lj = lt + z.mj, lk = lt + z.mk;
+            const double *ti = z.ti, *tj = z.tj, *tk = z.tk;
+            double ddi = sqrt(ti[li] * ti[li] + ti[li + nm] * ti[li + nm]);
+            ddi = ddi + sqrt(ti[lt] * ti[lt] + ti[lt + nm] * ti[lt + nm]);
+            double ddj = sqrt(tj[lj] * tj[lj] + tj[lj + nm] * tj[lj + nm]);
+            ddj = ddj + sqrt(tj[lt] * tj[lt] + tj[lt + nm] * tj[lt + nm]);
+            double ddk = sqrt(tk[lk] * tk[lk]);
+            ddk = ddk + sqrt(tk[lt] * tk[lt]);
+            surf = 1. / fmax(fmax(ddi, ddj), ddk); vol = z.vol[lt];
+        } else {
+            const double ddi = 2. * sqrt(z.tc0[0] * z.tc0[0]), ddj = 2. * sqrt(z.tc0[1] * z.tc0[1]), ddk = 2. * sqrt(z.tc0[2] * z.tc0[2]);
+            surf = 1. / fmax(fmax(ddi, ddj), ddk); vol = z.vol0;
+        }
+        const double r = rop[l], u = rop[l + nd], v = rop[l + 2 * nd], w = rop[l + 3 * nd], t = rop[l + 4 * nd];
+        const double c = sqrt(z.gam * z.rgp * t);
+        const double sp = sqrt(u * u + v * v + w * w);
+        const double xinvspc = 1. / (sp + c);
+        const double conv = 2. * vol * surf * xinvspc;
+        double comp = conv;
+        if (z.iflow >= 2) {
+            const double xinvkt = (z.gam / z.prandt) / z.xmut[l];
+            const double vis = 2. * r * vol * vol * surf * surf * xinvkt;
+            comp = fmin(vis, conv);
+        }
+        const double cfloc = z.dtc / comp;
+        cmax = cfloc; cmin = cfloc; csum = cfloc;
+        double fin = r + u + v + w + t;
+        if (z.neq == 6) fin += rop[l + 5 * nd];
+        if (!isfinite(fin) || !isfinite(cfloc)) { bad = 1.; cmax = 0.; cmin = 100000000.; csum = 0.; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        cmax = fmax(cmax, __shfl_xor_sync(0xffffffffu, cmax, o)); cmin = fmin(cmin, __shfl_xor_sync(0xffffffffu, cmin, o));
+        csum += __shfl_xor_sync(0xffffffffu, csum, o); bad += __shfl_xor_sync(0xffffffffu, bad, o);
+    }
+    __shared__ double sh[8][4];
+    const int t = threadIdx.y * blockDim.x + threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (lane == 0) { sh[warp][0] = cmax; sh[warp][1] = cmin; sh[warp][2] = csum; sh[warp][3] = bad; }
+    __syncthreads();
+    if (t == 0) {
+        const int nw = (blockDim.x * blockDim.y + 31) >> 5;
+        for (int q = 1; q < nw; q++) { cmax = fmax(cmax, sh[q][0]); cmin = fmin(cmin, sh[q][1]); csum += sh[q][2]; bad += sh[q][3]; }
+        atomic_max_pos(cflv, cmax); atomic_min_pos(cflv + 1, cmin); atomicAdd(cflv + 2, csum);
+        if (bad > 0.) atomicAdd(cflv + 3, bad);
+    }
+}
+
+void launch_cfl(const ZoneDev &z, const double *rop, double *cflv, cudaStream_t st)
+{
+    k_cfl_init<<<1, 32, 0, st>>>(cflv);
+    dim3 b(64, 4, 1);
+    dim3 g = grid3i(z.iv, z.jv, z.kv, b);
+    if (z.typ == 0) k_cfl<0><<<g, b, 0, st>>>(z, rop, cflv);
+    else if (z.typ == 1) k_cfl<1><<<g, b, 0, st>>>(z, rop, cflv);
+    else k_cfl<2><<<g, b, 0, st>>>(z, rop, cflv);
 }
 
 // ------------------------------------------------------------------------------------------------ SA ghost ring
@@ -123,18 +219,13 @@ void launch_sa_ring(const ZoneDev &z, const double *rop, cudaStream_t st)
 }
 
 // ------------------------------------------------------------------------------------------------ residual norms
-__device__ __forceinline__ void atomic_max_pos(double *addr, double v)
-{   // v >= 0: IEEE ordering of non-negative doubles == ordering of their bit patterns
-    atomicMax((unsigned long long *)addr, (unsigned long long)__double_as_longlong(v));
-}
-
 __global__ void k_resid_zero(double *rdm, int slot, int nss, int neq)
 {
     const int e = threadIdx.x;
     if (e < neq) { rdm[slot + e * nss] = 0.; rdm[slot + e * nss + neq * nss] = 0.; }
 }
 
-__global__ void k_resid(ZoneDev z, double *rdm, int slot, int nss)
+__global__ void k_resid(ZoneDev z, double *rdm, int slot, int nss, double *cflv)
 {
     const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
     const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
@@ -158,6 +249,7 @@ __global__ void k_resid(ZoneDev z, double *rdm, int slot, int nss)
         for (int q = 0; q < nw; q++) { s += ss[q][t]; m = fmax(m, sm[q][t]); }
         atomicAdd(&rdm[slot + t * nss], s);
         atomic_max_pos(&rdm[slot + t * nss + z.neq * nss], m);
+        if (!isfinite(s)) atomicAdd(cflv + 3, 1.);      // device side of stopAtNan (S/PyTree.py:2070-2073)
     }
 }
 
@@ -288,10 +380,10 @@ int launch_lu(const ZoneDev &z, const LuPlan &p, const double *rop, double *rop_
     return run_lu<2, 5>(z, p, rop, rop_out, lu_match, st);
 }
 
-void launch_resid(const ZoneDev &z, double *rdm, int nitcfg, int nss, cudaStream_t st)
+void launch_resid(const ZoneDev &z, double *rdm, double *cflv, int nitcfg, int nss, cudaStream_t st)
 {
     const int slot = nitcfg - 1;
     k_resid_zero<<<1, 32, 0, st>>>(rdm, slot, nss, z.neq);
     dim3 b(64, 4, 1);
-    k_resid<<<grid3i(z.iv, z.jv, z.kv, b), b, 0, st>>>(z, rdm, slot, nss);
+    k_resid<<<grid3i(z.iv, z.jv, z.kv, b), b, 0, st>>>(z, rdm, slot, nss, cflv);
 }

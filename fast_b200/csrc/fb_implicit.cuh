@@ -25,20 +25,18 @@ int  lu_plan_build(LuPlan &p, const ZoneDev &z, const int box[6]);
 void lu_plan_free(LuPlan &p);
 void lu_plan_metrics(LuPlan &p, const ZoneDev &z, cudaStream_t st);   // after the metrics exist
 int  lu_plan_error(const LuPlan &p);
-bool lu_use_lines();                                                  // fb_lu2.cu (default) or fb_lu.cu (FAST_B200_LU=tile)
-void lu2_tile_dims(int mesh, int neq, int &tj, int &tk);
-int  launch_lu_lines(const ZoneDev &z, const LuPlan &p, const double *rop_ssiter, double *rop_out, int lu_match, cudaStream_t st);
 int  launch_lu_tiles(const ZoneDev &z, const LuPlan &p, const double *rop_ssiter, double *rop_out, int lu_match, cudaStream_t st);
 // all zones of a multi-zone solver swept by one pair of launches (fb_lu.cu: k_lu_tile_b); nullptr when the zones cannot share
-// a launch (different mesh family / number of equations, line kernel selected)
+// a launch (different mesh family / number of equations)
 struct LuBatch;
 LuBatch *lu_batch_create(int nz, const ZoneDev *const *zs, const LuPlan *const *plans);
 void lu_batch_free(LuBatch *b);
 int  lu_batch_launch(LuBatch *b, const ZoneDev *const *zs, const LuPlan *const *plans, const double *const *rop_ssiter,
                      double *const *rop_out, int lu_match, cudaStream_t st);
-void launch_coe(const ZoneDev &z, const double *rop, int first_it, int lssiter_verif, double *cfl, cudaStream_t st);
+void launch_coe(const ZoneDev &z, const double *rop, int first_it, cudaStream_t st);
+void launch_cfl(const ZoneDev &z, const double *rop, double *cflv, cudaStream_t st);   // cflv: [max, min, sum, non-finite cells]
 void launch_sa_ring(const ZoneDev &z, const double *rop, cudaStream_t st);
-void launch_resid(const ZoneDev &z, double *rdm, int nitcfg, int nss, cudaStream_t st);
+void launch_resid(const ZoneDev &z, double *rdm, double *cflv, int nitcfg, int nss, cudaStream_t st);
 int  launch_lu(const ZoneDev &z, const LuPlan &p, const double *rop_ssiter, double *rop_out, int lu_match, cudaStream_t st);
 
 // match joins (1 donor, coefficient 1: C/Com/setInterpTransfersFast.cpp:440-955 for interpolation type 0/1)
@@ -51,6 +49,7 @@ struct JoinSet {
     long long send_doubles = 0, recv_doubles = 0;
     double **d_ptrs = nullptr; // per-zone base pointers (refreshed at every apply)
     int nz = 0;
+    int flip = 0;              // slot of d_ptrs the next launch uses
 };
 int  joins_build(JoinSet &j, const int *ji, int n, int nz, const int *ndimdx, const int *neqs, std::string &err);
 void joins_free(JoinSet &j);

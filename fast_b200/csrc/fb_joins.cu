@@ -84,8 +84,8 @@ static int run(JoinSet &j, double **zone_ptr, int nz, double *buf, int kind, cud
     if (!any) return 0;
     // the zone pointers rotate every iteration: pass them through a small device table (two slots, alternating,
     // so that an in-flight launch never sees its table overwritten)
-    static thread_local int flip = 0; flip ^= 1;
-    double **tab = j.d_ptrs + flip * nz;
+    j.flip ^= 1;
+    double **tab = j.d_ptrs + j.flip * nz;
     cudaMemcpyAsync(tab, zone_ptr, nz * sizeof(double *), cudaMemcpyHostToDevice, st);
     dim3 b(128), g((j.maxpts + 127) / 128, j.njoin);
     k_join<<<g, b, 0, st>>>(j.d_desc, j.d_idx, tab, buf, kind);

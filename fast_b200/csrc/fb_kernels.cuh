@@ -1,6 +1,15 @@
 // fb_kernels.cuh -- launchers shared between fb_kernels.cu / fb_implicit.cu and the C-ABI driver (fb_api.cu).
 #pragma once
+#include <atomic>
 #include "fb_common.cuh"
+
+// cudaFuncSetAttribute is per device: true the first time a call site runs on the current device (one bit per device)
+static inline bool fb_first_on_device(std::atomic<unsigned long long> &done)
+{
+    int d = 0; cudaGetDevice(&d);
+    const unsigned long long bit = 1ull << (d & 63);
+    return !(done.fetch_or(bit) & bit);
+}
 
 struct BcWin {          // one BC window, ghost range already resolved (C/BC/indice_cl_sdm.for, npass = 0)
     int type, idir;     // reference tag (C/PyTree.py:30-70), 1..6

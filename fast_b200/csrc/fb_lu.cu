@@ -30,6 +30,7 @@
 #include <map>
 #include <cstring>
 #include "fb_implicit.cuh"
+#include "fb_kernels.cuh"
 
 #define LU_CI 8            // cells per line per staged chunk
 #define LU_TJ 8
@@ -470,8 +471,7 @@ int lu_plan_build(LuPlan &p, const ZoneDev &z, const int box[6])
     for (int i = 0; i < 6; i++) p.box[i] = box[i];
     const int bi = box[1] - box[0] + 1, bj = box[3] - box[2] + 1, bk = box[5] - box[4] + 1;
     p.nplanes = bi + bj + bk - 2;
-    if (lu_use_lines()) lu2_tile_dims(z.typ, z.neq, p.tj, p.tk);
-    else { p.tj = LU_TJ; p.tk = lu_tile_tk(z.typ, z.neq); }
+    p.tj = LU_TJ; p.tk = lu_tile_tk(z.typ, z.neq);
     p.NJ = (bj + p.tj - 1) / p.tj; p.NK = (bk + p.tk - 1) / p.tk;
     std::vector<int> ord;
     for (int K = 0; K < p.NK; K++) for (int J = 0; J < p.NJ; J++) ord.push_back(J | (K << 16));
@@ -499,7 +499,8 @@ int lu_plan_build(LuPlan &p, const ZoneDev &z, const int box[6])
         if (cudaMalloc(&p.d_tcm, (size_t)nt * p.tstride * sizeof(double)) != cudaSuccess) return 1;
         cudaMemset(p.d_tcm, 0, (size_t)nt * p.tstride * sizeof(double));
     }
-    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+    // the fills above ran on the legacy default stream; the solver's streams are non-blocking
+    return (cudaDeviceSynchronize() == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : 1;
 }
 
 void lu_plan_free(LuPlan &p)
@@ -570,11 +571,10 @@ void lu_batch_free(LuBatch *b)
 template <int MESH, int NEQ>
 static void run_lu_batch(const LuBatch *b, const LuBatchItem *items, cudaStream_t st)
 {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static std::atomic<unsigned long long> attr_done{0};
+    if (fb_first_on_device(attr_done)) {
         cudaFuncSetAttribute(k_lu_tile_b<MESH, NEQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LuCfg<MESH, NEQ, false>::SMEM);
         cudaFuncSetAttribute(k_lu_tile_b<MESH, NEQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LuCfg<MESH, NEQ, true>::SMEM);
-        attr_done = true;
     }
     cudaMemsetAsync(b->d_ticket, 0, 2 * sizeof(int), st);
     k_lu_tile_b<MESH, NEQ, false><<<b->ntiles, LU_NT, LuCfg<MESH, NEQ, false>::SMEM, st>>>(items, b->d_order, b->d_ticket);
@@ -610,11 +610,10 @@ static int run_lu_tiles(const ZoneDev &z, const LuPlan &p, const double *rop, do
 {
     LuTileArgs a;
     lu_fill_args(a, z, p, rop, rop_out, lu_match);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static std::atomic<unsigned long long> attr_done{0};
+    if (fb_first_on_device(attr_done)) {
         cudaFuncSetAttribute(k_lu_tile<MESH, NEQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LuCfg<MESH, NEQ, false>::SMEM);
         cudaFuncSetAttribute(k_lu_tile<MESH, NEQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LuCfg<MESH, NEQ, true>::SMEM);
-        attr_done = true;
     }
     cudaMemsetAsync(p.d_ctl, 0, 2 * sizeof(int), st);
     const int ntiles = p.NJ * p.NK;
@@ -705,11 +704,10 @@ static int run_lu_ssor(const ZoneDev &z, const LuPlan &p, const double *rop, dou
 {
     LuTileArgs a;
     lu_fill_args(a, z, p, rop, rop_out, 1);       // Newton box = interior (ind_loop_sdm)
-    static bool attr_done = false;
-    if (!attr_done) {
+    static std::atomic<unsigned long long> attr_done{0};
+    if (fb_first_on_device(attr_done)) {
         cudaFuncSetAttribute(k_lu_tile<MESH, NEQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LuCfg<MESH, NEQ, false>::SMEM);
         cudaFuncSetAttribute(k_lu_tile<MESH, NEQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LuCfg<MESH, NEQ, true>::SMEM);
-        attr_done = true;
     }
     const int ntiles = p.NJ * p.NK, alias = a.alias;
     const int *bx = p.box;
@@ -733,22 +731,12 @@ static int run_lu_ssor(const ZoneDev &z, const LuPlan &p, const double *rop, dou
     return launches;
 }
 
-bool lu_use_lines()
-{   // default: the 4-lanes-per-line tile kernel of this file; FAST_B200_LU=line selects the one-thread-per-line kernel
-    // (fb_lu2.cu: 5x fewer instructions per cell, two tiles per SM, parity-green, but a single warp evaluating the three
-    // products in sequence needs 2.0 us per step against 0.69 us here -- measured 3.4 ms per sweep on C3 against 1.0 ms,
-    // see DESIGN.md 3.4)
-    static const bool lines = [] { const char *e = getenv("FAST_B200_LU"); return e && e[0] == 'l'; }();
-    return lines;
-}
-
 int launch_lu_tiles(const ZoneDev &z, const LuPlan &p, const double *rop, double *rop_out, int lu_match, cudaStream_t st)
 {
     if (p.nrelax >= 2) {      // LU-SSOR relaxations: always the tile kernel
         if (z.neq == 6) return z.typ == 0 ? run_lu_ssor<0, 6>(z, p, rop, rop_out, st) : (z.typ == 1 ? run_lu_ssor<1, 6>(z, p, rop, rop_out, st) : run_lu_ssor<2, 6>(z, p, rop, rop_out, st));
         return z.typ == 0 ? run_lu_ssor<0, 5>(z, p, rop, rop_out, st) : (z.typ == 1 ? run_lu_ssor<1, 5>(z, p, rop, rop_out, st) : run_lu_ssor<2, 5>(z, p, rop, rop_out, st));
     }
-    if (lu_use_lines()) return launch_lu_lines(z, p, rop, rop_out, lu_match, st);
     if (z.neq == 6) {
         if (z.typ == 0) return run_lu_tiles<0, 6>(z, p, rop, rop_out, lu_match, st);
         if (z.typ == 1) return run_lu_tiles<1, 6>(z, p, rop, rop_out, lu_match, st);
@@ -760,8 +748,11 @@ int launch_lu_tiles(const ZoneDev &z, const LuPlan &p, const double *rop, double
 }
 
 int lu_plan_error(const LuPlan &p)
-{
+{   // reports the spin-timeout flag once and clears it (the caller raises; a later sweep starts clean)
     int e = 0;
-    if (p.d_ctl) cudaMemcpy(&e, p.d_ctl + 2, sizeof(int), cudaMemcpyDeviceToHost);
+    if (p.d_ctl) {
+        cudaMemcpy(&e, p.d_ctl + 2, sizeof(int), cudaMemcpyDeviceToHost);
+        if (e) cudaMemset(p.d_ctl + 2, 0, sizeof(int));
+    }
     return e;
 }

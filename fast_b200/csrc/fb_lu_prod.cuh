@@ -1,4 +1,4 @@
-// fb_lu_prod.cuh -- Jacobian-times-increment product shared by the LU sweep kernels (fb_lu.cu, fb_lu2.cu)
+// fb_lu_prod.cuh -- Jacobian-times-increment product shared by the LU sweep kernels (fb_lu.cu, fb_implicit.cu)
 #pragma once
 
 // B_d(l) . dW(l) with the cell-centred mean normal (tcx,tcy,tcz) of cell l (lu_{i,j,k}_*.for; signe folded into cd).

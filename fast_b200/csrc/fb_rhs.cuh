@@ -29,12 +29,17 @@ __device__ __forceinline__ void st_wig(unsigned char *p, unsigned v) { asm("st.g
 // per-tile completion count (fence + atomic, even predicated off) at the end of the kernel -- cost the TGV stage 40 %
 // (1.0 -> 1.43 ms, profiles/r01_rhs_overlap_variants.md) with the overlap switched OFF.
 #include "fb_tiles.cuh"   // rhs_face_first, rhs_face_flags, rhs_face_tiles
+// which directions end in a tile of a single cell (the donors of a join are the two cell layers behind the face)
+static inline int rhs_thin(const ZoneDev &z, dim3 g, int ti, int tj, int tk)
+{
+    return ((z.iv - (int)(g.x - 1) * ti < 2) ? 1 : 0) | ((z.jv - (int)(g.y - 1) * tj < 2) ? 2 : 0) | ((z.kv - (int)(g.z - 1) * tk < 2) ? 4 : 0);
+}
 // launch grid of a part (RhsArgs::part: 0 whole zone as a 3-D grid, 1 face tiles, 2 interior tiles); false = nothing to launch
 static inline bool rhs_part_grid(RhsArgs &a, dim3 &g)
 {
     a.gx = a.gy = a.gz = a.tile0 = 0;
     if (a.part == 0) return true;
-    a.faces = (int)rhs_face_flags((unsigned)a.faces, g.x, g.y, g.z);
+    a.faces = (int)rhs_face_flags((unsigned)a.faces, (unsigned)a.thin, g.x, g.y, g.z);
     const unsigned nb = rhs_face_tiles(g.x, g.y, g.z, (unsigned)a.faces), total = g.x * g.y * g.z;
     a.gx = (int)g.x; a.gy = (int)g.y; a.gz = (int)g.z;
     a.tile0 = a.part == 1 ? 0 : (int)nb;
@@ -482,6 +487,7 @@ static void launch_rhs2_t(const ZoneDev &z, RhsArgs &a, bool impl, cudaStream_t 
 {
     dim3 b(32, RHS2_RJ + 1, 1);
     dim3 g((z.iv + 30) / 31, (z.jv + RHS2_RJ - 1) / RHS2_RJ, (z.kv + RHS2_KC - 1) / RHS2_KC);
+    a.thin = rhs_thin(z, g, 31, RHS2_RJ, RHS2_KC);
     if (!rhs_part_grid(a, g)) return;
     // WC: first sub-iteration of a SENSOR zone -- the switch is evaluated inside the flux and stored
     if (SCHEME == 2 && a.nitcfg == 1 && a.wfuse) {
@@ -502,16 +508,16 @@ static bool launch_rhs3_t(const ZoneDev &z, RhsArgs &a, bool impl, cudaStream_t 
     const CUtensorMap *tr = fb_tma_map(a.rop, z.ni, z.nj, z.nk, z.nd, C::NEQ, C::ROWS, C::NEQ);
     const CUtensorMap *tm = FLOW >= 2 ? fb_tma_map(z.xmut, z.ni, z.nj, z.nk, z.nd, FLOW == 3 ? 2 : 1, C::ROWS, 1) : tr;
     if (!tr || !tm) return false;
-    static bool attr = false;
-    if (!attr) {
+    static std::atomic<unsigned long long> attr{0};
+    if (fb_first_on_device(attr)) {
         cudaFuncSetAttribute(k_rhs3<MESH, FLOW, SCHEME, SLOPE, true, RJ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::template smem<MESH>());
         cudaFuncSetAttribute(k_rhs3<MESH, FLOW, SCHEME, SLOPE, false, RJ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::template smem<MESH>());
         cudaFuncSetAttribute(k_rhs3<MESH, FLOW, SCHEME, SLOPE, true, RJ, SCHEME == 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::template smem<MESH>());
         cudaFuncSetAttribute(k_rhs3<MESH, FLOW, SCHEME, SLOPE, false, RJ, SCHEME == 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::template smem<MESH>());
-        attr = true;
     }
     dim3 b(32, RJ + 1, 1);
     dim3 g((z.iv + 30) / 31, (z.jv + RJ - 1) / RJ, (z.kv + RHS3_KC - 1) / RHS3_KC);
+    a.thin = rhs_thin(z, g, 31, RJ, RHS3_KC);
     if (!rhs_part_grid(a, g)) return true;
     if (SCHEME == 2 && a.nitcfg == 1 && a.wfuse) {   // first sub-iteration of a SENSOR zone: the switch is evaluated in the flux
         if (impl) k_rhs3<MESH, FLOW, SCHEME, SLOPE, true, RJ, SCHEME == 2><<<g, b, C::template smem<MESH>(), st>>>(*tr, *tm, z, a);

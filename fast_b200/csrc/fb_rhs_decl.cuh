@@ -13,7 +13,9 @@ struct RhsArgs {
     // a zone face / only the interior tiles, as a 1-D grid whose CTA c works on tile rhs_face_first(tile0 + c) of the
     // gx x gy x gz tile grid (fb_rhs.cuh); part 0 = the whole zone as a 3-D grid (gx = 0)
     int part, tile0, gx, gy, gz;
-    int faces;              // faces of the zone that carry cross-rank joins: bit 0..5 = imin, imax, jmin, jmax, kmin, kmax
+    int faces;              // in: faces of the zone that carry cross-rank joins, bit 0..5 = imin, imax, jmin, jmax, kmin, kmax;
+                            // in the kernel: tile layers of part 1 behind each face, two bits per face (fb_tiles.cuh: rhs_face_flags)
+    int thin;               // bit d: the last tile of direction d is less than two cells thick
     int wfuse;              // SENSOR switch evaluated inside the first-sub-iteration kernel (default) instead of k_sensor
 };
 

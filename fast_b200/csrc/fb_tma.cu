@@ -11,6 +11,7 @@
 #include <map>
 #include <tuple>
 #include <memory>
+#include <mutex>
 
 typedef CUresult (*EncodeTiled_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -30,9 +31,12 @@ static EncodeTiled_t encode_fn()
 
 const CUtensorMap *fb_tma_map(const double *base, int ni, int nj, int nk, long long var_stride, int nvar_total, int box_rows, int box_vars)
 {
-    typedef std::tuple<const double *, int, int, int, long long, int, int, int> Key;
+    typedef std::tuple<int, const double *, int, int, int, long long, int, int, int> Key;
     static std::map<Key, std::unique_ptr<CUtensorMap>> cache;
-    const Key key(base, ni, nj, nk, var_stride, nvar_total, box_rows, box_vars);
+    static std::mutex mtx;
+    std::lock_guard<std::mutex> lock(mtx);
+    int dev = 0; cudaGetDevice(&dev);
+    const Key key(dev, base, ni, nj, nk, var_stride, nvar_total, box_rows, box_vars);
     auto it = cache.find(key);
     if (it != cache.end()) return it->second.get();
     std::unique_ptr<CUtensorMap> m;

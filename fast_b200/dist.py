@@ -76,18 +76,21 @@ def local_case(workload, rank, world, n=None):
     """Per-rank share of a multi-block synthetic case.  Returns (tree with this rank's zones, join table of this rank,
     peers, description, cells of the whole job)."""
     from . import synth
-    if workload in ('tgv256', 'tgv'):
+    if workload in ('tgv256', 'tgv', 'tgv_cut_i', 'tgv_cut_j', 'tgv_cut_k'):
         n = n or 256
         nblk = grid_for(world)
+        if workload.startswith('tgv_cut_'):        # all blocks in a row along one direction (tests: thin last tiles on the cut faces)
+            nblk = [1, 1, 1]; nblk['ijk'.index(workload[-1])] = world; nblk = tuple(nblk)
+        n3 = (n, n, n) if isinstance(n, int) else tuple(n)
         nz = nblk[0] * nblk[1] * nblk[2]
         rank_of = partition(nz, world)
         mine = {z for z, r in rank_of.items() if r == rank}
         t, layout = synth.case_tgv_blocks(n=n, nblk=nblk, only=mine)
         periodic = tuple(b > 1 for b in nblk)
-        table, peers = synth.build_joins(layout, nblk, (n, n, n), periodic=periodic, rank_of=rank_of, rank=rank, neq=5)
-        desc = 'laminar TGV %d^3 per GPU (%dx%dx%d blocks, periodic match joins), SENSOR o3, explicit RK3 ' \
-               '(BASELINE configs[1], one block per GPU)' % ((n,) + nblk)
-        return t, table, peers, desc, nz * n ** 3
+        table, peers = synth.build_joins(layout, nblk, n3, periodic=periodic, rank_of=rank_of, rank=rank, neq=5)
+        desc = 'laminar TGV %dx%dx%d per GPU (%dx%dx%d blocks, periodic match joins), SENSOR o3, explicit RK3 ' \
+               '(BASELINE configs[1], one block per GPU)' % (n3 + nblk)
+        return t, table, peers, desc, nz * n3[0] * n3[1] * n3[2]
     if workload == 'multiblock':
         n = n or 128
         nblk = (2, 2, 2)

@@ -13,9 +13,15 @@ def init_metric(zones, metrics, hook):
 
 
 def souszones_list(zones, metrics, hook, nitrun, nstep, verbose=0):
-    """fastc.souszones_list (C/Compute/souszones_list.cpp): one task per zone on the GPU; only the two flags matter."""
+    """fastc.souszones_list (C/Compute/souszones_list.cpp:98-213; flags :36-83), called at S/PyTree.py:122,258,403 as
+    ``hook1.update(fastc.souszones_list(...))``: returns the reference's dictionary {'lexit_lu', 'lssiter_verif'}
+    (souszones_list.cpp:198-213).  There is one task per zone on the GPU, so the sub-zone lists the reference also refreshes in
+    HOOK have no counterpart; the C layer (fb_compute) evaluates the same two flags itself."""
+    from .FastC.PyTree import Internal
+    from . import VSHARE
     dtloc = hook['dtloc']
     verif = 1 if nitrun % int(dtloc[1]) == 0 else 0
-    itypcp = 1
+    pi = Internal.getNodeFromName1(Internal.getNodeFromName1(zones[0], '.Solver#ownData'), 'Parameter_int')[1]
+    itypcp = int(pi[VSHARE.ITYPCP])
     lexit = 1 if (verif and nstep == int(dtloc[0]) and itypcp != 2) else 0
     return {'lexit_lu': lexit, 'lssiter_verif': verif}

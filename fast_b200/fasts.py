@@ -146,6 +146,7 @@ def display_ss_iteration(zones, metrics, nitrun, nssiter, lft, iverb):
         Internal.getNodeFromName1(own, 'CFL_minmaxmoy')[1][:] = [cfl[1], cfl[0], cfl[2]]
         r = rdm.reshape((int(nssiter), neq, 2), order='F')
         ncell = float(pi[V.IJKV]) * float(pi[V.IJKV + 1]) * float(pi[V.IJKV + 2])
-        out[z[0]] = {'L2': numpy.sqrt(r[:, :, 0] / ncell), 'Loo': r[:, :, 1].copy(), 'CFL': cfl}
+        bad = ctypes.c_longlong(0); _lib.check(L.fb_zone_isfinite(s, nd, ctypes.byref(bad)))
+        out[z[0]] = {'L2': numpy.sqrt(r[:, :, 0] / ncell), 'Loo': r[:, :, 1].copy(), 'CFL': cfl, 'nonfinite': int(bad.value)}
         if iverb == 1: print("zone %s nitrun %d: L2 %s" % (z[0], nitrun, out[z[0]]['L2'][:, 0]))
     return out

@@ -1,7 +1,7 @@
 """Host-side integer part of ``fasts.allocate_metric`` (reference: FastS/Metric/allocate_metric.cpp:34-481
 and FastC/Metric/nature_geom_dom.for): zone sizes, ghost counts, mesh-family detection and the metric
 strides written into Parameter_int.  Pure numpy -- this is control logic, the metric arithmetic itself
-runs in CUDA (csrc/fb_metric.cu)."""
+runs in CUDA (csrc/fb_kernels.cu: k_tijk, k_vol)."""
 import numpy
 from . import VSHARE as V
 

@@ -203,22 +203,23 @@ def case_tgv_blocks(n=256, nblk=(2, 1, 1), only=None, scheme='senseur', Re=1600.
     from .FastC import PyTree as FastC
     state = adim1(MInf=MInf, ReInf=Re)
     L = 2 * math.pi
-    ng = tuple(n * b for b in nblk)
+    n3 = (n, n, n) if isinstance(n, int) else tuple(n)
+    ng = tuple(n3[d] * nblk[d] for d in range(3))
     layout, zones = {}, []
     for bk in range(nblk[2]):
         for bj in range(nblk[1]):
             for bi in range(nblk[0]):
                 zid = len(layout); layout[(bi, bj, bk)] = zid
                 if only is not None and zid not in only: continue
-                z = make_block('tgv_%d_%d_%d' % (bi, bj, bk), (n, n, n), L=tuple(L * b for b in nblk),
-                               index_offset=(bi * n, bj * n, bk * n), nglob=ng)
+                z = make_block('tgv_%d_%d_%d' % (bi, bj, bk), n3, L=tuple(L * b for b in nblk),
+                               index_offset=(bi * n3[0], bj * n3[1], bk * n3[2]), nglob=ng)
                 _tgv_fields(z, state)
                 for d, f in enumerate('ijk'):
                     if nblk[d] == 1:
                         add_bc(z, f + 'min', 'BCautoperiod', f + 'min'); add_bc(z, f + 'max', 'BCautoperiod', f + 'max')
                 zones.append(z)
     t = new_tree(zones, state, 'NSLaminar')
-    FastC._setNum2Zones(t, {'scheme': scheme, 'slope': 'o3', 'time_step': time_step * (256. / n)})
+    FastC._setNum2Zones(t, {'scheme': scheme, 'slope': 'o3', 'time_step': time_step * (256. / max(n3))})
     FastC._setNum2Base(t, {'temporal_scheme': 'explicit', 'rk': 3, 'modulo_verif': 50})
     return t, layout
 

@@ -68,9 +68,14 @@ int fb_transfers(fb_solver *s, int level);
 int fb_compute_mut(fb_solver *s);
 
 /* fasts.display_ss_iteration inputs (S/DISPLAY/display_ss_iteration.cpp:29): rdm(nssiter,neq,2) and
- * CFL (max,min,mean) of zone nd. */
+ * CFL (max,min,mean) of zone nd as gathered at S/Compute/computePT.cpp:619-645 from S/Compute/cpcfl3.for (reduced on the
+ * device at the first sub-iteration of every check iteration, S/Compute/cptst3.for:113-120). */
 int fb_zone_get_residuals(fb_solver *s, int nd, double *rdm, int n);
 int fb_zone_get_cfl(fb_solver *s, int nd, double cfl[3]);
+/* Device side of display_temporal_criteria's stopAtNan (S/PyTree.py:2070-2073): number of interior cells whose state was
+ * not finite at the last CFL check (S/Compute/cpcfl3.for runs over them anyway) + residual norms (cprdu3s1) that came out
+ * non-finite since; both are evaluated on the iterations the reference checks (nitrun % modulo_verif == 0). */
+int fb_zone_isfinite(fb_solver *s, int nd, long long *bad);
 
 /* End-to-end iteration on HOST buffers (what a reference-side caller holding the tree's numpy arrays does):
  * uploads the input time levels of every zone (ro; ro_M1 too for the implicit BDF term), runs one fb_compute
@@ -86,14 +91,15 @@ int fb_timing_reset(fb_solver *s);
 int fb_timing_get(fb_solver *s, const char *name, double *ms, long long *launches);
 int fb_sync(fb_solver *s);
 /* Which kernels ran (process-wide): "rhs_tma" / "rhs_l1" = launches of the TMA-staged (k_rhs3) and of the L1-path
- * (k_rhs2) residual kernel, "lu_line" = 1 when the one-thread-per-line LU kernel is selected, "lu_batch" = multi-zone
- * LU launch pairs (k_lu_tile_b).  New with this library
+ * (k_rhs2) residual kernel, "lu_batch" = multi-zone LU launch pairs (k_lu_tile_b).  New with this library
  * (no reference counterpart); bench.py names the kernel it reports a roofline for from it. */
 int fb_counter(const char *name, long long *out);
 /* Test hook, needs no device: the order in which the two-part explicit stage of the halo-exchange overlap visits a
  * gx x gy x gz tile grid (tiles on the faces flagged in `faces` -- bit 0..5 = imin, imax, jmin, jmax, kmin, kmax -- first),
- * computed by the function the kernels use.  out: 3 ints (x, y, z) per tile in launch order; *nface: tiles of part 1. */
-int fb_debug_tile_order(int gx, int gy, int gz, int faces, int *out, int *nface);
+ * computed by the function the kernels use; thin: bit d = the last tile of direction d is a single cell thick, so that the
+ * upper face of that direction takes its two outermost tile layers (the donors are the two cell layers behind a face).
+ * out: 3 ints (x, y, z) per tile in launch order; *nface: tiles of part 1. */
+int fb_debug_tile_order(int gx, int gy, int gz, int faces, int thin, int *out, int *nface);
 /* Device pointer of a zone's state block (uintptr) so the Python host can hand halo buffers to
  * torch.distributed/NCCL without a host copy. */
 unsigned long long fb_zone_device_ptr(fb_solver *s, int nd, int level);

@@ -189,6 +189,67 @@ void fo_tstb3_global(const int *pi, const double *pr, const int ind[6], double *
     }
 }
 
+/* FastS/Compute/cpcfl3.for:6-800, fixed meshes (LALE = 0): viscous models :276-440, Euler :635-790.  Per interior cell
+   cfloc = dt / min(vis, conv) (Euler: dt / conv) with conv = 2 vol surf / (|u| + c), vis = 2 rho vol^2 surf^2 (gamma/Pr) / mu,
+   surf = 1 / max_d(|t_d(l)| + |t_d(l+d)|); cfl = [max, min, sum] (the caller divides the sum by the cell count,
+   computePT.cpp:645). */
+void fo_cpcfl3(const int *pi, const double *pr, const int ind[6], double cfl[3], const double *rop, const double *xmut,
+               const double *ti, const double *tj, const double *tk, const double *vol)
+{
+    const int nd = pi[FO_NDIMDX], nm = pi[FO_NDIMDX_MTR], typ = pi[FO_ITYPZONE];
+    const int inci = pi[FO_NIJK_MTR], incj = pi[FO_NIJK_MTR + 1], inck = pi[FO_NIJK_MTR + 2];
+    const double rgp = pr[FO_CVINF] * (pr[FO_GAMMA] - 1.);
+    const double gam1 = pr[FO_GAMMA] / pr[FO_PRANDT], gam2 = pr[FO_GAMMA] * rgp;
+    const double dt = pr[FO_DTC];                       /* EXPLOC = 0 */
+    const int visc = pi[FO_IFLOW] >= 2;
+    double surf_cart = 0.;
+    if (typ == 2) {
+        const double ddi = 2. * sqrt(ti[0] * ti[0]), ddj = 2. * sqrt(tj[0] * tj[0]), ddk = 2. * sqrt(tk[0] * tk[0]);
+        surf_cart = 1. / fmax(fmax(ddi, ddj), ddk);
+    }
+    FO_LOOP(ind) {
+        const int l = fo_inddm(pi, i, j, k), lt = typ == 2 ? 0 : fo_indmtr(pi, i, j, k);
+        double surf;
+        if (typ == 0) {
+            double ddi = sqrt(ti[lt + inci] * ti[lt + inci] + ti[lt + inci + nm] * ti[lt + inci + nm] + ti[lt + inci + 2 * nm] * ti[lt + inci + 2 * nm]);
+            ddi = ddi + sqrt(ti[lt] * ti[lt] + ti[lt + nm] * ti[lt + nm] + ti[lt + 2 * nm] * ti[lt + 2 * nm]);
+            double ddj = sqrt(tj[lt + incj] * tj[lt + incj] + tj[lt + incj + nm] * tj[lt + incj + nm] + tj[lt + incj + 2 * nm] * tj[lt + incj + 2 * nm]);
+            ddj = ddj + sqrt(tj[lt] * tj[lt] + tj[lt + nm] * tj[lt + nm] + tj[lt + 2 * nm] * tj[lt + 2 * nm]);
+            double ddk = sqrt(tk[lt + inck] * tk[lt + inck] + tk[lt + inck + nm] * tk[lt + inck + nm] + tk[lt + inck + 2 * nm] * tk[lt + inck + 2 * nm]);
+            ddk = ddk + sqrt(tk[lt] * tk[lt] + tk[lt + nm] * tk[lt + nm] + tk[lt + 2 * nm] * tk[lt + 2 * nm]);
+            surf = 1. / fmax(fmax(ddi, ddj), ddk);
+        } else if (typ == 1) {
+            double ddi = sqrt(ti[lt + inci] * ti[lt + inci] + ti[lt + inci + nm] * ti[lt + inci + nm]);
+            ddi = ddi + sqrt(ti[lt] * ti[lt] + ti[lt + nm] * ti[lt + nm]);
+            double ddj = sqrt(tj[lt + incj] * tj[lt + incj] + tj[lt + incj + nm] * tj[lt + incj + nm]);
+            ddj = ddj + sqrt(tj[lt] * tj[lt] + tj[lt + nm] * tj[lt + nm]);
+            double ddk = sqrt(tk[lt + inck] * tk[lt + inck]);
+            ddk = ddk + sqrt(tk[lt] * tk[lt]);
+            surf = 1. / fmax(fmax(ddi, ddj), ddk);
+        } else if (typ == 2) surf = surf_cart;
+        else {      /* 2-D */
+            double ddi = sqrt(ti[lt + inci] * ti[lt + inci] + ti[lt + inci + nm] * ti[lt + inci + nm]);
+            ddi = ddi + sqrt(ti[lt] * ti[lt] + ti[lt + nm] * ti[lt + nm]);
+            double ddj = sqrt(tj[lt + incj] * tj[lt + incj] + tj[lt + incj + nm] * tj[lt + incj + nm]);
+            ddj = ddj + sqrt(tj[lt] * tj[lt] + tj[lt + nm] * tj[lt + nm]);
+            surf = 1. / fmax(ddi, ddj);
+        }
+        const double u = rop[l + nd], v = rop[l + 2 * nd], w = typ == 3 ? 0. : rop[l + 3 * nd], r = rop[l];
+        const double c = sqrt(gam2 * rop[l + 4 * nd]);
+        const double sp = sqrt(u * u + v * v + w * w);
+        const double xinvspc = 1. / (sp + c);
+        const double conv = 2. * vol[lt] * surf * xinvspc;
+        double comp = conv;
+        if (visc) {
+            const double xinvkt = gam1 / xmut[l];
+            const double vis = 2. * r * vol[lt] * vol[lt] * surf * surf * xinvkt;
+            comp = fmin(vis, conv);
+        }
+        const double cfloc = dt / comp;
+        cfl[0] = fmax(cfl[0], cfloc); cfl[1] = fmin(cfl[1], cfloc); cfl[2] = cfl[2] + cfloc;
+    }
+}
+
 /* FastS/Compute/init_rhs.for:31-129 */
 void fo_init_rhs(const int *pi, int nitcfg, const int ind[6], double *drodm)
 {

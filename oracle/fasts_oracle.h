@@ -53,6 +53,8 @@ void fo_tstb3_impli(const int *pi, const double *pr, int first_it, const int ind
 void fo_tstb3_expli(const int *pi, const double *pr, const int ind[6], const double *rop,
                double *coe, const double *xmut, const double *ti, const double *tj,
                const double *tk, const double *vol);
+void fo_cpcfl3(const int *pi, const double *pr, const int ind[6], double cfl[3], const double *rop, const double *xmut,
+               const double *ti, const double *tj, const double *tk, const double *vol);
 void fo_init_rhs(const int *pi, int nitcfg, const int ind[6], double *drodm);
 void fo_wiggle2001(const int *pi, const double *pr, const int ind[6], const double *rop, double *wig);
 void fo_spsource_SA(const int *pi, const double *pr, int nitcfg, const int ind[6], const double *xmut,

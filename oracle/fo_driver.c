@@ -73,6 +73,17 @@ static void rhs_zone(fo_zone *z, int nitcfg, int nssiter, int nitrun, int first_
                 fo_tstb3_global(pi, pr, s_coe, z->coe, z->vol);
                 fo_tstb3c(pi, pr, first_it, s_coe, rop_ssiter, z->coe, z->xmut, z->ti, z->tj, z->tk, z->vol);
             } else fo_tstb3_global(pi, pr, s_sdm, z->coe, z->vol);
+            /* cptst3.for:113-120: CFL statistics at the first sub-iteration of a check iteration; initial values and the final
+               division by the cell count: computePT.cpp:519-522, 619-645 */
+            if (lssiter_verif != 0) {
+#pragma omp barrier
+#pragma omp single
+                {
+                    z->cfl[0] = 0.; z->cfl[1] = 100000000.; z->cfl[2] = 0.;
+                    fo_cpcfl3(pi, pr, sdm, z->cfl, rop_ssiter, z->xmut, z->ti, z->tj, z->tk, z->vol);
+                    z->cfl[2] = z->cfl[2] / ((double)sdm[1] * (double)sdm[3] * (double)sdm[5]);
+                }
+            }
         }
 #pragma omp barrier
         /* src_term.for: init_rhs, SA source, sensor */
@@ -96,7 +107,6 @@ static void rhs_zone(fo_zone *z, int nitcfg, int nssiter, int nitrun, int first_
         else if (nitcfg % 2 == 1) fo_core3ark3(pi, pr, nitcfg, s_sdm, z->ro_p1, z->ro, z->drodm, z->coe);
         else fo_core3ark3(pi, pr, nitcfg, s_sdm, z->ro, z->ro_p1, z->drodm, z->coe);
     }
-    (void)lssiter_verif;
 }
 
 void fo_gsdr3(fo_zone *zones, int nz, int nitcfg, int nssiter, int nitrun, int first_it,
@@ -173,7 +183,11 @@ void fo_compute(fo_zone *zones, int nz, int nitrun, int nit, int nssiter, int mo
             fo_gsdr3(zones, nz, nstep, nssiter, nitrun_loc, *first_it, lssiter_verif, lexit_lu, pitc, prtc, nthreads);
         }
         *first_it = 1;
-        for (int n = 0; n < nz; n++) {   /* computePT.cpp:675-679 */
+        /* computePT.cpp:675-679 swaps local pointers only; the persistent rotation is FastS._compute's switchPointers__(zones,
+           case, nitmax%2+2) (S/PyTree.py:226-228), a no-op (order 2, C/PyTree.py:2299) for explicit schemes with an even number
+           of stages: RK2's last stage has written `ro` itself (gsdr3.cpp:162-173) */
+        if (itypcp == 2 && nssiter % 2 == 0) continue;
+        for (int n = 0; n < nz; n++) {
             double *sv = zones[n].ro_m1; zones[n].ro_m1 = zones[n].ro; zones[n].ro = zones[n].ro_p1; zones[n].ro_p1 = sv;
         }
     }

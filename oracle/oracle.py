@@ -85,6 +85,9 @@ class Oracle:
         for z, s in zip(self.zones, self.arr): z.fill(s)
         self.L.fo_compute(self.arr, len(self.zones), nitrun, nit, nssiter, modulo_verif, ctypes.byref(self.first_it),
                           _p(self.pitc, _ip), _p(self.prtc), nthreads)
+        from fast_b200 import VSHARE as V
+        for z, s in zip(self.zones, self.arr): z.cfl = numpy.array([s.cfl[0], s.cfl[1], s.cfl[2]])   # max, min, mean
+        if int(self.zones[0].pi[V.ITYPCP]) == 2 and nssiter % 2 == 0: return self.first_it.value   # RK2: no rotation (fo_driver.c)
         for z in self.zones:
             for _ in range(nit): z.lev = [z.lev[2], z.lev[0], z.lev[1]]   # ro<-ro_p1, ro_m1<-ro, ro_p1<-old ro_m1
         return self.first_it.value

@@ -68,6 +68,9 @@ def main_gpu(workload):
     torch.cuda.set_device(local)
     dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     n = 16 if workload != 'c5' else (16, 24, 8)
+    # last tile of a direction one cell thick (94 = 3 x 31 + 1, 17 = 2 x 8 + 1, 33 = 32 + 1) -- the second donor layer
+    # of the cut face then lives in the penultimate tile, which must belong to part 1 of the overlapped stage
+    if workload.startswith('tgv_cut_'): n = (94, 17, 33)
     t, table, peers, desc, cells = fdist.local_case(workload, rank, world, n=n)
     t, metrics, hx = fdist.warmup_rank(t, table, peers, local)
     for it in range(1, 4): FastS._compute(t, metrics, it)
@@ -85,8 +88,9 @@ def main_gpu(workload):
         j2 = synth.build_joins(layout, (2, 2, 2), (n, n, n))
     else:
         nblk = fdist.grid_for(world)
+        if workload.startswith('tgv_cut_'): nblk = tuple(world if d == 'ijk'.index(workload[-1]) else 1 for d in range(3))
         t2, layout = synth.case_tgv_blocks(n=n, nblk=nblk)
-        j2 = synth.build_joins(layout, nblk, (n, n, n), periodic=tuple(b > 1 for b in nblk))
+        j2 = synth.build_joins(layout, nblk, (n, n, n) if isinstance(n, int) else n, periodic=tuple(b > 1 for b in nblk))
     (t2, tc2, m2) = FastS.warmup(t2, j2)
     for it in range(1, 4): FastS._compute(t2, m2, it)
     FastS.sync_tree(t2)

@@ -40,7 +40,10 @@ def run_pair(kw, nit=3):
 @pytest.mark.parametrize('name', sorted(CASES))
 def test_explicit_parity(name):
     o, t2, metrics = run_pair(CASES[name])
+    crit = FastS.display_temporal_criteria(t2, metrics, 3)
     for zo, z in zip(o.zones, Internal.getZones(t2)):
+        cfl = crit[z[0]]['CFL']        # cpcfl3.for at stage 1 of a check iteration (modulo_verif = 1 here)
+        assert cfl[0] > 0. and numpy.allclose(cfl[:2], zo.cfl[:2], rtol=1e-10, atol=0.) and numpy.allclose(cfl[2], zo.cfl[2], rtol=1e-8, atol=0.)
         for lev, suf in enumerate(('', '_M1')):
             a = interior(zo.pi, FastC.block_of(z, suf)); b = interior(zo.pi, zo.lev[lev])
             assert numpy.isfinite(a).all()
@@ -49,6 +52,24 @@ def test_explicit_parity(name):
         a = FastC.block_of(z, ''); b = zo.lev[0]
         sc = numpy.abs(b).max()
         assert numpy.abs(a - b).max() / sc <= TOL
+
+
+@pytest.mark.gpu
+def test_rk2_is_heun_and_lands_in_density():
+    """Oracle-independent pin of RK2 through the FastS surface: after one iteration `Density` holds W0 + dt/2 (R0 + R1), with
+    R0 / R1 measured by two forward-Euler iterations of the same kernels (the levels do not rotate, S/PyTree.py:226-228)."""
+    from helpers import heun_pin
+    def step(t):
+        (t, tc, metrics) = FastS.warmup(t, None)
+        FastS._compute(t, metrics, 1)
+        FastS.sync_tree(t)
+        z = Internal.getZones(t)[0]
+        own = Internal.getNodeFromName1(z, '.Solver#ownData')
+        pi = Internal.getNodeFromName1(own, 'Parameter_int')[1]; pr = Internal.getNodeFromName1(own, 'Parameter_real')[1]
+        return pi, pr, interior(pi, FastC.block_of(z, '')).copy()
+    err, dist_from_stage1 = heun_pin(step)
+    assert err <= 1e-12, err
+    assert dist_from_stage1 > 1e3 * err
 
 
 @pytest.mark.gpu

@@ -63,9 +63,37 @@ def test_implicit_parity(name):
             a = interior(zo.pi, FastC.block_of(z, suf)); b = interior(zo.pi, zo.lev[lev])
             assert numpy.isfinite(a).all()
             assert relerr(a, b) <= TOL, (name, z[0], suf, relerr(a, b))
+        # CFL statistics of the check iteration (cpcfl3.for via cptst3.for:113-120; max / min exact up to the last bit of the
+        # fused arithmetic, the mean is an atomic sum in arbitrary order)
+        cfl = crit[z[0]]['CFL']
+        assert cfl[0] > 0. and numpy.allclose(cfl[:2], zo.cfl[:2], rtol=1e-10, atol=0.), (name, cfl, zo.cfl)
+        assert numpy.allclose(cfl[2], zo.cfl[2], rtol=1e-8, atol=0.), (name, cfl, zo.cfl)
+        own = Internal.getNodeFromName1(z, '.Solver#ownData')
+        assert numpy.array_equal(Internal.getNodeFromName1(own, 'CFL_minmaxmoy')[1], [cfl[1], cfl[0], cfl[2]])
+        assert crit[z[0]]['nonfinite'] == 0
         if int(zo.pi[V.ITYPCP]) <= 1:
             r = zo.rdm.reshape((nss, zo.neq, 2), order='F')
             ncell = float(zo.pi[V.IJKV]) * float(zo.pi[V.IJKV + 1]) * float(zo.pi[V.IJKV + 2])
             l2 = numpy.sqrt(r[:, :, 0] / ncell)
             assert numpy.allclose(crit[z[0]]['L2'], l2, rtol=1e-8, atol=1e-300)
             assert numpy.allclose(crit[z[0]]['Loo'], r[:, :, 1], rtol=1e-8, atol=1e-300)
+
+
+@pytest.mark.gpu
+def test_device_isfinite_check_raises():
+    """stopAtNan (S/PyTree.py:2070-2073): a NaN planted in the state is seen by the device-side checks of the next check
+    iteration and display_temporal_criteria raises."""
+    t, j = synth.case_flatplate(n=(16, 12, 4))
+    (t, tc, metrics) = FastS.warmup(t, j)
+    FastS._compute(t, metrics, 1)
+    assert FastS.display_temporal_criteria(t, metrics, 1)[Internal.getZones(t)[0][0]]['nonfinite'] == 0
+    z = Internal.getZones(t)[0]
+    FastS.sync_tree(t)
+    blk = FastC.block_of(z, '')
+    pi = Internal.getNodeFromName1(Internal.getNodeFromName1(z, '.Solver#ownData'), 'Parameter_int')[1]
+    interior(pi, blk)[4, 1, 5, 7] = numpy.nan
+    from fast_b200 import _lib
+    import ctypes
+    _lib.check(_lib.lib().fb_zone_upload_state(FastC.HOOK['solver'], 0, 0, blk.ctypes.data_as(_lib.c_dp)))
+    FastS._compute(t, metrics, 2)
+    with pytest.raises(FloatingPointError): FastS.display_temporal_criteria(t, metrics, 2)

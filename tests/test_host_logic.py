@@ -112,17 +112,22 @@ def test_overlap_tile_order_is_a_face_first_bijection():
     L = _lib.lib()
     for gx, gy, gz in itertools.product((1, 2, 3, 5), (1, 2, 4), (1, 2, 3)):
         n = gx * gy * gz
+        g = (gx, gy, gz)
         for faces in range(64):
-            out = (ctypes.c_int * (3 * n))(); nf = ctypes.c_int(0)
-            assert L.fb_debug_tile_order(gx, gy, gz, faces, out, ctypes.byref(nf)) == 0
-            tiles = [(out[3 * c], out[3 * c + 1], out[3 * c + 2]) for c in range(n)]
-            assert len(set(tiles)) == n and all(0 <= x < gx and 0 <= y < gy and 0 <= z < gz for x, y, z in tiles)
+            for thin in (0, 1, 2, 4, 7):
+                out = (ctypes.c_int * (3 * n))(); nf = ctypes.c_int(0)
+                assert L.fb_debug_tile_order(gx, gy, gz, faces, thin, out, ctypes.byref(nf)) == 0
+                tiles = [(out[3 * c], out[3 * c + 1], out[3 * c + 2]) for c in range(n)]
+                assert len(set(tiles)) == n and all(0 <= x < gx and 0 <= y < gy and 0 <= z < gz for x, y, z in tiles)
+                # layers of part 1 behind every face: 1, or 2 on an upper face whose last tile is a single cell thick (ADVICE r1:
+                # the second donor layer then lives in the penultimate tile), never more than the direction holds
+                lo = [(faces >> (2 * d)) & 1 for d in range(3)]
+                hi = [min(((faces >> (2 * d + 1)) & 1) * (2 if (thin >> d) & 1 else 1), g[d] - lo[d]) for d in range(3)]
 
-            def on_face(t):
-                g = (gx, gy, gz)
-                return any(((faces >> (2 * d)) & 1 and t[d] == 0) or ((faces >> (2 * d + 1)) & 1 and t[d] == g[d] - 1) for d in range(3))
-            assert all(on_face(t) for t in tiles[:nf.value]) and not any(on_face(t) for t in tiles[nf.value:]), (gx, gy, gz, faces)
-    assert L.fb_debug_tile_order(0, 1, 1, 0, None, None) != 0
+                def on_face(t):
+                    return any(t[d] < lo[d] or t[d] >= g[d] - hi[d] for d in range(3))
+                assert all(on_face(t) for t in tiles[:nf.value]) and not any(on_face(t) for t in tiles[nf.value:]), (gx, gy, gz, faces, thin)
+    assert L.fb_debug_tile_order(0, 1, 1, 0, 0, None, None) != 0
 
 
 def test_no_cpu_fallback():

@@ -50,7 +50,7 @@ def test_c5_bricks(world):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('workload', ['tgv', 'multiblock', 'c5'])
+@pytest.mark.parametrize('workload', ['tgv', 'multiblock', 'c5', 'tgv_cut_i', 'tgv_cut_j', 'tgv_cut_k'])
 def test_sharded_solve_nccl(workload):
     import torch
     if torch.cuda.device_count() < 2: pytest.skip("needs 2 GPUs (run: gpurun --gpus 2 -- python -m pytest tests -m gpu -k nccl)")

@@ -47,6 +47,18 @@ def test_roe_wall_flux_correction_keeps_fluid_at_rest(wall):
         assert numpy.abs(a[e] - v).max() < 5e-13
 
 
+def test_rk2_is_heun_and_lands_in_density():
+    """RK2 (the time levels must NOT rotate after an even number of explicit stages)."""
+    from helpers import heun_pin
+    def step(t):
+        o = oracle_from_tree(t); z = o.zones[0]
+        o.compute(1, 1, int(z.pi[V.NSSITER]), 1)
+        return z.pi, z.pr, interior(z.pi, z.lev[0]).copy()
+    err, dist_from_stage1 = heun_pin(step)
+    assert err <= 1e-12, err
+    assert dist_from_stage1 > 1e3 * err          # ... and it is not the forward-Euler intermediate
+
+
 def test_conservation_periodic():
     """Telescoping fluxes: total mass, momentum and energy constant to round-off in a periodic Cartesian box (Euler:
     the viscous cross terms read the edge ghost cells, which correct_coins replaces by averages -- reference behaviour)."""
