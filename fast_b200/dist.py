@@ -60,6 +60,9 @@ class HaloExchange:
         L.fb_set_exchange_cb.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         _lib.check(L.fb_set_exchange_cb(solver, ctypes.cast(self._cb, ctypes.c_void_p), None))
 
+    def describe(self):
+        return 'NCCL isend/irecv per neighbour (torch.distributed) on the exchange stream'
+
     def _exchange(self, user, which):
         torch, dist = self.torch, self.dist
         self.calls += 1

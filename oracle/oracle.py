@@ -49,7 +49,7 @@ class Zone:
         self.ti = numpy.zeros(nm * int(pi[V.NEQ_IJ])); self.tj = numpy.zeros(nm * int(pi[V.NEQ_IJ]))
         self.tk = numpy.zeros(nm * max(int(pi[V.NEQ_K]), 1)); self.vol = numpy.zeros(nm)
         self.drodm = numpy.zeros(nd * neq); self.coe = numpy.zeros(nd * max(int(pi[V.NEQ_COE]), 1))
-        self.wig = numpy.zeros(nd * 3)
+        self.wig = numpy.zeros(nd * 3 if int(pi[V.KFLUDOM]) == 2 else 3)     # SENSOR switch (wiggle2001.for)
         nblk = 1
         self.rdm = numpy.zeros(int(pi[V.NSSITER]) * neq * 2 * nblk)
         self.neq = neq; self.nd = nd

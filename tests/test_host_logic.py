@@ -142,3 +142,16 @@ def test_no_cpu_fallback():
     for f in glob.glob(os.path.join(ROOT, 'fast_b200', '**', '*.py'), recursive=True) + \
             glob.glob(os.path.join(ROOT, 'fast_b200', 'csrc', '*.cu*')):
         assert 'oracle' not in open(f).read().lower(), f + " must not reference the oracle"
+
+
+def test_bench_reference_arm_contract():
+    """bench.py --impl reference: one JSON line with the contract keys, the oracle timed on the requested mesh (tiny here)."""
+    import json, subprocess, sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--n', '12,12,8', '--steps', '2', '--warmup', '1',
+                        '--ref-budget', '0.5'], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d['impl'] == 'reference' and d['unit'] == 'Mcell.it/s' and d['value'] > 0 and d['higher_is_better'] is True
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
+    assert d['e2e'] == {'value': d['value'], 'unit': 'Mcell.it/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    assert 'configs[4]' in d['config']['workload'] and d['config']['steps_timed'] >= 2

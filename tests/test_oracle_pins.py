@@ -59,6 +59,24 @@ def test_rk2_is_heun_and_lands_in_density():
     assert dist_from_stage1 > 1e3 * err          # ... and it is not the forward-Euler intermediate
 
 
+@pytest.mark.parametrize('case', ['tgv', 'plate_blocks', 'multiblock'])
+def test_threaded_oracle_is_bit_identical(case):
+    """The thread decomposition of the oracle (k slabs for the rhs, one zone per thread for the LU) used by the full-size GPU
+    parity tests and the timed CPU baseline must not change a single bit of the result."""
+    def mk():
+        if case == 'tgv': return synth.case_tgv(n=20, perturb=1e-3), None
+        if case == 'plate_blocks': return synth.case_flatplate(n=(24, 16, 12), nblocks=(2, 1, 2))
+        return synth.case_multiblock(nblk=(2, 1, 2), n=10)
+    res = []
+    for nth in (1, 5):
+        t, j = mk()
+        o = oracle_from_tree(t, joins=j)
+        nss = int(o.zones[0].pi[V.NSSITER])
+        for it in (1, 2): o.compute(it, 1, nss, 1, nthreads=nth)
+        res.append([z.lev[0].copy() for z in o.zones])
+    for a, b in zip(*res): assert numpy.array_equal(a, b)
+
+
 def test_conservation_periodic():
     """Telescoping fluxes: total mass, momentum and energy constant to round-off in a periodic Cartesian box (Euler:
     the viscous cross terms read the edge ghost cells, which correct_coins replaces by averages -- reference behaviour)."""
