@@ -171,6 +171,8 @@ def measure(workload, steps, warmup, ctx, do_e2e=True, min_timed_s=0.):
         cells += int(pi[V.IJKV]) * int(pi[V.IJKV + 1]) * int(pi[V.IJKV + 2])
     if cells_total is None: cells_total = cells
     stream = torch.cuda.ExternalStream(L.fb_stream(s))
+    v0 = ctypes.c_longlong(0); _lib.check(L.fb_counter(b'lu_batch', ctypes.byref(v0)))
+    lu_batch0 = int(v0.value)          # process-wide counter: launches of the multi-zone LU kernel before this workload
 
     def fence():
         torch.cuda.synchronize(); _lib.check(L.fb_sync(s))
@@ -182,12 +184,13 @@ def measure(workload, steps, warmup, ctx, do_e2e=True, min_timed_s=0.):
 
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     nit = 1
-    fence(); e0.record(stream)
+    fence()
     for w in range(warmup):
+        if w == warmup - 1: e0.record(stream)
         FastS._compute(t, metrics, nit); nit += 1
     e1.record(stream); fence()
     if min_timed_s > 0. and warmup > 0:      # secondary workloads: enough iterations for a timed region of min_timed_s
-        per = max_over_ranks(e0.elapsed_time(e1)) / warmup * 1e-3
+        per = max_over_ranks(e0.elapsed_time(e1)) * 1e-3
         steps = max(steps, int(min_timed_s / max(per, 1e-6)) + 1)
     _lib.check(L.fb_timing_enable(s, 1)); _lib.check(L.fb_timing_reset(s))
     clk = Clocks(); clk.start()
@@ -218,7 +221,7 @@ def measure(workload, steps, warmup, ctx, do_e2e=True, min_timed_s=0.):
     per_kernel = {rhs_kern: {'avg_launch_ms_per_zone': tm['rhs'] / (steps * nsub * len(zones)), 'bytes_per_cell': b_rhs,
                              'GBs': cells * b_rhs * nsub * steps / (tm['rhs'] * 1e-3) / 1e9 if tm['rhs'] else None}}
     if implicit and tm['lu']:
-        per_kernel['k_lu_tile_b' if ctx['lu_batch0'] < cnt['lu_batch'] else 'k_lu_tile'] = {
+        per_kernel['k_lu_tile_b' if lu_batch0 < cnt['lu_batch'] else 'k_lu_tile'] = {
             'avg_sweep_ms_all_zones': tm['lu'] / (2 * steps * nsub), 'bytes_per_cell': b_lu,
             'GBs': cells * b_lu * 2 * nsub * steps / (tm['lu'] * 1e-3) / 1e9}
     for k in per_kernel.values():
@@ -226,14 +229,13 @@ def measure(workload, steps, warmup, ctx, do_e2e=True, min_timed_s=0.):
     if tm['lu'] > tm['rhs']:
         kern = 'k_lu_tile'
         nl, bpl = 2 * steps * nsub * len(zones), b_lu   # lower + upper launch
-        if ctx['lu_batch0'] < cnt['lu_batch']:      # one lower + one upper launch sweep ALL zones of the rank (k_lu_tile_b)
+        if lu_batch0 < cnt['lu_batch']:      # one lower + one upper launch sweep ALL zones of the rank (k_lu_tile_b)
             kern, nl, cz = 'k_lu_tile_b', 2 * steps * nsub, cells
         avg_ms = tm['lu'] / nl
     else:
         kern = rhs_kern
         nl, bpl = steps * nsub * len(zones), b_rhs
         avg_ms = tm['rhs'] / nl
-    ctx['lu_batch0'] = cnt['lu_batch']
     ach = cz * bpl / (avg_ms * 1e-3) / 1e9
     sub_gbs = cells_total * b_sub * nsub * steps / (ms * 1e-3) / 1e9
     roof = {'bound': 'hbm', 'kernel': kern, 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
@@ -301,7 +303,7 @@ def run_gpu(args):
     if world == 1 and not args.no_secondary:
         for w in WORKLOADS:
             if w == args.workload: continue
-            r = measure(w, min(args.steps, 10), max(3, min(args.warmup, 5)), ctx, do_e2e=not args.no_e2e, min_timed_s=0.5)
+            r = measure(w, min(args.steps, 10), max(3, min(args.warmup, 5)), ctx, do_e2e=not args.no_e2e, min_timed_s=1.0)
             if not args.no_cpu:
                 cv, nth, sample, _, _, _ = cpu_oracle_rate(w, n=CPU_SAMPLE[w], budget_s=4.)
                 r['cpu_baseline'] = {'value': cv, 'unit': 'Mcell.it/s', 'cores': nth, 'kind': 'port', 'sample': sample}
