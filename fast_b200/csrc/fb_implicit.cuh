@@ -12,6 +12,7 @@ struct LuPlan {
     int modulo_verif = 0;
     // tile-pipelined wavefront (fb_lu.cu)
     int tj = 8, tk = 8, NJ = 0, NK = 0;   // tile size in j and k (lines), tiles per direction of the (j,k) cross-section
+    bool cell = false;                // thread-per-cell kernel k_lu_cell (16-byte staging) instead of k_lu_tile
     int *d_order = nullptr;           // ticket -> tile, i+j+k order
     int *d_ctl = nullptr;             // [ticket lower, ticket upper, error flag, pad]
     double *d_mb = nullptr;           // inter-tile mailboxes: j interfaces then k interfaces

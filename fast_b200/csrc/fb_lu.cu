@@ -431,6 +431,354 @@ __global__ void __launch_bounds__(LU_NT, 1) k_lu_tile_b(const LuBatchItem *items
     lu_tile_body<MESH, NEQ, UPPER>(s_it.z, s_it.a, s_t.y, smem);
 }
 
+// ================================================================================================ k_lu_cell
+// Thread-per-cell variant of the same tile-pipelined wavefront (default whenever the zone's arrays allow 16-byte staging:
+// NDIMDX even, ni*nj even for the plane-shaped 3dhomo normals; k_lu_tile above stays the 8-byte path for the other zones).
+// What changed against k_lu_tile, and why (profiles/r01_summary.md: the four-lanes-per-line step was a chain of 207 / 255
+// instructions per warp at 5.5 - 8 cycles each, every lane redoing dW*, the Newton update evaluated by all four lanes AND again
+// by the write-back role):
+//   * ONE thread owns a line: it gathers the three incoming products, forms dW, evaluates the three outgoing products (their
+//     common factors once), keeps B_i.dW in registers for its own next cell and, in the upper sweep, applies the Newton update
+//     once -- the updated state feeds both the k product (aliased sweeps) and the write-back.  ~4x fewer instructions per cell.
+//   * a tile is 8 x 16 lines (8 x 12 for 3dfull SA): 128 cells per step and CTA instead of 64, four compute warps (one per
+//     scheduler) + four service warps.
+//   * the ring holds 8 cells per line (four 16-byte granules of two cells) instead of 16: the service thread of a line fetches
+//     the granule of the cell needed four steps ahead with ONE 16-byte cp.async per staged array, and writes results back as
+//     16-byte stores once both cells of a granule are final.  Granules are aligned on even cell addresses, whatever the
+//     parity of the line start, in both sweep directions.
+//   * shared-memory layouts are chosen for the thread-per-line access: ring[array][granule][line][2] (8-byte accesses of 32
+//     consecutive lines: 2-way conflicts at worst), exchange buffers [dir][line][6] (16-byte accesses, conflict-free).
+// Mailboxes, tickets, error flag and the (J + K) tile order are those of k_lu_tile.
+#define LC_PF 4            // refill distance (steps)
+#define LC_NG 4            // granules per line in the ring
+#define LC_NSV 128         // service threads
+
+template <int MESH, int NEQ, bool UPPER>
+struct LcCfg {
+    static constexpr int TJ = 8;
+    static constexpr int TK = (MESH == 0 && NEQ == 6) ? 12 : 16;
+    static constexpr int L = TJ * TK;
+    static constexpr int NC = NEQ == 6 ? 6 : 5;
+    static constexpr int NS = UPPER ? NEQ : 4;
+    static constexpr int S0 = UPPER ? 0 : 1;
+    static constexpr int NT = MESH == 0 ? 9 : (MESH == 1 ? 5 : 0);
+    static constexpr int A_DW = 0, A_COE = NEQ, A_ST = NEQ + NC, A_T = NEQ + NC + NS;
+    static constexpr int A = NEQ + NC + NS + NT;
+    static constexpr int NIF = TJ + TK;                 // interface lines: TK towards (J-1,K), TJ towards (J,K-1)
+    static constexpr int NTHR = L + LC_NSV;
+    static constexpr int AS = LC_NG * L * 2;            // doubles per staged array
+    static constexpr size_t SMEM = (size_t)(A * AS + 2 * 2 * L * LU_MB + 6 * NIF * LU_MB) * sizeof(double);
+};
+int lu_cell_tk(int mesh, int neq) { return (mesh == 0 && neq == 6) ? 12 : 16; }
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+
+template <int MESH, int NEQ, bool UPPER>
+__device__ __forceinline__ void lu_cell_body(const ZoneDev &z, const LuTileArgs &a, const int tile, double *smem)
+{
+    using C = LcCfg<MESH, NEQ, UPPER>;
+    constexpr int TJ = C::TJ, TK = C::TK, L = C::L, EX = LU_MB, NIF = C::NIF, AS = C::AS;
+    double *ring = smem;                                   // [A][LC_NG][L][2]
+    double *exb = smem + C::A * AS;                        // [2][2][L][EX]: products handed to (jj+1) and (kk+1)
+    unsigned long long *mbs = (unsigned long long *)(exb + 2 * 2 * L * EX);   // [4][NIF][EX] prefetched mailbox words
+    double *mbx = (double *)(mbs + 4 * NIF * EX);          // [2][NIF][EX] validated products of the neighbour tiles
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 2 * 2 * L * EX + 6 * NIF * EX; i += C::NTHR) exb[i] = 0.;
+    __syncthreads();
+    const int J = tile & 0xffff, K = tile >> 16;
+    const int bi = a.bi, bj = a.bj, bk = a.bk;
+    const int nst = bi + TJ + TK - 2;
+    const int nd = z.nd;
+    const int sg = UPPER ? -1 : 1;
+    const int l0 = UPPER ? inddm(z, a.box[1], a.box[3], a.box[5]) : inddm(z, a.box[0], a.box[2], a.box[4]);
+
+    if (tid >= L) {
+        // ------------------------------------------------------------------------------------ service warps
+        const int st = tid - L;
+        // -- the line this thread stages (refill + write-back)
+        const int lam = st, jj = lam % TJ, kk = lam / TJ;
+        const int jjg = J * TJ + jj, kkg = K * TK + kk;
+        const bool lok = lam < L && jjg < bj && kkg < bk;
+        const int sigma = jj + kk;
+        const int lrow = l0 + sg * (jjg * z.incj + kkg * z.inck);
+        const int jg = UPPER ? a.box[3] - jjg : a.box[2] + jjg, kg = UPPER ? a.box[5] - kkg : a.box[4] + kkg;
+        const bool line_in_nb = jg >= a.nbx[2] && jg <= a.nbx[3] && kg >= a.nbx[4] && kg <= a.nbx[5];
+        auto refill = [&](int s) {
+            const int ii = s + LC_PF - sigma;
+            if (!(lok && ii >= 0 && ii < bi)) return;
+            const int ca = lrow + sg * ii;
+            if (!(ii == 0 || (ca & 1) == (UPPER ? 1 : 0))) return;      // the granule was fetched with its first cell
+            const int G = ca >> 1;
+            double *dst = ring + ((size_t)((G & (LC_NG - 1)) * L + lam)) * 2;
+            const int g0 = 2 * G;
+#pragma unroll
+            for (int e = 0; e < NEQ; e++) cp_async16(dst + (size_t)(C::A_DW + e) * AS, a.dw + g0 + e * nd);
+#pragma unroll
+            for (int e = 0; e < C::NC; e++) cp_async16(dst + (size_t)(C::A_COE + e) * AS, a.coe + g0 + e * nd);
+#pragma unroll
+            for (int e = 0; e < C::NS; e++) cp_async16(dst + (size_t)(C::A_ST + e) * AS, a.rop + g0 + (C::S0 + e) * nd);
+            if (MESH != 2) {
+                const int gt = MESH == 1 ? g0 % a.plane : g0;
+#pragma unroll
+                for (int e = 0; e < C::NT; e++) cp_async16(dst + (size_t)(C::A_T + e) * AS, a.tcm + gt + e * a.tstride);
+            }
+        };
+        // results of the cell computed two steps ago; a granule leaves as one 16-byte store once its second cell is final
+        auto writeback = [&](int s) {
+            const int ii = s - 2 - sigma;
+            if (!(lok && ii >= 0 && ii < bi)) return;
+            const int ca = lrow + sg * ii;
+            const bool second = (ca & 1) == (UPPER ? 0 : 1);
+            const bool last = ii == bi - 1;
+            if (!second && !last) return;
+            const bool nwt = UPPER && a.newton;
+            bool v1 = true, v0 = second && ii >= 1;              // this cell, its partner (ii - 1) in the same granule
+            if (nwt) {
+                const int ig = a.box[1] - ii;
+                v1 = line_in_nb && ig >= a.nbx[0] && ig <= a.nbx[1];
+                v0 = v0 && line_in_nb && ig + 1 >= a.nbx[0] && ig + 1 <= a.nbx[1];
+            }
+            if (!v1 && !v0) return;
+            const int G = ca >> 1;
+            const double *src = ring + ((size_t)((G & (LC_NG - 1)) * L + lam)) * 2;
+            double *out = nwt ? a.rop_out : a.dw;
+            constexpr int A0 = UPPER ? C::A_ST : C::A_DW;       // (upper, newton = 0: dW from the A_DW slots, below)
+            const int arr0 = nwt ? A0 : C::A_DW;
+            const int cb = ca - sg;                              // partner address
+            if (v1 && v0) {
+#pragma unroll
+                for (int e = 0; e < NEQ; e++)
+                    *(double2 *)(out + 2 * G + (size_t)e * nd) = *(const double2 *)(src + (size_t)(arr0 + e) * AS);
+            } else {
+                const int c1 = v1 ? ca : cb;
+#pragma unroll
+                for (int e = 0; e < NEQ; e++) out[c1 + (size_t)e * nd] = src[(size_t)(arr0 + e) * AS + (c1 & 1)];
+            }
+        };
+        // -- mailboxes: thread st < 3 NIF owns 16 bytes of the entry of interface line il (0..TK-1: j interface, row kk = il;
+        // TK..: k interface, column jj = il - TK).  Words needed at step X are loaded at iteration X-3 (registers carried over
+        // the loop edge), parked in shared memory at X-2 and, before the barrier of step X, delivered validated into mbx
+        // (polling global memory while the producer tile has not delivered); the entry is re-armed.
+        const int il = st / 3, part = st % 3;
+        const bool isj = il < TK;
+        const int mjj = isj ? 0 : il - TK, mkk = isj ? il : 0;
+        const int mjg = J * TJ + mjj, mkg = K * TK + mkk;
+        const bool mth = st < 3 * NIF;
+        const bool mvalid = mth && mjg < bj && mkg < bk && (isj ? J > 0 : K > 0);
+        volatile unsigned long long *mrow = (volatile unsigned long long *)a.order;   // harmless readable dummy
+        if (mvalid) mrow = (unsigned long long *)(isj ? a.ifj + ((size_t)((J - 1) * bk + mkg) * bi) * LU_MB
+                                                        : a.ifk + ((size_t)((K - 1) * bj + mjg) * bi) * LU_MB) + 2 * part;
+        const int msig = mjj + mkk;
+        unsigned long long *mpre = mbs + (size_t)(mth ? il : 0) * EX + 2 * part;     // + (step & 3) * NIF * EX
+        double *mout = mbx + (size_t)(mth ? il : 0) * EX + 2 * part;                  // + (step & 1) * NIF * EX
+        auto entry = [&](int X) {    // clamped: always a readable address
+            int ii = X - msig; ii = ii < 0 ? 0 : (ii >= bi ? bi - 1 : ii);
+            return mrow + (mvalid ? (size_t)ii * LU_MB : 0);
+        };
+        auto needed = [&](int X) { const int ii = X - msig; return mvalid && ii >= 0 && ii < bi; };
+        auto deliver = [&](int X) {
+            if (!needed(X)) return;
+            const unsigned long long *pre = mpre + (size_t)(X & 3) * NIF * EX;
+            unsigned long long v0 = pre[0], v1 = pre[1];
+            volatile unsigned long long *p = entry(X);
+            int spin = 0;
+            while (mb_empty(v0) || mb_empty(v1)) {
+                v0 = p[0]; v1 = p[1];
+                if (++spin > LU_SPIN_MAX || (((spin & 1023) == 0) && *(volatile int *)a.err)) { *a.err = 1; break; }
+            }
+            double *o = mout + (size_t)(X & 1) * NIF * EX;
+            o[0] = __longlong_as_double((long long)v0); o[1] = __longlong_as_double((long long)v1);
+            p[0] = LU_EMPTY; p[1] = LU_EMPTY;                                  // self-cleaning: ready for the next sweep
+        };
+        for (int X = 0; X < 2; X++) {
+            volatile unsigned long long *p = entry(X);
+            unsigned long long *d = mpre + (size_t)(X & 3) * NIF * EX;
+            if (mth) { d[0] = p[0]; d[1] = p[1]; }
+        }
+        unsigned long long w0 = 0, w1 = 0;
+        if (mth) { volatile unsigned long long *p = entry(2); w0 = p[0]; w1 = p[1]; }
+        for (int s = -LC_PF; s < 0; s++) { refill(s); cp_async_commit(); }
+        for (int s = 0; s < nst; s++) {
+            refill(s);
+            cp_async_commit();
+            if (mth) {
+                unsigned long long *d = mpre + (size_t)((s + 2) & 3) * NIF * EX; d[0] = w0; d[1] = w1;
+                volatile unsigned long long *p = entry(s + 3); w0 = p[0]; w1 = p[1];
+            }
+            writeback(s);
+            deliver(s);
+            cp_async_wait<LC_PF>();
+            __syncthreads();
+        }
+        __syncthreads();
+        cp_async_wait<0>();
+        writeback(nst); writeback(nst + 1);
+        return;
+    }
+
+    // ---------------------------------------------------------------------------------------- compute warps: one thread per line
+    const int lam = tid;
+    const int jj = lam % TJ, kk = lam / TJ;
+    const int jjg = J * TJ + jj, kkg = K * TK + kk;
+    const bool lvalid = jjg < bj && kkg < bk;
+    const int sigma = jj + kk;
+    const int lrow = l0 + sg * (jjg * z.incj + kkg * z.inck);
+    const bool has_j = jjg > 0, has_k = kkg > 0;
+    volatile unsigned long long *mbj = nullptr, *mbk = nullptr;
+    if (lvalid && jj == TJ - 1 && J + 1 < a.NJ) mbj = (unsigned long long *)(a.ifj + ((size_t)(J * bk + kkg) * bi) * LU_MB);
+    if (lvalid && kk == TK - 1 && K + 1 < a.NK) mbk = (unsigned long long *)(a.ifk + ((size_t)(K * bj + jjg) * bi) * LU_MB);
+    const int jg = UPPER ? a.box[3] - jjg : a.box[2] + jjg, kg = UPPER ? a.box[5] - kkg : a.box[4] + kkg;
+    const bool line_in_nb = jg >= a.nbx[2] && jg <= a.nbx[3] && kg >= a.nbx[4] && kg <= a.nbx[5];
+    const double signe = UPPER ? -0.5 : 0.5;
+    const double gam = z.gam, cp = z.gam * z.cv;
+    // incoming j / k products: neighbour line of the tile (exb, other parity) or neighbour tile (mbx)
+    const int offj = jj > 0 ? (lam - 1) * EX : -1, offk = kk > 0 ? (L + lam - TJ) * EX : -1;
+    const int mofj = kk * EX, mofk = (TK + jj) * EX;
+    double pi_[EX];
+#pragma unroll
+    for (int e = 0; e < EX; e++) pi_[e] = 0.;
+    for (int s = 0; s < nst; s++) {
+        __syncthreads();
+        const int ii = s - sigma;
+        if (!(lvalid && ii >= 0 && ii < bi)) continue;
+        const int ca = lrow + sg * ii;
+        double *R = ring + ((size_t)(((ca >> 1) & (LC_NG - 1)) * L + lam)) * 2 + (ca & 1);
+#define RING(arr) R[(size_t)(arr) * AS]
+        double acc[NEQ];
+#pragma unroll
+        for (int e = 0; e < NEQ; e++) acc[e] = RING(C::A_DW + e);
+        const double coe1 = RING(C::A_COE), coe5 = RING(C::A_COE + 4);
+        double coe6 = 1.;
+        if (NEQ == 6) coe6 = RING(C::A_COE + 5);
+        double ro = 0., u, v, w, t, nut = 0.;
+        if (UPPER) {
+            ro = RING(C::A_ST); u = RING(C::A_ST + 1); v = RING(C::A_ST + 2); w = RING(C::A_ST + 3); t = RING(C::A_ST + 4);
+            if (NEQ == 6) nut = RING(C::A_ST + NEQ - 1);
+        } else { u = RING(C::A_ST); v = RING(C::A_ST + 1); w = RING(C::A_ST + 2); t = RING(C::A_ST + 3); }
+        double ti0 = 0., ti1 = 0., ti2 = 0., tj0 = 0., tj1 = 0., tj2 = 0., tk0 = 0., tk1 = 0., tk2 = 0.;
+        if (MESH == 0) {
+            ti0 = RING(C::A_T); ti1 = RING(C::A_T + 1); ti2 = RING(C::A_T + 2); tj0 = RING(C::A_T + 3); tj1 = RING(C::A_T + 4);
+            tj2 = RING(C::A_T + 5); tk0 = RING(C::A_T + 6); tk1 = RING(C::A_T + 7); tk2 = RING(C::A_T + 8);
+        } else if (MESH == 1) {
+            ti0 = RING(C::A_T); ti1 = RING(C::A_T + 1); tj0 = RING(C::A_T + 2); tj1 = RING(C::A_T + 3); tk2 = RING(C::A_T + 4);
+        } else { ti0 = z.tc0[0]; tj1 = z.tc0[1]; tk2 = z.tc0[2]; }
+        const double cdi = RING(C::A_COE + 1) * signe, cdj = RING(C::A_COE + 2) * signe, cdk = RING(C::A_COE + 3) * signe;
+        const double *xin = exb + (size_t)((s + 1) & 1) * 2 * L * EX;
+        const double *xmb = mbx + (size_t)(s & 1) * NIF * EX;
+        const double2 *pj_ = (const double2 *)(offj >= 0 ? xin + offj : xmb + mofj);
+        const double2 *pk_ = (const double2 *)(offk >= 0 ? xin + offk : xmb + mofk);
+        const double2 j0 = pj_[0], j1 = pj_[1], j2 = pj_[2], k0 = pk_[0], k1 = pk_[1], k2 = pk_[2];
+        const double xal = coe1 * signe;
+        const double xi = ii > 0 ? xal : 0., xj = has_j ? xal : 0., xk = has_k ? xal : 0.;
+        if (UPPER) {
+#pragma unroll
+            for (int e = 0; e < 5; e++) acc[e] = acc[e] * coe5;
+            if (NEQ == 6) acc[NEQ - 1] = acc[NEQ - 1] * coe6;
+        }
+        // the sum follows the reference's k, j, i order (invlu_l.for / invlu_u.for)
+        acc[0] = ((acc[0] + k0.x * xk) + j0.x * xj) + pi_[0] * xi;
+        acc[1] = ((acc[1] + k0.y * xk) + j0.y * xj) + pi_[1] * xi;
+        acc[2] = ((acc[2] + k1.x * xk) + j1.x * xj) + pi_[2] * xi;
+        acc[3] = ((acc[3] + k1.y * xk) + j1.y * xj) + pi_[3] * xi;
+        acc[4] = ((acc[4] + k2.x * xk) + j2.x * xj) + pi_[4] * xi;
+        if (NEQ == 6) acc[NEQ - 1] = ((acc[NEQ - 1] + k2.y * xk) + j2.y * xj) + pi_[EX - 1] * xi;
+        const double diag = lu_rcp(coe5);
+        double dwn[NEQ];
+#pragma unroll
+        for (int e = 0; e < 5; e++) dwn[e] = acc[e] * diag;
+        if (NEQ == 6) dwn[NEQ - 1] = acc[NEQ - 1] * lu_rcp(coe6);
+        double uk = u, vk = v, wk = w, tk_ = t;     // state of the k product
+        if (UPPER && a.newton) {
+            // mjr_newton[_SA].for, once per cell: the updated state goes back through the ring (write-back role) and, when rop
+            // aliases rop_out, into the k product -- the reference has already updated plane k+1 when it sweeps plane k
+            const int ig = a.box[1] - ii;
+            const bool in_nb = line_in_nb && ig >= a.nbx[0] && ig <= a.nbx[1];
+            const double cvinv = 1. / z.cv, cvinv2 = 0.5 * cvinv;
+            const double rn = ro + dwn[0];
+            const double r_1 = lu_rcp(rn);
+            const double un = (ro * u + dwn[1]) * r_1, vn = (ro * v + dwn[2]) * r_1, wn = (ro * w + dwn[3]) * r_1;
+            const double roe_old = ro * (z.cv * t + 0.5 * (u * u + v * v + w * w));
+            const double tn = (roe_old + dwn[4]) * r_1 * cvinv - cvinv2 * (un * un + vn * vn + wn * wn);
+            if (in_nb) {
+                RING(C::A_ST) = rn; RING(C::A_ST + 1) = un; RING(C::A_ST + 2) = vn; RING(C::A_ST + 3) = wn; RING(C::A_ST + 4) = tn;
+                if (NEQ == 6) {
+                    double anulam = z.coesut * sqrt(tn * z.temp01) * tn * lu_rcp(tn + z.cmus1);   // = coesut sqrt(T/T0) / (1 + Cs/T)
+                    anulam = anulam * r_1 * z.ratiom;
+                    double tt = (ro * nut + dwn[NEQ - 1]) * r_1;
+                    tt = fmin(tt, anulam);
+                    RING(C::A_ST + NEQ - 1) = fmax(tt, 0.);
+                }
+                if (a.alias) { uk = un; vk = vn; wk = wn; tk_ = tn; }
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < NEQ; e++) RING(C::A_DW + e) = dwn[e];
+        }
+        // outgoing products
+        double bj_[EX], bk_[EX];
+        pi_[EX - 1] = 0.; bj_[EX - 1] = 0.; bk_[EX - 1] = 0.;
+        lu_prod<NEQ>(ti0, ti1, ti2, u, v, w, t, cdi, gam, cp, dwn, pi_);
+        lu_prod<NEQ>(tj0, tj1, tj2, u, v, w, t, cdj, gam, cp, dwn, bj_);
+        lu_prod<NEQ>(tk0, tk1, tk2, uk, vk, wk, tk_, cdk, gam, cp, dwn, bk_);
+        {
+            double2 *p = (double2 *)(exb + ((size_t)(s & 1) * 2 * L + lam) * EX);
+            p[0] = make_double2(bj_[0], bj_[1]); p[1] = make_double2(bj_[2], bj_[3]); p[2] = make_double2(bj_[4], bj_[5]);
+            double2 *q = (double2 *)(exb + ((size_t)(s & 1) * 2 * L + L + lam) * EX);
+            q[0] = make_double2(bk_[0], bk_[1]); q[1] = make_double2(bk_[2], bk_[3]); q[2] = make_double2(bk_[4], bk_[5]);
+        }
+        if (mbj) {
+            volatile unsigned long long *o = mbj + (size_t)ii * LU_MB;
+#pragma unroll
+            for (int e = 0; e < LU_MB; e++) o[e] = (unsigned long long)__double_as_longlong(bj_[e]);
+        }
+        if (mbk) {
+            volatile unsigned long long *o = mbk + (size_t)ii * LU_MB;
+#pragma unroll
+            for (int e = 0; e < LU_MB; e++) o[e] = (unsigned long long)__double_as_longlong(bk_[e]);
+        }
+#undef RING
+    }
+    __syncthreads();
+}
+
+template <int MESH, int NEQ, bool UPPER>
+__global__ void __launch_bounds__(LcCfg<MESH, NEQ, UPPER>::NTHR, 1) k_lu_cell(ZoneDev z, LuTileArgs a)
+{
+    extern __shared__ __align__(16) double smem[];
+    __shared__ int s_tile;
+    if (threadIdx.x == 0) s_tile = a.order[atomicAdd(a.ticket, 1)];
+    __syncthreads();
+    lu_cell_body<MESH, NEQ, UPPER>(z, a, s_tile, smem);
+}
+
+template <int MESH, int NEQ, bool UPPER>
+__global__ void __launch_bounds__(LcCfg<MESH, NEQ, UPPER>::NTHR, 1) k_lu_cell_b(const LuBatchItem *items, const int2 *order, int *ticket)
+{
+    extern __shared__ __align__(16) double smem[];
+    __shared__ int2 s_t;
+    __shared__ __align__(16) LuBatchItem s_it;
+    if (threadIdx.x == 0) s_t = order[atomicAdd(ticket, 1)];
+    __syncthreads();
+    const unsigned long long *src = (const unsigned long long *)(items + s_t.x);
+    for (int i = threadIdx.x; i < (int)(sizeof(LuBatchItem) / 8); i += LcCfg<MESH, NEQ, UPPER>::NTHR) ((unsigned long long *)&s_it)[i] = src[i];
+    __syncthreads();
+    lu_cell_body<MESH, NEQ, UPPER>(s_it.z, s_it.a, s_t.y, smem);
+}
+
+// 16-byte staging needs even array strides (NDIMDX, and the plane of the 3dhomo normals); FAST_B200_LU=tile forces the 8-byte kernel
+bool lu_use_cell(const ZoneDev &z)
+{
+    static const bool force_tile = [] { const char *e = getenv("FAST_B200_LU"); return e && e[0] == 't'; }();
+    if (force_tile) return false;
+    if (z.nd % 2) return false;
+    if (z.typ == 1 && ((z.ni * z.nj) % 2)) return false;
+    return true;
+}
+
 // cell-centred mean normals 0.5*(t_d(l) + t_d(l + d)) of every cell (lu_{i,j,k}_*.for build them on the fly)
 template <int MESH>
 __global__ void k_lunorm(ZoneDev z, double *tcm, long long tstride)
@@ -471,7 +819,8 @@ int lu_plan_build(LuPlan &p, const ZoneDev &z, const int box[6])
     for (int i = 0; i < 6; i++) p.box[i] = box[i];
     const int bi = box[1] - box[0] + 1, bj = box[3] - box[2] + 1, bk = box[5] - box[4] + 1;
     p.nplanes = bi + bj + bk - 2;
-    p.tj = LU_TJ; p.tk = lu_tile_tk(z.typ, z.neq);
+    p.cell = lu_use_cell(z);
+    p.tj = LU_TJ; p.tk = p.cell ? lu_cell_tk(z.typ, z.neq) : lu_tile_tk(z.typ, z.neq);
     p.NJ = (bj + p.tj - 1) / p.tj; p.NK = (bk + p.tk - 1) / p.tk;
     std::vector<int> ord;
     for (int K = 0; K < p.NK; K++) for (int J = 0; J < p.NJ; J++) ord.push_back(J | (K << 16));
@@ -532,6 +881,7 @@ static void lu_fill_args(LuTileArgs &a, const ZoneDev &z, const LuPlan &p, const
 // ------------------------------------------------------------------------------------------------ multi-zone launch
 struct LuBatch {
     int nz = 0, typ = 0, neq = 0, ntiles = 0;
+    bool cell = false;
     int2 *d_order = nullptr;          // ticket -> (zone, J | K << 16), ordered by J + K with the zones interleaved
     int *d_ticket = nullptr;          // [lower, upper]
     // device tables of {ZoneDev, LuTileArgs} per zone, one per combination of state pointers the time-level rotation and
@@ -541,11 +891,12 @@ struct LuBatch {
 
 LuBatch *lu_batch_create(int nz, const ZoneDev *const *zs, const LuPlan *const *plans)
 {
-    if (nz < 2 || getenv("FAST_B200_LU")) return nullptr;        // the A/B kernels (plane, line) keep one launch per zone
+    { const char *e = getenv("FAST_B200_LU"); if (nz < 2 || (e && e[0] == 'p')) return nullptr; }   // the hyperplane A/B kernels keep one launch per zone
     for (int n = 0; n < nz; n++)
-        if (zs[n]->typ != zs[0]->typ || zs[n]->neq != zs[0]->neq || zs[n]->itypcp > 1 || !plans[n]->d_order || plans[n]->nrelax >= 2) return nullptr;
+        if (zs[n]->typ != zs[0]->typ || zs[n]->neq != zs[0]->neq || zs[n]->itypcp > 1 || !plans[n]->d_order || plans[n]->nrelax >= 2 ||
+            plans[n]->cell != plans[0]->cell) return nullptr;
     LuBatch *b = new LuBatch();
-    b->nz = nz; b->typ = zs[0]->typ; b->neq = zs[0]->neq;
+    b->nz = nz; b->typ = zs[0]->typ; b->neq = zs[0]->neq; b->cell = plans[0]->cell;
     std::vector<std::pair<int, int2>> ord;     // (J + K, (zone, tile))
     for (int n = 0; n < nz; n++)
         for (int K = 0; K < plans[n]->NK; K++) for (int J = 0; J < plans[n]->NJ; J++) ord.push_back({J + K, make_int2(n, J | (K << 16))});
@@ -575,8 +926,15 @@ static void run_lu_batch(const LuBatch *b, const LuBatchItem *items, cudaStream_
     if (fb_first_on_device(attr_done)) {
         cudaFuncSetAttribute(k_lu_tile_b<MESH, NEQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LuCfg<MESH, NEQ, false>::SMEM);
         cudaFuncSetAttribute(k_lu_tile_b<MESH, NEQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LuCfg<MESH, NEQ, true>::SMEM);
+        cudaFuncSetAttribute(k_lu_cell_b<MESH, NEQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LcCfg<MESH, NEQ, false>::SMEM);
+        cudaFuncSetAttribute(k_lu_cell_b<MESH, NEQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LcCfg<MESH, NEQ, true>::SMEM);
     }
     cudaMemsetAsync(b->d_ticket, 0, 2 * sizeof(int), st);
+    if (b->cell) {
+        k_lu_cell_b<MESH, NEQ, false><<<b->ntiles, LcCfg<MESH, NEQ, false>::NTHR, LcCfg<MESH, NEQ, false>::SMEM, st>>>(items, b->d_order, b->d_ticket);
+        k_lu_cell_b<MESH, NEQ, true><<<b->ntiles, LcCfg<MESH, NEQ, true>::NTHR, LcCfg<MESH, NEQ, true>::SMEM, st>>>(items, b->d_order, b->d_ticket + 1);
+        return;
+    }
     k_lu_tile_b<MESH, NEQ, false><<<b->ntiles, LU_NT, LuCfg<MESH, NEQ, false>::SMEM, st>>>(items, b->d_order, b->d_ticket);
     k_lu_tile_b<MESH, NEQ, true><<<b->ntiles, LU_NT, LuCfg<MESH, NEQ, true>::SMEM, st>>>(items, b->d_order, b->d_ticket + 1);
 }
@@ -605,49 +963,30 @@ int lu_batch_launch(LuBatch *b, const ZoneDev *const *zs, const LuPlan *const *p
     return 3;
 }
 
+template <int MESH, int NEQ, bool UPPER>
+static void launch_sweep(const ZoneDev &z, const LuPlan &p, const LuTileArgs &a, cudaStream_t st)
+{
+    static std::atomic<unsigned long long> attr_done{0};
+    if (fb_first_on_device(attr_done)) {
+        cudaFuncSetAttribute(k_lu_tile<MESH, NEQ, UPPER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LuCfg<MESH, NEQ, UPPER>::SMEM);
+        cudaFuncSetAttribute(k_lu_cell<MESH, NEQ, UPPER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LcCfg<MESH, NEQ, UPPER>::SMEM);
+    }
+    const int ntiles = p.NJ * p.NK;
+    if (p.cell) k_lu_cell<MESH, NEQ, UPPER><<<ntiles, LcCfg<MESH, NEQ, UPPER>::NTHR, LcCfg<MESH, NEQ, UPPER>::SMEM, st>>>(z, a);
+    else k_lu_tile<MESH, NEQ, UPPER><<<ntiles, LU_NT, LuCfg<MESH, NEQ, UPPER>::SMEM, st>>>(z, a);
+}
+
 template <int MESH, int NEQ>
 static int run_lu_tiles(const ZoneDev &z, const LuPlan &p, const double *rop, double *rop_out, int lu_match, cudaStream_t st)
 {
     LuTileArgs a;
     lu_fill_args(a, z, p, rop, rop_out, lu_match);
-    static std::atomic<unsigned long long> attr_done{0};
-    if (fb_first_on_device(attr_done)) {
-        cudaFuncSetAttribute(k_lu_tile<MESH, NEQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LuCfg<MESH, NEQ, false>::SMEM);
-        cudaFuncSetAttribute(k_lu_tile<MESH, NEQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LuCfg<MESH, NEQ, true>::SMEM);
-    }
     cudaMemsetAsync(p.d_ctl, 0, 2 * sizeof(int), st);
-    const int ntiles = p.NJ * p.NK;
-    static const bool dbg = getenv("FAST_B200_LU_DEBUG") != nullptr;
-    static unsigned long long *d_dbg = nullptr; static int dbg_calls = 0;
     a.dbg = nullptr;
-    if (dbg && dbg_calls < 3) { if (!d_dbg) cudaMalloc(&d_dbg, 2 * 16 * 65536 * sizeof(unsigned long long)); a.dbg = d_dbg; }
     a.ticket = p.d_ctl; a.order_mode = lu_match ? 1 : (MESH == 2 ? 2 : 0);
-    k_lu_tile<MESH, NEQ, false><<<ntiles, LU_NT, LuCfg<MESH, NEQ, false>::SMEM, st>>>(z, a);
+    launch_sweep<MESH, NEQ, false>(z, p, a, st);
     a.ticket = p.d_ctl + 1; a.order_mode = lu_match ? 1 : 0;
-    if (a.dbg) a.dbg += 16 * 65536;
-    k_lu_tile<MESH, NEQ, true><<<ntiles, LU_NT, LuCfg<MESH, NEQ, true>::SMEM, st>>>(z, a);
-    if (a.dbg) {
-        cudaStreamSynchronize(st);
-        std::vector<unsigned long long> h(2 * 16 * 65536);
-        cudaMemcpy(h.data(), d_dbg, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-        for (int sw = 0; sw < 2; sw++) {
-            const unsigned long long *q = h.data() + sw * 16 * 65536; unsigned long long t0 = ~0ULL, t1 = 0;
-            for (int t = 0; t < ntiles; t++) { t0 = std::min(t0, q[16 * t]); t1 = std::max(t1, q[16 * t + 2]); }
-            fprintf(stderr, "LUDBG sweep %d call %d: NJ %d NK %d tiles %d bi %d total %.1f us\n", sw, dbg_calls, p.NJ, p.NK, ntiles, a.bi, (t1 - t0) * 1e-3);
-            for (int t = 0; t < ntiles; t++) {
-                const int J = t % p.NJ, K = t / p.NJ;
-                if (dbg_calls == 1 && (J % 4 == 0) && (K % 2 == 0 || K == p.NK - 1))
-                    fprintf(stderr, "LUDBG   tile J %2d K %2d sm %3llu start %8.1f s16 %8.1f s128 %8.1f s256 %8.1f s384 %8.1f end %8.1f dur %8.1f\n", J, K, q[16 * t + 3],
-                            (q[16 * t] - t0) * 1e-3, (q[16 * t + 4] - t0) * 1e-3, (q[16 * t + 5] - t0) * 1e-3, (q[16 * t + 6] - t0) * 1e-3, (q[16 * t + 7] - t0) * 1e-3,
-                            (q[16 * t + 2] - t0) * 1e-3, (q[16 * t + 2] - q[16 * t]) * 1e-3);
-                if (dbg_calls == 1 && (J % 8 == 0) && (K % 4 == 0))
-                    fprintf(stderr, "LUCLK   tile J %2d K %2d cycles/step: compute(w0) %6.0f compute(w7) %6.0f | refill issue %6.0f wait %6.0f | wb: park %6.0f writeback %6.0f deliver %6.0f\n", J, K,
-                            (double)q[16 * t + 8] / a.bi, (double)q[16 * t + 14] / a.bi, (double)q[16 * t + 9] / (a.bi + 14), (double)q[16 * t + 10] / (a.bi + 14),
-                            (double)q[16 * t + 11] / (a.bi + 14), (double)q[16 * t + 12] / (a.bi + 14), (double)q[16 * t + 13] / (a.bi + 14));
-            }
-        }
-        dbg_calls++;
-    }
+    launch_sweep<MESH, NEQ, true>(z, p, a, st);
     return 3;
 }
 
@@ -704,12 +1043,7 @@ static int run_lu_ssor(const ZoneDev &z, const LuPlan &p, const double *rop, dou
 {
     LuTileArgs a;
     lu_fill_args(a, z, p, rop, rop_out, 1);       // Newton box = interior (ind_loop_sdm)
-    static std::atomic<unsigned long long> attr_done{0};
-    if (fb_first_on_device(attr_done)) {
-        cudaFuncSetAttribute(k_lu_tile<MESH, NEQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LuCfg<MESH, NEQ, false>::SMEM);
-        cudaFuncSetAttribute(k_lu_tile<MESH, NEQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LuCfg<MESH, NEQ, true>::SMEM);
-    }
-    const int ntiles = p.NJ * p.NK, alias = a.alias;
+    const int alias = a.alias;
     const int *bx = p.box;
     dim3 b(64, 4, 1), g((bx[1] - bx[0] + 64) / 64, (bx[3] - bx[2] + 4) / 4, bx[5] - bx[4] + 1);
     cudaMemcpyAsync(p.d_rhs, z.drodm, (size_t)z.nd * NEQ * sizeof(double), cudaMemcpyDeviceToDevice, st);
@@ -722,10 +1056,10 @@ static int run_lu_ssor(const ZoneDev &z, const LuPlan &p, const double *rop, dou
         }
         cudaMemsetAsync(p.d_ctl, 0, 2 * sizeof(int), st);
         a.ticket = p.d_ctl; a.newton = 0; a.alias = 0;
-        k_lu_tile<MESH, NEQ, false><<<ntiles, LU_NT, LuCfg<MESH, NEQ, false>::SMEM, st>>>(z, a);
+        launch_sweep<MESH, NEQ, false>(z, p, a, st);
         if (m > 1) { k_ssor_in<NEQ, true><<<g, b, 0, st>>>(z, bx[0], bx[1], bx[2], bx[3], bx[4], p.d_rhs, p.d_us); launches++; }
         a.ticket = p.d_ctl + 1; a.newton = m == p.nrelax ? 1 : 0; a.alias = a.newton ? alias : 0;
-        k_lu_tile<MESH, NEQ, true><<<ntiles, LU_NT, LuCfg<MESH, NEQ, true>::SMEM, st>>>(z, a);
+        launch_sweep<MESH, NEQ, true>(z, p, a, st);
         launches += 3;
     }
     return launches;

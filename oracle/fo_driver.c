@@ -88,6 +88,9 @@ static void rhs_zone(fo_zone *z, int nitcfg, int nssiter, int nitrun, int first_
 #pragma omp barrier
         /* src_term.for: init_rhs, SA source, sensor */
         fo_init_rhs(pi, nitcfg, s_sdm, z->drodm);
+        /* the slabs of ind_ssa (interior +- 1) are not those of ind_sdm: a plane may be zeroed by one thread and receive its
+           source from another */
+#pragma omp barrier
         if (pi[FO_IFLOW] == 3 && pi[FO_ILES] == 0)
             fo_spsource_SA(pi, pr, nitcfg, s_ssa, z->xmut, rop_ssiter, z->coe, z->ti, z->tj, z->tk, z->vol,
                            z->xmut + nd, z->drodm);

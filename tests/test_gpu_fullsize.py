@@ -31,7 +31,12 @@ def _run(workload, nit=1, n=None):
         for zo, z in zip(o.zones, Internal.getZones(t2)):
             a = FastC.block_of(z, ''); b = zo.lev[0]
             assert numpy.isfinite(a).all()
-            errs.append((relerr(interior(zo.pi, a), interior(zo.pi, b)), float(numpy.abs(a - b).max() / numpy.abs(b).max()), a, b, zo.pi))
+            ia, ib = interior(zo.pi, a), interior(zo.pi, b)
+            per_var = [float(numpy.abs(ia[e] - ib[e]).max() / max(numpy.abs(ib[e]).max(), 1e-300)) for e in range(ia.shape[0])]
+            worst = int(numpy.argmax(per_var))
+            where = numpy.unravel_index(int(numpy.argmax(numpy.abs(ia[worst] - ib[worst]))), ia[worst].shape)
+            print("%s zone %s it %d: per-variable max rel diff %s, worst at (k,j,i) = %s" % (workload, z[0], it, ' '.join('%.2e' % x for x in per_var), where))
+            errs.append((relerr(ia, ib), float(numpy.abs(a - b).max() / numpy.abs(b).max()), a, b, zo.pi))
         out.append(errs)
     return out
 

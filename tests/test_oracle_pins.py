@@ -65,10 +65,10 @@ def test_threaded_oracle_is_bit_identical(case):
     parity tests and the timed CPU baseline must not change a single bit of the result."""
     def mk():
         if case == 'tgv': return synth.case_tgv(n=20, perturb=1e-3), None
-        if case == 'plate_blocks': return synth.case_flatplate(n=(24, 16, 12), nblocks=(2, 1, 2))
+        if case == 'plate_blocks': return synth.case_flatplate(n=(48, 32, 32), nblocks=(2, 1, 1))
         return synth.case_multiblock(nblk=(2, 1, 2), n=10)
     res = []
-    for nth in (1, 5):
+    for nth in (1, 8):
         t, j = mk()
         o = oracle_from_tree(t, joins=j)
         nss = int(o.zones[0].pi[V.NSSITER])
