@@ -445,6 +445,20 @@ int fb_set_joins(fb_solver *s, const int *ji, int n)
     return FB_OK;
 }
 
+int fb_set_joins_tc(fb_solver *s, const int *param_int_tc, int n_int, const double *param_real_tc, int n_real)
+{
+    if (!s || !param_int_tc || !param_real_tc || n_int < 1 || n_real < 0) return fail(FB_EINVAL, "fb_set_joins_tc: bad arguments");
+    CK(cudaSetDevice(s->dev));
+    std::vector<int> nds(s->nz), neqs(s->nz);
+    for (int i = 0; i < s->nz; i++) { nds[i] = s->z[i].d.nd; neqs[i] = s->z[i].d.neq; }
+    std::string err;
+    if (joins_build_tc(s->joins, param_int_tc, n_int, param_real_tc, n_real, s->nz, nds.data(), neqs.data(), err))
+        return fail(FB_EINVAL, "fb_set_joins_tc: " + err);
+    for (auto &z : s->z) z.xfaces = 0;                 // no cross-rank entries in this format (NoTransfert = 1: intra-process joins)
+    cudaFree(s->halo_send); cudaFree(s->halo_recv); s->halo_send = s->halo_recv = nullptr;
+    return FB_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------- driver
 static void apply_bc_zone(fb_solver *s, Zone &z, double *rop, int lrhs)
 {
@@ -519,8 +533,13 @@ static int gsdr3(fb_solver *s, int nitcfg, int nssiter, int nitrun, int first_it
     static const bool no_overlap = [] { const char *e = getenv("FAST_B200_OVERLAP"); return e && e[0] == '0'; }();   // A/B switch
     const bool overlap = !implicit && lexit_lu == 0 && cross_rank(s) && !no_overlap;
     std::vector<double *> cl(s->nz);
-    static const bool no_fan = [] { const char *e = getenv("FAST_B200_FAN"); return e && e[0] == '0'; }();   // A/B switch
-    const bool fan = s->nz > 1 && !no_fan;
+    // bit 0: the nstep-1 kernels (viscosity, coe, CFL, SENSOR) of the zones fan out over the lanes; bit 1: the rhs kernels too.
+    // Default 1: with the rhs kernels of several zones running concurrently from different streams the TMA-staged kernel
+    // k_rhs3 is NOT deterministic -- about one 1e-5 perturbation per ten iterations of the 8-block C5 brick, none with one
+    // stream, none with the L1-path kernel k_rhs2, whatever the descriptor placement or cache policy of its global loads
+    // (profiles/r02_race.md) -- so they are launched back to back on the solver stream.  FAST_B200_FAN=3 restores the r01 behaviour.
+    static const int fan_mode = [] { const char *e = getenv("FAST_B200_FAN"); return e ? atoi(e) : 1; }();
+    const bool fan = s->nz > 1 && (fan_mode & 2), fan_coe = s->nz > 1 && (fan_mode & 1);
     {
         Scope all(s, 5);
         std::vector<double *> ss(s->nz);
@@ -536,7 +555,7 @@ static int gsdr3(fb_solver *s, int nitcfg, int nssiter, int nitrun, int first_it
         }
         if (nitcfg == 1) {   // navier_stokes_struct.for:216-301
             Scope c(s, 4);
-            Fan f(s, fan);
+            Fan f(s, fan_coe);
             for (int n = 0; n < s->nz; n++) {
                 Zone &z = s->z[n]; double *ssiter = ss[n]; cudaStream_t zst = f.stream(n);
                 if (z.d.iflow >= 2) { launch_invist(z.d, ssiter, implicit || z.d.iflow == 3 ? z.d.nf : 1, zst); s->launches++; }

@@ -57,6 +57,12 @@ struct ZoneDev {
     int ncorr; CorrWin corr[FB_MAXCORR];
 };
 
+// Loads of arrays that OTHER kernels rewrite between two launches of the reader (time levels, coe, drodm) go to L2 (ld.global.cg):
+// with the per-zone kernels of a phase spread over several streams, L1-cached copies of such data were observed to survive
+// from one sub-iteration into the next (profiles/r02_race.md) -- the hardware keeps the L1s of the SMs coherent only between
+// dependent grids of ONE stream.  Staged data (TMA, cp.async) already bypasses L1.
+#define FB_LD(p) __ldcg(p)
+
 __device__ __forceinline__ int inddm(const ZoneDev &z, int i, int j, int k)
 {
     return (i + z.nf - 1) + (j + z.nf - 1) * z.incj + (k + z.nfk - 1) * z.inck;

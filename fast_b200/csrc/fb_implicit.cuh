@@ -12,7 +12,9 @@ struct LuPlan {
     int modulo_verif = 0;
     // tile-pipelined wavefront (fb_lu.cu)
     int tj = 8, tk = 8, NJ = 0, NK = 0;   // tile size in j and k (lines), tiles per direction of the (j,k) cross-section
-    bool cell = false;                // thread-per-cell kernel k_lu_cell (16-byte staging) instead of k_lu_tile
+    bool cell = false;                // thread-per-cell kernel k_lu_cell (TMA-staged) instead of k_lu_tile
+    void *d_tm = nullptr;             // k_lu_cell: 9 CUtensorMap in device memory: drodm, coe, tcm, then {lower, upper} of up to 3 rop levels
+    mutable const double *rop_seen[3] = {nullptr, nullptr, nullptr};
     int *d_order = nullptr;           // ticket -> tile, i+j+k order
     int *d_ctl = nullptr;             // [ticket lower, ticket upper, error flag, pad]
     double *d_mb = nullptr;           // inter-tile mailboxes: j interfaces then k interfaces
@@ -53,6 +55,8 @@ struct JoinSet {
     int flip = 0;              // slot of d_ptrs the next launch uses
 };
 int  joins_build(JoinSet &j, const int *ji, int n, int nz, const int *ndimdx, const int *neqs, std::string &err);
+int  joins_build_tc(JoinSet &j, const int *pit, int n_int, const double *prt, int n_real, int nz, const int *ndimdx, const int *neqs,
+                    std::string &err);   // Connector's param_int_tc / param_real_tc (match joins)
 void joins_free(JoinSet &j);
 int  joins_apply(JoinSet &j, double **zone_ptr, int nz, cudaStream_t st);          // kind 0 (local) joins
 int  joins_pack(JoinSet &j, double **zone_ptr, double *buf, long long nbytes, cudaStream_t st);      // kind 1

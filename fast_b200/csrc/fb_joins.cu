@@ -70,6 +70,76 @@ int joins_build(JoinSet &j, const int *ji, int n, int nz, const int *ndimdx, con
     return 0;
 }
 
+// Connector's flattened donor tree (miseAPlatDonorTree__): HOOK['param_int_tc'] / HOOK['param_real_tc'] as
+// K_FASTC::setInterpTransfersIntra reads them (C/Com/setInterpTransfersFast.cpp:469-477 header, :563-566 and :641-654 per-join
+// tables, :750-760 point lists; documented in TD 2.4.3.1).  Layout followed here:
+//   sizecomIBC = pit[2], sizecomID = pit[3 + sizecomIBC], shift_graph = sizecomIBC + sizecomID + 3,
+//   ech = pit[NoTransfert + shift_graph] (NoTransfert = 1: the joins inside this process),
+//   nrac = pit[ech+1], nrac_inst = pit[ech+2], timelevel = pit[ech+3], tables of nrac ints from T = ech + 4 + 2 timelevel:
+//   T+0 nrac: size of the donor point list   T+1: number of coefficients   T+3: IBC type (< 0: plain interpolation)
+//   T+5: donor zone   T+6: address of the donor points   T+7: address of [ntype, count per type..., type per point...]
+//   T+8: address of the coefficients in param_real_tc   T+10: receiver points   T+11: receiver zone   T+12: address of the
+//   receiver points   T+13: variables (5 / 6)   T+14: azimuthal periodicity   T+16: conservative-flux windows.
+// Scope of this library: match joins -- interpolation type 0 / 1 with ONE donor of coefficient 1 (ST/tgvMpi.py:136-139); anything
+// else (IBC, chimera stencils, unsteady joins, rotation, nearmatch flux windows) is rejected loudly.  Point addresses are the
+// 0-based cell addresses l of the ghosted zones.  Converts to the internal table and goes through joins_build.
+int joins_build_tc(JoinSet &j, const int *pit, int n_int, const double *prt, int n_real, int nz, const int *ndimdx, const int *neqs,
+                   std::string &err)
+{
+    auto bad = [&](const char *m) { err = m; return 1; };
+    if (n_int < 6) return bad("param_int_tc too short");
+    const int sizecomIBC = pit[2];
+    if (sizecomIBC < 0 || 3 + sizecomIBC >= n_int) return bad("param_int_tc: bad IBC communication header");
+    const int sizecomID = pit[3 + sizecomIBC];
+    const int shift_graph = sizecomIBC + sizecomID + 3;
+    const int NoTransfert = 1;
+    if (sizecomID < 0 || NoTransfert + shift_graph >= n_int) return bad("param_int_tc: bad ID communication header");
+    const int ech = pit[NoTransfert + shift_graph];
+    if (ech < 0 || ech + 4 > n_int) return bad("param_int_tc: bad address of the intra-process exchange");
+    const int nrac = pit[ech + 1], nrac_inst = pit[ech + 2], timelevel = pit[ech + 3];
+    if (nrac < 0 || timelevel < 0) return bad("param_int_tc: negative join count");
+    if (nrac_inst != 0) return bad("unsteady joins (nrac_inst > 0) are outside the hot-path scope");
+    const int T = ech + 4 + timelevel * 2;
+    if (T + 18 * nrac > n_int) return bad("param_int_tc: join tables run past the end of the array");
+    std::vector<int> tab(2 + 7 * (size_t)nrac), idx;
+    tab[0] = nrac;
+    for (int irac = 0; irac < nrac; irac++) {
+        const int sr = T + irac;
+        if (pit[sr + nrac * 3] >= 0) return bad("IBC joins are outside the hot-path scope");
+        const int NoD = pit[sr + nrac * 5], NoR = pit[sr + nrac * 11], nv = pit[sr + nrac * 13];
+        const int npts = pit[sr + nrac * 10], ncoef = pit[sr + nrac];
+        if (pit[sr + nrac * 14] != 0) return bad("azimuthal periodicity (rotation) is outside the hot-path scope");
+        if (pit[sr + nrac * 16] != 0) return bad("conservative nearmatch flux windows are outside the hot-path scope");
+        if (NoD < 0 || NoD >= nz || NoR < 0 || NoR >= nz) return bad("param_int_tc: zone number out of range");
+        if (nv != neqs[NoD] || nv != neqs[NoR]) return bad("join carries a number of variables different from the zones' NEQ");
+        const int pt = pit[sr + nrac * 7], pd = pit[sr + nrac * 6], pr_ = pit[sr + nrac * 12], pc = pit[sr + nrac * 8];
+        if (npts < 0 || pt < 0 || pt + 1 >= n_int || pd < 0 || pd + npts > n_int || pr_ < 0 || pr_ + npts > n_int)
+            return bad("param_int_tc: point list address out of range");
+        const int ntype = pit[pt];
+        if (ntype < 0 || pt + 1 + ntype + npts > n_int) return bad("param_int_tc: interpolation type list out of range");
+        int tot = 0;
+        for (int q = 0; q < ntype; q++) tot += pit[pt + 1 + q];
+        if (tot != npts) return bad("param_int_tc: interpolation type counts do not add up to the receiver points");
+        for (int n = 0; n < npts; n++) {
+            const int ty = pit[pt + 1 + ntype + n];
+            if (ty != 0 && ty != 1) return bad("only match joins (interpolation type 0 / 1, one donor) are built");
+        }
+        if (ncoef != npts || pc < 0 || pc + npts > n_real) return bad("match joins carry one coefficient per point");
+        for (int n = 0; n < npts; n++) if (prt[pc + n] != 1.) return bad("match-join coefficient different from 1");
+        for (int n = 0; n < npts; n++) {
+            const int ld = pit[pd + n], lr = pit[pr_ + n];
+            if (ld < 0 || ld >= ndimdx[NoD] || lr < 0 || lr >= ndimdx[NoR]) return bad("param_int_tc: cell address out of range");
+        }
+        int *d = tab.data() + 2 + 7 * irac;
+        d[0] = 0; d[1] = NoD; d[2] = NoR; d[3] = npts; d[4] = (int)idx.size(); d[5] = (int)idx.size() + npts; d[6] = 0;
+        idx.insert(idx.end(), pit + pd, pit + pd + npts);
+        idx.insert(idx.end(), pit + pr_, pit + pr_ + npts);
+    }
+    tab[1] = (int)idx.size();
+    tab.insert(tab.end(), idx.begin(), idx.end());
+    return joins_build(j, tab.data(), (int)tab.size(), nz, ndimdx, neqs, err);
+}
+
 void joins_free(JoinSet &j)
 {
     cudaFree(j.d_desc); cudaFree(j.d_idx); cudaFree(j.d_ptrs);

@@ -29,6 +29,7 @@
 #include <type_traits>
 #include <map>
 #include <cstring>
+#include <cuda.h>
 #include "fb_implicit.cuh"
 #include "fb_kernels.cuh"
 
@@ -80,6 +81,8 @@ struct LuTileArgs {
     int alias, order_mode;
     int newton;             // upper sweep: 1 = Newton update written to rop_out (mjr_newton fused), 0 = dW stored back (nb_relax >= 2)
     int plane;              // ni*nj (3dhomo: tcm is a plane array)
+    const CUtensorMap *tm;     // k_lu_cell: skewed views of drodm, coe, tcm (device memory)
+    const CUtensorMap *tm_rop; // ... and of rop_ssiter (u, v, w, T for the lower sweep, all variables for the upper one)
     unsigned long long *dbg;   // FAST_B200_LU_DEBUG: per tile {start, first step, end, smid} (globaltimer ns)
 };
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
@@ -432,25 +435,35 @@ __global__ void __launch_bounds__(LU_NT, 1) k_lu_tile_b(const LuBatchItem *items
 }
 
 // ================================================================================================ k_lu_cell
-// Thread-per-cell variant of the same tile-pipelined wavefront (default whenever the zone's arrays allow 16-byte staging:
-// NDIMDX even, ni*nj even for the plane-shaped 3dhomo normals; k_lu_tile above stays the 8-byte path for the other zones).
+// Thread-per-cell variant of the same tile-pipelined wavefront, staged by TMA (default whenever the zone's strides can be
+// encoded: ni and NDIMDX even; k_lu_tile above stays the 8-byte cp.async path for the other zones).
 // What changed against k_lu_tile, and why (profiles/r01_summary.md: the four-lanes-per-line step was a chain of 207 / 255
-// instructions per warp at 5.5 - 8 cycles each, every lane redoing dW*, the Newton update evaluated by all four lanes AND again
-// by the write-back role):
-//   * ONE thread owns a line: it gathers the three incoming products, forms dW, evaluates the three outgoing products (their
-//     common factors once), keeps B_i.dW in registers for its own next cell and, in the upper sweep, applies the Newton update
-//     once -- the updated state feeds both the k product (aliased sweeps) and the write-back.  ~4x fewer instructions per cell.
-//   * a tile is 8 x 16 lines (8 x 12 for 3dfull SA): 128 cells per step and CTA instead of 64, four compute warps (one per
-//     scheduler) + four service warps.
-//   * the ring holds 8 cells per line (four 16-byte granules of two cells) instead of 16: the service thread of a line fetches
-//     the granule of the cell needed four steps ahead with ONE 16-byte cp.async per staged array, and writes results back as
-//     16-byte stores once both cells of a granule are final.  Granules are aligned on even cell addresses, whatever the
-//     parity of the line start, in both sweep directions.
-//   * shared-memory layouts are chosen for the thread-per-line access: ring[array][granule][line][2] (8-byte accesses of 32
-//     consecutive lines: 2-way conflicts at worst), exchange buffers [dir][line][6] (16-byte accesses, conflict-free).
-// Mailboxes, tickets, error flag and the (J + K) tile order are those of k_lu_tile.
-#define LC_PF 4            // refill distance (steps)
-#define LC_NG 4            // granules per line in the ring
+// instructions per warp at 5.5 - 8 cycles each, every lane redoing dW*, the Newton update evaluated by all four lanes AND
+// again by the write-back role; profiles/r02_lu_cell_v1.md: a first thread-per-cell version fed by 16-byte cp.async spent
+// 2200 cycles per step in its service warps, 23 scattered LDGSTS per line):
+//   * ONE thread owns a line: it gathers the three incoming products, forms dW, evaluates the three outgoing products,
+//     keeps B_i.dW in registers for its own next cell and, in the upper sweep, applies the Newton update once -- the updated
+//     state feeds both the k product (aliased sweeps) and the write-back.  ~4x fewer instructions per cell.
+//   * a tile is 8 x 16 lines (8 x 12 for 3dfull SA) and advances by SUPER-STEPS of two cells per line (one 16-byte granule):
+//     256 cells per barrier and CTA instead of 64; the two cells of a thread are consecutive along i, so only B_i.dW of the
+//     first feeds the second and the rest of their work overlaps.
+//   * staging is ONE TMA box per staged array group and super-step.  The tensor maps describe each zone array through a
+//     SKEWED view: element (c0, c1, c2, e) -> array[e][c0 + c1 (ni - 2) + c2 (ni nj - 2)], i.e. c0 = i + 2 j + 2 k.  In that
+//     view the granules needed by the lines (jj, kk) of a tile at super-step S -- cells i = 2 (S - jj - kk) + {0, 1} of
+//     rows that are ni apart -- form a dense (2, 8, TK, nvar) box at c0 = 2 S + const: the skew of the wavefront is folded
+//     into the strides, nothing is fetched twice and no load instruction is issued by any thread (the four-lanes kernel
+//     needs 23 cp.async per cell).  The view overlaps itself (stride of c1 < extent of c0), which cuTensorMapEncodeTiled
+//     accepts; coordinates outside [0, ni + 2 nj + 2 nk) x [0, nj) x [0, nk) are zero-filled and the largest address of the
+//     view is the last cell of the array (tools/probe/tma_skew_probe.cu checks all of this on the device).  Box starts must
+//     be 16-byte aligned, so the pairing of cells into granules follows the parity of the first column of the sweep box.
+//     The k-invariant normals of 3dhomo zones come through a rank-3 view (c0 = i + 2 j) into their own ring of 20 super-steps:
+//     line kk needs at super-step S what line 0 needed at S - kk.
+//   * three slots of (all arrays) x (lines) x (2 cells): compute works on slot S, the service threads write the results of
+//     S-1 back (16-byte stores, masked per cell) and then re-arm that slot for S+2.
+// Mailboxes (one 48-byte entry per boundary cell, two per super-step), tickets, error flag and the (J + K) tile order are those of
+// k_lu_tile.
+#define LC_SLOTS 3
+#define LC_NSL 20          // super-steps kept in the 3dhomo normals ring (>= TK + 3)
 #define LC_NSV 128         // service threads
 
 template <int MESH, int NEQ, bool UPPER>
@@ -461,108 +474,139 @@ struct LcCfg {
     static constexpr int NC = NEQ == 6 ? 6 : 5;
     static constexpr int NS = UPPER ? NEQ : 4;
     static constexpr int S0 = UPPER ? 0 : 1;
-    static constexpr int NT = MESH == 0 ? 9 : (MESH == 1 ? 5 : 0);
+    static constexpr int NT = MESH == 0 ? 9 : 0;        // normals staged in the slot (3dfull); 3dhomo: separate ring
     static constexpr int A_DW = 0, A_COE = NEQ, A_ST = NEQ + NC, A_T = NEQ + NC + NS;
     static constexpr int A = NEQ + NC + NS + NT;
     static constexpr int NIF = TJ + TK;                 // interface lines: TK towards (J-1,K), TJ towards (J,K-1)
     static constexpr int NTHR = L + LC_NSV;
-    static constexpr int AS = LC_NG * L * 2;            // doubles per staged array
-    static constexpr size_t SMEM = (size_t)(A * AS + 2 * 2 * L * LU_MB + 6 * NIF * LU_MB) * sizeof(double);
+    static constexpr int AS = L * 2;                    // doubles per staged array and slot
+    static constexpr int SLOT = A * AS;
+    static constexpr int NRS = 5 * TJ * 2;              // doubles per super-step of the 3dhomo normals ring
+    static constexpr int NRING = MESH == 1 ? LC_NSL * NRS : 0;
+    static constexpr int EXB = 2 * 2 * 2 * L * LU_MB;   // [buffer][direction][cell][line][6]
+    static constexpr int MBW = 2 * LU_MB;               // words per interface line and super-step
+    static constexpr unsigned TX = (unsigned)((SLOT + (MESH == 1 ? NRS : 0)) * sizeof(double));
+    static constexpr size_t SMEM = (size_t)(LC_SLOTS * SLOT + NRING + EXB + 6 * NIF * MBW) * sizeof(double) + 64;
 };
 int lu_cell_tk(int mesh, int neq) { return (mesh == 0 && neq == 6) ? 12 : 16; }
 
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+__device__ __forceinline__ void lc_mbar_init(unsigned long long *bar, int count)
 {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void lc_mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void lc_mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+                 ::"r"(b), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void lc_tma4(void *dst, const CUtensorMap *tm, int c0, int c1, int c2, int c3, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+                   "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void lc_tma3(void *dst, const CUtensorMap *tm, int c0, int c1, int c2, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(c2),
+                   "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
 
 template <int MESH, int NEQ, bool UPPER>
 __device__ __forceinline__ void lu_cell_body(const ZoneDev &z, const LuTileArgs &a, const int tile, double *smem)
 {
     using C = LcCfg<MESH, NEQ, UPPER>;
-    constexpr int TJ = C::TJ, TK = C::TK, L = C::L, EX = LU_MB, NIF = C::NIF, AS = C::AS;
-    double *ring = smem;                                   // [A][LC_NG][L][2]
-    double *exb = smem + C::A * AS;                        // [2][2][L][EX]: products handed to (jj+1) and (kk+1)
-    unsigned long long *mbs = (unsigned long long *)(exb + 2 * 2 * L * EX);   // [4][NIF][EX] prefetched mailbox words
-    double *mbx = (double *)(mbs + 4 * NIF * EX);          // [2][NIF][EX] validated products of the neighbour tiles
+    constexpr int TJ = C::TJ, TK = C::TK, L = C::L, EX = LU_MB, NIF = C::NIF, AS = C::AS, MBW = C::MBW;
+    double *ring = smem;                                   // [LC_SLOTS][A][L][2]
+    double *nring = smem + LC_SLOTS * C::SLOT;             // 3dhomo: [LC_NSL][5][TJ][2]
+    double *exb = nring + C::NRING;                        // [2][2][2][L][EX]: products handed to (jj+1) and (kk+1)
+    unsigned long long *mbs = (unsigned long long *)(exb + C::EXB);   // [4][NIF][MBW] prefetched mailbox words
+    double *mbx = (double *)(mbs + 4 * NIF * MBW);         // [2][NIF][MBW] validated products of the neighbour tiles
+    unsigned long long *full = (unsigned long long *)(mbx + 2 * NIF * MBW);   // [LC_SLOTS] "slot has landed"
     const int tid = threadIdx.x;
-    for (int i = tid; i < 2 * 2 * L * EX + 6 * NIF * EX; i += C::NTHR) exb[i] = 0.;
+    for (int i = tid; i < C::EXB + 6 * NIF * MBW; i += C::NTHR) exb[i] = 0.;
+    if (tid == 0) {
+        for (int q = 0; q < LC_SLOTS; q++) lc_mbar_init(full + q, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
     const int J = tile & 0xffff, K = tile >> 16;
     const int bi = a.bi, bj = a.bj, bk = a.bk;
-    const int nst = bi + TJ + TK - 2;
     const int nd = z.nd;
     const int sg = UPPER ? -1 : 1;
     const int l0 = UPPER ? inddm(z, a.box[1], a.box[3], a.box[5]) : inddm(z, a.box[0], a.box[2], a.box[4]);
+    // pairing of the cells of a line into 16-byte granules: super-step m of a line holds cells 2m - p and 2m - p + 1
+    const int ir = (UPPER ? a.box[1] : a.box[0]) + z.nf - 1;            // array column of the first cell of the sweep
+    const int p = UPPER ? ((ir + 1) & 1) : (ir & 1);
+    const int nm = (bi - 1 + p) / 2 + 1;                                 // super-steps of a line
+    const int nst = nm + TJ + TK - 2;
 
     if (tid >= L) {
         // ------------------------------------------------------------------------------------ service warps
         const int st = tid - L;
-        // -- the line this thread stages (refill + write-back)
         const int lam = st, jj = lam % TJ, kk = lam / TJ;
         const int jjg = J * TJ + jj, kkg = K * TK + kk;
         const bool lok = lam < L && jjg < bj && kkg < bk;
         const int sigma = jj + kk;
+        const int lam_s = UPPER ? L - 1 - lam : lam;                    // line index inside the TMA box
         const int lrow = l0 + sg * (jjg * z.incj + kkg * z.inck);
         const int jg = UPPER ? a.box[3] - jjg : a.box[2] + jjg, kg = UPPER ? a.box[5] - kkg : a.box[4] + kkg;
         const bool line_in_nb = jg >= a.nbx[2] && jg <= a.nbx[3] && kg >= a.nbx[4] && kg <= a.nbx[5];
-        auto refill = [&](int s) {
-            const int ii = s + LC_PF - sigma;
-            if (!(lok && ii >= 0 && ii < bi)) return;
-            const int ca = lrow + sg * ii;
-            if (!(ii == 0 || (ca & 1) == (UPPER ? 1 : 0))) return;      // the granule was fetched with its first cell
-            const int G = ca >> 1;
-            double *dst = ring + ((size_t)((G & (LC_NG - 1)) * L + lam)) * 2;
-            const int g0 = 2 * G;
-#pragma unroll
-            for (int e = 0; e < NEQ; e++) cp_async16(dst + (size_t)(C::A_DW + e) * AS, a.dw + g0 + e * nd);
-#pragma unroll
-            for (int e = 0; e < C::NC; e++) cp_async16(dst + (size_t)(C::A_COE + e) * AS, a.coe + g0 + e * nd);
-#pragma unroll
-            for (int e = 0; e < C::NS; e++) cp_async16(dst + (size_t)(C::A_ST + e) * AS, a.rop + g0 + (C::S0 + e) * nd);
-            if (MESH != 2) {
-                const int gt = MESH == 1 ? g0 % a.plane : g0;
-#pragma unroll
-                for (int e = 0; e < C::NT; e++) cp_async16(dst + (size_t)(C::A_T + e) * AS, a.tcm + gt + e * a.tstride);
-            }
+        // box origin of the tile in the skewed views (see the header): c0 = cbase + 2 S (lower) / cbase - 2 S (upper)
+        const int jr = (UPPER ? a.box[3] : a.box[2]) + z.nf - 1, kr = (UPPER ? a.box[5] : a.box[4]) + z.nfk - 1;
+        const int c1 = UPPER ? jr - TJ * J - (TJ - 1) : jr + TJ * J;
+        const int c2 = UPPER ? kr - TK * K - (TK - 1) : kr + TK * K;
+        const int cn = UPPER ? ir + p - 1 + 2 * (jr - TJ * J) : ir - p + 2 * (jr + TJ * J);       // rank-3 view of the 3dhomo normals
+        const int cb = cn + (UPPER ? 2 * (kr - TK * K) : 2 * (kr + TK * K));
+        auto fetch = [&](int S) {       // one thread: every staged array of super-step S
+            if (S >= nst) return;
+            const int q = S % LC_SLOTS;
+            double *dst = ring + (size_t)q * C::SLOT;
+            const int c0 = cb + sg * 2 * S;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the slot was last written through the generic proxy
+            lc_mbar_expect_tx(full + q, C::TX);
+            lc_tma4(dst + (size_t)C::A_DW * AS, a.tm + 0, c0, c1, c2, 0, full + q);
+            lc_tma4(dst + (size_t)C::A_COE * AS, a.tm + 1, c0, c1, c2, 0, full + q);
+            lc_tma4(dst + (size_t)C::A_ST * AS, a.tm_rop + (UPPER ? 1 : 0), c0, c1, c2, C::S0, full + q);
+            if (MESH == 0) lc_tma4(dst + (size_t)C::A_T * AS, a.tm + 2, c0, c1, c2, 0, full + q);
+            if (MESH == 1) lc_tma3(nring + (size_t)(S % LC_NSL) * C::NRS, a.tm + 2, cn + sg * 2 * S, c1, 0, full + q);
         };
-        // results of the cell computed two steps ago; a granule leaves as one 16-byte store once its second cell is final
-        auto writeback = [&](int s) {
-            const int ii = s - 2 - sigma;
-            if (!(lok && ii >= 0 && ii < bi)) return;
-            const int ca = lrow + sg * ii;
-            const bool second = (ca & 1) == (UPPER ? 0 : 1);
-            const bool last = ii == bi - 1;
-            if (!second && !last) return;
+        // results of super-step S: one 16-byte store per array when both cells of the granule are to be written
+        auto writeback = [&](int S) {
+            const int m = S - sigma;
+            if (!(lok && m >= 0 && m < nm)) return;
+            const int iiA = 2 * m - p, iiB = iiA + 1;
             const bool nwt = UPPER && a.newton;
-            bool v1 = true, v0 = second && ii >= 1;              // this cell, its partner (ii - 1) in the same granule
+            bool vA = iiA >= 0, vB = iiB < bi;
             if (nwt) {
-                const int ig = a.box[1] - ii;
-                v1 = line_in_nb && ig >= a.nbx[0] && ig <= a.nbx[1];
-                v0 = v0 && line_in_nb && ig + 1 >= a.nbx[0] && ig + 1 <= a.nbx[1];
+                const int ig = a.box[1] - iiA;
+                vA = vA && line_in_nb && ig >= a.nbx[0] && ig <= a.nbx[1];
+                vB = vB && line_in_nb && ig - 1 >= a.nbx[0] && ig - 1 <= a.nbx[1];
             }
-            if (!v1 && !v0) return;
-            const int G = ca >> 1;
-            const double *src = ring + ((size_t)((G & (LC_NG - 1)) * L + lam)) * 2;
+            if (!vA && !vB) return;
+            const double *src = ring + (size_t)(S % LC_SLOTS) * C::SLOT + (size_t)lam_s * 2;
             double *out = nwt ? a.rop_out : a.dw;
-            constexpr int A0 = UPPER ? C::A_ST : C::A_DW;       // (upper, newton = 0: dW from the A_DW slots, below)
-            const int arr0 = nwt ? A0 : C::A_DW;
-            const int cb = ca - sg;                              // partner address
-            if (v1 && v0) {
+            const int arr0 = nwt ? C::A_ST : C::A_DW;
+            const int g0 = UPPER ? lrow - iiB : lrow + iiA;              // even cell address: start of the granule
+            if (vA && vB) {
 #pragma unroll
                 for (int e = 0; e < NEQ; e++)
-                    *(double2 *)(out + 2 * G + (size_t)e * nd) = *(const double2 *)(src + (size_t)(arr0 + e) * AS);
+                    *(double2 *)(out + g0 + (size_t)e * nd) = *(const double2 *)(src + (size_t)(arr0 + e) * AS);
             } else {
-                const int c1 = v1 ? ca : cb;
+                const int pos = vA ? (UPPER ? 1 : 0) : (UPPER ? 0 : 1);
 #pragma unroll
-                for (int e = 0; e < NEQ; e++) out[c1 + (size_t)e * nd] = src[(size_t)(arr0 + e) * AS + (c1 & 1)];
+                for (int e = 0; e < NEQ; e++) out[g0 + pos + (size_t)e * nd] = src[(size_t)(arr0 + e) * AS + pos];
             }
         };
-        // -- mailboxes: thread st < 3 NIF owns 16 bytes of the entry of interface line il (0..TK-1: j interface, row kk = il;
-        // TK..: k interface, column jj = il - TK).  Words needed at step X are loaded at iteration X-3 (registers carried over
-        // the loop edge), parked in shared memory at X-2 and, before the barrier of step X, delivered validated into mbx
-        // (polling global memory while the producer tile has not delivered); the entry is re-armed.
+        // -- mailboxes: thread st < 3 NIF owns 16 bytes of the two entries (cells A and B) of interface line il (0..TK-1: j
+        // interface, row kk = il; TK..: k interface, column jj = il - TK) at every super-step.  Words needed at super-step X
+        // are loaded at iteration X-3 (registers carried over the loop edge), parked in shared memory at X-2 and delivered
+        // validated into mbx at X-1 (polling global memory while the producer tile has not delivered); the entries are re-armed.
         const int il = st / 3, part = st % 3;
         const bool isj = il < TK;
         const int mjj = isj ? 0 : il - TK, mkk = isj ? il : 0;
@@ -573,50 +617,60 @@ __device__ __forceinline__ void lu_cell_body(const ZoneDev &z, const LuTileArgs 
         if (mvalid) mrow = (unsigned long long *)(isj ? a.ifj + ((size_t)((J - 1) * bk + mkg) * bi) * LU_MB
                                                         : a.ifk + ((size_t)((K - 1) * bj + mjg) * bi) * LU_MB) + 2 * part;
         const int msig = mjj + mkk;
-        unsigned long long *mpre = mbs + (size_t)(mth ? il : 0) * EX + 2 * part;     // + (step & 3) * NIF * EX
-        double *mout = mbx + (size_t)(mth ? il : 0) * EX + 2 * part;                  // + (step & 1) * NIF * EX
-        auto entry = [&](int X) {    // clamped: always a readable address
-            int ii = X - msig; ii = ii < 0 ? 0 : (ii >= bi ? bi - 1 : ii);
+        unsigned long long *mpre = mbs + (size_t)(mth ? il : 0) * MBW + 2 * part;     // + (X & 3) * NIF * MBW; cell B: + EX
+        double *mout = mbx + (size_t)(mth ? il : 0) * MBW + 2 * part;                  // + (X & 1) * NIF * MBW
+        auto cell_of = [&](int X, int c) { return 2 * (X - msig) - p + c; };
+        auto entry = [&](int ii) {    // clamped: always a readable address
+            ii = ii < 0 ? 0 : (ii >= bi ? bi - 1 : ii);
             return mrow + (mvalid ? (size_t)ii * LU_MB : 0);
         };
-        auto needed = [&](int X) { const int ii = X - msig; return mvalid && ii >= 0 && ii < bi; };
         auto deliver = [&](int X) {
-            if (!needed(X)) return;
-            const unsigned long long *pre = mpre + (size_t)(X & 3) * NIF * EX;
-            unsigned long long v0 = pre[0], v1 = pre[1];
-            volatile unsigned long long *p = entry(X);
-            int spin = 0;
-            while (mb_empty(v0) || mb_empty(v1)) {
-                v0 = p[0]; v1 = p[1];
-                if (++spin > LU_SPIN_MAX || (((spin & 1023) == 0) && *(volatile int *)a.err)) { *a.err = 1; break; }
+            if (!mvalid) return;
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                const int ii = cell_of(X, c);
+                if (ii < 0 || ii >= bi) continue;
+                const unsigned long long *pre = mpre + (size_t)(X & 3) * NIF * MBW + c * EX;
+                unsigned long long v0 = pre[0], v1 = pre[1];
+                volatile unsigned long long *q = entry(ii);
+                int spin = 0;
+                while (mb_empty(v0) || mb_empty(v1)) {
+                    v0 = q[0]; v1 = q[1];
+                    if (++spin > LU_SPIN_MAX || (((spin & 1023) == 0) && *(volatile int *)a.err)) { *a.err = 1; break; }
+                }
+                double *o = mout + (size_t)(X & 1) * NIF * MBW + c * EX;
+                o[0] = __longlong_as_double((long long)v0); o[1] = __longlong_as_double((long long)v1);
+                q[0] = LU_EMPTY; q[1] = LU_EMPTY;                              // self-cleaning: ready for the next sweep
             }
-            double *o = mout + (size_t)(X & 1) * NIF * EX;
-            o[0] = __longlong_as_double((long long)v0); o[1] = __longlong_as_double((long long)v1);
-            p[0] = LU_EMPTY; p[1] = LU_EMPTY;                                  // self-cleaning: ready for the next sweep
         };
-        for (int X = 0; X < 2; X++) {
-            volatile unsigned long long *p = entry(X);
-            unsigned long long *d = mpre + (size_t)(X & 3) * NIF * EX;
-            if (mth) { d[0] = p[0]; d[1] = p[1]; }
-        }
-        unsigned long long w0 = 0, w1 = 0;
-        if (mth) { volatile unsigned long long *p = entry(2); w0 = p[0]; w1 = p[1]; }
-        for (int s = -LC_PF; s < 0; s++) { refill(s); cp_async_commit(); }
-        for (int s = 0; s < nst; s++) {
-            refill(s);
-            cp_async_commit();
-            if (mth) {
-                unsigned long long *d = mpre + (size_t)((s + 2) & 3) * NIF * EX; d[0] = w0; d[1] = w1;
-                volatile unsigned long long *p = entry(s + 3); w0 = p[0]; w1 = p[1];
-            }
-            writeback(s);
-            deliver(s);
-            cp_async_wait<LC_PF>();
-            __syncthreads();
+        unsigned long long wa0 = 0, wa1 = 0, wb0 = 0, wb1 = 0;
+        auto load = [&](int X) {
+            volatile unsigned long long *qa = entry(cell_of(X, 0)), *qb = entry(cell_of(X, 1));
+            wa0 = qa[0]; wa1 = qa[1]; wb0 = qb[0]; wb1 = qb[1];
+        };
+        auto park = [&](int X) {
+            unsigned long long *d = mpre + (size_t)(X & 3) * NIF * MBW;
+            d[0] = wa0; d[1] = wa1; d[EX] = wb0; d[EX + 1] = wb1;
+        };
+        if (st == 0) { fetch(0); fetch(1); }
+        if (mth) { load(0); park(0); load(1); park(1); load(2); }
+        deliver(0);
+        for (int S = 0; S < nst; S++) {
+            __syncthreads();                                   // B_S: compute has finished super-step S-1
+            writeback(S - 1);
+            // every line of slot S-1 has been read (barrier.sync, not the .aligned bar.sync: the lanes of a service warp leave
+            // writeback() on different paths and the compiler does not reconverge them in front of inline assembly)
+            __syncwarp();
+            asm volatile("barrier.sync 1, %0;" ::"n"(LC_NSV) : "memory");
+            if (st == 0) fetch(S + 2);
+            if (mth) { park(S + 2); load(S + 3); }
+            deliver(S + 1);
+            // every box that was asked for is seen to land before the CTA can leave (a ragged tile may have no compute thread
+            // left waiting on the last slots)
+            if (st == 0) lc_mbar_wait(full + S % LC_SLOTS, (unsigned)(S / LC_SLOTS) & 1u);
         }
         __syncthreads();
-        cp_async_wait<0>();
-        writeback(nst); writeback(nst + 1);
+        writeback(nst - 1);
         return;
     }
 
@@ -626,7 +680,7 @@ __device__ __forceinline__ void lu_cell_body(const ZoneDev &z, const LuTileArgs 
     const int jjg = J * TJ + jj, kkg = K * TK + kk;
     const bool lvalid = jjg < bj && kkg < bk;
     const int sigma = jj + kk;
-    const int lrow = l0 + sg * (jjg * z.incj + kkg * z.inck);
+    const int lam_s = UPPER ? L - 1 - lam : lam;
     const bool has_j = jjg > 0, has_k = kkg > 0;
     volatile unsigned long long *mbj = nullptr, *mbk = nullptr;
     if (lvalid && jj == TJ - 1 && J + 1 < a.NJ) mbj = (unsigned long long *)(a.ifj + ((size_t)(J * bk + kkg) * bi) * LU_MB);
@@ -635,120 +689,141 @@ __device__ __forceinline__ void lu_cell_body(const ZoneDev &z, const LuTileArgs 
     const bool line_in_nb = jg >= a.nbx[2] && jg <= a.nbx[3] && kg >= a.nbx[4] && kg <= a.nbx[5];
     const double signe = UPPER ? -0.5 : 0.5;
     const double gam = z.gam, cp = z.gam * z.cv;
-    // incoming j / k products: neighbour line of the tile (exb, other parity) or neighbour tile (mbx)
-    const int offj = jj > 0 ? (lam - 1) * EX : -1, offk = kk > 0 ? (L + lam - TJ) * EX : -1;
-    const int mofj = kk * EX, mofk = (TK + jj) * EX;
+    // incoming j / k products: neighbour line of the tile (exb, other parity) or neighbour tile (mbx); offsets of cell A
+    const int offj = jj > 0 ? (lam - 1) * EX : -1, offk = kk > 0 ? (2 * L + lam - TJ) * EX : -1;
+    const int mofj = kk * MBW, mofk = (TK + jj) * MBW;
+    const int jj_s = UPPER ? TJ - 1 - jj : jj;
     double pi_[EX];
 #pragma unroll
     for (int e = 0; e < EX; e++) pi_[e] = 0.;
-    for (int s = 0; s < nst; s++) {
-        __syncthreads();
-        const int ii = s - sigma;
-        if (!(lvalid && ii >= 0 && ii < bi)) continue;
-        const int ca = lrow + sg * ii;
-        double *R = ring + ((size_t)(((ca >> 1) & (LC_NG - 1)) * L + lam)) * 2 + (ca & 1);
+    if (a.dbg && tid == 0) { a.dbg[16 * (K * a.NJ + J)] = gtime(); a.dbg[16 * (K * a.NJ + J) + 3] = smid(); }
+    long long tcomp = 0;
+    for (int S = 0; S < nst; S++) {
+        __syncthreads();                                       // B_S
+        // every compute thread observes every phase of the slot barriers, active or not: the normals ring of a 3dhomo zone is
+        // read up to TK - 1 super-steps after it landed
+        lc_mbar_wait(full + S % LC_SLOTS, (unsigned)(S / LC_SLOTS) & 1u);
+        const int m = S - sigma;
+        if (!(lvalid && m >= 0 && m < nm)) continue;
+        const long long tc0 = LU_CLOCK();
+        double *R0 = ring + (size_t)(S % LC_SLOTS) * C::SLOT + (size_t)lam_s * 2;
+        const double *N0 = nring + (size_t)((S - kk + LC_NSL) % LC_NSL) * C::NRS + jj_s * 2;
+        const double *xin = exb + (size_t)((S + 1) & 1) * 4 * L * EX;
+        double *xout = exb + (size_t)(S & 1) * 4 * L * EX;
+        const double *xmb = mbx + (size_t)(S & 1) * NIF * MBW;
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            const int ii = 2 * m - p + c;
+            if (ii < 0 || ii >= bi) continue;
+            const int pos = UPPER ? 1 - c : c;
+            double *R = R0 + pos;
 #define RING(arr) R[(size_t)(arr) * AS]
-        double acc[NEQ];
+            double acc[NEQ];
 #pragma unroll
-        for (int e = 0; e < NEQ; e++) acc[e] = RING(C::A_DW + e);
-        const double coe1 = RING(C::A_COE), coe5 = RING(C::A_COE + 4);
-        double coe6 = 1.;
-        if (NEQ == 6) coe6 = RING(C::A_COE + 5);
-        double ro = 0., u, v, w, t, nut = 0.;
-        if (UPPER) {
-            ro = RING(C::A_ST); u = RING(C::A_ST + 1); v = RING(C::A_ST + 2); w = RING(C::A_ST + 3); t = RING(C::A_ST + 4);
-            if (NEQ == 6) nut = RING(C::A_ST + NEQ - 1);
-        } else { u = RING(C::A_ST); v = RING(C::A_ST + 1); w = RING(C::A_ST + 2); t = RING(C::A_ST + 3); }
-        double ti0 = 0., ti1 = 0., ti2 = 0., tj0 = 0., tj1 = 0., tj2 = 0., tk0 = 0., tk1 = 0., tk2 = 0.;
-        if (MESH == 0) {
-            ti0 = RING(C::A_T); ti1 = RING(C::A_T + 1); ti2 = RING(C::A_T + 2); tj0 = RING(C::A_T + 3); tj1 = RING(C::A_T + 4);
-            tj2 = RING(C::A_T + 5); tk0 = RING(C::A_T + 6); tk1 = RING(C::A_T + 7); tk2 = RING(C::A_T + 8);
-        } else if (MESH == 1) {
-            ti0 = RING(C::A_T); ti1 = RING(C::A_T + 1); tj0 = RING(C::A_T + 2); tj1 = RING(C::A_T + 3); tk2 = RING(C::A_T + 4);
-        } else { ti0 = z.tc0[0]; tj1 = z.tc0[1]; tk2 = z.tc0[2]; }
-        const double cdi = RING(C::A_COE + 1) * signe, cdj = RING(C::A_COE + 2) * signe, cdk = RING(C::A_COE + 3) * signe;
-        const double *xin = exb + (size_t)((s + 1) & 1) * 2 * L * EX;
-        const double *xmb = mbx + (size_t)(s & 1) * NIF * EX;
-        const double2 *pj_ = (const double2 *)(offj >= 0 ? xin + offj : xmb + mofj);
-        const double2 *pk_ = (const double2 *)(offk >= 0 ? xin + offk : xmb + mofk);
-        const double2 j0 = pj_[0], j1 = pj_[1], j2 = pj_[2], k0 = pk_[0], k1 = pk_[1], k2 = pk_[2];
-        const double xal = coe1 * signe;
-        const double xi = ii > 0 ? xal : 0., xj = has_j ? xal : 0., xk = has_k ? xal : 0.;
-        if (UPPER) {
+            for (int e = 0; e < NEQ; e++) acc[e] = RING(C::A_DW + e);
+            const double coe1 = RING(C::A_COE), coe5 = RING(C::A_COE + 4);
+            double coe6 = 1.;
+            if (NEQ == 6) coe6 = RING(C::A_COE + 5);
+            double ro = 0., u, v, w, t, nut = 0.;
+            if (UPPER) {
+                ro = RING(C::A_ST); u = RING(C::A_ST + 1); v = RING(C::A_ST + 2); w = RING(C::A_ST + 3); t = RING(C::A_ST + 4);
+                if (NEQ == 6) nut = RING(C::A_ST + NEQ - 1);
+            } else { u = RING(C::A_ST); v = RING(C::A_ST + 1); w = RING(C::A_ST + 2); t = RING(C::A_ST + 3); }
+            double ti0 = 0., ti1 = 0., ti2 = 0., tj0 = 0., tj1 = 0., tj2 = 0., tk0 = 0., tk1 = 0., tk2 = 0.;
+            if (MESH == 0) {
+                ti0 = RING(C::A_T); ti1 = RING(C::A_T + 1); ti2 = RING(C::A_T + 2); tj0 = RING(C::A_T + 3); tj1 = RING(C::A_T + 4);
+                tj2 = RING(C::A_T + 5); tk0 = RING(C::A_T + 6); tk1 = RING(C::A_T + 7); tk2 = RING(C::A_T + 8);
+            } else if (MESH == 1) {
+                const double *N = N0 + pos;
+                ti0 = N[0]; ti1 = N[TJ * 2]; tj0 = N[2 * TJ * 2]; tj1 = N[3 * TJ * 2]; tk2 = N[4 * TJ * 2];
+            } else { ti0 = z.tc0[0]; tj1 = z.tc0[1]; tk2 = z.tc0[2]; }
+            const double cdi = RING(C::A_COE + 1) * signe, cdj = RING(C::A_COE + 2) * signe, cdk = RING(C::A_COE + 3) * signe;
+            const double2 *pj_ = (const double2 *)(offj >= 0 ? xin + offj + c * L * EX : xmb + mofj + c * EX);
+            const double2 *pk_ = (const double2 *)(offk >= 0 ? xin + offk + c * L * EX : xmb + mofk + c * EX);
+            const double2 j0 = pj_[0], j1 = pj_[1], j2 = pj_[2], k0 = pk_[0], k1 = pk_[1], k2 = pk_[2];
+            const double xal = coe1 * signe;
+            const double xi = ii > 0 ? xal : 0., xj = has_j ? xal : 0., xk = has_k ? xal : 0.;
+            if (UPPER) {
 #pragma unroll
-            for (int e = 0; e < 5; e++) acc[e] = acc[e] * coe5;
-            if (NEQ == 6) acc[NEQ - 1] = acc[NEQ - 1] * coe6;
-        }
-        // the sum follows the reference's k, j, i order (invlu_l.for / invlu_u.for)
-        acc[0] = ((acc[0] + k0.x * xk) + j0.x * xj) + pi_[0] * xi;
-        acc[1] = ((acc[1] + k0.y * xk) + j0.y * xj) + pi_[1] * xi;
-        acc[2] = ((acc[2] + k1.x * xk) + j1.x * xj) + pi_[2] * xi;
-        acc[3] = ((acc[3] + k1.y * xk) + j1.y * xj) + pi_[3] * xi;
-        acc[4] = ((acc[4] + k2.x * xk) + j2.x * xj) + pi_[4] * xi;
-        if (NEQ == 6) acc[NEQ - 1] = ((acc[NEQ - 1] + k2.y * xk) + j2.y * xj) + pi_[EX - 1] * xi;
-        const double diag = lu_rcp(coe5);
-        double dwn[NEQ];
-#pragma unroll
-        for (int e = 0; e < 5; e++) dwn[e] = acc[e] * diag;
-        if (NEQ == 6) dwn[NEQ - 1] = acc[NEQ - 1] * lu_rcp(coe6);
-        double uk = u, vk = v, wk = w, tk_ = t;     // state of the k product
-        if (UPPER && a.newton) {
-            // mjr_newton[_SA].for, once per cell: the updated state goes back through the ring (write-back role) and, when rop
-            // aliases rop_out, into the k product -- the reference has already updated plane k+1 when it sweeps plane k
-            const int ig = a.box[1] - ii;
-            const bool in_nb = line_in_nb && ig >= a.nbx[0] && ig <= a.nbx[1];
-            const double cvinv = 1. / z.cv, cvinv2 = 0.5 * cvinv;
-            const double rn = ro + dwn[0];
-            const double r_1 = lu_rcp(rn);
-            const double un = (ro * u + dwn[1]) * r_1, vn = (ro * v + dwn[2]) * r_1, wn = (ro * w + dwn[3]) * r_1;
-            const double roe_old = ro * (z.cv * t + 0.5 * (u * u + v * v + w * w));
-            const double tn = (roe_old + dwn[4]) * r_1 * cvinv - cvinv2 * (un * un + vn * vn + wn * wn);
-            if (in_nb) {
-                RING(C::A_ST) = rn; RING(C::A_ST + 1) = un; RING(C::A_ST + 2) = vn; RING(C::A_ST + 3) = wn; RING(C::A_ST + 4) = tn;
-                if (NEQ == 6) {
-                    double anulam = z.coesut * sqrt(tn * z.temp01) * tn * lu_rcp(tn + z.cmus1);   // = coesut sqrt(T/T0) / (1 + Cs/T)
-                    anulam = anulam * r_1 * z.ratiom;
-                    double tt = (ro * nut + dwn[NEQ - 1]) * r_1;
-                    tt = fmin(tt, anulam);
-                    RING(C::A_ST + NEQ - 1) = fmax(tt, 0.);
-                }
-                if (a.alias) { uk = un; vk = vn; wk = wn; tk_ = tn; }
+                for (int e = 0; e < 5; e++) acc[e] = acc[e] * coe5;
+                if (NEQ == 6) acc[NEQ - 1] = acc[NEQ - 1] * coe6;
             }
-        } else {
+            // the sum follows the reference's k, j, i order (invlu_l.for / invlu_u.for)
+            acc[0] = ((acc[0] + k0.x * xk) + j0.x * xj) + pi_[0] * xi;
+            acc[1] = ((acc[1] + k0.y * xk) + j0.y * xj) + pi_[1] * xi;
+            acc[2] = ((acc[2] + k1.x * xk) + j1.x * xj) + pi_[2] * xi;
+            acc[3] = ((acc[3] + k1.y * xk) + j1.y * xj) + pi_[3] * xi;
+            acc[4] = ((acc[4] + k2.x * xk) + j2.x * xj) + pi_[4] * xi;
+            if (NEQ == 6) acc[NEQ - 1] = ((acc[NEQ - 1] + k2.y * xk) + j2.y * xj) + pi_[EX - 1] * xi;
+            const double diag = lu_rcp(coe5);
+            double dwn[NEQ];
 #pragma unroll
-            for (int e = 0; e < NEQ; e++) RING(C::A_DW + e) = dwn[e];
-        }
-        // outgoing products
-        double bj_[EX], bk_[EX];
-        pi_[EX - 1] = 0.; bj_[EX - 1] = 0.; bk_[EX - 1] = 0.;
-        lu_prod<NEQ>(ti0, ti1, ti2, u, v, w, t, cdi, gam, cp, dwn, pi_);
-        lu_prod<NEQ>(tj0, tj1, tj2, u, v, w, t, cdj, gam, cp, dwn, bj_);
-        lu_prod<NEQ>(tk0, tk1, tk2, uk, vk, wk, tk_, cdk, gam, cp, dwn, bk_);
-        {
-            double2 *p = (double2 *)(exb + ((size_t)(s & 1) * 2 * L + lam) * EX);
-            p[0] = make_double2(bj_[0], bj_[1]); p[1] = make_double2(bj_[2], bj_[3]); p[2] = make_double2(bj_[4], bj_[5]);
-            double2 *q = (double2 *)(exb + ((size_t)(s & 1) * 2 * L + L + lam) * EX);
-            q[0] = make_double2(bk_[0], bk_[1]); q[1] = make_double2(bk_[2], bk_[3]); q[2] = make_double2(bk_[4], bk_[5]);
-        }
-        if (mbj) {
-            volatile unsigned long long *o = mbj + (size_t)ii * LU_MB;
+            for (int e = 0; e < 5; e++) dwn[e] = acc[e] * diag;
+            if (NEQ == 6) dwn[NEQ - 1] = acc[NEQ - 1] * lu_rcp(coe6);
+            double uk = u, vk = v, wk = w, tk_ = t;     // state of the k product
+            if (UPPER && a.newton) {
+                // mjr_newton[_SA].for, once per cell: the updated state goes back through the slot (write-back role) and, when
+                // rop aliases rop_out, into the k product -- the reference has already updated plane k+1 when it sweeps plane k
+                const int ig = a.box[1] - ii;
+                const bool in_nb = line_in_nb && ig >= a.nbx[0] && ig <= a.nbx[1];
+                const double cvinv = 1. / z.cv, cvinv2 = 0.5 * cvinv;
+                const double rn = ro + dwn[0];
+                const double r_1 = lu_rcp(rn);
+                const double un = (ro * u + dwn[1]) * r_1, vn = (ro * v + dwn[2]) * r_1, wn = (ro * w + dwn[3]) * r_1;
+                const double roe_old = ro * (z.cv * t + 0.5 * (u * u + v * v + w * w));
+                const double tn = (roe_old + dwn[4]) * r_1 * cvinv - cvinv2 * (un * un + vn * vn + wn * wn);
+                if (in_nb) {
+                    RING(C::A_ST) = rn; RING(C::A_ST + 1) = un; RING(C::A_ST + 2) = vn; RING(C::A_ST + 3) = wn; RING(C::A_ST + 4) = tn;
+                    if (NEQ == 6) {
+                        double anulam = z.coesut * sqrt(tn * z.temp01) * tn * lu_rcp(tn + z.cmus1);   // = coesut sqrt(T/T0) / (1 + Cs/T)
+                        anulam = anulam * r_1 * z.ratiom;
+                        double tt = (ro * nut + dwn[NEQ - 1]) * r_1;
+                        tt = fmin(tt, anulam);
+                        RING(C::A_ST + NEQ - 1) = fmax(tt, 0.);
+                    }
+                    if (a.alias) { uk = un; vk = vn; wk = wn; tk_ = tn; }
+                }
+            } else {
 #pragma unroll
-            for (int e = 0; e < LU_MB; e++) o[e] = (unsigned long long)__double_as_longlong(bj_[e]);
-        }
-        if (mbk) {
-            volatile unsigned long long *o = mbk + (size_t)ii * LU_MB;
+                for (int e = 0; e < NEQ; e++) RING(C::A_DW + e) = dwn[e];
+            }
+            // outgoing products
+            double bj_[EX], bk_[EX];
+            pi_[EX - 1] = 0.; bj_[EX - 1] = 0.; bk_[EX - 1] = 0.;
+            lu_prod<NEQ>(ti0, ti1, ti2, u, v, w, t, cdi, gam, cp, dwn, pi_);
+            lu_prod<NEQ>(tj0, tj1, tj2, u, v, w, t, cdj, gam, cp, dwn, bj_);
+            lu_prod<NEQ>(tk0, tk1, tk2, uk, vk, wk, tk_, cdk, gam, cp, dwn, bk_);
+            {
+                double2 *q = (double2 *)(xout + (size_t)(c * L + lam) * EX);
+                q[0] = make_double2(bj_[0], bj_[1]); q[1] = make_double2(bj_[2], bj_[3]); q[2] = make_double2(bj_[4], bj_[5]);
+                double2 *r = (double2 *)(xout + (size_t)(2 * L + c * L + lam) * EX);
+                r[0] = make_double2(bk_[0], bk_[1]); r[1] = make_double2(bk_[2], bk_[3]); r[2] = make_double2(bk_[4], bk_[5]);
+            }
+            if (mbj) {
+                volatile unsigned long long *o = mbj + (size_t)ii * LU_MB;
 #pragma unroll
-            for (int e = 0; e < LU_MB; e++) o[e] = (unsigned long long)__double_as_longlong(bk_[e]);
-        }
+                for (int e = 0; e < LU_MB; e++) o[e] = (unsigned long long)__double_as_longlong(bj_[e]);
+            }
+            if (mbk) {
+                volatile unsigned long long *o = mbk + (size_t)ii * LU_MB;
+#pragma unroll
+                for (int e = 0; e < LU_MB; e++) o[e] = (unsigned long long)__double_as_longlong(bk_[e]);
+            }
 #undef RING
+        }
+        // the results were written into the slot through the generic proxy; the slot is re-armed by TMA (async proxy) two
+        // barriers from here
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tcomp += LU_CLOCK() - tc0;
     }
     __syncthreads();
+    if (a.dbg && tid == 0) { a.dbg[16 * (K * a.NJ + J) + 1] = gtime(); a.dbg[16 * (K * a.NJ + J) + 2] = tcomp; }
 }
 
 template <int MESH, int NEQ, bool UPPER>
 __global__ void __launch_bounds__(LcCfg<MESH, NEQ, UPPER>::NTHR, 1) k_lu_cell(ZoneDev z, LuTileArgs a)
 {
-    extern __shared__ __align__(16) double smem[];
+    extern __shared__ __align__(128) double smem[];
     __shared__ int s_tile;
     if (threadIdx.x == 0) s_tile = a.order[atomicAdd(a.ticket, 1)];
     __syncthreads();
@@ -758,7 +833,7 @@ __global__ void __launch_bounds__(LcCfg<MESH, NEQ, UPPER>::NTHR, 1) k_lu_cell(Zo
 template <int MESH, int NEQ, bool UPPER>
 __global__ void __launch_bounds__(LcCfg<MESH, NEQ, UPPER>::NTHR, 1) k_lu_cell_b(const LuBatchItem *items, const int2 *order, int *ticket)
 {
-    extern __shared__ __align__(16) double smem[];
+    extern __shared__ __align__(128) double smem[];
     __shared__ int2 s_t;
     __shared__ __align__(16) LuBatchItem s_it;
     if (threadIdx.x == 0) s_t = order[atomicAdd(ticket, 1)];
@@ -769,14 +844,12 @@ __global__ void __launch_bounds__(LcCfg<MESH, NEQ, UPPER>::NTHR, 1) k_lu_cell_b(
     lu_cell_body<MESH, NEQ, UPPER>(s_it.z, s_it.a, s_t.y, smem);
 }
 
-// 16-byte staging needs even array strides (NDIMDX, and the plane of the 3dhomo normals); FAST_B200_LU=tile forces the 8-byte kernel
+// the skewed tensor maps need even strides (ni, NDIMDX); FAST_B200_LU=tile forces the 8-byte kernel
 bool lu_use_cell(const ZoneDev &z)
 {
     static const bool force_tile = [] { const char *e = getenv("FAST_B200_LU"); return e && e[0] == 't'; }();
     if (force_tile) return false;
-    if (z.nd % 2) return false;
-    if (z.typ == 1 && ((z.ni * z.nj) % 2)) return false;
-    return true;
+    return z.ni % 2 == 0 && z.nd % 2 == 0 && z.nfk > 0;
 }
 
 // cell-centred mean normals 0.5*(t_d(l) + t_d(l + d)) of every cell (lu_{i,j,k}_*.for build them on the fly)
@@ -813,6 +886,10 @@ __global__ void k_fill_u64(unsigned long long *p, size_t n, unsigned long long v
 }
 
 // ------------------------------------------------------------------------------------------------ host side
+bool fb_tma_encode_skew(CUtensorMap *out, const double *base, int ni, int nj, int nk, long long estride, int nvar, int box_k, int box_vars, int rank3);
+int lu_cell_tk(int mesh, int neq);
+bool lu_use_cell(const ZoneDev &z);
+
 int lu_plan_build(LuPlan &p, const ZoneDev &z, const int box[6])
 {
     lu_plan_free(p);
@@ -820,6 +897,15 @@ int lu_plan_build(LuPlan &p, const ZoneDev &z, const int box[6])
     const int bi = box[1] - box[0] + 1, bj = box[3] - box[2] + 1, bk = box[5] - box[4] + 1;
     p.nplanes = bi + bj + bk - 2;
     p.cell = lu_use_cell(z);
+    if (p.cell) {       // skewed tensor maps of the arrays whose address never changes; the rop levels follow on first use
+        const int tk = lu_cell_tk(z.typ, z.neq);
+        CUtensorMap h[2];
+        p.cell = fb_tma_encode_skew(&h[0], z.drodm, z.ni, z.nj, z.nk, z.nd, z.neq, tk, z.neq, 0) &&
+                 fb_tma_encode_skew(&h[1], z.coe, z.ni, z.nj, z.nk, z.nd, z.neq_coe, tk, z.neq_coe, 0) &&
+                 cudaMalloc(&p.d_tm, 9 * sizeof(CUtensorMap)) == cudaSuccess;
+        if (p.cell) cudaMemcpy(p.d_tm, h, sizeof(h), cudaMemcpyHostToDevice);
+        for (int q = 0; q < 3; q++) p.rop_seen[q] = nullptr;
+    }
     p.tj = LU_TJ; p.tk = p.cell ? lu_cell_tk(z.typ, z.neq) : lu_tile_tk(z.typ, z.neq);
     p.NJ = (bj + p.tj - 1) / p.tj; p.NK = (bk + p.tk - 1) / p.tk;
     std::vector<int> ord;
@@ -847,6 +933,13 @@ int lu_plan_build(LuPlan &p, const ZoneDev &z, const int box[6])
         const int nt = z.typ == 0 ? 9 : 5;
         if (cudaMalloc(&p.d_tcm, (size_t)nt * p.tstride * sizeof(double)) != cudaSuccess) return 1;
         cudaMemset(p.d_tcm, 0, (size_t)nt * p.tstride * sizeof(double));
+        if (p.cell) {
+            CUtensorMap h;
+            const bool ok = z.typ == 0 ? fb_tma_encode_skew(&h, p.d_tcm, z.ni, z.nj, z.nk, p.tstride, 9, p.tk, 9, 0)
+                                       : fb_tma_encode_skew(&h, p.d_tcm, z.ni, z.nj, z.nk, p.tstride, 5, p.tk, 5, 1);
+            if (!ok) return 1;
+            cudaMemcpy((CUtensorMap *)p.d_tm + 2, &h, sizeof(h), cudaMemcpyHostToDevice);
+        }
     }
     // the fills above ran on the legacy default stream; the solver's streams are non-blocking
     return (cudaDeviceSynchronize() == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : 1;
@@ -854,8 +947,8 @@ int lu_plan_build(LuPlan &p, const ZoneDev &z, const int box[6])
 
 void lu_plan_free(LuPlan &p)
 {
-    cudaFree(p.d_order); cudaFree(p.d_ctl); cudaFree(p.d_mb); cudaFree(p.d_tcm); cudaFree(p.d_rhs); cudaFree(p.d_us);
-    p.d_order = nullptr; p.d_ctl = nullptr; p.d_mb = nullptr; p.d_tcm = nullptr; p.d_rhs = nullptr; p.d_us = nullptr;
+    cudaFree(p.d_order); cudaFree(p.d_ctl); cudaFree(p.d_mb); cudaFree(p.d_tcm); cudaFree(p.d_rhs); cudaFree(p.d_us); cudaFree(p.d_tm);
+    p.d_tm = nullptr; p.d_order = nullptr; p.d_ctl = nullptr; p.d_mb = nullptr; p.d_tcm = nullptr; p.d_rhs = nullptr; p.d_us = nullptr;
 }
 
 void lu_plan_metrics(LuPlan &p, const ZoneDev &z, cudaStream_t st)
@@ -876,6 +969,20 @@ static void lu_fill_args(LuTileArgs &a, const ZoneDev &z, const LuPlan &p, const
     if (lu_match) { a.nbx[0] = 1; a.nbx[1] = z.iv; a.nbx[2] = 1; a.nbx[3] = z.jv; a.nbx[4] = 1; a.nbx[5] = z.kv; }
     a.bi = p.box[1] - p.box[0] + 1; a.bj = p.box[3] - p.box[2] + 1; a.bk = p.box[5] - p.box[4] + 1;
     a.NJ = p.NJ; a.NK = p.NK; a.alias = (rop == rop_out) ? 1 : 0; a.plane = z.ni * z.nj; a.newton = 1;
+    if (p.cell) {
+        a.tm = (const CUtensorMap *)p.d_tm;
+        int q = 0;
+        while (q < 3 && p.rop_seen[q] != rop && p.rop_seen[q] != nullptr) q++;
+        if (q == 3) q = 0;                                   // (cannot happen: a zone has three time levels)
+        if (p.rop_seen[q] != rop) {
+            CUtensorMap h[2];
+            fb_tma_encode_skew(&h[0], rop, z.ni, z.nj, z.nk, z.nd, z.neq, p.tk, 4, 0);
+            fb_tma_encode_skew(&h[1], rop, z.ni, z.nj, z.nk, z.nd, z.neq, p.tk, z.neq, 0);
+            cudaMemcpy((CUtensorMap *)p.d_tm + 3 + 2 * q, h, sizeof(h), cudaMemcpyHostToDevice);   // blocking, three times per zone
+            p.rop_seen[q] = rop;
+        }
+        a.tm_rop = (const CUtensorMap *)p.d_tm + 3 + 2 * q;  // + 1: upper sweep (lu_cell_body)
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ multi-zone launch
@@ -982,11 +1089,37 @@ static int run_lu_tiles(const ZoneDev &z, const LuPlan &p, const double *rop, do
     LuTileArgs a;
     lu_fill_args(a, z, p, rop, rop_out, lu_match);
     cudaMemsetAsync(p.d_ctl, 0, 2 * sizeof(int), st);
+    // FAST_B200_LU_DEBUG (k_lu_cell, build with -DLU_CLK for the cycle counters): per tile start / end (globaltimer) and cycles per role
+    static const bool dbg = getenv("FAST_B200_LU_DEBUG") != nullptr;
+    static unsigned long long *d_dbg = nullptr; static int dbg_calls = 0;
+    const int ntiles = p.NJ * p.NK;
     a.dbg = nullptr;
+    if (dbg && p.cell && dbg_calls < 3) { if (!d_dbg) cudaMalloc(&d_dbg, 2 * 16 * 65536 * sizeof(unsigned long long)); cudaMemsetAsync(d_dbg, 0, 2 * 16 * 65536 * 8, st); a.dbg = d_dbg; }
     a.ticket = p.d_ctl; a.order_mode = lu_match ? 1 : (MESH == 2 ? 2 : 0);
     launch_sweep<MESH, NEQ, false>(z, p, a, st);
     a.ticket = p.d_ctl + 1; a.order_mode = lu_match ? 1 : 0;
+    if (a.dbg) a.dbg += 16 * 65536;
     launch_sweep<MESH, NEQ, true>(z, p, a, st);
+    if (a.dbg) {
+        cudaStreamSynchronize(st);
+        std::vector<unsigned long long> h(2 * 16 * 65536);
+        cudaMemcpy(h.data(), d_dbg, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+        for (int sw = 0; sw < 2; sw++) {
+            const unsigned long long *q = h.data() + sw * 16 * 65536; unsigned long long t0 = ~0ULL, t1 = 0;
+            for (int t = 0; t < ntiles; t++) { t0 = std::min(t0, q[16 * t]); t1 = std::max(t1, q[16 * t + 1]); }
+            fprintf(stderr, "LUDBG sweep %d call %d: NJ %d NK %d tiles %d bi %d total %.1f us\n", sw, dbg_calls, p.NJ, p.NK, ntiles, a.bi, (t1 - t0) * 1e-3);
+            const double n = a.bi + 22.;
+            for (int t = 0; t < ntiles; t++) {
+                const int J = t % p.NJ, K = t / p.NJ;
+                if (dbg_calls == 1 && (J % 8 == 0 || J == p.NJ - 1))
+                    fprintf(stderr, "LUDBG   tile J %2d K %2d sm %3llu start %8.1f end %8.1f dur %8.1f us | cycles/step: compute %6.0f | svc line0: refill %5.0f mbox %5.0f wb %5.0f deliver %5.0f wait %5.0f | svc line33: %5.0f %5.0f %5.0f %5.0f %5.0f\n",
+                            J, K, q[16 * t + 3], (q[16 * t] - t0) * 1e-3, (q[16 * t + 1] - t0) * 1e-3, (q[16 * t + 1] - q[16 * t]) * 1e-3, q[16 * t + 2] / (double)a.bi,
+                            q[16 * t + 4] / n, q[16 * t + 5] / n, q[16 * t + 6] / n, q[16 * t + 7] / n, q[16 * t + 8] / n,
+                            q[16 * t + 9] / n, q[16 * t + 10] / n, q[16 * t + 11] / n, q[16 * t + 12] / n, q[16 * t + 13] / n);
+            }
+        }
+        dbg_calls++;
+    }
     return 3;
 }
 

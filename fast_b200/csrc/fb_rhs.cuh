@@ -189,9 +189,9 @@ __global__ void __launch_bounds__(32 * (RHS2_RJ + 1)) k_rhs2(ZoneDev z, RhsArgs 
         if (cell && !last) {
             if (!(IMPL || a.nitcfg == 1)) {
 #pragma unroll
-                for (int e = 0; e < NEQ; e++) accn[e] = z.drodm[l + e * nd];
+                for (int e = 0; e < NEQ; e++) accn[e] = FB_LD(z.drodm + l + e * nd);
             }
-            if (IMPL) coe1 = z.coe[l];
+            if (IMPL) coe1 = FB_LD(z.coe + l);
             else coe1 = MESH == 2 ? z.dtc / z.vol0 : z.dtc / __ldg(z.vol + lt);
         }
         unsigned wg = (SCHEME == 2 && !wcomp && (cell || fi || fj)) ? z.wigb[l] : 0u;
@@ -329,7 +329,7 @@ template <int MESH, int SCHEME> struct Rhs3MinB { static constexpr int V = (SCHE
 
 template <int MESH, int FLOW, int SCHEME, int SLOPE, bool IMPL, int RJ, bool WC>
 __global__ void __launch_bounds__(32 * (RJ + 1), Rhs3MinB<MESH, SCHEME>::V)
-k_rhs3(const __grid_constant__ CUtensorMap tm_rop, const __grid_constant__ CUtensorMap tm_mu, ZoneDev z, RhsArgs a)
+k_rhs3(const CUtensorMap *__restrict__ tm_rop, const CUtensorMap *__restrict__ tm_mu, ZoneDev z, RhsArgs a)
 {
     using C = Rhs3Cfg<FLOW, RJ>;
     constexpr int NEQ = C::NEQ, NS = RHS3_NS, PS = C::PS, RS = C::RS, VS = C::VS;
@@ -359,8 +359,8 @@ k_rhs3(const __grid_constant__ CUtensorMap tm_rop, const __grid_constant__ CUten
     auto issue = [&](int p) {
         const int slot = (p - pfirst) % NS;
         mbar_expect_tx(bar + slot, C::TX);
-        tma_load_4d(ring + slot * PS, &tm_rop, ca, cb, p + z.nfk - 1, 0, bar + slot);
-        if (FLOW >= 2) tma_load_4d(ring + slot * PS + C::MUOFF, &tm_mu, ca, cb, p + z.nfk - 1, 0, bar + slot);
+        tma_load_4d(ring + slot * PS, tm_rop, ca, cb, p + z.nfk - 1, 0, bar + slot);
+        if (FLOW >= 2) tma_load_4d(ring + slot * PS + C::MUOFF, tm_mu, ca, cb, p + z.nfk - 1, 0, bar + slot);
     };
     if (leader) {
         for (int s = 0; s < NS; s++) mbar_init(bar + s, 1);
@@ -385,7 +385,7 @@ k_rhs3(const __grid_constant__ CUtensorMap tm_rop, const __grid_constant__ CUten
     {
         const int l = inddm(z, cell ? i : 1, cell ? j : 1, k0 - 2);
 #pragma unroll
-        for (int e = 0; e < NEQ; e++) km2[e] = a.rop[l + e * nd];
+        for (int e = 0; e < NEQ; e++) km2[e] = FB_LD(a.rop + l + e * nd);
     }
     double acc[NEQ], f[NEQ];
 #pragma unroll
@@ -408,9 +408,9 @@ k_rhs3(const __grid_constant__ CUtensorMap tm_rop, const __grid_constant__ CUten
             if (cell && k <= k1) {
                 if (!(IMPL || a.nitcfg == 1)) {
 #pragma unroll
-                    for (int e = 0; e < NEQ; e++) accn[e] = z.drodm[lg + e * nd];
+                    for (int e = 0; e < NEQ; e++) accn[e] = FB_LD(z.drodm + lg + e * nd);
                 }
-                if (IMPL) coe1 = z.coe[lg];
+                if (IMPL) coe1 = FB_LD(z.coe + lg);
                 else coe1 = MESH == 2 ? z.dtc / z.vol0 : z.dtc / __ldg(z.vol + indmtr(z, i, j, k));
             }
         }
@@ -478,8 +478,8 @@ k_rhs3(const __grid_constant__ CUtensorMap tm_rop, const __grid_constant__ CUten
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
-// tensor maps of rop(ni,nj,nk,neq) / xmut(ni,nj,nk,naux) with a (36, rows, 1, nvar) box; nullptr when the strides
-// cannot be encoded (odd ni or NDIMDX) or the driver entry point is missing (fb_tma.cu)
+// tensor maps (in device memory) of rop(ni,nj,nk,neq) / xmut(ni,nj,nk,naux) with a (36, rows, 1, nvar) box; nullptr when the
+// strides cannot be encoded (odd ni or NDIMDX) or the driver entry point is missing (fb_tma.cu)
 const CUtensorMap *fb_tma_map(const double *base, int ni, int nj, int nk, long long var_stride, int nvar_total, int box_rows, int box_vars);
 
 template <int MESH, int FLOW, int SCHEME, int SLOPE>
@@ -520,11 +520,11 @@ static bool launch_rhs3_t(const ZoneDev &z, RhsArgs &a, bool impl, cudaStream_t 
     a.thin = rhs_thin(z, g, 31, RJ, RHS3_KC);
     if (!rhs_part_grid(a, g)) return true;
     if (SCHEME == 2 && a.nitcfg == 1 && a.wfuse) {   // first sub-iteration of a SENSOR zone: the switch is evaluated in the flux
-        if (impl) k_rhs3<MESH, FLOW, SCHEME, SLOPE, true, RJ, SCHEME == 2><<<g, b, C::template smem<MESH>(), st>>>(*tr, *tm, z, a);
-        else k_rhs3<MESH, FLOW, SCHEME, SLOPE, false, RJ, SCHEME == 2><<<g, b, C::template smem<MESH>(), st>>>(*tr, *tm, z, a);
+        if (impl) k_rhs3<MESH, FLOW, SCHEME, SLOPE, true, RJ, SCHEME == 2><<<g, b, C::template smem<MESH>(), st>>>(tr, tm, z, a);
+        else k_rhs3<MESH, FLOW, SCHEME, SLOPE, false, RJ, SCHEME == 2><<<g, b, C::template smem<MESH>(), st>>>(tr, tm, z, a);
     } else {
-        if (impl) k_rhs3<MESH, FLOW, SCHEME, SLOPE, true, RJ, false><<<g, b, C::template smem<MESH>(), st>>>(*tr, *tm, z, a);
-        else k_rhs3<MESH, FLOW, SCHEME, SLOPE, false, RJ, false><<<g, b, C::template smem<MESH>(), st>>>(*tr, *tm, z, a);
+        if (impl) k_rhs3<MESH, FLOW, SCHEME, SLOPE, true, RJ, false><<<g, b, C::template smem<MESH>(), st>>>(tr, tm, z, a);
+        else k_rhs3<MESH, FLOW, SCHEME, SLOPE, false, RJ, false><<<g, b, C::template smem<MESH>(), st>>>(tr, tm, z, a);
     }
     return true;
 }

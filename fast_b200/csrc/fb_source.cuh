@@ -126,7 +126,7 @@ __device__ __forceinline__ double sa_source_cell(const ZoneDev &z, const V &v, c
         double amutild = anutild * rho;
         amutild = fmax(amutild, 0.0000000000000001);
         const double tsourcenu = vol * tsourceb / amutild;
-        z.coe[lg + 5 * nd] = z.coe[lg + 4 * nd] - fmin(tsourcenu, 0.) * coe1;
+        z.coe[lg + 5 * nd] = FB_LD(z.coe + lg + 4 * nd) - fmin(tsourcenu, 0.) * coe1;
     }
     return vol * tsource;
 }
@@ -155,8 +155,8 @@ __device__ __forceinline__ void implicit_assemble(const ZoneDev &z, const V &v, 
     // level n-1 only enters with BDF2 (c3 != 0): first-order / local time stepping skips its loads (0 * W(n-1) = 0)
     double m0 = 0., m1 = 0., m2 = 0., m3 = 0., m4 = 0., m5 = 0.;
     if (c3 != 0.) {
-        m0 = rm[l]; m1 = rm[l + nd]; m2 = rm[l + 2 * nd]; m3 = rm[l + 3 * nd]; m4 = rm[l + 4 * nd];
-        if (NEQ == 6) m5 = rm[l + 5 * nd];
+        m0 = FB_LD(rm + l); m1 = FB_LD(rm + l + nd); m2 = FB_LD(rm + l + 2 * nd); m3 = FB_LD(rm + l + 3 * nd); m4 = FB_LD(rm + l + 4 * nd);
+        if (NEQ == 6) m5 = FB_LD(rm + l + 5 * nd);
     }
     const double roe = a0 * (cv * a4 + 0.5 * (a1 * a1 + a2 * a2 + a3 * a3));
     const double roe_n1 = m0 * (cv * m4 + 0.5 * (m1 * m1 + m2 * m2 + m3 * m3));
@@ -169,7 +169,7 @@ __device__ __forceinline__ void implicit_assemble(const ZoneDev &z, const V &v, 
         acc[4] = coe1 * acc[4] + c4 * roe + c3 * roe_n1;
         if (NEQ == 6) acc[NEQ - 1] = coe1 * acc[NEQ - 1] + c4 * v.q(5, lv) * a0 + c3 * m5 * m0;
     } else {
-        const double n0 = rn[l], n1 = rn[l + nd], n2 = rn[l + 2 * nd], n3 = rn[l + 3 * nd], n4 = rn[l + 4 * nd];
+        const double n0 = FB_LD(rn + l), n1 = FB_LD(rn + l + nd), n2 = FB_LD(rn + l + 2 * nd), n3 = FB_LD(rn + l + 3 * nd), n4 = FB_LD(rn + l + 4 * nd);
         const double roe_n = n0 * (cv * n4 + 0.5 * (n1 * n1 + n2 * n2 + n3 * n3));
         acc[0] = coe1 * acc[0] + c1 * a0 + c2 * n0 + c3 * m0;
         acc[1] = coe1 * acc[1] + c1 * a1 * a0 + c2 * n1 * n0 + c3 * m1 * m0;
@@ -177,6 +177,6 @@ __device__ __forceinline__ void implicit_assemble(const ZoneDev &z, const V &v, 
         acc[3] = coe1 * acc[3] + c1 * a3 * a0 + c2 * n3 * n0 + c3 * m3 * m0;
         acc[4] = coe1 * acc[4] + c1 * roe + c2 * roe_n + c3 * roe_n1;
         if (NEQ == 6)
-            acc[NEQ - 1] = coe1 * acc[NEQ - 1] + c1 * v.q(5, lv) * a0 + c2 * rn[l + 5 * nd] * n0 + c3 * m5 * m0;
+            acc[NEQ - 1] = coe1 * acc[NEQ - 1] + c1 * v.q(5, lv) * a0 + c2 * FB_LD(rn + l + 5 * nd) * n0 + c3 * m5 * m0;
     }
 }

@@ -64,9 +64,16 @@ def register(zones, metrics, hook, tc=None, device=None):
 
 
 def set_joins(hook, tc):
-    """tc = flattened match-join table (numpy int32, layout in csrc/fb_joins.cu) -- stand-in for Connector's
-    miseAPlatDonorTree__ output stored in HOOK['param_int_tc'] (S/PyTree.py:495)."""
+    """The flattened donor tree, stored like the reference in HOOK['param_int_tc'] / HOOK['param_real_tc'] (S/PyTree.py:495-500):
+    tc = (param_int_tc, param_real_tc) in Connector's miseAPlatDonorTree__ layout (C/Com/setInterpTransfersFast.cpp:469-477) ->
+    fb_set_joins_tc; a single int32 array = this library's own table (csrc/fb_joins.cu; it also carries the pack / unpack
+    entries of the cross-rank joins of fast_b200.dist)."""
     L = _lib.lib()
+    if isinstance(tc, (tuple, list)) and len(tc) == 2:
+        pit = numpy.ascontiguousarray(tc[0], dtype=numpy.int32); prt = numpy.ascontiguousarray(tc[1], dtype=numpy.float64)
+        hook['param_int_tc'] = pit; hook['param_real_tc'] = prt
+        _lib.check(L.fb_set_joins_tc(_solver(hook), pit.ctypes.data_as(_lib.c_ip), pit.size, _dp(prt), prt.size))
+        return
     ji = numpy.ascontiguousarray(tc, dtype=numpy.int32)
     hook['param_int_tc'] = ji
     _lib.check(L.fb_set_joins(_solver(hook), ji.ctypes.data_as(_lib.c_ip), ji.size))

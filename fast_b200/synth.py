@@ -401,3 +401,37 @@ def build_joins(layout, nblk, nloc, periodic=(False, False, False), rank_of=None
     table = numpy.concatenate([numpy.array([nj, off], numpy.int32), numpy.array(desc, numpy.int32).reshape(-1)] + idx) \
         if nj else numpy.array([0, 0], numpy.int32)
     return table.astype(numpy.int32), peers
+
+
+def build_joins_tc(layout, nblk, nloc, periodic=(False, False, False), neq=5):
+    """The same match joins in the REFERENCE wire format: (param_int_tc, param_real_tc) as Connector's miseAPlatDonorTree__ lays
+    them out and K_FASTC::setInterpTransfersIntra reads them (C/Com/setInterpTransfersFast.cpp:469-477, 641-654, 750-760;
+    technical document 2.4.3.1): header [-, NbP2P, sizecomIBC = 0, sizecomID = 1, NbcomID = 0, Ptr_P2P_1], then the intra-process
+    exchange [dest, nrac, nrac_inst = 0, timelevel = 0, 18 tables of nrac ints, 27 ints per join (local time stepping levels)],
+    then per join the interpolation type block [ntype = 1, npts, type (= 1) per point], the donor and the receiver point lists.
+    Coefficients (1.0 per point, ST/tgvMpi.py:136-139) go to param_real_tc.  Returns None when the case has no join."""
+    recs = join_records(layout, nblk, nloc, periodic)
+    if not recs: return None
+    nrac = len(recs)
+    head = [0, 1, 0, 1, 0]                      # pit[2] = sizecomIBC, pit[3] = sizecomID, one entry (NbcomID = 0)
+    ech = len(head) + 1                          # pit[NoTransfert + shift_graph] = pit[5] -> first P2P block
+    T = ech + 4
+    end_tables = T + 18 * nrac + 27 * nrac
+    tables = numpy.zeros((18, nrac), numpy.int64)
+    blocks, pos, cpos, coefs = [], end_tables, 0, []
+    for q, (dz, rz, sidx, ridx) in enumerate(recs):
+        npts = int(sidx.size)
+        tables[0, q] = npts; tables[1, q] = npts; tables[2, q] = 1; tables[3, q] = -1; tables[4, q] = 0
+        tables[5, q] = dz; tables[9, q] = 0; tables[10, q] = npts; tables[11, q] = rz; tables[13, q] = neq
+        tables[14, q] = 0; tables[15, q] = -1; tables[16, q] = 0
+        tblock = numpy.concatenate([[1, npts], numpy.ones(npts, numpy.int64)])
+        tables[7, q] = pos; pos += tblock.size
+        tables[6, q] = pos; pos += npts
+        tables[12, q] = pos; pos += npts
+        tables[8, q] = cpos; cpos += npts
+        blocks += [tblock, sidx.astype(numpy.int64), ridx.astype(numpy.int64)]
+        coefs.append(numpy.ones(npts))
+    lev = numpy.zeros((nrac, 27), numpy.int64); lev[:, 24] = 1; lev[:, 25] = 1
+    pit = numpy.concatenate([numpy.array(head + [ech], numpy.int64), numpy.array([0, nrac, 0, 0], numpy.int64), tables.ravel(), lev.ravel()] + blocks)
+    assert pit.size == pos
+    return pit.astype(numpy.int32), numpy.concatenate(coefs)

@@ -55,6 +55,12 @@ int fb_zone_download_work(fb_solver *s, int nd, double *drodm, double *coe);
 /* Match joins: flattened donor tree in this repo's documented layout (DESIGN.md "match joins"), the
  * stand-in for Connector's miseAPlatDonorTree__ tables read at C/Com/setInterpTransfersFast.cpp:469-477. */
 int fb_set_joins(fb_solver *s, const int *join_int, int n_int);
+/* The reference's own wire format: HOOK['param_int_tc'] / HOOK['param_real_tc'], the donor tree flattened by Connector's
+ * miseAPlatDonorTree__ (S/PyTree.py:495), read field by field as K_FASTC::setInterpTransfersIntra does
+ * (C/Com/setInterpTransfersFast.cpp:469-477, 641-654, 750-760; layout documented in the FastS technical document 2.4.3.1).
+ * Match joins only (interpolation type 0 / 1, one donor of coefficient 1): IBC, chimera stencils, unsteady joins, azimuthal
+ * periodicity and conservative nearmatch windows return FB_EINVAL.  Point lists are 0-based cell addresses of the ghosted zones. */
+int fb_set_joins_tc(fb_solver *s, const int *param_int_tc, int n_int, const double *param_real_tc, int n_real);
 
 /* fasts._computePT(zones, metrics, nitrun, nstep_deb, nstep_fin, layer_mode, nit_c, hook)
  * (S/Compute/computePT.cpp:44): runs nit_c iterations x sub-iterations nstep_deb..nstep_fin with

@@ -66,11 +66,34 @@ class Zone:
         L.fo_cp_vol(_p(self.pi, _ip), _p(self.x), _p(self.y), _p(self.z), _p(self.ti), _p(self.tj), _p(self.tk), _p(self.vol))
 
 
+def tc_to_table(pit, prt):
+    """Connector's flattened donor tree (param_int_tc, param_real_tc) -> the match-join table fo_transfers applies, reading the
+    fields exactly where K_FASTC::setInterpTransfersIntra reads them (C/Com/setInterpTransfersFast.cpp:469-477 header, :641-654
+    zones / variables, :750-760 point lists).  Match joins only: type 0 / 1, coefficient 1."""
+    pit = numpy.asarray(pit); prt = numpy.asarray(prt)
+    sizecomIBC = int(pit[2]); sizecomID = int(pit[3 + sizecomIBC]); shift_graph = sizecomIBC + sizecomID + 3
+    ech = int(pit[1 + shift_graph])                                  # NoTransfert = 1
+    nrac, nrac_inst, timelevel = int(pit[ech + 1]), int(pit[ech + 2]), int(pit[ech + 3])
+    assert nrac_inst == 0
+    desc, idx, off = [], [], 0
+    for irac in range(nrac):
+        sr = ech + 4 + timelevel * 2 + irac
+        assert pit[sr + nrac * 3] < 0 and pit[sr + nrac * 14] == 0
+        NoD, NoR, npts = int(pit[sr + nrac * 5]), int(pit[sr + nrac * 11]), int(pit[sr + nrac * 10])
+        pt = int(pit[sr + nrac * 7]); ntype = int(pit[pt]); types = pit[pt + 1 + ntype: pt + 1 + ntype + npts]
+        assert numpy.all((types == 0) | (types == 1))
+        pc = int(pit[sr + nrac * 8]); assert numpy.all(prt[pc:pc + npts] == 1.)
+        pd, pr = int(pit[sr + nrac * 6]), int(pit[sr + nrac * 12])
+        desc += [0, NoD, NoR, npts, off, off + npts, 0]; idx += [pit[pd:pd + npts], pit[pr:pr + npts]]; off += 2 * npts
+    return numpy.concatenate([numpy.array([nrac, off], numpy.int32), numpy.array(desc, numpy.int32)] + idx).astype(numpy.int32)
+
+
 class Oracle:
     """Runs fo_compute on a list of Zone objects, rotating the python-side level list like the reference."""
     def __init__(self, zones, pitc=None, prtc=None, fast=False):
         self.L = lib(fast); self.zones = zones
         self.arr = (fo_zone * len(zones))()
+        if isinstance(pitc, (tuple, list)) and len(pitc) == 2: pitc = tc_to_table(*pitc)     # reference wire format
         self.pitc = None if pitc is None else numpy.ascontiguousarray(pitc, dtype=numpy.int32)
         self.prtc = None if prtc is None else numpy.ascontiguousarray(prtc, dtype=numpy.float64)
         for z in zones: z.metrics(self.L)
