@@ -274,9 +274,12 @@ def measure(workload, steps, warmup, ctx, do_e2e=True, min_timed_s=0.):
         e1.record(stream); fence()
         ms2 = max_over_ranks(e0.elapsed_time(e1))
         state_bytes = sum(x.numel() * 8 for x in hb[0])
-        h2d = state_bytes * (2 if implicit else 1) * world; d2h = state_bytes * world
+        # inputs of an iteration: ro, and ro_M1 where the BDF2 time term reads it (not with local time stepping: core3as2.for:37-46)
+        bdf2 = implicit and int(pi0[V.DTLOC]) != 1
+        h2d = state_bytes * (2 if bdf2 else 1) * world; d2h = state_bytes * world
         res['e2e'] = {'value': cells_total * e2e_steps / (ms2 * 1e-3) / 1e6, 'unit': 'Mcell.it/s', 'h2d_bytes_per_step': h2d,
-                      'd2h_bytes_per_step': d2h, 'steps': e2e_steps, 'ms_per_step': ms2 / e2e_steps}
+                      'd2h_bytes_per_step': d2h, 'steps': e2e_steps, 'ms_per_step': ms2 / e2e_steps,
+                      'copies': 'pinned host buffers; uploads zone by zone on a copy stream, overlapped with the first kernels of the zones already resident'}
         a = hb[order[0]][0].numpy()
         assert numpy.isfinite(a).all(), "non-finite state after the benchmark"
         del hb

@@ -402,15 +402,22 @@ def switchPointers__(zones, case, order=3):
 
 
 def createWorkArrays__(zones, dtloc, FIRST_IT):
-    """HOOK dictionary (PyTree.py:2064-2230).  On the GPU the work arrays (rhs, coe, wiggle) live in HBM and are
-    owned by the solver object; HOOK keeps their sizes and the flags the C layer reads."""
+    """HOOK dictionary (PyTree.py:2064-2230): the work arrays `rhs` (drodm), `coe` and `wiggle` are host numpys of the
+    reference's sizes, all zones concatenated with the per-zone offsets of gsdr3.cpp:282-290 (neq*NDIMDX, neq_coe*NDIMDX,
+    3*NDIMDX per zone).  On the GPU the live copies stay in HBM, owned by the solver object; FastS.sync_work(t) fills these
+    host arrays on demand (they are never read back by the solver).  numpy.zeros does not commit the pages before they are
+    touched, so unused work arrays cost nothing."""
     neq_max = 0; ndimt = 0; ndimcoe = 0; ndimwig = 0
+    offsets = []
     for z in zones:
         pi = Internal.getNodeFromName1(Internal.getNodeFromName1(z, '.Solver#ownData'), 'Parameter_int')[1]
         neq_max = max(neq_max, int(pi[VSHARE.NEQ]))
+        offsets.append((ndimt, ndimcoe, ndimwig))
         ndimt += int(pi[VSHARE.NEQ]) * int(pi[VSHARE.NDIMDX])
-        ndimcoe += int(pi[VSHARE.NEQ_COE]) * int(pi[VSHARE.NDIMDX])
+        ndimcoe += max(int(pi[VSHARE.NEQ_COE]), 0) * int(pi[VSHARE.NDIMDX])
         if pi[VSHARE.KFLUDOM] == 2: ndimwig += 3 * int(pi[VSHARE.NDIMDX])
-    return {'rhs': ndimt, 'coe': ndimcoe, 'wiggle': ndimwig, 'dtloc': dtloc, 'FIRST_IT': FIRST_IT, 'neq_max': neq_max,
-            'MX_SSZONE': MX_SSZONE, 'MX_SYNCHRO': MX_SYNCHRO, 'param_int_tc': None, 'param_real_tc': None,
-            'solver': None}
+    return {'rhs': numpy.zeros(ndimt, numpy.float64), 'coe': numpy.zeros(ndimcoe, numpy.float64),
+            'wiggle': numpy.zeros(ndimwig, numpy.float64), 'work_offsets': offsets,
+            'dtloc': dtloc, 'FIRST_IT': FIRST_IT, 'neq_max': neq_max,
+            'MX_SSZONE': MX_SSZONE, 'MX_SYNCHRO': MX_SYNCHRO, 'MX_OMP_SIZE_INT': MX_OMP_SIZE_INT, 'param_int_tc': None,
+            'param_real_tc': None, 'mpi': 0, 'lssiter_loc': 0, 'solver': None, 'timing': False, 'timed_subit': 0}

@@ -31,7 +31,14 @@ def _warmup_host(t, tc=None, Padding=None, verbose=0):
     zones = Internal.getZones(t)
     for z in zones:
         own, pi, pr, xyz = _zone_arrays(z)
-        geom.fill_sizes(pi, *xyz)
+        deg = geom.fill_sizes(pi, *xyz)
+        if deg is not None and numpy.any(deg):
+            # C/Metric/init_metric.cpp:318 -> tijk_extrap.for / dist_extrap.for rebuild the metrics (and the wall distance) of
+            # degenerate ghost cells from their interior mirror; that repair is not built here, and computing on collapsed
+            # cells would silently give other numbers than the reference
+            raise ValueError("fast_b200: zone %s has %d degenerate cells (edges <= 2e-8, nature_geom_dom.for:36-160); the "
+                             "tijk_extrap / dist_extrap repair of degenerate ghost cells is outside the hot-path scope"
+                             % (z[0], int(numpy.count_nonzero(deg))))
         Internal.getNodeFromName1(own, 'type_zone')[1] = numpy.array([pi[VSHARE.ITYPZONE]], Internal.E_NpyInt)
         if verbose > 0:
             names = {0: '3D curvilinear', 1: '3D homogenous k direction with constant step',
@@ -98,6 +105,8 @@ def _compute(t, metrics, nitrun, tc=None, graph=None, layer="c", NIT=1, ucData=N
     for _ in range(NIT): FastC.switchPointers__(zones, 1, order)
     FastC.FIRST_IT = 1
     FastC.HOOK['FIRST_IT'] = 1
+    if FastC.HOOK.get('timing'):
+        FastC.HOOK['timed_subit'] += NIT * (nitmax - 1 if itypcp < 2 else nitmax)
     return None
 
 
@@ -122,6 +131,48 @@ def sync_tree(t, levels=('', '_M1', '_P1'), aux=True):
     """Copy the device-resident state back into the tree's numpys (what save / display / post need)."""
     from .. import fasts
     fasts.download(Internal.getZones(t), FastC.HOOK, levels, aux)
+
+
+def sync_work(t):
+    """Copy the device-resident work arrays into HOOK['rhs'] / HOOK['coe'] / HOOK['wiggle'] (reference layout)."""
+    from .. import fasts
+    fasts.download_work(Internal.getZones(t), FastC.HOOK)
+
+
+def display_cpu_efficiency(t, mask_cpu=0.08, mask_cell=0.01, diag='compact', FILEOUT='listZonesSlow.dat', FILEOUT1='diagCPU.dat',
+                           RECORD=None):
+    """Cell updates per second (PyTree.py:2673-2806).  The reference derives, per zone, the time per cell and sub-iteration from
+    HOOK['TIMER_OMP'] and stores [mean, min, max] cell updates / s in the zone's `.Solver#define/Cups` node (:2764-2772:
+    1/CUPS = microseconds per (iteration x sub-iteration) per cell).  Here the clock is the library's CUDA-event timer over the
+    whole sub-iteration: the zones of a solver share its kernels (one LU launch sweeps all of them), so every zone gets the
+    solver-wide figure.  First call: starts the timers and returns None, like the reference when too few iterations have been
+    sampled (:2692-2695); later calls return microseconds per cell and sub-iteration (the reference's RECORD value)."""
+    from .. import fasts
+    hook = FastC.HOOK
+    if not hook.get('timing') or hook.get('timed_subit', 0) == 0:
+        fasts.timing(hook, True)
+        if RECORD is None: print('nombre iterations insuffisant pour diagnostic: nitrun * ss_iteration > 15')
+        return None
+    ms, _ = fasts.timing_get(hook, 'all')
+    zones = Internal.getZones(t)
+    cells = []
+    for z in zones:
+        pi = Internal.getNodeFromName1(Internal.getNodeFromName1(z, '.Solver#ownData'), 'Parameter_int')[1]
+        cells.append(int(pi[VSHARE.IJKV]) * int(pi[VSHARE.IJKV + 1]) * int(pi[VSHARE.IJKV + 2]))
+    tps_percell = ms * 1e3 / (hook['timed_subit'] * float(sum(cells)))          # microseconds per cell and sub-iteration
+    tps_percell = max(tps_percell, 1.e-11)
+    with open(FILEOUT1, 'w') as f1:
+        for z, c in zip(zones, cells):
+            perfo = numpy.empty(3, dtype=numpy.float64)
+            perfo[:] = int(1.e6 / tps_percell)
+            solver_def = Internal.createUniqueChild(z, '.Solver#define', 'UserDefinedData_t')
+            Internal.createUniqueChild(solver_def, 'Cups', 'DataArray_t', value=perfo)
+            f1.write('cpumoy/cell=  %s  dim zone=%d  %s\n' % (tps_percell, c, z[0]))
+            if RECORD is None: print('cpu/cell zone=', z[0], 'moy=', tps_percell, 'dim zone=', c, 'dim tot=', sum(cells))
+        f1.write('cpu moyen %%cell en microsec: %s\n' % tps_percell)
+    open(FILEOUT, 'w').close()          # no zone is slower than the others: they share the kernels
+    if RECORD is None: print('cpu moyen %cell en microsec: ', tps_percell)
+    return tps_percell if RECORD is not None else None
 
 
 def display_temporal_criteria(t, metrics, nitrun, format=None, gmres=None, verbose='firstlast', stopAtNan=True):

@@ -13,7 +13,7 @@ c_ip = ctypes.POINTER(ctypes.c_int)
 SYMBOLS = ['fb_version', 'fb_last_error', 'fb_device_count', 'fb_solver_create', 'fb_solver_destroy',
            'fb_zone_set_params', 'fb_zone_set_coords', 'fb_init_metric', 'fb_zone_get_metric',
            'fb_zone_upload_state', 'fb_zone_download_state', 'fb_zone_upload_aux', 'fb_zone_download_aux',
-           'fb_zone_download_work', 'fb_set_joins', 'fb_set_joins_tc', 'fb_compute', 'fb_apply_bc', 'fb_transfers', 'fb_compute_mut',
+           'fb_zone_download_work', 'fb_zone_download_wig', 'fb_set_joins', 'fb_set_joins_tc', 'fb_compute', 'fb_apply_bc', 'fb_transfers', 'fb_compute_mut',
            'fb_zone_get_residuals', 'fb_zone_get_cfl', 'fb_zone_isfinite', 'fb_compute_host', 'fb_timing_enable', 'fb_timing_reset',
            'fb_timing_get', 'fb_sync', 'fb_zone_device_ptr', 'fb_halo_pack', 'fb_halo_unpack', 'fb_set_modulo_verif',
            'fb_stream', 'fb_halo_sizes', 'fb_set_exchange_cb', 'fb_halo_buffers', 'fb_counter', 'fb_exchange_stream',

@@ -36,6 +36,7 @@ struct Zone {
     LuPlan lu;                      // hyperplane bookkeeping (fb_implicit.cu)
     int xfaces = 0;                 // faces whose interior cells are donors of cross-rank joins (bit 0..5 = imin .. kmax)
     bool has_params = false, has_xyz = false;
+    cudaEvent_t ev_up = nullptr; bool up_pending = false, up_pending_first = false;   // fb_compute_host: this zone's input levels are still on their way (copy stream)
     size_t n_state = 0, n_aux = 0;
 };
 
@@ -44,6 +45,7 @@ struct Timer { cudaEvent_t a, b; double ms = 0; long long n = 0; std::vector<std
 struct fb_solver {
     int dev = 0, nz = 0;
     cudaStream_t st = nullptr;
+    cudaStream_t st_h2d = nullptr;    // fb_compute_host: uploads of the zones' input levels, overlapped with the first kernels of the zones already there
     cudaStream_t st2 = nullptr;       // cross-rank halo exchange (pack, host transport, unpack): overlaps the interior tiles
     cudaEvent_t ev1 = nullptr, ev2 = nullptr;
     // multi-zone solvers: the per-zone kernels of a phase fan out over st + 3 lanes so that the tail of one zone's grid
@@ -99,6 +101,7 @@ int fb_solver_create(int device, int nzones, fb_solver **out)
     fb_solver *s = new fb_solver();
     s->dev = device; s->nz = nzones; s->z.resize(nzones);
     CK(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&s->st_h2d, cudaStreamNonBlocking));
     {   // the exchange stream outranks the others: its pack / unpack CTAs go ahead of the interior tiles still queued
         int lo = 0, hi = 0; CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         CK(cudaStreamCreateWithPriority(&s->st2, cudaStreamNonBlocking, hi));
@@ -123,6 +126,8 @@ void fb_solver_destroy(fb_solver *s)
     joins_free(s->joins);
     cudaFree(s->halo_send); cudaFree(s->halo_recv);
     if (s->st) cudaStreamDestroy(s->st);
+    if (s->st_h2d) cudaStreamDestroy(s->st_h2d);
+    for (auto &z : s->z) if (z.ev_up) cudaEventDestroy(z.ev_up);
     if (s->st2) cudaStreamDestroy(s->st2);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->ev2) cudaEventDestroy(s->ev2);
@@ -406,6 +411,17 @@ int fb_zone_download_work(fb_solver *s, int nd, double *drodm, double *coe)
     return FB_OK;
 }
 
+int fb_zone_download_wig(fb_solver *s, int nd, unsigned char *wig, int n)
+{
+    int rc = chk_zone(s, nd, 0); if (rc) return rc;
+    Zone &z = s->z[nd];
+    if (!wig || n != z.d.nd) return fail(FB_EINVAL, "fb_zone_download_wig: size must be NDIMDX");
+    if (!z.wigb) return fail(FB_ESTATE, "zone has no SENSOR switch (scheme != senseur)");
+    CK(cudaSetDevice(s->dev)); CK(cudaStreamSynchronize(s->st));
+    CK(cudaMemcpy(wig, z.wigb, (size_t)z.d.nd, cudaMemcpyDeviceToHost));
+    return FB_OK;
+}
+
 int fb_set_joins(fb_solver *s, const int *ji, int n)
 {
     if (!s || !ji || n < 1) return fail(FB_EINVAL, "fb_set_joins: bad arguments");
@@ -558,6 +574,7 @@ static int gsdr3(fb_solver *s, int nitcfg, int nssiter, int nitrun, int first_it
             Fan f(s, fan_coe);
             for (int n = 0; n < s->nz; n++) {
                 Zone &z = s->z[n]; double *ssiter = ss[n]; cudaStream_t zst = f.stream(n);
+                if (z.up_pending) cudaStreamWaitEvent(zst, z.ev_up, 0);      // fb_compute_host: the zone's inputs have landed
                 if (z.d.iflow >= 2) { launch_invist(z.d, ssiter, implicit || z.d.iflow == 3 ? z.d.nf : 1, zst); s->launches++; }
                 if (implicit) { launch_coe(z.d, ssiter, first_it, zst); s->launches++; }
                 if (lssiter_verif) { launch_cfl(z.d, ssiter, z.cflv, zst); s->launches += 2; }   // cptst3.for:113-120 -> cpcfl3
@@ -570,15 +587,23 @@ static int gsdr3(fb_solver *s, int nitcfg, int nssiter, int nitrun, int first_it
             Fan f(s, fan);
             for (int n = 0; n < s->nz; n++) {
                 Zone &z = s->z[n]; cudaStream_t zst = f.stream(n);
-                if (implicit && z.d.iflow == 3 && nitcfg == 1) { launch_sa_ring(z.d, ss[n], zst); s->launches++; }
-                // explicit: the stage writes the array that then gets the BCs
-                launch_rhs(z.d, ss[n], implicit ? nullptr : cl[n], z.rop[0], z.rop[1], nitcfg, first_it, zst); s->launches++;
+                z.up_pending_first = z.up_pending;
+                if (z.up_pending) { cudaStreamWaitEvent(zst, z.ev_up, 0); z.up_pending = false; }
+                const bool ring = implicit && z.d.iflow == 3 && nitcfg == 1;
+                if (ring) { launch_sa_ring(z.d, ss[n], zst); s->launches++; }
+                // explicit: the stage writes the array that then gets the BCs.
+                // Zones are independent in this phase: on one stream the rhs kernel of zone n may start while that of zone n-1
+                // drains its last wave (programmatic dependent launch) -- unless a kernel of zone n itself sits in between
+                static const bool no_pdl = [] { const char *e = getenv("FAST_B200_PDL"); return e && e[0] == '0'; }();   // A/B switch
+                const int pdl = (!fan && !no_pdl && n > 0 && !ring && !s->z[n].up_pending_first) ? 1 : 0;
+                launch_rhs(z.d, ss[n], implicit ? nullptr : cl[n], z.rop[0], z.rop[1], nitcfg, first_it, zst, 0, 63, pdl); s->launches++;
             }
         } else {
             // explicit stage + cross-rank joins: the tiles that touch a zone face (their cells are the donors of the exchange)
             // run first on st; the exchange stream starts behind them (ev1) while the interior tiles, queued on a lane at the
             // same time, fill the SMs as the face tiles drain.  Everything joins back on st before the local joins and BCs.
             Scope r(s, 0);
+            for (int n = 0; n < s->nz; n++) if (s->z[n].up_pending) { cudaStreamWaitEvent(s->st, s->z[n].ev_up, 0); s->z[n].up_pending = false; }
             cudaEventRecord(s->ev_fork, s->st); cudaStreamWaitEvent(s->lane[0], s->ev_fork, 0);
             for (int n = 0; n < s->nz; n++) {
                 Zone &z = s->z[n];
@@ -728,11 +753,20 @@ int fb_compute_host(fb_solver *s, int nitrun, int nit_c, int *first_it, double *
     if (!s || !ro || !ro_m1 || !ro_p1 || !first_it) return fail(FB_EINVAL, "fb_compute_host: bad arguments");
     if (nit_c != 1) return fail(FB_EINVAL, "fb_compute_host: nit_c must be 1 (the host rotates its pointers after every iteration)");
     CK(cudaSetDevice(s->dev));
-    // inputs of one iteration: ro always, ro_M1 for the BDF2 time term (implicit); ro_P1 is pure output
+    // inputs of one iteration: ro always; ro_M1 only where the BDF2 time term reads it (core3as2.for:37-46: c3 = 0 at the first
+    // iteration and with local time stepping); ro_P1 is pure output.  The uploads run zone by zone on a copy stream, each
+    // followed by an event: a zone's first kernels (viscosity, coe, rhs) start as soon as ITS levels are there, while the
+    // next zones are still crossing the bus.  Everything that couples the zones (LU launch, joins) comes after all of them.
     const bool implicit = s->z[0].d.itypcp <= 1;
+    cudaEventRecord(s->ev_fork, s->st); cudaStreamWaitEvent(s->st_h2d, s->ev_fork, 0);     // the previous iteration is done with the buffers
     for (int n = 0; n < s->nz; n++) {
-        CK(cudaMemcpyAsync(s->z[n].rop[0], ro[n], s->z[n].n_state * sizeof(double), cudaMemcpyHostToDevice, s->st));
-        if (implicit) CK(cudaMemcpyAsync(s->z[n].rop[1], ro_m1[n], s->z[n].n_state * sizeof(double), cudaMemcpyHostToDevice, s->st));
+        Zone &z = s->z[n];
+        if (!z.ev_up) CK(cudaEventCreateWithFlags(&z.ev_up, cudaEventDisableTiming));
+        CK(cudaMemcpyAsync(z.rop[0], ro[n], z.n_state * sizeof(double), cudaMemcpyHostToDevice, s->st_h2d));
+        const bool bdf2 = implicit && *first_it != 0 && z.d.dtloc != 1;
+        if (bdf2) CK(cudaMemcpyAsync(z.rop[1], ro_m1[n], z.n_state * sizeof(double), cudaMemcpyHostToDevice, s->st_h2d));
+        CK(cudaEventRecord(z.ev_up, s->st_h2d));
+        z.up_pending = true;
     }
     const int nssiter = s->z[0].pi[PI_NSSITER];
     int rc = fb_compute(s, nitrun, 1, nssiter, 1, first_it); if (rc) return rc;

@@ -277,9 +277,9 @@ static void launch_rhs_f(const ZoneDev &z, RhsArgs &a, bool impl, cudaStream_t s
 }
 
 void launch_rhs(const ZoneDev &z, const double *rop, double *rop_out, const double *ro_n, const double *ro_n1,
-                int nitcfg, int first_it, cudaStream_t st, int part, int faces)
+                int nitcfg, int first_it, cudaStream_t st, int part, int faces, int pdl)
 {
-    RhsArgs a; a.part = z.itypcp <= 1 ? 0 : part; a.tile0 = a.gx = a.gy = a.gz = 0; a.faces = faces;
+    RhsArgs a; a.part = z.itypcp <= 1 ? 0 : part; a.tile0 = a.gx = a.gy = a.gz = 0; a.faces = faces; a.pdl = pdl;
     a.rop = rop; a.rop_out = rop_out; a.ro_n = ro_n; a.ro_n1 = ro_n1; a.nitcfg = nitcfg; a.wfuse = fb_sensor_fused() ? 1 : 0;
     const bool impl = z.itypcp <= 1;
     a.coefH = 0.; a.coefW = 1.;

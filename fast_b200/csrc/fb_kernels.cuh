@@ -24,6 +24,6 @@ bool fb_sensor_fused();
 // part: 0 the whole zone, 1 only the tiles that touch a zone face, 2 only the interior tiles (halo-exchange overlap of the
 // explicit stages; implicit zones always run whole); faces: bit 0..5 = imin .. kmax faces that carry cross-rank joins
 void launch_rhs(const ZoneDev &z, const double *rop, double *rop_out, const double *ro_n, const double *ro_n1,
-                int nitcfg, int first_it, cudaStream_t st, int part = 0, int faces = 63);
+                int nitcfg, int first_it, cudaStream_t st, int part = 0, int faces = 63, int pdl = 0);
 void launch_bc(const ZoneDev &z, const BcWin *d_wins, int nwin, int maxcells, double *rop, int lrhs, cudaStream_t st);
 void launch_corners(const ZoneDev &z, double *rop, const int box[6], cudaStream_t st);

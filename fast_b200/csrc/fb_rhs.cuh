@@ -336,6 +336,9 @@ k_rhs3(const CUtensorMap *__restrict__ tm_rop, const CUtensorMap *__restrict__ t
     // (unsigned on purpose, like blockIdx: with signed tile coordinates the address arithmetic of the whole kernel grows by a quarter)
     unsigned bx = blockIdx.x, by = blockIdx.y, bz = blockIdx.z;
     if (!IMPL && a.gx) rhs_face_first(blockIdx.x + (unsigned)a.tile0, a.gx, a.gy, a.gz, a.faces, bx, by, bz);   // explicit stages only
+    // the rhs kernel of the next zone (launched with the programmatic-serialization attribute) may be scheduled as soon as
+    // every CTA of this grid has got here or finished, i.e. while the last wave drains
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     extern __shared__ __align__(128) double ring[];
     double (*sFj)[RJ + 1][NEQ][32] = (double (*)[RJ + 1][NEQ][32])(ring + NS * PS);
     constexpr int NSF = C::template nsf<MESH>();
@@ -519,12 +522,17 @@ static bool launch_rhs3_t(const ZoneDev &z, RhsArgs &a, bool impl, cudaStream_t 
     dim3 g((z.iv + 30) / 31, (z.jv + RJ - 1) / RJ, (z.kv + RHS3_KC - 1) / RHS3_KC);
     a.thin = rhs_thin(z, g, 31, RJ, RHS3_KC);
     if (!rhs_part_grid(a, g)) return true;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = g; cfg.blockDim = b; cfg.dynamicSmemBytes = C::template smem<MESH>(); cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = a.pdl ? 1 : 0;
     if (SCHEME == 2 && a.nitcfg == 1 && a.wfuse) {   // first sub-iteration of a SENSOR zone: the switch is evaluated in the flux
-        if (impl) k_rhs3<MESH, FLOW, SCHEME, SLOPE, true, RJ, SCHEME == 2><<<g, b, C::template smem<MESH>(), st>>>(tr, tm, z, a);
-        else k_rhs3<MESH, FLOW, SCHEME, SLOPE, false, RJ, SCHEME == 2><<<g, b, C::template smem<MESH>(), st>>>(tr, tm, z, a);
+        if (impl) cudaLaunchKernelEx(&cfg, k_rhs3<MESH, FLOW, SCHEME, SLOPE, true, RJ, SCHEME == 2>, tr, tm, z, a);
+        else cudaLaunchKernelEx(&cfg, k_rhs3<MESH, FLOW, SCHEME, SLOPE, false, RJ, SCHEME == 2>, tr, tm, z, a);
     } else {
-        if (impl) k_rhs3<MESH, FLOW, SCHEME, SLOPE, true, RJ, false><<<g, b, C::template smem<MESH>(), st>>>(tr, tm, z, a);
-        else k_rhs3<MESH, FLOW, SCHEME, SLOPE, false, RJ, false><<<g, b, C::template smem<MESH>(), st>>>(tr, tm, z, a);
+        if (impl) cudaLaunchKernelEx(&cfg, k_rhs3<MESH, FLOW, SCHEME, SLOPE, true, RJ, false>, tr, tm, z, a);
+        else cudaLaunchKernelEx(&cfg, k_rhs3<MESH, FLOW, SCHEME, SLOPE, false, RJ, false>, tr, tm, z, a);
     }
     return true;
 }

@@ -17,6 +17,8 @@ struct RhsArgs {
                             // in the kernel: tile layers of part 1 behind each face, two bits per face (fb_tiles.cuh: rhs_face_flags)
     int thin;               // bit d: the last tile of direction d is less than two cells thick
     int wfuse;              // SENSOR switch evaluated inside the first-sub-iteration kernel (default) instead of k_sensor
+    int pdl;                // 1: this launch may start while the previous kernel of the stream (the rhs of ANOTHER zone) drains its
+                            // last wave (programmatic dependent launch); it consumes nothing that kernel writes
 };
 
 template <int MESH, int FLOW>

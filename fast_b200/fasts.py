@@ -124,6 +124,38 @@ def download(zones, hook, levels=('', '_M1', '_P1'), aux=True):
             if a is not None: _lib.check(L.fb_zone_download_aux(s, nd, _dp(a), a.size))
 
 
+def download_work(zones, hook):
+    """HOOK['rhs'] / HOOK['coe'] / HOOK['wiggle'] <- HBM (per-zone offsets of gsdr3.cpp:282-290); wiggle is expanded from the
+    device's one byte per cell (bit d = lower face in direction d) to the reference's three doubles per cell."""
+    L = _lib.lib(); s = _solver(hook)
+    for nd, z in enumerate(zones):
+        pi = Internal.getNodeFromName1(Internal.getNodeFromName1(z, '.Solver#ownData'), 'Parameter_int')[1]
+        ndx, neq, nco = int(pi[V.NDIMDX]), int(pi[V.NEQ]), max(int(pi[V.NEQ_COE]), 0)
+        o_r, o_c, o_w = hook['work_offsets'][nd]
+        rhs = hook['rhs'][o_r:o_r + neq * ndx]
+        coe = hook['coe'][o_c:o_c + nco * ndx] if nco and int(pi[V.ITYPCP]) <= 1 else None
+        _lib.check(L.fb_zone_download_work(s, nd, _dp(rhs), _dp(coe) if coe is not None else None))
+        if int(pi[V.KFLUDOM]) == 2:
+            b = numpy.zeros(ndx, numpy.uint8)
+            _lib.check(L.fb_zone_download_wig(s, nd, b.ctypes.data_as(ctypes.POINTER(ctypes.c_ubyte)), ndx))
+            w = hook['wiggle'][o_w:o_w + 3 * ndx].reshape(3, ndx)
+            for d in range(3): w[d] = (b >> d) & 1
+
+
+def timing(hook, on):
+    """CUDA-event timers of the library (fb_timing_*), the GPU stand-in for HOOK['TIMER_OMP']."""
+    L = _lib.lib(); s = _solver(hook)
+    _lib.check(L.fb_timing_enable(s, 1 if on else 0))
+    if on: _lib.check(L.fb_timing_reset(s))
+    hook['timing'] = bool(on); hook['timed_subit'] = 0
+
+
+def timing_get(hook, name='all'):
+    L = _lib.lib(); v = ctypes.c_double(0); n = ctypes.c_longlong(0)
+    _lib.check(L.fb_timing_get(_solver(hook), name.encode(), ctypes.byref(v), ctypes.byref(n)))
+    return v.value, int(n.value)
+
+
 def get_metric(zones, metrics, hook):
     """Fill the host numpy of the metrics list from HBM (tests / post-processing)."""
     L = _lib.lib(); s = _solver(hook)

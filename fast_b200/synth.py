@@ -225,7 +225,8 @@ def case_tgv_blocks(n=256, nblk=(2, 1, 1), only=None, scheme='senseur', Re=1600.
 
 
 def case_flatplate(n=(64, 48, 8), seed=2025, MInf=0.2, ReInf=25.e6, ss_iteration=5, cfl=7., sheared=False,
-                   scheme='ausmpred', modulo_verif=1, nblocks=(1, 1, 1), only=None, return_layout=False, lu_match=0, nb_relax=1):
+                   scheme='ausmpred', modulo_verif=1, nblocks=(1, 1, 1), only=None, return_layout=False, lu_match=0, nb_relax=1,
+                   tc_format=False):
     """C3 / C5-style RANS-SA flat plate: x geometric stretch, y tanh clustering toward the wall (jmin = viscous wall),
     z uniform => typezone 1 (3dhomo); `sheared=True` adds a smooth 3-D shear => typezone 0 (3dfull).
     Farfield on imin/imax/jmax, autoperiodic in k.  nblocks splits the plate into match-joined blocks; `only` (a set of
@@ -280,13 +281,14 @@ def case_flatplate(n=(64, 48, 8), seed=2025, MInf=0.2, ReInf=25.e6, ss_iteration
     FastC._setNum2Zones(t, {'scheme': scheme, 'slope': 'o3', 'time_step_nature': 'local', 'cfl': cfl, 'nb_relax': nb_relax, 'lu_match': lu_match})
     FastC._setNum2Base(t, {'temporal_scheme': 'implicit', 'ss_iteration': ss_iteration, 'modulo_verif': modulo_verif})
     if return_layout: return t, layout
+    if tc_format: return t, build_joins_tc(layout, nb, tuple(nloc), periodic=(False, False, nb[2] > 1), neq=6)   # reference wire format
     joins = build_joins(layout, nb, tuple(nloc), periodic=(False, False, nb[2] > 1))
     return t, joins
 
 
 def case_multiblock(nblk=(2, 2, 2), n=16, seed=99, scheme='roe', model='NSLaminar', deform_amp=0.015, lu_match=1,
                     ss_iteration=3, ReInf=5000., MInf=0.3, time_step=None, temporal='implicit', modulo_verif=1,
-                    only=None, return_layout=False, extra_numz=None):
+                    only=None, return_layout=False, extra_numz=None, tc_format=False):
     """C4-style case: nblk blocks of n^3 cells, smooth sinusoidal deformation (3dfull), match joins inside, farfield
     outside, Roe o3, implicit LU-SGS with lu_match."""
     from .FastC import PyTree as FastC
@@ -328,6 +330,7 @@ def case_multiblock(nblk=(2, 2, 2), n=16, seed=99, scheme='roe', model='NSLamina
     if extra_numz: numz.update(extra_numz)
     FastC._setNum2Zones(t, numz); FastC._setNum2Base(t, numb)
     if return_layout: return t, layout
+    if tc_format: return t, build_joins_tc(layout, nblk, (n, n, n), neq=5)        # reference wire format
     return t, build_joins(layout, nblk, (n, n, n))
 
 

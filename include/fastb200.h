@@ -51,6 +51,9 @@ int fb_zone_download_state(fb_solver *s, int nd, int level, double *rop);
 int fb_zone_upload_aux(fb_solver *s, int nd, const double *aux, int n);
 int fb_zone_download_aux(fb_solver *s, int nd, double *aux, int n);
 int fb_zone_download_work(fb_solver *s, int nd, double *drodm, double *coe);
+/* HOOK['wiggle'] (C/PyTree.py:2201): the SENSOR switch of S/Compute/SENSOR/wiggle2001.for, kept on the device as one byte per
+ * cell (bit d = lower face in direction d; the reference stores three doubles per cell); n = NDIMDX. */
+int fb_zone_download_wig(fb_solver *s, int nd, unsigned char *wig, int n);
 
 /* Match joins: flattened donor tree in this repo's documented layout (DESIGN.md "match joins"), the
  * stand-in for Connector's miseAPlatDonorTree__ tables read at C/Com/setInterpTransfersFast.cpp:469-477. */
@@ -84,7 +87,9 @@ int fb_zone_get_cfl(fb_solver *s, int nd, double cfl[3]);
 int fb_zone_isfinite(fb_solver *s, int nd, long long *bad);
 
 /* End-to-end iteration on HOST buffers (what a reference-side caller holding the tree's numpy arrays does):
- * uploads the input time levels of every zone (ro; ro_M1 too for the implicit BDF term), runs one fb_compute
+ * uploads the input time levels of every zone (ro; ro_M1 too where the BDF2 term of S/Compute/core3as2.for:37-46 reads it,
+ * i.e. implicit, global time step, after the first iteration), zone by zone on a copy stream so that a zone's first kernels
+ * overlap the upload of the next zones (pinned buffers make the copies asynchronous), runs one fb_compute
  * iteration (nit_c must be 1), downloads the new solution into the caller's ro_P1 buffers.  The caller then rotates
  * its three pointers like FastC.switchPointers__ (C/PyTree.py:2298).  ro/ro_m1/ro_p1[nd]: NDIMDX*NEQ doubles each. */
 int fb_compute_host(fb_solver *s, int nitrun, int nit_c, int *first_it,

@@ -136,3 +136,88 @@ def test_tgv_conservation_full_size_planes():
     s1 = totals()
     scale = numpy.array([s0[0], s0[0], s0[0], s0[0], s0[4]])      # momentum sums vanish for the TGV: scale with the mass
     assert numpy.all(numpy.abs(s1 - s0) <= 1e-11 * numpy.abs(scale)), (s1 - s0) / scale
+
+
+@pytest.mark.gpu
+def test_reference_style_script_runs_through_the_aliases():
+    """A Fast/valid-style driver -- the body of ST/tgvMpi.py:268-300 (numerics dictionaries, warmup, time loop with
+    display_temporal_criteria every 5 iterations) with the Cassiopee mesh generation replaced by the synthetic TGV blocks --
+    runs unchanged through `import FastS.PyTree as FastS` once fast_b200.install_aliases() has registered the modules, and
+    lands on the oracle's state."""
+    import subprocess, sys, os, textwrap
+    from helpers import ROOT
+    script = textwrap.dedent('''
+        import sys, numpy
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        import fast_b200; fast_b200.install_aliases()
+        import FastC.PyTree as FastC
+        import FastS.PyTree as FastS
+        import Fast.PyTree as Fast
+        from fast_b200 import synth
+        from fast_b200.FastC.PyTree import Internal
+        t, layout = synth.case_tgv_blocks(n=16, nblk=(2, 1, 1))
+        tc = synth.build_joins_tc(layout, (2, 1, 1), (16, 16, 16), periodic=(True, False, False))
+        # ---- ST/tgvMpi.py:268-300 -------------------------------------------------------------------------------
+        numb = {}
+        numb["temporal_scheme"] = "explicit"
+        numb["modulo_verif"]    = 50
+        numz = {}
+        numz["time_step"]          = 0.003
+        numz["scheme"]             = "senseur"
+        FastC._setNum2Zones(t, numz); FastC._setNum2Base(t, numb)
+        (t, tc, metrics) = FastS.warmup(t, tc)
+        nit = 10; time = 0.
+        for it in range(nit):
+            FastS._compute(t, metrics, it, tc)
+            if it %% 5 == 0:
+                print('- %%d - %%f -' %% (it, time)); sys.stdout.flush()
+                FastS.display_temporal_criteria(t, metrics, it)
+            time += numz['time_step']
+        # ----------------------------------------------------------------------------------------------------------
+        FastS.sync_tree(t)
+        numpy.save(sys.argv[1], numpy.concatenate([FastC.block_of(z, '') for z in Internal.getZones(t)]))
+        ''') % (ROOT, os.path.join(ROOT, 'tests'))
+    out = os.path.join(ROOT, 'gpurun_out', '_script_state.npy')
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    r = subprocess.run([sys.executable, '-c', script, out], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-3000:]
+    assert '- 5 -' in r.stdout
+    got = numpy.load(out); os.remove(out)
+    # the oracle on the same script
+    t, layout = synth.case_tgv_blocks(n=16, nblk=(2, 1, 1))
+    tc = synth.build_joins_tc(layout, (2, 1, 1), (16, 16, 16), periodic=(True, False, False))
+    FastC._setNum2Zones(t, {"time_step": 0.003, "scheme": "senseur"}); FastC._setNum2Base(t, {"temporal_scheme": "explicit", "modulo_verif": 50})
+    o = oracle_from_tree(t, joins=tc)
+    for it in range(10): o.compute(it, 1, 3, 50)
+    ref = numpy.concatenate([z.lev[0] for z in o.zones])
+    assert numpy.abs(got - ref).max() / numpy.abs(ref).max() <= 1e-9
+
+
+@pytest.mark.gpu
+def test_hook_work_arrays_and_cups():
+    """FastC.HOOK['rhs'|'coe'|'wiggle'] are host arrays in the reference layout (C/PyTree.py:2201-2230, per-zone offsets of
+    gsdr3.cpp:282-290) filled on demand from HBM; display_cpu_efficiency writes the `Cups` node (S/PyTree.py:2764-2772)."""
+    kw = dict(n=12, scheme='senseur', model='NSLaminar', ReInf=2000., deform_amp=0.02)
+    t1 = synth.case_euler_box(**kw); t2 = synth.case_euler_box(**kw)
+    o = oracle_from_tree(t1)
+    (t2, tc, metrics) = FastS.warmup(t2, None)
+    assert FastS.display_cpu_efficiency(t2) is None          # first call starts the timers
+    for it in (1, 2):
+        o.compute(it, 1, 3, 1); FastS._compute(t2, metrics, it)
+    FastS.sync_work(t2)
+    zo = o.zones[0]
+    nd = int(zo.pi[V.NDIMDX])
+    hook = FastC.HOOK
+    assert hook['rhs'].size == 5 * nd and hook['wiggle'].size == 3 * nd and hook['coe'].size == nd      # explicit: coe(NDIMDX, 1) = dt/vol, kept in registers here
+    a = interior(zo.pi, hook['rhs']); b = interior(zo.pi, zo.drodm)
+    assert relerr(a, b) <= 1e-9
+    wa = interior(zo.pi, hook['wiggle']); wb = interior(zo.pi, zo.wig)
+    assert set(numpy.unique(wa)) <= {0., 1.} and (wa != wb).mean() <= 1e-3      # sign tests: identical up to round-off ties
+    us = FastS.display_cpu_efficiency(t2, RECORD=True)
+    assert us > 0.
+    z = Internal.getZones(t2)[0]
+    cups = Internal.getNodeFromName1(Internal.getNodeFromName1(z, '.Solver#define'), 'Cups')[1]
+    assert cups.shape == (3,) and cups[0] == int(1e6 / us)
+    import os
+    for f in ('listZonesSlow.dat', 'diagCPU.dat'):
+        if os.path.exists(f): os.remove(f)

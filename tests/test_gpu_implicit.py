@@ -42,6 +42,9 @@ CASES = {
     'lamin_full_roe_ssor3': _box(n=12, scheme='roe', model='NSLaminar', ReInf=1000., deform_amp=0.02, temporal='implicit',
                                  extra_numz={'nb_relax': 3}),
     'multiblock_roe_lumatch_ssor2': lambda: synth.case_multiblock(nblk=(2, 1, 1), n=10, extra_numz={'nb_relax': 2}),
+    # the same joins in the reference's wire format: Connector's param_int_tc / param_real_tc through fb_set_joins_tc
+    'sa_plate_blocks_tc': lambda: synth.case_flatplate(n=(24, 16, 8), nblocks=(2, 2, 2), tc_format=True),
+    'multiblock_roe_lumatch_tc': lambda: synth.case_multiblock(nblk=(2, 2, 1), n=8, tc_format=True),
     'multiblock_explicit': lambda: synth.case_multiblock(nblk=(2, 1, 2), n=8, temporal='explicit', scheme='senseur'),
 }
 
@@ -97,3 +100,34 @@ def test_device_isfinite_check_raises():
     _lib.check(_lib.lib().fb_zone_upload_state(FastC.HOOK['solver'], 0, 0, blk.ctypes.data_as(_lib.c_dp)))
     FastS._compute(t, metrics, 2)
     with pytest.raises(FloatingPointError): FastS.display_temporal_criteria(t, metrics, 2)
+
+
+@pytest.mark.gpu
+def test_reference_join_tables_match_private_ones_and_reject_out_of_scope():
+    """fb_set_joins_tc: the reference layout gives bit-identical results to the library's own table, HOOK holds the two arrays
+    like S/PyTree.py:495-500, and content outside the match-join scope is refused (never silently ignored)."""
+    from fast_b200 import _lib
+    res = []
+    for fmt in (False, True):
+        t, j = synth.case_multiblock(nblk=(2, 1, 2), n=8, tc_format=fmt)
+        (t, tc, metrics) = FastS.warmup(t, j)
+        if fmt: assert FastC.HOOK['param_int_tc'].dtype == numpy.int32 and FastC.HOOK['param_real_tc'].dtype == numpy.float64
+        for it in (1, 2): FastS._compute(t, metrics, it)
+        FastS.sync_tree(t)
+        res.append([FastC.block_of(z, '').copy() for z in Internal.getZones(t)])
+    for a, b in zip(*res): assert numpy.array_equal(a, b)
+    L = _lib.lib(); s = FastC.HOOK['solver']
+    pit, prt = [x.copy() for x in j]
+    def rc(pi_, pr_): return L.fb_set_joins_tc(s, pi_.ctypes.data_as(_lib.c_ip), pi_.size, pr_.ctypes.data_as(_lib.c_dp), pr_.size)
+    ech = int(pit[1 + int(pit[2]) + int(pit[3 + int(pit[2])]) + 3]); nrac = int(pit[ech + 1]); T = ech + 4
+    bad = pit.copy(); bad[T + 3 * nrac] = 3                      # an IBC join
+    assert rc(bad, prt) == -1 and b'IBC' in L.fb_last_error()
+    bad = pit.copy(); bad[T + 14 * nrac] = 1                     # azimuthal periodicity
+    assert rc(bad, prt) == -1 and b'rotation' in L.fb_last_error()
+    bad = pit.copy(); bad[int(pit[T + 7 * nrac]) + 2] = 2        # a chimera stencil (interpolation type 2)
+    assert rc(bad, prt) == -1 and b'match joins' in L.fb_last_error()
+    badr = prt.copy(); badr[5] = 0.5
+    assert rc(pit, badr) == -1 and b'coefficient' in L.fb_last_error()
+    bad = pit.copy(); bad[ech + 2] = 1                            # unsteady joins
+    assert rc(bad, prt) == -1
+    assert rc(pit, prt) == 0

@@ -96,6 +96,18 @@ def test_out_of_scope_options_fail_loudly():
     with pytest.raises(ValueError): FastS._warmup_host(t)
 
 
+def test_degenerate_cells_are_refused():
+    """nature_geom_dom.for flags collapsed cells; the reference repairs their metrics (tijk_extrap.for), this library refuses
+    them instead of computing on them silently (VERDICT r1 #4)."""
+    t = synth.case_euler_box(n=6)
+    z = Internal.getZones(t)[0]
+    gc = Internal.getNodeFromName1(z, 'GridCoordinates')
+    for n in ('CoordinateX', 'CoordinateY', 'CoordinateZ'):
+        a = Internal.getNodeFromName1(gc, n)[1]
+        a[0, :, :] = a[1, :, :]                       # collapse the outer ghost layer in i
+    with pytest.raises(ValueError, match='degenerate'): FastS._warmup_host(t)
+
+
 def test_abi_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, 'include', 'fastb200.h')).read()
     names = sorted(set(re.findall(r'\b(fb_[a-z_0-9]+)\s*\(', hdr)))
