@@ -172,7 +172,8 @@ def measure(workload, steps, warmup, ctx, do_e2e=True, min_timed_s=0.):
     if cells_total is None: cells_total = cells
     stream = torch.cuda.ExternalStream(L.fb_stream(s))
     v0 = ctypes.c_longlong(0); _lib.check(L.fb_counter(b'lu_batch', ctypes.byref(v0)))
-    lu_batch0 = int(v0.value)          # process-wide counter: launches of the multi-zone LU kernel before this workload
+    lu_batch0 = int(v0.value)          # process-wide counters: launches of the multi-zone / thread-per-cell LU kernels before this workload
+    _lib.check(L.fb_counter(b'lu_cell', ctypes.byref(v0))); lu_cell0 = int(v0.value)
 
     def fence():
         torch.cuda.synchronize(); _lib.check(L.fb_sync(s))
@@ -215,22 +216,23 @@ def measure(workload, steps, warmup, ctx, do_e2e=True, min_timed_s=0.):
     peak, pk = peaks()
     cz = cells / len(zones)
     cnt = {}
-    for name in ('rhs_tma', 'rhs_l1', 'lu_batch'):
+    for name in ('rhs_tma', 'rhs_l1', 'lu_batch', 'lu_cell'):
         v = ctypes.c_longlong(0); _lib.check(L.fb_counter(name.encode(), ctypes.byref(v))); cnt[name] = int(v.value)
     rhs_kern = 'k_rhs3' if cnt['rhs_tma'] >= cnt['rhs_l1'] else 'k_rhs2'
     per_kernel = {rhs_kern: {'avg_launch_ms_per_zone': tm['rhs'] / (steps * nsub * len(zones)), 'bytes_per_cell': b_rhs,
                              'GBs': cells * b_rhs * nsub * steps / (tm['rhs'] * 1e-3) / 1e9 if tm['rhs'] else None}}
     if implicit and tm['lu']:
-        per_kernel['k_lu_tile_b' if lu_batch0 < cnt['lu_batch'] else 'k_lu_tile'] = {
+        lu_name = ('k_lu_cell' if lu_cell0 < cnt['lu_cell'] else 'k_lu_tile') + ('_b' if lu_batch0 < cnt['lu_batch'] else '')
+        per_kernel[lu_name] = {
             'avg_sweep_ms_all_zones': tm['lu'] / (2 * steps * nsub), 'bytes_per_cell': b_lu,
             'GBs': cells * b_lu * 2 * nsub * steps / (tm['lu'] * 1e-3) / 1e9}
     for k in per_kernel.values():
         if k['GBs']: k['frac'] = k['GBs'] / peak
     if tm['lu'] > tm['rhs']:
-        kern = 'k_lu_tile'
+        kern = lu_name
         nl, bpl = 2 * steps * nsub * len(zones), b_lu   # lower + upper launch
-        if lu_batch0 < cnt['lu_batch']:      # one lower + one upper launch sweep ALL zones of the rank (k_lu_tile_b)
-            kern, nl, cz = 'k_lu_tile_b', 2 * steps * nsub, cells
+        if lu_batch0 < cnt['lu_batch']:      # one lower + one upper launch sweep ALL zones of the rank
+            nl, cz = 2 * steps * nsub, cells
         avg_ms = tm['lu'] / nl
     else:
         kern = rhs_kern

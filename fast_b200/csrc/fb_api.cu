@@ -798,6 +798,7 @@ int fb_timing_get(fb_solver *s, const char *name, double *ms, long long *launche
     return fail(FB_EINVAL, "unknown timer name");
 }
 extern long long g_fb_rhs_launches[2];
+extern long long g_lu_cell_launches;
 // test hook (tests/test_host_logic.py): the tile order of the two-part explicit stage on a gx x gy x gz tile grid, computed
 // by the very function the kernels use; out = 3 ints per tile in launch order, *nface = tiles of part 1
 int fb_debug_tile_order(int gx, int gy, int gz, int faces, int thin, int *out, int *nface)
@@ -818,6 +819,7 @@ int fb_counter(const char *name, long long *out)
     if (!strcmp(name, "rhs_tma")) { *out = g_fb_rhs_launches[0]; return FB_OK; }
     if (!strcmp(name, "rhs_l1")) { *out = g_fb_rhs_launches[1]; return FB_OK; }
     if (!strcmp(name, "lu_batch")) { *out = g_lu_batch_launches; return FB_OK; }
+    if (!strcmp(name, "lu_cell")) { *out = g_lu_cell_launches; return FB_OK; }
     return fail(FB_EINVAL, "unknown counter");
 }
 static int check_lu(fb_solver *s)

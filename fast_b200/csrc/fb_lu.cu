@@ -489,6 +489,7 @@ struct LcCfg {
     static constexpr size_t SMEM = (size_t)(LC_SLOTS * SLOT + NRING + EXB + 6 * NIF * MBW) * sizeof(double) + 64;
 };
 int lu_cell_tk(int mesh, int neq) { return (mesh == 0 && neq == 6) ? 12 : 16; }
+long long g_lu_cell_launches = 0;   // sweeps run by the TMA-staged thread-per-cell kernel (fb_counter "lu_cell")
 
 __device__ __forceinline__ void lc_mbar_init(unsigned long long *bar, int count)
 {
@@ -655,19 +656,32 @@ __device__ __forceinline__ void lu_cell_body(const ZoneDev &z, const LuTileArgs 
         if (st == 0) { fetch(0); fetch(1); }
         if (mth) { load(0); park(0); load(1); park(1); load(2); }
         deliver(0);
+        long long c_wb = 0, c_sb = 0, c_mb = 0, c_dl = 0, c_fw = 0, c_b0 = 0;
         for (int S = 0; S < nst; S++) {
+            const long long q0 = LU_CLOCK();
             __syncthreads();                                   // B_S: compute has finished super-step S-1
+            const long long q1 = LU_CLOCK();
             writeback(S - 1);
             // every line of slot S-1 has been read (barrier.sync, not the .aligned bar.sync: the lanes of a service warp leave
             // writeback() on different paths and the compiler does not reconverge them in front of inline assembly)
             __syncwarp();
+            const long long q2 = LU_CLOCK();
             asm volatile("barrier.sync 1, %0;" ::"n"(LC_NSV) : "memory");
+            const long long q3 = LU_CLOCK();
             if (st == 0) fetch(S + 2);
             if (mth) { park(S + 2); load(S + 3); }
+            const long long q4 = LU_CLOCK();
             deliver(S + 1);
+            const long long q5 = LU_CLOCK();
             // every box that was asked for is seen to land before the CTA can leave (a ragged tile may have no compute thread
             // left waiting on the last slots)
             if (st == 0) lc_mbar_wait(full + S % LC_SLOTS, (unsigned)(S / LC_SLOTS) & 1u);
+            const long long q6 = LU_CLOCK();
+            c_b0 += q1 - q0; c_wb += q2 - q1; c_sb += q3 - q2; c_mb += q4 - q3; c_dl += q5 - q4; c_fw += q6 - q5;
+        }
+        if (a.dbg && (st == 0 || st == 40)) {
+            unsigned long long *q = a.dbg + 16 * (K * a.NJ + J) + (st == 0 ? 4 : 10);
+            q[0] = c_b0; q[1] = c_wb; q[2] = c_sb; q[3] = c_mb; q[4] = c_dl; q[5] = c_fw;
         }
         __syncthreads();
         writeback(nst - 1);
@@ -696,13 +710,15 @@ __device__ __forceinline__ void lu_cell_body(const ZoneDev &z, const LuTileArgs 
     double pi_[EX];
 #pragma unroll
     for (int e = 0; e < EX; e++) pi_[e] = 0.;
-    if (a.dbg && tid == 0) { a.dbg[16 * (K * a.NJ + J)] = gtime(); a.dbg[16 * (K * a.NJ + J) + 3] = smid(); }
-    long long tcomp = 0;
+    if (a.dbg && tid == 0) a.dbg[16 * (K * a.NJ + J)] = gtime();
+    long long tcomp = 0, tmbar = 0;
     for (int S = 0; S < nst; S++) {
         __syncthreads();                                       // B_S
         // every compute thread observes every phase of the slot barriers, active or not: the normals ring of a 3dhomo zone is
         // read up to TK - 1 super-steps after it landed
+        const long long tm0 = LU_CLOCK();
         lc_mbar_wait(full + S % LC_SLOTS, (unsigned)(S / LC_SLOTS) & 1u);
+        tmbar += LU_CLOCK() - tm0;
         const int m = S - sigma;
         if (!(lvalid && m >= 0 && m < nm)) continue;
         const long long tc0 = LU_CLOCK();
@@ -711,13 +727,31 @@ __device__ __forceinline__ void lu_cell_body(const ZoneDev &z, const LuTileArgs 
         const double *xin = exb + (size_t)((S + 1) & 1) * 4 * L * EX;
         double *xout = exb + (size_t)(S & 1) * 4 * L * EX;
         const double *xmb = mbx + (size_t)(S & 1) * NIF * MBW;
+        // both cells of the granule at once: one 16-byte load per staged array (conflict-free: 32 lines x 16 bytes), all of them
+        // issued before the first dependent instruction
+        double2 g[C::A];
+#pragma unroll
+        for (int q = 0; q < C::A; q++) g[q] = *(const double2 *)(R0 + (size_t)q * AS);
+        double2 gn[5];
+        if (MESH == 1) {
+#pragma unroll
+            for (int q = 0; q < 5; q++) gn[q] = *(const double2 *)(N0 + q * TJ * 2);
+        }
+        double2 pj[2][3], pk[2][3];
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            const double2 *pj_ = (const double2 *)(offj >= 0 ? xin + offj + c * L * EX : xmb + mofj + c * EX);
+            const double2 *pk_ = (const double2 *)(offk >= 0 ? xin + offk + c * L * EX : xmb + mofk + c * EX);
+            pj[c][0] = pj_[0]; pj[c][1] = pj_[1]; pj[c][2] = pj_[2]; pk[c][0] = pk_[0]; pk[c][1] = pk_[1]; pk[c][2] = pk_[2];
+        }
+#define GET(v, POS) ((POS) ? (v).y : (v).x)
+#define PUT(v, POS, val) do { if (POS) (v).y = (val); else (v).x = (val); } while (0)
 #pragma unroll
         for (int c = 0; c < 2; c++) {
             const int ii = 2 * m - p + c;
             if (ii < 0 || ii >= bi) continue;
-            const int pos = UPPER ? 1 - c : c;
-            double *R = R0 + pos;
-#define RING(arr) R[(size_t)(arr) * AS]
+            const int pos = UPPER ? 1 - c : c;            // compile-time after unrolling
+#define RING(arr) GET(g[arr], pos)
             double acc[NEQ];
 #pragma unroll
             for (int e = 0; e < NEQ; e++) acc[e] = RING(C::A_DW + e);
@@ -734,13 +768,10 @@ __device__ __forceinline__ void lu_cell_body(const ZoneDev &z, const LuTileArgs 
                 ti0 = RING(C::A_T); ti1 = RING(C::A_T + 1); ti2 = RING(C::A_T + 2); tj0 = RING(C::A_T + 3); tj1 = RING(C::A_T + 4);
                 tj2 = RING(C::A_T + 5); tk0 = RING(C::A_T + 6); tk1 = RING(C::A_T + 7); tk2 = RING(C::A_T + 8);
             } else if (MESH == 1) {
-                const double *N = N0 + pos;
-                ti0 = N[0]; ti1 = N[TJ * 2]; tj0 = N[2 * TJ * 2]; tj1 = N[3 * TJ * 2]; tk2 = N[4 * TJ * 2];
+                ti0 = GET(gn[0], pos); ti1 = GET(gn[1], pos); tj0 = GET(gn[2], pos); tj1 = GET(gn[3], pos); tk2 = GET(gn[4], pos);
             } else { ti0 = z.tc0[0]; tj1 = z.tc0[1]; tk2 = z.tc0[2]; }
             const double cdi = RING(C::A_COE + 1) * signe, cdj = RING(C::A_COE + 2) * signe, cdk = RING(C::A_COE + 3) * signe;
-            const double2 *pj_ = (const double2 *)(offj >= 0 ? xin + offj + c * L * EX : xmb + mofj + c * EX);
-            const double2 *pk_ = (const double2 *)(offk >= 0 ? xin + offk + c * L * EX : xmb + mofk + c * EX);
-            const double2 j0 = pj_[0], j1 = pj_[1], j2 = pj_[2], k0 = pk_[0], k1 = pk_[1], k2 = pk_[2];
+            const double2 j0 = pj[c][0], j1 = pj[c][1], j2 = pj[c][2], k0 = pk[c][0], k1 = pk[c][1], k2 = pk[c][2];
             const double xal = coe1 * signe;
             const double xi = ii > 0 ? xal : 0., xj = has_j ? xal : 0., xk = has_k ? xal : 0.;
             if (UPPER) {
@@ -773,19 +804,20 @@ __device__ __forceinline__ void lu_cell_body(const ZoneDev &z, const LuTileArgs 
                 const double roe_old = ro * (z.cv * t + 0.5 * (u * u + v * v + w * w));
                 const double tn = (roe_old + dwn[4]) * r_1 * cvinv - cvinv2 * (un * un + vn * vn + wn * wn);
                 if (in_nb) {
-                    RING(C::A_ST) = rn; RING(C::A_ST + 1) = un; RING(C::A_ST + 2) = vn; RING(C::A_ST + 3) = wn; RING(C::A_ST + 4) = tn;
+                    PUT(g[C::A_ST], pos, rn); PUT(g[C::A_ST + 1], pos, un); PUT(g[C::A_ST + 2], pos, vn); PUT(g[C::A_ST + 3], pos, wn);
+                    PUT(g[C::A_ST + 4], pos, tn);
                     if (NEQ == 6) {
                         double anulam = z.coesut * sqrt(tn * z.temp01) * tn * lu_rcp(tn + z.cmus1);   // = coesut sqrt(T/T0) / (1 + Cs/T)
                         anulam = anulam * r_1 * z.ratiom;
                         double tt = (ro * nut + dwn[NEQ - 1]) * r_1;
                         tt = fmin(tt, anulam);
-                        RING(C::A_ST + NEQ - 1) = fmax(tt, 0.);
+                        PUT(g[C::A_ST + NEQ - 1], pos, fmax(tt, 0.));
                     }
                     if (a.alias) { uk = un; vk = vn; wk = wn; tk_ = tn; }
                 }
             } else {
 #pragma unroll
-                for (int e = 0; e < NEQ; e++) RING(C::A_DW + e) = dwn[e];
+                for (int e = 0; e < NEQ; e++) PUT(g[C::A_DW + e], pos, dwn[e]);
             }
             // outgoing products
             double bj_[EX], bk_[EX];
@@ -811,13 +843,23 @@ __device__ __forceinline__ void lu_cell_body(const ZoneDev &z, const LuTileArgs 
             }
 #undef RING
         }
+        // results of both cells back into the slot (cells outside the line keep what was staged; the write-back role masks them)
+        if (UPPER && a.newton) {
+#pragma unroll
+            for (int e = 0; e < NEQ; e++) *(double2 *)(R0 + (size_t)(C::A_ST + e) * AS) = g[C::A_ST + e];
+        } else {
+#pragma unroll
+            for (int e = 0; e < NEQ; e++) *(double2 *)(R0 + (size_t)(C::A_DW + e) * AS) = g[C::A_DW + e];
+        }
+#undef GET
+#undef PUT
         // the results were written into the slot through the generic proxy; the slot is re-armed by TMA (async proxy) two
         // barriers from here
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         tcomp += LU_CLOCK() - tc0;
     }
     __syncthreads();
-    if (a.dbg && tid == 0) { a.dbg[16 * (K * a.NJ + J) + 1] = gtime(); a.dbg[16 * (K * a.NJ + J) + 2] = tcomp; }
+    if (a.dbg && tid == 0) { a.dbg[16 * (K * a.NJ + J) + 1] = gtime(); a.dbg[16 * (K * a.NJ + J) + 2] = tcomp; a.dbg[16 * (K * a.NJ + J) + 3] = tmbar; }
 }
 
 template <int MESH, int NEQ, bool UPPER>
@@ -1038,6 +1080,7 @@ static void run_lu_batch(const LuBatch *b, const LuBatchItem *items, cudaStream_
     }
     cudaMemsetAsync(b->d_ticket, 0, 2 * sizeof(int), st);
     if (b->cell) {
+        g_lu_cell_launches += 2;
         k_lu_cell_b<MESH, NEQ, false><<<b->ntiles, LcCfg<MESH, NEQ, false>::NTHR, LcCfg<MESH, NEQ, false>::SMEM, st>>>(items, b->d_order, b->d_ticket);
         k_lu_cell_b<MESH, NEQ, true><<<b->ntiles, LcCfg<MESH, NEQ, true>::NTHR, LcCfg<MESH, NEQ, true>::SMEM, st>>>(items, b->d_order, b->d_ticket + 1);
         return;
@@ -1079,6 +1122,7 @@ static void launch_sweep(const ZoneDev &z, const LuPlan &p, const LuTileArgs &a,
         cudaFuncSetAttribute(k_lu_cell<MESH, NEQ, UPPER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LcCfg<MESH, NEQ, UPPER>::SMEM);
     }
     const int ntiles = p.NJ * p.NK;
+    if (p.cell) g_lu_cell_launches++;
     if (p.cell) k_lu_cell<MESH, NEQ, UPPER><<<ntiles, LcCfg<MESH, NEQ, UPPER>::NTHR, LcCfg<MESH, NEQ, UPPER>::SMEM, st>>>(z, a);
     else k_lu_tile<MESH, NEQ, UPPER><<<ntiles, LU_NT, LuCfg<MESH, NEQ, UPPER>::SMEM, st>>>(z, a);
 }
@@ -1108,14 +1152,14 @@ static int run_lu_tiles(const ZoneDev &z, const LuPlan &p, const double *rop, do
             const unsigned long long *q = h.data() + sw * 16 * 65536; unsigned long long t0 = ~0ULL, t1 = 0;
             for (int t = 0; t < ntiles; t++) { t0 = std::min(t0, q[16 * t]); t1 = std::max(t1, q[16 * t + 1]); }
             fprintf(stderr, "LUDBG sweep %d call %d: NJ %d NK %d tiles %d bi %d total %.1f us\n", sw, dbg_calls, p.NJ, p.NK, ntiles, a.bi, (t1 - t0) * 1e-3);
-            const double n = a.bi + 22.;
+            const double n = (a.bi + 1) / 2 + 22.;        // super-steps of a tile
             for (int t = 0; t < ntiles; t++) {
                 const int J = t % p.NJ, K = t / p.NJ;
                 if (dbg_calls == 1 && (J % 8 == 0 || J == p.NJ - 1))
-                    fprintf(stderr, "LUDBG   tile J %2d K %2d sm %3llu start %8.1f end %8.1f dur %8.1f us | cycles/step: compute %6.0f | svc line0: refill %5.0f mbox %5.0f wb %5.0f deliver %5.0f wait %5.0f | svc line33: %5.0f %5.0f %5.0f %5.0f %5.0f\n",
-                            J, K, q[16 * t + 3], (q[16 * t] - t0) * 1e-3, (q[16 * t + 1] - t0) * 1e-3, (q[16 * t + 1] - q[16 * t]) * 1e-3, q[16 * t + 2] / (double)a.bi,
-                            q[16 * t + 4] / n, q[16 * t + 5] / n, q[16 * t + 6] / n, q[16 * t + 7] / n, q[16 * t + 8] / n,
-                            q[16 * t + 9] / n, q[16 * t + 10] / n, q[16 * t + 11] / n, q[16 * t + 12] / n, q[16 * t + 13] / n);
+                    fprintf(stderr, "LUDBG   tile J %2d K %2d start %8.1f end %8.1f dur %8.1f us | cycles / super-step: compute %6.0f (+ wait for the slot %5.0f) | service thread 0: B_S %5.0f wb %5.0f svc-barrier %5.0f mbox %5.0f deliver %5.0f slot-wait %5.0f | thread 40: %5.0f %5.0f %5.0f %5.0f %5.0f %5.0f\n",
+                            J, K, (q[16 * t] - t0) * 1e-3, (q[16 * t + 1] - t0) * 1e-3, (q[16 * t + 1] - q[16 * t]) * 1e-3, q[16 * t + 2] / n, q[16 * t + 3] / n,
+                            q[16 * t + 4] / n, q[16 * t + 5] / n, q[16 * t + 6] / n, q[16 * t + 7] / n, q[16 * t + 8] / n, q[16 * t + 9] / n,
+                            q[16 * t + 10] / n, q[16 * t + 11] / n, q[16 * t + 12] / n, q[16 * t + 13] / n, q[16 * t + 14] / n, q[16 * t + 15] / n);
             }
         }
         dbg_calls++;

@@ -102,7 +102,8 @@ int fb_timing_reset(fb_solver *s);
 int fb_timing_get(fb_solver *s, const char *name, double *ms, long long *launches);
 int fb_sync(fb_solver *s);
 /* Which kernels ran (process-wide): "rhs_tma" / "rhs_l1" = launches of the TMA-staged (k_rhs3) and of the L1-path
- * (k_rhs2) residual kernel, "lu_batch" = multi-zone LU launch pairs (k_lu_tile_b).  New with this library
+ * (k_rhs2) residual kernel, "lu_batch" = multi-zone LU launch pairs (one lower + one upper launch over all zones), "lu_cell" = sweeps run by the
+ * TMA-staged thread-per-cell kernel k_lu_cell[_b] (the others ran the 8-byte cp.async kernel k_lu_tile[_b]).  New with this library
  * (no reference counterpart); bench.py names the kernel it reports a roofline for from it. */
 int fb_counter(const char *name, long long *out);
 /* Test hook, needs no device: the order in which the two-part explicit stage of the halo-exchange overlap visits a
