@@ -17,7 +17,7 @@ SYMBOLS = ['fb_version', 'fb_last_error', 'fb_device_count', 'fb_solver_create',
            'fb_zone_get_residuals', 'fb_zone_get_cfl', 'fb_zone_isfinite', 'fb_compute_host', 'fb_timing_enable', 'fb_timing_reset',
            'fb_timing_get', 'fb_sync', 'fb_zone_device_ptr', 'fb_halo_pack', 'fb_halo_unpack', 'fb_set_modulo_verif',
            'fb_stream', 'fb_halo_sizes', 'fb_set_exchange_cb', 'fb_halo_buffers', 'fb_counter', 'fb_exchange_stream',
-           'fb_debug_tile_order']
+           'fb_debug_tile_order', 'fb_nccl_unique_id', 'fb_nccl_init', 'fb_set_peers']
 
 
 def lib():

@@ -11,6 +11,7 @@
 #include <string>
 #include <vector>
 #include <cmath>
+#include <dlfcn.h>
 #include "../../include/fastb200.h"
 #include "fb_kernels.cuh"
 #include "fb_implicit.cuh"
@@ -55,7 +56,10 @@ struct fb_solver {
     std::vector<Zone> z;
     bool metric_done = false;
     JoinSet joins;
-    fb_exchange_fn xcb = nullptr; void *xuser = nullptr;   // cross-rank halo exchange (fb_set_exchange_cb)
+    fb_exchange_fn xcb = nullptr; void *xuser = nullptr;   // cross-rank halo exchange through a host transport (fb_set_exchange_cb)
+    void *nccl = nullptr;                                  // ... or natively: ncclComm_t created by fb_nccl_init
+    struct Peer { int rank; long long so, sn, ro, rn; };
+    std::vector<Peer> peers;                               // fb_set_peers: slices of the send / receive buffers per neighbour rank
     double *halo_send = nullptr, *halo_recv = nullptr;
     bool timing = false;
     Timer tm[6];     // rhs, lu, bc, transfer, coe, all
@@ -81,6 +85,38 @@ static void resolve(fb_solver *s)
         }
         s->tm[i].pend.clear();
     }
+}
+
+namespace {
+typedef struct { char internal[128]; } fb_ncclUniqueId;
+typedef int (*nccl_getid_t)(fb_ncclUniqueId *);
+typedef int (*nccl_init_t)(void **, int, fb_ncclUniqueId, int);
+typedef int (*nccl_sr_t)(const void *, size_t, int, int, void *, cudaStream_t);
+typedef int (*nccl_rv_t)(void *, size_t, int, int, void *, cudaStream_t);
+typedef int (*nccl_v_t)(void);
+typedef int (*nccl_destroy_t)(void *);
+typedef const char *(*nccl_err_t)(int);
+struct NcclApi {
+    void *h = nullptr; nccl_getid_t getid = nullptr; nccl_init_t init = nullptr; nccl_sr_t send = nullptr; nccl_rv_t recv = nullptr;
+    nccl_v_t gstart = nullptr, gend = nullptr; nccl_destroy_t destroy = nullptr; nccl_err_t errstr = nullptr;
+};
+NcclApi *nccl_api()
+{
+    static NcclApi api; static bool tried = false;
+    if (!tried) {
+        tried = true;
+        for (const char *name : {"libnccl.so.2", "libnccl.so"}) { api.h = dlopen(name, RTLD_NOW | RTLD_GLOBAL); if (api.h) break; }
+        if (api.h) {
+            api.getid = (nccl_getid_t)dlsym(api.h, "ncclGetUniqueId"); api.init = (nccl_init_t)dlsym(api.h, "ncclCommInitRank");
+            api.send = (nccl_sr_t)dlsym(api.h, "ncclSend"); api.recv = (nccl_rv_t)dlsym(api.h, "ncclRecv");
+            api.gstart = (nccl_v_t)dlsym(api.h, "ncclGroupStart"); api.gend = (nccl_v_t)dlsym(api.h, "ncclGroupEnd");
+            api.destroy = (nccl_destroy_t)dlsym(api.h, "ncclCommDestroy"); api.errstr = (nccl_err_t)dlsym(api.h, "ncclGetErrorString");
+            if (!api.getid || !api.init || !api.send || !api.recv || !api.gstart || !api.gend) api.h = nullptr;
+        }
+    }
+    return api.h ? &api : nullptr;
+}
+const int FB_NCCL_DOUBLE = 8;   // ncclFloat64 (nccl.h: ncclDataType_t)
 }
 
 extern "C" {
@@ -134,6 +170,7 @@ void fb_solver_destroy(fb_solver *s)
     for (int q = 0; q < 3; q++) { if (s->lane[q]) cudaStreamDestroy(s->lane[q]); if (s->ev_lane[q]) cudaEventDestroy(s->ev_lane[q]); }
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
     lu_batch_free(s->lub);
+    if (s->nccl) { NcclApi *n = nccl_api(); if (n && n->destroy) n->destroy(s->nccl); }
     delete s;
 }
 
@@ -475,6 +512,46 @@ int fb_set_joins_tc(fb_solver *s, const int *param_int_tc, int n_int, const doub
     return FB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------- NCCL (native exchange)
+// The cross-rank halo exchange of C/Com/setInterpTransfersFast.cpp:962-1790 (one message per neighbour rank and sub-iteration)
+// runs inside the library: ncclSend / ncclRecv of the packed donor values on the exchange stream, grouped per exchange.  NCCL
+// is bound at run time (dlopen) so that single-GPU users need no NCCL at all; whichever libnccl.so.2 the process has already
+// loaded (e.g. torch's) is the one that answers.
+
+int fb_nccl_unique_id(char id[128])
+{
+    NcclApi *n = nccl_api();
+    if (!n || !id) return fail(FB_ECUDA, "fb_nccl_unique_id: libnccl.so.2 cannot be loaded");
+    fb_ncclUniqueId u; const int rc = n->getid(&u);
+    if (rc) return fail(FB_ECUDA, std::string("ncclGetUniqueId: ") + (n->errstr ? n->errstr(rc) : "error"));
+    memcpy(id, u.internal, 128);
+    return FB_OK;
+}
+int fb_nccl_init(fb_solver *s, int rank, int world, const char id[128])
+{
+    NcclApi *n = nccl_api();
+    if (!s || !id || world < 1 || rank < 0 || rank >= world) return fail(FB_EINVAL, "fb_nccl_init: bad arguments");
+    if (!n) return fail(FB_ECUDA, "fb_nccl_init: libnccl.so.2 cannot be loaded");
+    CK(cudaSetDevice(s->dev));
+    fb_ncclUniqueId u; memcpy(u.internal, id, 128);
+    void *comm = nullptr; const int rc = n->init(&comm, world, u, rank);
+    if (rc) return fail(FB_ECUDA, std::string("ncclCommInitRank: ") + (n->errstr ? n->errstr(rc) : "error"));
+    s->nccl = comm;
+    return FB_OK;
+}
+int fb_set_peers(fb_solver *s, int npeers, const int *rank, const long long *send_off, const long long *send_n,
+                 const long long *recv_off, const long long *recv_n)
+{
+    if (!s || npeers < 0 || (npeers && (!rank || !send_off || !send_n || !recv_off || !recv_n))) return fail(FB_EINVAL, "fb_set_peers: bad arguments");
+    s->peers.clear();
+    for (int p = 0; p < npeers; p++) {
+        if (send_off[p] < 0 || recv_off[p] < 0 || send_off[p] + send_n[p] > s->joins.send_doubles || recv_off[p] + recv_n[p] > s->joins.recv_doubles)
+            return fail(FB_EINVAL, "fb_set_peers: slice outside the halo buffers (call fb_set_joins first)");
+        s->peers.push_back({rank[p], send_off[p], send_n[p], recv_off[p], recv_n[p]});
+    }
+    return FB_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------- driver
 static void apply_bc_zone(fb_solver *s, Zone &z, double *rop, int lrhs)
 {
@@ -494,7 +571,7 @@ static void apply_bc_zone(fb_solver *s, Zone &z, double *rop, int lrhs)
 // stream st2: pack the donor cells (ordered after everything queued on st so far), let the host transport move the send
 // buffer to the peers' receive buffers (fb_exchange_stream), unpack into the ghost cells.  transfers_begin returns at once;
 // whatever the caller queues on st before transfers_end overlaps the exchange.  Local joins run on st in transfers_end.
-static bool cross_rank(fb_solver *s) { return s->xcb && (s->joins.send_doubles || s->joins.recv_doubles); }
+static bool cross_rank(fb_solver *s) { return (s->xcb || s->nccl) && (s->joins.send_doubles || s->joins.recv_doubles); }
 
 // ev1_recorded: the caller has already recorded ev1 on st behind the kernels that produce the donor cells (the face tiles of
 // an explicit stage, gsdr3) and may have queued more work since; otherwise the exchange waits for everything queued on st so far
@@ -506,7 +583,15 @@ static void transfers_begin(fb_solver *s, int which, double **target, bool ev1_r
     if (!ev1_recorded) cudaEventRecord(s->ev1, s->st);
     cudaStreamWaitEvent(s->st2, s->ev1, 0);
     if (s->joins.send_doubles) { joins_pack(s->joins, ptr.data(), s->halo_send, s->joins.send_doubles * 8, s->st2); s->launches++; }
-    s->xcb(s->xuser, which);
+    if (s->nccl) {       // one grouped send / receive pair per neighbour rank, stream-ordered on the exchange stream: no host in the loop
+        NcclApi *n = nccl_api();
+        n->gstart();
+        for (auto &p : s->peers) {
+            if (p.sn) n->send(s->halo_send + p.so, (size_t)p.sn, FB_NCCL_DOUBLE, p.rank, s->nccl, s->st2);
+            if (p.rn) n->recv(s->halo_recv + p.ro, (size_t)p.rn, FB_NCCL_DOUBLE, p.rank, s->nccl, s->st2);
+        }
+        n->gend();
+    } else s->xcb(s->xuser, which);
     if (s->joins.recv_doubles) { joins_unpack(s->joins, ptr.data(), s->halo_recv, s->joins.recv_doubles * 8, s->st2); s->launches++; }
     cudaEventRecord(s->ev2, s->st2);
 }

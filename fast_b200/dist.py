@@ -38,7 +38,11 @@ class _DevArray:
 
 
 class HaloExchange:
-    """Transport behind fb_set_exchange_cb: torch.distributed point-to-point on the library's exchange stream."""
+    """Cross-rank exchange of the packed donor values.  Default: the library's own NCCL transport (fb_nccl_init + fb_set_peers:
+    ncclSend / ncclRecv on the exchange stream, nothing of the host on the data path) -- this class only carries the 128-byte
+    NCCL id from rank 0 to the other ranks over the existing torch.distributed group.  FAST_B200_EXCHANGE=torch keeps the
+    host-callback transport of round 1 (fb_set_exchange_cb -> torch.distributed batch_isend_irecv), which is also the hook for
+    a foreign transport such as the reference's MPI layer."""
 
     def __init__(self, solver, peers, device, group=None):
         import torch
@@ -47,21 +51,37 @@ class HaloExchange:
         L = _lib.lib()
         ns, nr = ctypes.c_longlong(0), ctypes.c_longlong(0)
         _lib.check(L.fb_halo_sizes(solver, ctypes.byref(ns), ctypes.byref(nr)))
-        ps, pr = ctypes.c_ulonglong(0), ctypes.c_ulonglong(0)
-        _lib.check(L.fb_halo_buffers(solver, ctypes.byref(ps), ctypes.byref(pr)))
-        dev = torch.device('cuda', device)
-        self.send = torch.as_tensor(_DevArray(ps.value, ns.value), device=dev) if ns.value else None
-        self.recv = torch.as_tensor(_DevArray(pr.value, nr.value), device=dev) if nr.value else None
         self.peers = dict(peers)
-        self.stream = torch.cuda.ExternalStream(L.fb_exchange_stream(solver), device=dev)   # the library's exchange stream
         self.bytes_per_exchange = 8 * (ns.value + nr.value)
         self.calls = 0
+        self.native = os.environ.get('FAST_B200_EXCHANGE', 'nccl') != 'torch'
+        dev = torch.device('cuda', device)
+        if self.native:
+            rank, world = dist.get_rank(group), dist.get_world_size(group)
+            idbuf = (ctypes.c_char * 128)()
+            if rank == 0: _lib.check(L.fb_nccl_unique_id(idbuf))
+            t = torch.frombuffer(bytearray(idbuf.raw), dtype=torch.uint8).clone().to(dev)
+            dist.broadcast(t, src=0, group=group)
+            raw = bytes(t.cpu().numpy().tobytes())
+            _lib.check(L.fb_nccl_init(solver, rank, world, ctypes.create_string_buffer(raw, 128)))
+            order = sorted(self.peers.items())
+            n = len(order)
+            IA = ctypes.c_int * max(n, 1); LA = ctypes.c_longlong * max(n, 1)
+            _lib.check(L.fb_set_peers(solver, n, IA(*[p for p, _ in order]), LA(*[v[0] for _, v in order]), LA(*[v[1] for _, v in order]),
+                                      LA(*[v[2] for _, v in order]), LA(*[v[3] for _, v in order])))
+            return
+        ps, pr = ctypes.c_ulonglong(0), ctypes.c_ulonglong(0)
+        _lib.check(L.fb_halo_buffers(solver, ctypes.byref(ps), ctypes.byref(pr)))
+        self.send = torch.as_tensor(_DevArray(ps.value, ns.value), device=dev) if ns.value else None
+        self.recv = torch.as_tensor(_DevArray(pr.value, nr.value), device=dev) if nr.value else None
+        self.stream = torch.cuda.ExternalStream(L.fb_exchange_stream(solver), device=dev)   # the library's exchange stream
         self._cb = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_int)(self._exchange)
         L.fb_set_exchange_cb.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         _lib.check(L.fb_set_exchange_cb(solver, ctypes.cast(self._cb, ctypes.c_void_p), None))
 
     def describe(self):
-        return 'NCCL isend/irecv per neighbour (torch.distributed) on the exchange stream'
+        if self.native: return 'ncclSend / ncclRecv per neighbour inside the library (fb_nccl_init), on its exchange stream'
+        return 'NCCL isend/irecv per neighbour (torch.distributed, host callback) on the exchange stream'
 
     def _exchange(self, user, which):
         torch, dist = self.torch, self.dist

@@ -129,6 +129,16 @@ int fb_halo_sizes(fb_solver *s, long long *send_doubles, long long *recv_doubles
 typedef void (*fb_exchange_fn)(void *user, int which);
 int fb_set_exchange_cb(fb_solver *s, fb_exchange_fn cb, void *user);
 int fb_halo_buffers(fb_solver *s, unsigned long long *send_ptr, unsigned long long *recv_ptr);
+/* Native transport (default of fast_b200.dist): the library itself moves the packed donor values between the ranks with
+ * ncclSend / ncclRecv on its exchange stream -- no host callback on the data path.  libnccl.so.2 is bound at run time.
+ * fb_nccl_unique_id: rank 0 draws the 128-byte NCCL id, the host side hands it to every rank (any out-of-band channel: the
+ * reference would use MPI_Bcast, S/Mpi.py); fb_nccl_init: collective over the ranks, creates this rank's communicator on the
+ * solver's device; fb_set_peers: per neighbour rank the slices [off, off + n) (in doubles) of the send and receive buffers that
+ * fb_set_joins sized -- the message of C/Com/setInterpTransfersFast.cpp:962 (setInterpTransfersInter) towards that rank. */
+int fb_nccl_unique_id(char id[128]);
+int fb_nccl_init(fb_solver *s, int rank, int world, const char id[128]);
+int fb_set_peers(fb_solver *s, int npeers, const int *rank, const long long *send_off, const long long *send_n,
+                 const long long *recv_off, const long long *recv_n);
 /* dtloc[1] of .Solver#dtloc (C/PyTree.py:1188-1200): residual / CFL check every modulo_verif iterations. */
 int fb_set_modulo_verif(fb_solver *s, int modulo_verif);
 /* cudaStream_t of the solver (uintptr) so that torch/NCCL work can be ordered against it. */

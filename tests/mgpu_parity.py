@@ -101,7 +101,7 @@ def main_gpu(workload):
         assert numpy.isfinite(a).all()
         worst = max(worst, float(numpy.abs(a - b).max() / numpy.abs(b).max()))
     w = torch.tensor([worst], device='cuda', dtype=torch.float64); dist.all_reduce(w, op=dist.ReduceOp.MAX)
-    if rank == 0: print("MGPU_GPU %s world=%d exchanges=%d max_rel_diff=%.3e %s" % (workload, world, calls, w.item(), "OK" if w.item() <= 1e-12 else "FAIL"))
+    if rank == 0: print("MGPU_GPU %s world=%d transport=%s exchanges(host callbacks)=%d max_rel_diff=%.3e %s" % (workload, world, "native NCCL" if hx.native else "torch callback", calls, w.item(), "OK" if w.item() <= 1e-12 else "FAIL"))
     dist.destroy_process_group()
     assert w.item() <= 1e-12
 
