@@ -1,0 +1,13 @@
+#!/bin/bash
+mkdir -p gpurun_out
+N=8
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29661 bench.py --gpus $N --steps 10 --warmup 3 --no-e2e > gpurun_out/r02_bench_c5_${N}gpu.json 2> gpurun_out/r02_bench_c5_${N}gpu.err
+tail -2 gpurun_out/r02_bench_c5_${N}gpu.err | cut -c1-300
+python - <<PY
+import json
+try:
+    d=json.loads(open('gpurun_out/r02_bench_c5_${N}gpu.json').read().strip().splitlines()[-1])
+    print('c5 ${N} GPUs', round(d['value'],1), round(d['ms_per_step'],2), d['roofline']['whole_subiteration']['frac'], d['config'].get('halo'), d['roofline']['step_share'], d['config']['workload'], d['config']['cells'])
+except Exception as e: print('ERR', e)
+PY
+timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29662 tests/mgpu_parity.py c5 2>&1 | grep MGPU
