@@ -171,8 +171,9 @@ __device__ __forceinline__ double visc_face(const ZoneDev &z, const V &v, const 
     double xmutvol, xktvol;
     const double Tl = v.q(4, il), Tr = v.q(4, ir);
     if (FLOW == 3) {
-        double xmulam = z.coesut * sqrt(Tl * z.temp01) / (1. + z.cmus1 / Tl);
-        xmulam = xmulam + z.coesut * sqrt(Tr * z.temp01) / (1. + z.cmus1 / Tr);
+        // SA/mut_interface.for: Sutherland at both cells, one division each (mulam, fb_source.cuh)
+        double xmulam = z.coesut * sqrt(Tl * z.temp01) * Tl / (Tl + z.cmus1);
+        xmulam = xmulam + z.coesut * sqrt(Tr * z.temp01) * Tr / (Tr + z.cmus1);
         const double xmutot = v.mu(ir) + v.mu(il);
         const double xmutur = xmutot - xmulam;
         xktvol = (xmulam * z.gam3 + xmutur * z.gam4) * volinv;
@@ -205,8 +206,9 @@ __device__ __forceinline__ double visc_face(const ZoneDev &z, const V &v, const 
     }
     (void)f6;
     if (FLOW == 3) {
-        double xmulam = z.coesut * sqrt(Tl * z.temp01) / (1. + z.cmus1 / Tl);
-        xmulam = xmulam + z.coesut * sqrt(Tr * z.temp01) / (1. + z.cmus1 / Tr);
+        // SA/mut_interface.for: Sutherland at both cells, one division each (mulam, fb_source.cuh)
+        double xmulam = z.coesut * sqrt(Tl * z.temp01) * Tl / (Tl + z.cmus1);
+        xmulam = xmulam + z.coesut * sqrt(Tr * z.temp01) * Tr / (Tr + z.cmus1);
         double xsa = xmulam + v.q(5, il) * v.q(0, il) + v.q(5, ir) * v.q(0, ir);
         xsa = xsa * volinv * z.sigma_1;
         constexpr int C = NV - 1;

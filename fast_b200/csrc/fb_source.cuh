@@ -6,8 +6,8 @@
 #include "fb_view.cuh"
 
 __device__ __forceinline__ double mulam(const ZoneDev &z, double T)
-{   // S/Compute/mulam.for
-    return z.coesut * sqrt(T * z.temp01) / (1. + z.cmus1 / T);
+{   // S/Compute/mulam.for: coesut sqrt(T/T0) / (1 + Cs/T), written with one division (= coesut sqrt(T/T0) T / (T + Cs))
+    return z.coesut * sqrt(T * z.temp01) * T / (T + z.cmus1);
 }
 
 // SA/vispalart.for: mu + min(max(rho nutilde fv1, 0), ratiom mu)
@@ -107,19 +107,24 @@ __device__ __forceinline__ double sa_source_cell(const ZoneDev &z, const V &v, c
     const double anulam = rho / amulam;
     const double anutild = fmax(v.q(5, l), 1.e-27);
     const double chi = fmax(anutild * anulam, 1.e-7);
-    const double f1 = 1. / (1. + SA_CV1 / (chi * chi * chi));
+    // (the same algebra as sourceSA_prod_dest.for with the divisions shared: fv1 = chi^3 / (chi^3 + cv1), one reciprocal of
+    // (kappa d)^2 for S~, r and the destruction term, x^(1/6) as cbrt(sqrt(x)) -- the FP64 pipe is what bounds this kernel, and
+    // pow() alone costs more instructions than the rest of the source; differences at round-off level)
+    const double chi3 = chi * chi * chi;
+    const double f1 = chi3 / (chi3 + SA_CV1);
     const double f2 = 1. - chi / (1. + chi * f1);
     const double dist = fmax(z.xmut[lg + nd], 1.e-27);
-    double stild = rot + (anutild * f2) / (SA_CKARM * SA_CKARM * dist * dist);
+    const double ikd2 = 1. / (SA_CKARM * SA_CKARM * dist * dist);
+    double stild = rot + (anutild * f2) * ikd2;
     const double prod = rho * SA_CB1 * stild * anutild;
     stild = fmax(stild, 0.00000000000000000001);
-    double r = anutild / (stild * SA_CKARM * SA_CKARM * dist * dist);
+    double r = anutild * ikd2 / stild;
     r = fmin(r, 10.);
     const double r5 = r * r * r * r * r - 1.;
     const double gg = r * (1. + SA_CW2 * r5);
     const double g2 = gg * gg, g6 = g2 * g2 * g2;
-    const double fwg = gg * pow((1. + SA_CW3) / (g6 + SA_CW3), 1. / 6.);
-    const double destruc = rho * cw1 * fwg * (anutild / dist) * (anutild / dist);
+    const double fwg = gg * cbrt(sqrt((1. + SA_CW3) / (g6 + SA_CW3)));
+    const double destruc = rho * cw1 * fwg * (anutild * anutild) * (ikd2 * (SA_CKARM * SA_CKARM));
     const double tsource = (prod + anvisc - destruc);
     if (store) {   // sourceSA_LU.for
         const double tsourceb = prod - destruc;

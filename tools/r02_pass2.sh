@@ -22,4 +22,4 @@ try:
 except Exception as e: print('$w ERR', e); print(open('gpurun_out/r02_p2_$w.err').read()[-1500:])
 PY
 done
-FAST_B200_PDL=0 timeout 400 python bench.py --steps 10 --warmup 3 --workload c5 --no-secondary --no-cpu --no-e2e 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('c5 PDL=0', round(d['value'],1), d['roofline']['kernels'])"
+
