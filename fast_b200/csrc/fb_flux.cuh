@@ -306,7 +306,7 @@ __device__ __forceinline__ void face_flux(const ZoneDev &z, const V &vw, const M
         double u, tdu;
         if (SCHEME == 1) {
             const double cs = rgp * z.gam * T0;
-            const double son = sqrt(qn1 * qn1 / cs);
+            const double son = fabs(qn1) * rsqrt(cs);      // = sqrt(qn1^2 / cs) of fluFaceEuler.for without the division
             const double tam = -2. * son + s;
             const double tam1 = fmax(0., tam) * z.c2;
             u = 0.25 * (qn1 + qn2) - tam1 * (p2 - p1);

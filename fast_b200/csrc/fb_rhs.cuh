@@ -270,14 +270,36 @@ __global__ void __launch_bounds__(32 * (RHS2_RJ + 1)) k_rhs2(ZoneDev z, RhsArgs 
 #define RHS3_MINB 2         // resident CTAs per SM the register allocation aims at
 #endif
 #ifndef RHS3_SMET_SA
-#define RHS3_SMET_SA 0      // 3dhomo SA zones: 1 = k-invariant metric tile in shared memory; 0 = read through L1, which frees the
-                            // 19 KB per CTA that let two CTAs of RJ = 7 stay resident (measured: C5 rhs 34.6 -> 31.9 ms)
+#define RHS3_SMET_SA 1      // 3dhomo SA zones: 1 = k-invariant metric tile in shared memory (19 KB per CTA), paid for with one ring
+                            // slot (RHS3_NS_SA = 3) so that two CTAs of RJ = 7 stay resident; 0 = metrics through L1 and a 4-slot ring
+                            // (measured on one B200: C5 rhs 0.752 -> 0.673 ms per block, plate 1.52 -> 1.35 ms with the tile)
+#endif
+#ifndef RHS3_NS_SA
+#define RHS3_NS_SA (RHS3_SMET_SA ? 3 : RHS3_NS)
+#endif
+#ifndef RHS3_RJ_1B
+#define RHS3_RJ_1B 11       // tile rows of the kernels that run one CTA per SM (Roe, 3dfull: 168 registers): 12 warps fill the
+                            // register file (measured: C4 rhs 0.625 -> 0.550 ms per 128^3 block against 8 / 7 rows); 0 = as the others
+#endif
+#ifndef RHS3_NSF_SA
+#define RHS3_NSF_SA 2       // F_j exchange buffers of the 3dhomo SA kernel (1 = second barrier per plane, 12 KB less shared memory)
 #endif
 #ifndef RHS3_KC
 #define RHS3_KC 32          // k planes per CTA (measured: 32 < 64 < 128 on TGV 256^3 and the plate)
 #endif
+#ifndef RHS3_KC_SA
+#define RHS3_KC_SA 16       // ... of the 3dhomo SA kernel (measured: C5 rhs 0.674 -> 0.664 ms per block, plate 1.349 -> 1.290 ms)
+#endif
+#ifndef RHS3_KC_1B
+#define RHS3_KC_1B RHS3_KC  // ... of the kernels that run one CTA per SM
+#endif
 
 template <int MESH, int FLOW> struct Rhs3SMet { static constexpr bool V = MESH == 1 && (FLOW != 3 || RHS3_SMET_SA != 0); };
+// register budget: two resident CTAs per SM where the flux fits 96-128 registers; Roe and the 3dfull metrics need more
+template <int MESH, int SCHEME> struct Rhs3MinB { static constexpr int V = (SCHEME == 5 || MESH == 0) ? 1 : RHS3_MINB; };
+template <int MESH, int FLOW, int SCHEME> struct Rhs3NS {   // ring slots (a kernel alone on its SM has room for the deeper ring)
+    static constexpr int V = (MESH == 1 && FLOW == 3 && Rhs3MinB<MESH, SCHEME>::V > 1) ? RHS3_NS_SA : RHS3_NS;
+};
 template <bool SM, int RS, int VS>
 __device__ __forceinline__ typename std::conditional<SM, SMet1<RS, VS>, GMet1>::type make_met(const ZoneDev &z, const double *smet)
 {
@@ -297,10 +319,10 @@ struct Rhs3Cfg {
     static constexpr unsigned TX = (unsigned)(NV * VS * sizeof(double));   // bytes one plane brings in
     // F_j exchange: double-buffered by plane parity (one barrier per plane); 3dhomo SA keeps a single buffer and pays a
     // second barrier per plane so that ring + metric tile leave room for two CTAs per SM
-    template <int MESH> __host__ __device__ static constexpr int nsf() { return (MESH == 1 && FLOW == 3) ? 1 : 2; }
+    template <int MESH> __host__ __device__ static constexpr int nsf() { return (MESH == 1 && FLOW == 3) ? RHS3_NSF_SA : 2; }
     template <int MESH> __host__ __device__ static constexpr int sfj() { return nsf<MESH>() * (RJ + 1) * NEQ * 32; }
     template <int MESH> __host__ __device__ static constexpr int met() { return Rhs3SMet<MESH, FLOW>::V ? 6 * VS : 0; }   // 3dhomo: metric tile (k-invariant)
-    template <int MESH> __host__ __device__ static constexpr size_t smem() { return (size_t)(RHS3_NS * PS + sfj<MESH>() + met<MESH>()) * sizeof(double) + RHS3_NS * sizeof(unsigned long long); }
+    template <int MESH, int SCHEME> __host__ __device__ static constexpr size_t smem() { return (size_t)(Rhs3NS<MESH, FLOW, SCHEME>::V * PS + sfj<MESH>() + met<MESH>()) * sizeof(double) + Rhs3NS<MESH, FLOW, SCHEME>::V * sizeof(unsigned long long); }
 };
 
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
@@ -324,15 +346,16 @@ __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *tm, in
                    "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
 
-// register budget: two resident CTAs per SM where the flux fits 96-128 registers; Roe and the 3dfull metrics need more
-template <int MESH, int SCHEME> struct Rhs3MinB { static constexpr int V = (SCHEME == 5 || MESH == 0) ? 1 : RHS3_MINB; };
+template <int MESH, int FLOW, int SCHEME> struct Rhs3KC {   // k planes per CTA
+    static constexpr int V = Rhs3MinB<MESH, SCHEME>::V == 1 ? RHS3_KC_1B : ((MESH == 1 && FLOW == 3) ? RHS3_KC_SA : RHS3_KC);
+};
 
 template <int MESH, int FLOW, int SCHEME, int SLOPE, bool IMPL, int RJ, bool WC>
 __global__ void __launch_bounds__(32 * (RJ + 1), Rhs3MinB<MESH, SCHEME>::V)
 k_rhs3(const CUtensorMap *__restrict__ tm_rop, const CUtensorMap *__restrict__ tm_mu, ZoneDev z, RhsArgs a)
 {
     using C = Rhs3Cfg<FLOW, RJ>;
-    constexpr int NEQ = C::NEQ, NS = RHS3_NS, PS = C::PS, RS = C::RS, VS = C::VS;
+    constexpr int NEQ = C::NEQ, NS = Rhs3NS<MESH, FLOW, SCHEME>::V, PS = C::PS, RS = C::RS, VS = C::VS;
     // (unsigned on purpose, like blockIdx: with signed tile coordinates the address arithmetic of the whole kernel grows by a quarter)
     unsigned bx = blockIdx.x, by = blockIdx.y, bz = blockIdx.z;
     if (!IMPL && a.gx) rhs_face_first(blockIdx.x + (unsigned)a.tile0, a.gx, a.gy, a.gz, a.faces, bx, by, bz);   // explicit stages only
@@ -347,7 +370,8 @@ k_rhs3(const CUtensorMap *__restrict__ tm_rop, const CUtensorMap *__restrict__ t
     const int li = threadIdx.x, m = threadIdx.y;
     const bool leader = li == 0 && m == 0;
     const int i = 1 + bx * 31 + li, j = 1 + by * RJ + m;
-    const int k0 = 1 + bz * RHS3_KC, k1 = min(k0 + RHS3_KC - 1, z.kv);
+    constexpr int KC = Rhs3KC<MESH, FLOW, SCHEME>::V;
+    const int k0 = 1 + bz * KC, k1 = min(k0 + KC - 1, z.kv);
     const bool cell = li < 31 && m < RJ && i <= z.iv && j <= z.jv;
     const bool fi = m < RJ && j <= z.jv && i <= z.iv + 1;
     const bool fj = li < 31 && i <= z.iv && j <= z.jv + 1;
@@ -505,7 +529,7 @@ static void launch_rhs2_t(const ZoneDev &z, RhsArgs &a, bool impl, cudaStream_t 
 template <int MESH, int FLOW, int SCHEME, int SLOPE>
 static bool launch_rhs3_t(const ZoneDev &z, RhsArgs &a, bool impl, cudaStream_t st)
 {
-    constexpr int RJ = FLOW == 3 ? RHS3_RJ_SA : RHS3_RJ_NS;
+    constexpr int RJ = (RHS3_RJ_1B && Rhs3MinB<MESH, SCHEME>::V == 1) ? RHS3_RJ_1B : (FLOW == 3 ? RHS3_RJ_SA : RHS3_RJ_NS);
     using C = Rhs3Cfg<FLOW, RJ>;
     if (z.nf != 2 || z.nfk != 2) return false;
     const CUtensorMap *tr = fb_tma_map(a.rop, z.ni, z.nj, z.nk, z.nd, C::NEQ, C::ROWS, C::NEQ);
@@ -513,17 +537,18 @@ static bool launch_rhs3_t(const ZoneDev &z, RhsArgs &a, bool impl, cudaStream_t 
     if (!tr || !tm) return false;
     static std::atomic<unsigned long long> attr{0};
     if (fb_first_on_device(attr)) {
-        cudaFuncSetAttribute(k_rhs3<MESH, FLOW, SCHEME, SLOPE, true, RJ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::template smem<MESH>());
-        cudaFuncSetAttribute(k_rhs3<MESH, FLOW, SCHEME, SLOPE, false, RJ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::template smem<MESH>());
-        cudaFuncSetAttribute(k_rhs3<MESH, FLOW, SCHEME, SLOPE, true, RJ, SCHEME == 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::template smem<MESH>());
-        cudaFuncSetAttribute(k_rhs3<MESH, FLOW, SCHEME, SLOPE, false, RJ, SCHEME == 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::template smem<MESH>());
+        cudaFuncSetAttribute(k_rhs3<MESH, FLOW, SCHEME, SLOPE, true, RJ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::template smem<MESH, SCHEME>());
+        cudaFuncSetAttribute(k_rhs3<MESH, FLOW, SCHEME, SLOPE, false, RJ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::template smem<MESH, SCHEME>());
+        cudaFuncSetAttribute(k_rhs3<MESH, FLOW, SCHEME, SLOPE, true, RJ, SCHEME == 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::template smem<MESH, SCHEME>());
+        cudaFuncSetAttribute(k_rhs3<MESH, FLOW, SCHEME, SLOPE, false, RJ, SCHEME == 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::template smem<MESH, SCHEME>());
     }
     dim3 b(32, RJ + 1, 1);
-    dim3 g((z.iv + 30) / 31, (z.jv + RJ - 1) / RJ, (z.kv + RHS3_KC - 1) / RHS3_KC);
-    a.thin = rhs_thin(z, g, 31, RJ, RHS3_KC);
+    constexpr int KC = Rhs3KC<MESH, FLOW, SCHEME>::V;
+    dim3 g((z.iv + 30) / 31, (z.jv + RJ - 1) / RJ, (z.kv + KC - 1) / KC);
+    a.thin = rhs_thin(z, g, 31, RJ, KC);
     if (!rhs_part_grid(a, g)) return true;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = g; cfg.blockDim = b; cfg.dynamicSmemBytes = C::template smem<MESH>(); cfg.stream = st;
+    cfg.gridDim = g; cfg.blockDim = b; cfg.dynamicSmemBytes = C::template smem<MESH, SCHEME>(); cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = a.pdl ? 1 : 0;
