@@ -458,12 +458,16 @@ __global__ void __launch_bounds__(LU_NT, 1) k_lu_tile_b(const LuBatchItem *items
 //     be 16-byte aligned, so the pairing of cells into granules follows the parity of the first column of the sweep box.
 //     The k-invariant normals of 3dhomo zones come through a rank-3 view (c0 = i + 2 j) into their own ring of 20 super-steps:
 //     line kk needs at super-step S what line 0 needed at S - kk.
-//   * three slots of (all arrays) x (lines) x (2 cells): compute works on slot S, the service threads write the results of
-//     S-1 back (16-byte stores, masked per cell) and then re-arm that slot for S+2.
+//   * three slots (LC_SLOTS_MAX) of (all arrays) x (lines) x (2 cells): compute works on slot S, the service threads write
+//     the results of S-1 back (16-byte stores, masked per cell) and then re-arm that slot for S + slots - 1.
 // Mailboxes (one 48-byte entry per boundary cell, two per super-step), tickets, error flag and the (J + K) tile order are those of
 // k_lu_tile.
-#define LC_SLOTS 3
-#define LC_NSL 20          // super-steps kept in the 3dhomo normals ring (>= TK + 3)
+#ifndef LC_SLOTS_MAX
+#define LC_SLOTS_MAX 3     // slots of the staging ring; boxes are asked for SLOTS - 1 super-steps ahead.  4 (where they fit in 227 KB:
+                           // all but the 3dfull 5-equation zones) measured no faster (C5 598 v 600, plate 396 v 398 Mcell.it/s): the
+                           // sweep does not wait for its boxes
+#endif
+#define LC_NSL 20          // super-steps kept in the 3dhomo normals ring (>= TK + slots)
 #define LC_NSV 128         // service threads
 
 template <int MESH, int NEQ, bool UPPER>
@@ -486,7 +490,9 @@ struct LcCfg {
     static constexpr int EXB = 2 * 2 * 2 * L * LU_MB;   // [buffer][direction][cell][line][6]
     static constexpr int MBW = 2 * LU_MB;               // words per interface line and super-step
     static constexpr unsigned TX = (unsigned)((SLOT + (MESH == 1 ? NRS : 0)) * sizeof(double));
-    static constexpr size_t SMEM = (size_t)(LC_SLOTS * SLOT + NRING + EXB + 6 * NIF * MBW) * sizeof(double) + 64;
+    static constexpr size_t smem_of(int slots) { return (size_t)(slots * SLOT + NRING + EXB + 6 * NIF * MBW) * sizeof(double) + 64; }
+    static constexpr int SLOTS = smem_of(LC_SLOTS_MAX) <= 227 * 1024 ? LC_SLOTS_MAX : 3;
+    static constexpr size_t SMEM = smem_of(SLOTS);
 };
 int lu_cell_tk(int mesh, int neq) { return (mesh == 0 && neq == 6) ? 12 : 16; }
 long long g_lu_cell_launches = 0;   // sweeps run by the TMA-staged thread-per-cell kernel (fb_counter "lu_cell")
@@ -522,7 +528,7 @@ template <int MESH, int NEQ, bool UPPER>
 __device__ __forceinline__ void lu_cell_body(const ZoneDev &z, const LuTileArgs &a, const int tile, double *smem)
 {
     using C = LcCfg<MESH, NEQ, UPPER>;
-    constexpr int TJ = C::TJ, TK = C::TK, L = C::L, EX = LU_MB, NIF = C::NIF, AS = C::AS, MBW = C::MBW;
+    constexpr int TJ = C::TJ, TK = C::TK, L = C::L, EX = LU_MB, NIF = C::NIF, AS = C::AS, MBW = C::MBW, LC_SLOTS = C::SLOTS;
     double *ring = smem;                                   // [LC_SLOTS][A][L][2]
     double *nring = smem + LC_SLOTS * C::SLOT;             // 3dhomo: [LC_NSL][5][TJ][2]
     double *exb = nring + C::NRING;                        // [2][2][2][L][EX]: products handed to (jj+1) and (kk+1)
@@ -653,7 +659,9 @@ __device__ __forceinline__ void lu_cell_body(const ZoneDev &z, const LuTileArgs 
             unsigned long long *d = mpre + (size_t)(X & 3) * NIF * MBW;
             d[0] = wa0; d[1] = wa1; d[EX] = wb0; d[EX + 1] = wb1;
         };
-        if (st == 0) { fetch(0); fetch(1); }
+        if (st == 0) {
+            for (int q = 0; q < LC_SLOTS - 1; q++) fetch(q);
+        }
         if (mth) { load(0); park(0); load(1); park(1); load(2); }
         deliver(0);
         long long c_wb = 0, c_sb = 0, c_mb = 0, c_dl = 0, c_fw = 0, c_b0 = 0;
@@ -668,7 +676,7 @@ __device__ __forceinline__ void lu_cell_body(const ZoneDev &z, const LuTileArgs 
             const long long q2 = LU_CLOCK();
             asm volatile("barrier.sync 1, %0;" ::"n"(LC_NSV) : "memory");
             const long long q3 = LU_CLOCK();
-            if (st == 0) fetch(S + 2);
+            if (st == 0) fetch(S + LC_SLOTS - 1);          // into the slot that was just written back
             if (mth) { park(S + 2); load(S + 3); }
             const long long q4 = LU_CLOCK();
             deliver(S + 1);

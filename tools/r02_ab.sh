@@ -17,8 +17,16 @@ except Exception as e: print('${v:-base} $w ERR', e); print(open('gpurun_out/ab_
 PY
   done
 }
-run "" c5 plate multiblock tgv256
-run kc1b16 multiblock
-run rsq c5 plate tgv256
-run kcsa8 c5 plate
-run "" c5 multiblock
+run "" c5 plate multiblock
+run slots3 c5 plate multiblock
+run "" c5
+export STRIDE=1
+for r in 1 2 3; do timeout 600 python tools/race_check.py c5 8 gpurun_out/race_e$r.json > /dev/null 2>&1; done
+python - <<'PY'
+import json
+R=[json.load(open('gpurun_out/race_e%d.json'%r)) for r in (1,2,3)]
+for a in range(3):
+    for b in range(a+1,3):
+        bad=[(it,z) for it,(r,s) in enumerate(zip(R[a],R[b])) for z,(p,q) in enumerate(zip(r,s)) if p!=q]
+        print('default config determinism', a+1,'v',b+1, bad[:6], len(bad))
+PY
