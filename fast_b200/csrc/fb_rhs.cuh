@@ -112,7 +112,8 @@ __device__ __noinline__ void wall_corr(const ZoneDev &z, const double *rop, int 
 // explicit: core3ark3.for:108-154 (+203-236 for nutilde) -- the stage is updated from its own input
 // (navier_stokes_struct.for:477-483); implicit: core3as2.for:70-100.  l: cell in the view, lg: global cell index.
 template <int MESH, int FLOW, bool IMPL, class V>
-__device__ __forceinline__ void rhs_finish(const ZoneDev &z, const RhsArgs &a, const V &v, int l, int lg, double coe1, double *acc)
+__device__ __forceinline__ void rhs_finish(const ZoneDev &z, const RhsArgs &a, const V &v, int l, int lg, double coe1, double *acc,
+                                           const double *npre = nullptr)
 {
     constexpr int NEQ = FLOW == 3 ? 6 : 5;
     const int nd = z.nd;
@@ -140,7 +141,7 @@ __device__ __forceinline__ void rhs_finish(const ZoneDev &z, const RhsArgs &a, c
             out[lg + 5 * nd] = fmax(t, 0.);
         }
     } else {
-        implicit_assemble<NEQ>(z, v, l, a.rop, a.ro_n, a.ro_n1, lg, coe1, a.c1, a.c2, a.c3, acc);
+        implicit_assemble<NEQ>(z, v, l, a.rop, a.ro_n, a.ro_n1, lg, coe1, a.c1, a.c2, a.c3, acc, npre);
 #pragma unroll
         for (int e = 0; e < NEQ; e++) z.drodm[lg + e * nd] = acc[e];
     }
@@ -295,6 +296,11 @@ __global__ void __launch_bounds__(32 * (RHS2_RJ + 1)) k_rhs2(ZoneDev z, RhsArgs 
 #endif
 
 template <int MESH, int FLOW> struct Rhs3SMet { static constexpr bool V = MESH == 1 && (FLOW != 3 || RHS3_SMET_SA != 0); };
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap *tm, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
 // register budget: two resident CTAs per SM where the flux fits 96-128 registers; Roe and the 3dfull metrics need more
 template <int MESH, int SCHEME> struct Rhs3MinB { static constexpr int V = (SCHEME == 5 || MESH == 0) ? 1 : RHS3_MINB; };
 template <int MESH, int FLOW, int SCHEME> struct Rhs3NS {   // ring slots (a kernel alone on its SM has room for the deeper ring)
@@ -389,6 +395,10 @@ k_rhs3(const CUtensorMap *__restrict__ tm_rop, const CUtensorMap *__restrict__ t
         tma_load_4d(ring + slot * PS, tm_rop, ca, cb, p + z.nfk - 1, 0, bar + slot);
         if (FLOW >= 2) tma_load_4d(ring + slot * PS + C::MUOFF, tm_mu, ca, cb, p + z.nfk - 1, 0, bar + slot);
     };
+    auto prefetch = [&](int p) {
+        tma_prefetch_4d(tm_rop, ca, cb, p + z.nfk - 1, 0);
+        if (FLOW >= 2) tma_prefetch_4d(tm_mu, ca, cb, p + z.nfk - 1, 0);
+    };
     if (leader) {
         for (int s = 0; s < NS; s++) mbar_init(bar + s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -396,7 +406,10 @@ k_rhs3(const CUtensorMap *__restrict__ tm_rop, const CUtensorMap *__restrict__ t
     if (Rhs3SMet<MESH, FLOW>::V) {
         // the metrics of a 3dhomo zone do not depend on k: the tile's neighbourhood is copied once and serves every plane
         const int tid = m * 32 + li, mlast = z.nm - 1;
-        for (int n = tid; n < 6 * VS; n += C::NT) {
+#pragma unroll
+        for (int it = 0; it < (6 * VS + C::NT - 1) / C::NT; it++) {      // independent loads, all in flight together
+            const int n = tid + it * C::NT;
+            if (n >= 6 * VS) break;
             const int arr = n / VS, r = (n % VS) / RS, c = n % RS;
             int lt = indmtr(z, 1 + bx * 31 - 2 - sh + c, 1 + by * RJ - 2 + r, 1);
             lt = lt < 0 ? 0 : (lt > mlast ? mlast : lt);        // outside the arrays: never used, any finite value will do
@@ -418,6 +431,8 @@ k_rhs3(const CUtensorMap *__restrict__ tm_rop, const CUtensorMap *__restrict__ t
 #pragma unroll
     for (int e = 0; e < NEQ; e++) acc[e] = 0.;
     double coe1p = 0.;
+    // implicit_assemble reads W(n) unless rop is W(n) itself (first sub-iteration); loaded ahead of the flux
+    const bool ldn = IMPL && a.ro_n != a.rop;
     mbar_wait(bar + 0, 0);
     mbar_wait(bar + 1, 0);
     const int lcol = (m + 2) * RS + li + 2 + sh;
@@ -427,12 +442,17 @@ k_rhs3(const CUtensorMap *__restrict__ tm_rop, const CUtensorMap *__restrict__ t
         const int sk = pk % NS, su = (pk + 1) % NS, sd = (pk - 1) % NS;
         // early global loads of the cell of plane k (old rhs for the RK accumulation, dt/vol, SENSOR byte): issued
         // before the wait and the k-face flux, which hide their latency
-        double accn[NEQ], coe1 = 0.;
+        double accn[NEQ], coe1 = 0., distk = -1., wn[NEQ];
 #pragma unroll
-        for (int e = 0; e < NEQ; e++) accn[e] = 0.;
+        for (int e = 0; e < NEQ; e++) { accn[e] = 0.; wn[e] = 0.; }
         {
             const int lg = inddm(z, i, j, k);
+            if (IMPL && ldn && cell && k > k0) {       // W(n) of cell k-1, finished in this iteration
+#pragma unroll
+                for (int e = 0; e < NEQ; e++) wn[e] = FB_LD(a.ro_n + lg - z.inck + e * nd);
+            }
             if (cell && k <= k1) {
+                if (FLOW == 3) distk = z.xmut[lg + nd];
                 if (!(IMPL || a.nitcfg == 1)) {
 #pragma unroll
                     for (int e = 0; e < NEQ; e++) accn[e] = FB_LD(z.drodm + lg + e * nd);
@@ -455,7 +475,7 @@ k_rhs3(const CUtensorMap *__restrict__ tm_rop, const CUtensorMap *__restrict__ t
 #pragma unroll
                 for (int e = 0; e < NEQ; e++) acc[e] -= f[e];
                 if (SCHEME == 5 && z.ncorr) wall_corr<MESH, SLOPE, NEQ>(z, a.rop, i, j, k - 1, acc);
-                rhs_finish<MESH, FLOW, IMPL>(z, a, v, ls + v.kdn, l - z.inck, coe1p, acc);
+                rhs_finish<MESH, FLOW, IMPL>(z, a, v, ls + v.kdn, l - z.inck, coe1p, acc, (IMPL && ldn) ? wn : nullptr);
             }
         }
         if (last) {           // uniform; no TMA is in flight any more (plane k1+2 was waited for above)
@@ -465,7 +485,7 @@ k_rhs3(const CUtensorMap *__restrict__ tm_rop, const CUtensorMap *__restrict__ t
         if (cell) {
 #pragma unroll
             for (int e = 0; e < NEQ; e++) acc[e] = (IMPL || a.nitcfg == 1) ? 0. : accn[e] * a.coefH;
-            if (FLOW == 3) sa_source<MESH, IMPL>(z, v, mt, ls, l, lt, a.nitcfg, coe1, acc);
+            if (FLOW == 3) sa_source<MESH, IMPL>(z, v, mt, ls, l, lt, a.nitcfg, coe1, acc, distk);
 #pragma unroll
             for (int e = 0; e < NEQ; e++) acc[e] += f[e];
         }
@@ -496,6 +516,7 @@ k_rhs3(const CUtensorMap *__restrict__ tm_rop, const CUtensorMap *__restrict__ t
         __syncthreads();
         // every thread is done with plane k-1: its slot takes plane k+3
         if (leader && k + NS - 1 <= plast) issue(k + NS - 1);
+        if (NS < 4 && leader && k + NS <= plast) prefetch(k + NS);   // short ring: the box after that one is on its way to L2
         if (cell) {
 #pragma unroll
             for (int e = 0; e < NEQ; e++) acc[e] -= sFj[NSF == 2 ? (k & 1) : 0][m + 1][e][li];

@@ -27,7 +27,8 @@ __device__ __forceinline__ double vispalart_cell(const ZoneDev &z, const double 
 // SA source of cell l: returns vol*tsource; when STORE the LU diagonal coe(:,6) is updated (nitcfg<=1, implicit)
 // l: cell index in the view, lg: global cell index (wall distance, coe store)
 template <int MESH, class V, class M>
-__device__ __forceinline__ double sa_source_cell(const ZoneDev &z, const V &v, const M &mt, int l, int lg, int lt, bool store, double coe1)
+__device__ __forceinline__ double sa_source_cell(const ZoneDev &z, const V &v, const M &mt, int l, int lg, int lt, bool store, double coe1,
+                                                 double dist_in = -1.)
 {
     const int nd = z.nd, nm = z.nm;
     const int l1 = v.template up<0>(l), l2 = v.template dn<0>(l), l3 = v.template up<1>(l), l4 = v.template dn<1>(l),
@@ -113,7 +114,8 @@ __device__ __forceinline__ double sa_source_cell(const ZoneDev &z, const V &v, c
     const double chi3 = chi * chi * chi;
     const double f1 = chi3 / (chi3 + SA_CV1);
     const double f2 = 1. - chi / (1. + chi * f1);
-    const double dist = fmax(z.xmut[lg + nd], 1.e-27);
+    // dist_in: the wall distance when the caller has loaded it ahead of time (k_rhs3); < 0: read here
+    const double dist = fmax(dist_in >= 0. ? dist_in : z.xmut[lg + nd], 1.e-27);
     const double ikd2 = 1. / (SA_CKARM * SA_CKARM * dist * dist);
     double stild = rot + (anutild * f2) * ikd2;
     const double prod = rho * SA_CB1 * stild * anutild;
@@ -137,9 +139,10 @@ __device__ __forceinline__ double sa_source_cell(const ZoneDev &z, const V &v, c
 }
 
 template <int MESH, bool IMPL, class V, class M>
-__device__ __forceinline__ void sa_source(const ZoneDev &z, const V &v, const M &mt, int l, int lg, int lt, int nitcfg, double coe1, double *acc)
+__device__ __forceinline__ void sa_source(const ZoneDev &z, const V &v, const M &mt, int l, int lg, int lt, int nitcfg, double coe1, double *acc,
+                                          double dist_in = -1.)
 {
-    acc[5] += sa_source_cell<MESH>(z, v, mt, l, lg, lt, IMPL && nitcfg <= 1, coe1);
+    acc[5] += sa_source_cell<MESH>(z, v, mt, l, lg, lt, IMPL && nitcfg <= 1, coe1, dist_in);
 }
 
 // core3as2.for:37-195: Newton residual from the flux balance and the BDF time terms (conservative variables)
@@ -147,8 +150,8 @@ __device__ __forceinline__ void sa_source(const ZoneDev &z, const V &v, const M 
 template <int NEQ, class V>
 __device__ __forceinline__ void implicit_assemble(const ZoneDev &z, const V &v, int lv, const double *r0,
                                                   const double *__restrict__ rn, const double *__restrict__ rm, int l,
-                                                  double coe1, double c1, double c2, double c3, double *acc)
-{
+                                                  double coe1, double c1, double c2, double c3, double *acc, const double *npre = nullptr)
+{   // npre: W(n) of the cell when the caller has loaded it ahead of time (k_rhs3, only looked at when rn != r0)
     const int nd = z.nd; const double cv = z.cv;
     const bool first = (rn == r0);   // nitcfg == 1: rop_ssiter is ro itself => c4 = c1 + c2
     if (first && z.dtloc == 1) {
@@ -174,7 +177,12 @@ __device__ __forceinline__ void implicit_assemble(const ZoneDev &z, const V &v, 
         acc[4] = coe1 * acc[4] + c4 * roe + c3 * roe_n1;
         if (NEQ == 6) acc[NEQ - 1] = coe1 * acc[NEQ - 1] + c4 * v.q(5, lv) * a0 + c3 * m5 * m0;
     } else {
-        const double n0 = FB_LD(rn + l), n1 = FB_LD(rn + l + nd), n2 = FB_LD(rn + l + 2 * nd), n3 = FB_LD(rn + l + 3 * nd), n4 = FB_LD(rn + l + 4 * nd);
+        double n0, n1, n2, n3, n4, n5 = 0.;
+        if (npre) { n0 = npre[0]; n1 = npre[1]; n2 = npre[2]; n3 = npre[3]; n4 = npre[4]; if (NEQ == 6) n5 = npre[5]; }
+        else {
+            n0 = FB_LD(rn + l); n1 = FB_LD(rn + l + nd); n2 = FB_LD(rn + l + 2 * nd); n3 = FB_LD(rn + l + 3 * nd); n4 = FB_LD(rn + l + 4 * nd);
+            if (NEQ == 6) n5 = FB_LD(rn + l + 5 * nd);
+        }
         const double roe_n = n0 * (cv * n4 + 0.5 * (n1 * n1 + n2 * n2 + n3 * n3));
         acc[0] = coe1 * acc[0] + c1 * a0 + c2 * n0 + c3 * m0;
         acc[1] = coe1 * acc[1] + c1 * a1 * a0 + c2 * n1 * n0 + c3 * m1 * m0;
@@ -182,6 +190,6 @@ __device__ __forceinline__ void implicit_assemble(const ZoneDev &z, const V &v, 
         acc[3] = coe1 * acc[3] + c1 * a3 * a0 + c2 * n3 * n0 + c3 * m3 * m0;
         acc[4] = coe1 * acc[4] + c1 * roe + c2 * roe_n + c3 * roe_n1;
         if (NEQ == 6)
-            acc[NEQ - 1] = coe1 * acc[NEQ - 1] + c1 * v.q(5, lv) * a0 + c2 * FB_LD(rn + l + 5 * nd) * n0 + c3 * m5 * m0;
+            acc[NEQ - 1] = coe1 * acc[NEQ - 1] + c1 * v.q(5, lv) * a0 + c2 * n5 * n0 + c3 * m5 * m0;
     }
 }
