@@ -255,7 +255,8 @@ __global__ void __launch_bounds__(32 * (RHS2_RJ + 1)) k_rhs2(ZoneDev z, RhsArgs 
 // plane by plane into a shared-memory ring by TMA (one cp.async.bulk.tensor box of 36 x (RJ+4) x 1 x NEQ doubles per
 // plane and array, completion on an mbarrier).  Iteration k works on planes k-1, k, k+1 (the own column at k-2, which
 // only the k-face MUSCL stencil needs, is carried in registers) while plane k+2 is in flight; the slot of plane k-1
-// is re-armed for plane k+3 behind the end-of-plane barrier.  All stencil reads are LDS with immediate offsets: no
+// is re-armed for plane k+3 behind the end-of-plane barrier (4-slot ring; the 3-slot ring of the 3dhomo SA kernel asks for
+// plane k+2 there and has sent plane k+3 to L2).  All stencil reads are LDS with immediate offsets: no
 // address arithmetic, no L1 tag traffic, HBM sees every plane once per tile (+ halo, served by L2).
 #ifndef RHS3_NS
 #define RHS3_NS 4           // ring slots
@@ -296,11 +297,6 @@ __global__ void __launch_bounds__(32 * (RHS2_RJ + 1)) k_rhs2(ZoneDev z, RhsArgs 
 #endif
 
 template <int MESH, int FLOW> struct Rhs3SMet { static constexpr bool V = MESH == 1 && (FLOW != 3 || RHS3_SMET_SA != 0); };
-__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap *tm, int c0, int c1, int c2, int c3)
-{
-    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-
 // register budget: two resident CTAs per SM where the flux fits 96-128 registers; Roe and the 3dfull metrics need more
 template <int MESH, int SCHEME> struct Rhs3MinB { static constexpr int V = (SCHEME == 5 || MESH == 0) ? 1 : RHS3_MINB; };
 template <int MESH, int FLOW, int SCHEME> struct Rhs3NS {   // ring slots (a kernel alone on its SM has room for the deeper ring)
@@ -355,6 +351,12 @@ __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *tm, in
 template <int MESH, int FLOW, int SCHEME> struct Rhs3KC {   // k planes per CTA
     static constexpr int V = Rhs3MinB<MESH, SCHEME>::V == 1 ? RHS3_KC_1B : ((MESH == 1 && FLOW == 3) ? RHS3_KC_SA : RHS3_KC);
 };
+
+// the box of a plane on its way to L2 (no shared-memory destination, no completion): used one plane ahead of the 3-slot ring
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap *tm, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 
 template <int MESH, int FLOW, int SCHEME, int SLOPE, bool IMPL, int RJ, bool WC>
 __global__ void __launch_bounds__(32 * (RJ + 1), Rhs3MinB<MESH, SCHEME>::V)
