@@ -279,6 +279,10 @@ __global__ void __launch_bounds__(32 * (RHS2_RJ + 1)) k_rhs2(ZoneDev z, RhsArgs 
 #ifndef RHS3_NS_SA
 #define RHS3_NS_SA (RHS3_SMET_SA ? 3 : RHS3_NS)
 #endif
+#ifndef RHS3_NS_HOMO
+#define RHS3_NS_HOMO 3      // ring slots of the 3dhomo Euler / laminar kernels: with the metric tile, four slots leave one CTA per SM
+                            // (measured on a 256x128x64 laminar plate, tools/homo_lam_time.py: rhs 0.236 -> 0.198 ms per launch with three)
+#endif
 #ifndef RHS3_RJ_1B
 #define RHS3_RJ_1B 11       // tile rows of the kernels that run one CTA per SM (Roe, 3dfull: 168 registers): 12 warps fill the
                             // register file (measured: C4 rhs 0.625 -> 0.550 ms per 128^3 block against 8 / 7 rows); 0 = as the others
@@ -300,7 +304,7 @@ template <int MESH, int FLOW> struct Rhs3SMet { static constexpr bool V = MESH =
 // register budget: two resident CTAs per SM where the flux fits 96-128 registers; Roe and the 3dfull metrics need more
 template <int MESH, int SCHEME> struct Rhs3MinB { static constexpr int V = (SCHEME == 5 || MESH == 0) ? 1 : RHS3_MINB; };
 template <int MESH, int FLOW, int SCHEME> struct Rhs3NS {   // ring slots (a kernel alone on its SM has room for the deeper ring)
-    static constexpr int V = (MESH == 1 && FLOW == 3 && Rhs3MinB<MESH, SCHEME>::V > 1) ? RHS3_NS_SA : RHS3_NS;
+    static constexpr int V = (MESH == 1 && Rhs3MinB<MESH, SCHEME>::V > 1) ? (FLOW == 3 ? RHS3_NS_SA : RHS3_NS_HOMO) : RHS3_NS;
 };
 template <bool SM, int RS, int VS>
 __device__ __forceinline__ typename std::conditional<SM, SMet1<RS, VS>, GMet1>::type make_met(const ZoneDev &z, const double *smet)
@@ -554,6 +558,10 @@ static bool launch_rhs3_t(const ZoneDev &z, RhsArgs &a, bool impl, cudaStream_t 
 {
     constexpr int RJ = (RHS3_RJ_1B && Rhs3MinB<MESH, SCHEME>::V == 1) ? RHS3_RJ_1B : (FLOW == 3 ? RHS3_RJ_SA : RHS3_RJ_NS);
     using C = Rhs3Cfg<FLOW, RJ>;
+    // the configuration macros above must leave the residency they were measured with: 227 KB per CTA, 228 KB (+ 1 KB per CTA) per SM
+    static_assert(C::template smem<MESH, SCHEME>() <= 227 * 1024, "k_rhs3: shared memory of one CTA");
+    static_assert(Rhs3MinB<MESH, SCHEME>::V * (C::template smem<MESH, SCHEME>() + 1024) <= 228 * 1024, "k_rhs3: shared memory of the resident CTAs");
+    static_assert(Rhs3MinB<MESH, SCHEME>::V * 32 * (RJ + 1) * (Rhs3MinB<MESH, SCHEME>::V == 1 ? 168 : 128) <= 65536 || FLOW != 3, "k_rhs3: registers of the resident CTAs");
     if (z.nf != 2 || z.nfk != 2) return false;
     const CUtensorMap *tr = fb_tma_map(a.rop, z.ni, z.nj, z.nk, z.nd, C::NEQ, C::ROWS, C::NEQ);
     const CUtensorMap *tm = FLOW >= 2 ? fb_tma_map(z.xmut, z.ni, z.nj, z.nk, z.nd, FLOW == 3 ? 2 : 1, C::ROWS, 1) : tr;

@@ -226,10 +226,12 @@ def case_tgv_blocks(n=256, nblk=(2, 1, 1), only=None, scheme='senseur', Re=1600.
 
 def case_flatplate(n=(64, 48, 8), seed=2025, MInf=0.2, ReInf=25.e6, ss_iteration=5, cfl=7., sheared=False,
                    scheme='ausmpred', modulo_verif=1, nblocks=(1, 1, 1), only=None, return_layout=False, lu_match=0, nb_relax=1,
-                   tc_format=False):
+                   tc_format=False, model='NSTurbulent', temporal='implicit'):
     """C3 / C5-style RANS-SA flat plate: x geometric stretch, y tanh clustering toward the wall (jmin = viscous wall),
     z uniform => typezone 1 (3dhomo); `sheared=True` adds a smooth 3-D shear => typezone 0 (3dfull).
-    Farfield on imin/imax/jmax, autoperiodic in k.  nblocks splits the plate into match-joined blocks; `only` (a set of
+    Farfield on imin/imax/jmax, autoperiodic in k.  model='NSLaminar' / 'Euler' run the same mesh and state without the SA
+    equation (the 3dhomo instantiations of the 5-equation kernels); temporal='explicit' switches to RK3 with a global time
+    step.  nblocks splits the plate into match-joined blocks; `only` (a set of
     global block ids, k-major numbering) builds just those blocks -- the per-rank share of a sharded case, every block
     drawing from its own random stream -- and `return_layout` returns (tree, layout) for dist.local_case."""
     from .FastC import PyTree as FastC
@@ -268,7 +270,8 @@ def case_flatplate(n=(64, 48, 8), seed=2025, MInf=0.2, ReInf=25.e6, ss_iteration
                 T = numpy.ones_like(xc) * (1. + 0.2 * (state['Gamma'] - 1.) * MInf ** 2 * (1. - prof ** 2))
                 nut = state['TurbulentSANuTildeDensity'] * (0.1 + 3. * prof * numpy.exp(-numpy.abs(yc) / (4 * delta))) \
                     * (1. + 1e-2 * rng.random(xc.shape))
-                set_fields(z, ro, u, v, w, T, nutilde=nut, dist=d)
+                sa = model == 'NSTurbulent'
+                set_fields(z, ro, u, v, w, T, nutilde=nut if sa else None, dist=d if sa else None)
                 if only is None: layout[(bi, bj, bk)] = len(zones)
                 zones.append(z)
                 if bi == 0: add_bc(z, 'imin', 'BCFarfield', 'imin')
@@ -277,9 +280,13 @@ def case_flatplate(n=(64, 48, 8), seed=2025, MInf=0.2, ReInf=25.e6, ss_iteration
                 if bj == nb[1] - 1: add_bc(z, 'jmax', 'BCFarfield', 'jmax')
                 if nb[2] == 1:
                     add_bc(z, 'kmin', 'BCautoperiod', 'kmin'); add_bc(z, 'kmax', 'BCautoperiod', 'kmax')
-    t = new_tree(zones, state, 'NSTurbulent')
-    FastC._setNum2Zones(t, {'scheme': scheme, 'slope': 'o3', 'time_step_nature': 'local', 'cfl': cfl, 'nb_relax': nb_relax, 'lu_match': lu_match})
-    FastC._setNum2Base(t, {'temporal_scheme': 'implicit', 'ss_iteration': ss_iteration, 'modulo_verif': modulo_verif})
+    t = new_tree(zones, state, model)
+    if temporal == 'implicit':
+        FastC._setNum2Zones(t, {'scheme': scheme, 'slope': 'o3', 'time_step_nature': 'local', 'cfl': cfl, 'nb_relax': nb_relax, 'lu_match': lu_match})
+        FastC._setNum2Base(t, {'temporal_scheme': 'implicit', 'ss_iteration': ss_iteration, 'modulo_verif': modulo_verif})
+    else:
+        FastC._setNum2Zones(t, {'scheme': scheme, 'slope': 'o3', 'time_step': 2.e-5})
+        FastC._setNum2Base(t, {'temporal_scheme': 'explicit', 'modulo_verif': modulo_verif})
     if return_layout: return t, layout
     if tc_format: return t, build_joins_tc(layout, nb, tuple(nloc), periodic=(False, False, nb[2] > 1), neq=6)   # reference wire format
     joins = build_joins(layout, nb, tuple(nloc), periodic=(False, False, nb[2] > 1))

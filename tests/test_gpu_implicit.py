@@ -46,6 +46,10 @@ CASES = {
     'sa_plate_blocks_tc': lambda: synth.case_flatplate(n=(24, 16, 8), nblocks=(2, 2, 2), tc_format=True),
     'multiblock_roe_lumatch_tc': lambda: synth.case_multiblock(nblk=(2, 2, 1), n=8, tc_format=True),
     'multiblock_explicit': lambda: synth.case_multiblock(nblk=(2, 1, 2), n=8, temporal='explicit', scheme='senseur'),
+    # the 5-equation kernels on a 3dhomo zone (shared metric tile of k_rhs3, k_lu_cell<1,5,*>): the plate without the SA equation
+    'lamin_plate_homo': lambda: synth.case_flatplate(n=(24, 16, 6), model='NSLaminar', ReInf=2.e4),
+    'lamin_plate_homo_tiles': lambda: synth.case_flatplate(n=(40, 20, 20), model='NSLaminar', ReInf=2.e4),
+    'lamin_plate_homo_rk3': lambda: synth.case_flatplate(n=(24, 16, 6), model='NSLaminar', ReInf=2.e4, temporal='explicit', scheme='senseur'),
 }
 
 
