@@ -59,13 +59,14 @@ def test_rk2_is_heun_and_lands_in_density():
     assert dist_from_stage1 > 1e3 * err          # ... and it is not the forward-Euler intermediate
 
 
-@pytest.mark.parametrize('case', ['tgv', 'plate_blocks', 'multiblock'])
+@pytest.mark.parametrize('case', ['tgv', 'plate_blocks', 'multiblock', 'lamin_plate_homo'])
 def test_threaded_oracle_is_bit_identical(case):
     """The thread decomposition of the oracle (k slabs for the rhs, one zone per thread for the LU) used by the full-size GPU
     parity tests and the timed CPU baseline must not change a single bit of the result."""
     def mk():
         if case == 'tgv': return synth.case_tgv(n=20, perturb=1e-3), None
         if case == 'plate_blocks': return synth.case_flatplate(n=(48, 32, 32), nblocks=(2, 1, 1))
+        if case == 'lamin_plate_homo': return synth.case_flatplate(n=(40, 20, 20), model='NSLaminar', ReInf=2.e4)   # 5 equations on 3dhomo metrics
         return synth.case_multiblock(nblk=(2, 1, 2), n=10)
     res = []
     for nth in (1, 8):
