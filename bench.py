@@ -104,7 +104,8 @@ class Clocks(threading.Thread):
 
 # ------------------------------------------------------------------------------------------------------------ CPU arm
 def cpu_oracle_rate(workload, n=None, budget_s=15., max_iters=200, threads=None):
-    """Mcell.it/s of the CPU oracle (OpenMP: k slabs for the rhs, the zones' LU sweeps spread over the threads) on the case
+    """Mcell.it/s of the CPU oracle (OpenMP: k slabs for the rhs; the zones' LU sweeps spread over the threads, in teams of
+    several threads per zone when there are more threads than zones) on the case
     make_case(workload, n): one warm-up iteration (first touch), then whole iterations until `budget_s` is spent (at least 2)."""
     sys.path.insert(0, os.path.join(ROOT, 'tests')); sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     from helpers import oracle_from_tree, V
@@ -117,11 +118,23 @@ def cpu_oracle_rate(workload, n=None, budget_s=15., max_iters=200, threads=None)
     nss = int(o.zones[0].pi[V.NSSITER])
     cells = sum(int(z.pi[V.IJKV]) * int(z.pi[V.IJKV + 1]) * int(z.pi[V.IJKV + 2]) for z in o.zones)
     o.compute(1, 1, nss, 1000, nthreads=nthreads)                     # warm-up / first touch
+    # threads left over after one per zone can join the zones' LU sweeps (teams, same bits: fo_invlu_team); one iteration each
+    # way decides (a team of spinning threads loses where the process has fewer cores than its affinity mask says)
+    team, nz = 0, len(o.zones)
+    if int(o.zones[0].pi[V.ITYPCP]) != 2 and nthreads // min(nz, nthreads) >= 2:
+        tt = []
+        for mode in (0, 1):
+            o.L.fo_set_lu_team(mode); t1 = time.perf_counter(); o.compute(2, 1, nss, 1000, nthreads=nthreads); tt.append(time.perf_counter() - t1)
+        team = 1 if tt[1] < tt[0] else 0
+    o.L.fo_set_lu_team(team)
     nit, t0 = 0, time.perf_counter()
     while nit < max_iters and (nit < 2 or time.perf_counter() - t0 < budget_s):
-        o.compute(2 + nit, 1, nss, 1000, nthreads=nthreads); nit += 1
+        o.compute(3 + nit, 1, nss, 1000, nthreads=nthreads); nit += 1
     dt = time.perf_counter() - t0
-    lu_note = '' if int(o.zones[0].pi[V.ITYPCP]) == 2 else '; LU sweeps: one zone per thread (%d zones)' % len(o.zones)
+    o.L.fo_set_lu_team(0)
+    nper = nthreads // min(nz, nthreads)
+    lu_note = '' if int(o.zones[0].pi[V.ITYPCP]) == 2 else ('; LU sweeps: %d zones, %s' % (nz, 'one per thread' if not team else
+              'teams of %d threads per zone ((j slab, i chunk) wavefront, bit-identical to the serial sweep; faster than one zone per thread in a trial iteration)' % nper))
     return cells * nit / dt / 1e6, nthreads, '%s, %d iterations in %.1f s on %d threads%s' % (desc, nit, dt, nthreads, lu_note), nit, dt, desc
 
 

@@ -83,6 +83,14 @@ void fo_invlu(const int *pi, const double *pr, const int ind_lu[6], const double
               double *rop_out, double *drodm, const double *coe,
               const double *ti, const double *tj, const double *tk);
 
+/* the same sweeps by a team of `nper` threads (every thread of the team calls it with its rank; prog: 2 * nper zeroed counters);
+   bit-identical to fo_invlu, used by the timed CPU baseline only (fo_set_lu_team) */
+void fo_invlu_team(const int *pi, const double *pr, const int box[6], const double *rop, double *rop_out, double *drodm,
+                   const double *coe, const double *ti, const double *tj, const double *tk, int rank, int nper, long *prog);
+/* 1: fo_gsdr3 spreads the threads left over after one per zone over the zones' sweeps (fo_invlu_team); 0 (default): one zone per thread */
+void fo_set_lu_team(int on);
+int fo_get_lu_team(void);
+
 /* ghost cells: FastS/BC/BCzone.cpp:60, correct_coins.for */
 void fo_bczone(const int *pi, const double *pr, int lrhs, double *rop, const double *ti,
                const double *tj, const double *tk, int ishift_lu[6]);

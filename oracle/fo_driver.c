@@ -2,8 +2,9 @@
  * fo_driver.c -- one sub-iteration for every zone (FastS/Compute/gsdr3.cpp:57-484, rhs.cpp, lhs.cpp,
  * bcs.cpp, transfert_multiblock.cpp) and the NIT x nssiter loop (computePT.cpp:534-679).
  * TEST INFRASTRUCTURE, see fasts_oracle.h.  One task per zone (souszones_list with one sub-zone).
- * nthreads > 1 only changes HOW the work is cut (k slabs for the rhs, one zone per thread for the LU,
- * the reference's omp_mode=1 analogue); it is used by the timed CPU baseline, never by parity tests.
+ * nthreads > 1 only changes HOW the work is cut, never a bit of the result (tests/test_oracle_pins.py): k slabs for the rhs; for the
+ * LU one zone per thread, or -- fo_set_lu_team(1), the timed CPU baseline with more threads than zones -- teams of threads per zone
+ * (fo_invlu_team).  The small parity tests run one thread, the full-size GPU parity tests and the baseline all host threads.
  */
 #include <math.h>
 #include <stdio.h>
@@ -112,6 +113,10 @@ static void rhs_zone(fo_zone *z, int nitcfg, int nssiter, int nitrun, int first_
     }
 }
 
+static int g_lu_team = 0;
+void fo_set_lu_team(int on) { g_lu_team = on != 0; }
+int fo_get_lu_team(void) { return g_lu_team; }
+
 void fo_gsdr3(fo_zone *zones, int nz, int nitcfg, int nssiter, int nitrun, int first_it,
               int lssiter_verif, int lexit_lu, const int *pitc, const double *prtc, int nthreads)
 {
@@ -149,11 +154,37 @@ void fo_gsdr3(fo_zone *zones, int nz, int nitcfg, int nssiter, int nitrun, int f
                 if (z->rdm) fo_cprdu3s1(z->pi, nitcfg, ind, z->drodm, z->rdm);
             }
         if (lexit_lu == 0) {
+            /* threads: one zone per thread; with more threads than zones (and fo_set_lu_team(1): the timed baseline) the zones are
+               swept by teams of nper threads each (fo_invlu_team, same bits) */
+            const int nteam = nz < nthreads ? nz : nthreads, nper = nteam > 0 ? nthreads / nteam : 1;
+            int teams_ran = 0;
+            if (g_lu_team && nper > 1) {
+                long *prog = (long *)calloc((size_t)nz * 2 * nper, sizeof(long));
+                int ok = 1;
+#pragma omp parallel num_threads(nteam * nper)
+                {
+                    if (omp_get_num_threads() != nteam * nper) {      /* fewer threads than asked for: a team would wait forever */
+#pragma omp single
+                        ok = 0;
+                    } else {
+                        const int tid = omp_get_thread_num(), team = tid / nper, rank = tid % nper;
+                        for (int n = team; n < nz; n += nteam) {
+                            fo_zone *z = &zones[n];
+                            fo_invlu_team(z->pi, z->pr, shift + 6 * n, z->ro_p1 == NULL ? NULL : (nitcfg == 1 ? z->ro : z->ro_p1),
+                                          z->ro_p1, z->drodm, z->coe, z->ti, z->tj, z->tk, rank, nper, prog + (size_t)n * 2 * nper);
+                        }
+                    }
+                }
+                free(prog);
+                teams_ran = ok;
+            }
+            if (!teams_ran) {
 #pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads) if (nthreads > 1)
-            for (int n = 0; n < nz; n++) {
-                fo_zone *z = &zones[n];
-                fo_invlu(z->pi, z->pr, shift + 6 * n, z->ro_p1 == NULL ? NULL : (nitcfg == 1 ? z->ro : z->ro_p1),
-                         z->ro_p1, z->drodm, z->coe, z->ti, z->tj, z->tk);
+                for (int n = 0; n < nz; n++) {
+                    fo_zone *z = &zones[n];
+                    fo_invlu(z->pi, z->pr, shift + 6 * n, z->ro_p1 == NULL ? NULL : (nitcfg == 1 ? z->ro : z->ro_p1),
+                             z->ro_p1, z->drodm, z->coe, z->ti, z->tj, z->tk);
+                }
             }
         }
         free(shift);

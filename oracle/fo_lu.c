@@ -4,6 +4,7 @@
  * lu_ and mjr_ bodies), match-join transfers.  TEST INFRASTRUCTURE, see fasts_oracle.h.
  */
 #include <math.h>
+#include <sched.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -192,6 +193,55 @@ static void lu_term(const luctx *c, int d, int l1, int lta, int ltb, double sign
     if (c->neq == 6) b[5] = (qn + cd) * dw[l1 + 5 * nd];
 }
 
+/* One cell of the lower sweep (invlu_l.for:79-215): normals 0.5*(t(lt)+t(lt-m)) of the cell l-d.  Shared by the serial sweep
+   and the team sweep (fo_invlu_team): a cell's arithmetic only depends on its three lower neighbours being final. */
+static inline void lu_lower_cell(const luctx *c, const int box[6], int overlap, double *drodm, int i, int j, int k)
+{
+    const int *pi = c->pi; const double *coe = c->coe;
+    const int nd = c->nd, neq = c->neq;
+    double b[6];
+    const int l = fo_inddm(pi, i, j, k), lt = c->typ == 2 ? 0 : fo_indmtr(pi, i, j, k);
+    const double xal = coe[l] * 0.5;
+    int order[3], n = 0;
+    const int hi = i > box[0], hj = j > box[2], hk = k > box[4];
+    if (overlap) { if (hi) order[n++] = 0; if (hj) order[n++] = 1; if (hk) order[n++] = 2; }
+    else if (c->typ == 2 && hj && hk) { order[n++] = 1; order[n++] = 2; if (hi) order[n++] = 0; }
+    else { if (hk) order[n++] = 2; if (hj) order[n++] = 1; if (hi) order[n++] = 0; }
+    for (int q = 0; q < n; q++) {
+        const int d = order[q];
+        lu_term(c, d, l - c->inc[d], lt - c->incm[d], lt, 0.5, drodm, b);
+        for (int e = 0; e < neq; e++) drodm[l + e * nd] = drodm[l + e * nd] + b[e] * xal;
+    }
+    const double diag = 1. / coe[l + 4 * nd];
+    for (int e = 0; e < 5; e++) drodm[l + e * nd] = drodm[l + e * nd] * diag;
+    if (neq == 6) drodm[l + 5 * nd] = drodm[l + 5 * nd] / coe[l + 5 * nd];
+}
+
+/* One cell of the upper sweep (invlu_u.for:60-215): normals 0.5*(t(lt+2m)+t(lt+m)) of the cell l+d. */
+static inline void lu_upper_cell(const luctx *c, const int box[6], int overlap, double *drodm, int i, int j, int k)
+{
+    const int *pi = c->pi; const double *coe = c->coe;
+    const int nd = c->nd, neq = c->neq;
+    double b[6];
+    const int l = fo_inddm(pi, i, j, k), lt = c->typ == 2 ? 0 : fo_indmtr(pi, i, j, k);
+    const double xal = coe[l] * -0.5;
+    const double dg = coe[l + 4 * nd];
+    for (int e = 0; e < 5; e++) drodm[l + e * nd] = drodm[l + e * nd] * dg;
+    if (neq == 6) drodm[l + 5 * nd] = drodm[l + 5 * nd] * coe[l + 5 * nd];
+    int order[3], n = 0;
+    const int hi = i < box[1], hj = j < box[3], hk = k < box[5];
+    if (overlap) { if (hi) order[n++] = 0; if (hj) order[n++] = 1; if (hk) order[n++] = 2; }
+    else { if (hk) order[n++] = 2; if (hj) order[n++] = 1; if (hi) order[n++] = 0; }
+    for (int q = 0; q < n; q++) {
+        const int d = order[q];
+        lu_term(c, d, l + c->inc[d], lt + c->incm[d], c->typ == 1 && d == 2 ? lt : lt + 2 * c->incm[d], -0.5, drodm, b);
+        for (int e = 0; e < neq; e++) drodm[l + e * nd] = drodm[l + e * nd] + b[e] * xal;
+    }
+    const double diag = 1. / coe[l + 4 * nd];
+    for (int e = 0; e < 5; e++) drodm[l + e * nd] = drodm[l + e * nd] * diag;
+    if (neq == 6) drodm[l + 5 * nd] = drodm[l + 5 * nd] / coe[l + 5 * nd];
+}
+
 /* LU/mjr_newton.for / mjr_newton_SA.for */
 static void mjr_newton(const int *pi, const double *pr, int l, const double *rop, double *rop_1, const double *dw)
 {
@@ -287,6 +337,17 @@ static void fo_invlussor(const int *pi, const double *pr, const int box[6], luct
 /* LU/invlu.for:6-344 (nb_relax = 1, fixed mesh): invlu_l[_SA] then invlu_u[_SA]; lu_match = 1 selects the "overlap"
    variants whose only effect for a whole-zone box is the i,j,k accumulation order and a Newton update restricted to
    the interior (invlu_overlap_u.for).  In place: drodm holds rhs -> dW* -> dW. */
+static void lu_ctx_init(luctx *c, const int *pi, const double *pr, const double *rop, const double *coe,
+                        const double *ti, const double *tj, const double *tk)
+{
+    c->pi = pi; c->rop = rop; c->coe = coe; c->t[0] = ti; c->t[1] = tj; c->t[2] = tk;
+    c->inc[0] = 1; c->inc[1] = pi[FO_NIJK]; c->inc[2] = pi[FO_NIJK] * pi[FO_NIJK + 1];
+    c->incm[0] = pi[FO_NIJK_MTR]; c->incm[1] = pi[FO_NIJK_MTR + 1]; c->incm[2] = pi[FO_NIJK_MTR + 2];
+    c->nd = pi[FO_NDIMDX]; c->nm = pi[FO_NDIMDX_MTR]; c->typ = pi[FO_ITYPZONE]; c->neq = pi[FO_NEQ];
+    c->gam1 = pr[FO_GAMMA]; c->gamm1 = c->gam1 - 1.; c->cp = pr[FO_GAMMA] * pr[FO_CVINF]; c->gam2 = c->gamm1 - 1.;
+    c->tc0[0] = ti[0]; c->tc0[1] = tj[0]; c->tc0[2] = tk[0];
+}
+
 static void fo_invlu_impl(const int *pi, const double *pr, const int box[6], const double *rop, double *rop_out, double *drodm,
                           const double *coe, const double *ti, const double *tj, const double *tk, int nrelax_forced);
 void fo_invlu(const int *pi, const double *pr, const int box[6], const double *rop, double *rop_out, double *drodm,
@@ -305,66 +366,92 @@ static void fo_invlu_impl(const int *pi, const double *pr, const int box[6], con
 {
     if (box[1] < box[0]) return;
     luctx c;
-    c.pi = pi; c.rop = rop; c.coe = coe; c.t[0] = ti; c.t[1] = tj; c.t[2] = tk;
-    c.inc[0] = 1; c.inc[1] = pi[FO_NIJK]; c.inc[2] = pi[FO_NIJK] * pi[FO_NIJK + 1];
-    c.incm[0] = pi[FO_NIJK_MTR]; c.incm[1] = pi[FO_NIJK_MTR + 1]; c.incm[2] = pi[FO_NIJK_MTR + 2];
-    c.nd = pi[FO_NDIMDX]; c.nm = pi[FO_NDIMDX_MTR]; c.typ = pi[FO_ITYPZONE]; c.neq = pi[FO_NEQ];
-    c.gam1 = pr[FO_GAMMA]; c.gamm1 = c.gam1 - 1.; c.cp = pr[FO_GAMMA] * pr[FO_CVINF]; c.gam2 = c.gamm1 - 1.;
-    c.tc0[0] = ti[0]; c.tc0[1] = tj[0]; c.tc0[2] = tk[0];
-    const int nd = c.nd, neq = c.neq, overlap = pi[FO_LU_MATCH] == 1;
+    lu_ctx_init(&c, pi, pr, rop, coe, ti, tj, tk);
+    const int overlap = pi[FO_LU_MATCH] == 1;
     if (pi[FO_NB_RELAX] >= 2 || nrelax_forced > 0) { fo_invlussor(pi, pr, box, &c, rop_out, drodm, nrelax_forced > 0 ? nrelax_forced : pi[FO_NB_RELAX]); return; }
     /* SA + lu_match (invlu.for:32-49): invlu_overlap_{l,u}_SA.for are the 6-equation copies of the overlap variants
        (same includes with the _SA bodies).  extrap_coe.for:24-25,39,52,66 only acts on a face where the sweep box reaches
        the second ghost row (ind_loop = 1 - nfic), which for a whole-zone box needs a BC of type 18 / 30 (BCzone.cpp:117-127);
        with the BC families restated here the box stops at row 0, so extrap_coe is a no-op. */
     const int ideb = box[0], ifin = box[1], jdeb = box[2], jfin = box[3], kdeb = box[4], kfin = box[5];
-    double b[6];
     /* ---- lower sweep (invlu_l.for:79-215): normals 0.5*(t(lt)+t(lt-m)) of the cell l-d */
-    for (int k = kdeb; k <= kfin; k++) for (int j = jdeb; j <= jfin; j++) for (int i = ideb; i <= ifin; i++) {
-        const int l = fo_inddm(pi, i, j, k), lt = c.typ == 2 ? 0 : fo_indmtr(pi, i, j, k);
-        const double xal = coe[l] * 0.5;
-        int order[3], n = 0;
-        const int hi = i > ideb, hj = j > jdeb, hk = k > kdeb;
-        if (overlap) { if (hi) order[n++] = 0; if (hj) order[n++] = 1; if (hk) order[n++] = 2; }
-        else if (c.typ == 2 && hj && hk) { order[n++] = 1; order[n++] = 2; if (hi) order[n++] = 0; }
-        else { if (hk) order[n++] = 2; if (hj) order[n++] = 1; if (hi) order[n++] = 0; }
-        for (int q = 0; q < n; q++) {
-            const int d = order[q];
-            lu_term(&c, d, l - c.inc[d], lt - c.incm[d], lt, 0.5, drodm, b);
-            for (int e = 0; e < neq; e++) drodm[l + e * nd] = drodm[l + e * nd] + b[e] * xal;
-        }
-        const double diag = 1. / coe[l + 4 * nd];
-        for (int e = 0; e < 5; e++) drodm[l + e * nd] = drodm[l + e * nd] * diag;
-        if (neq == 6) drodm[l + 5 * nd] = drodm[l + 5 * nd] / coe[l + 5 * nd];
-    }
+    for (int k = kdeb; k <= kfin; k++) for (int j = jdeb; j <= jfin; j++) for (int i = ideb; i <= ifin; i++)
+        lu_lower_cell(&c, box, overlap, drodm, i, j, k);
     /* ---- upper sweep (invlu_u.for:60-215): normals 0.5*(t(lt+2m)+t(lt+m)) of the cell l+d, Newton update plane
        by plane (so the k term of plane k reads the already updated state of plane k+1 when rop aliases rop_out) */
     int nb[6];
     for (int q = 0; q < 6; q++) nb[q] = box[q];
     if (overlap) { nb[0] = 1; nb[1] = pi[FO_IJKV]; nb[2] = 1; nb[3] = pi[FO_IJKV + 1]; nb[4] = 1; nb[5] = pi[FO_IJKV + 2]; }
     for (int k = kfin; k >= kdeb; k--) {
-        for (int j = jfin; j >= jdeb; j--) for (int i = ifin; i >= ideb; i--) {
-            const int l = fo_inddm(pi, i, j, k), lt = c.typ == 2 ? 0 : fo_indmtr(pi, i, j, k);
-            const double xal = coe[l] * -0.5;
-            const double dg = coe[l + 4 * nd];
-            for (int e = 0; e < 5; e++) drodm[l + e * nd] = drodm[l + e * nd] * dg;
-            if (neq == 6) drodm[l + 5 * nd] = drodm[l + 5 * nd] * coe[l + 5 * nd];
-            int order[3], n = 0;
-            const int hi = i < ifin, hj = j < jfin, hk = k < kfin;
-            if (overlap) { if (hi) order[n++] = 0; if (hj) order[n++] = 1; if (hk) order[n++] = 2; }
-            else { if (hk) order[n++] = 2; if (hj) order[n++] = 1; if (hi) order[n++] = 0; }
-            for (int q = 0; q < n; q++) {
-                const int d = order[q];
-                lu_term(&c, d, l + c.inc[d], lt + c.incm[d], c.typ == 1 && d == 2 ? lt : lt + 2 * c.incm[d], -0.5, drodm, b);
-                for (int e = 0; e < neq; e++) drodm[l + e * nd] = drodm[l + e * nd] + b[e] * xal;
-            }
-            const double diag = 1. / coe[l + 4 * nd];
-            for (int e = 0; e < 5; e++) drodm[l + e * nd] = drodm[l + e * nd] * diag;
-            if (neq == 6) drodm[l + 5 * nd] = drodm[l + 5 * nd] / coe[l + 5 * nd];
-        }
+        for (int j = jfin; j >= jdeb; j--) for (int i = ifin; i >= ideb; i--)
+            lu_upper_cell(&c, box, overlap, drodm, i, j, k);
         if (k >= nb[4] && k <= nb[5])
             for (int j = nb[2]; j <= nb[3]; j++) for (int i = nb[0]; i <= nb[1]; i++)
                 mjr_newton(pi, pr, fo_inddm(pi, i, j, k), rop, rop_out, drodm);
+    }
+}
+
+/* The same two sweeps by a TEAM of threads, bit for bit (timed CPU baseline only: bench.py switches it on through
+   fo_set_lu_team; the parity tests keep the serial sweep above).  Thread `rank` of `nper` owns a slab of j rows; a plane is cut
+   into chunks of FO_LU_CHUNK cells along i and the team runs a (slab, chunk) wavefront: in the lower sweep rank r takes chunk
+   g = (plane, chunk) once rank r-1 has finished the same chunk (its last row feeds the first row of r), in the upper sweep once
+   rank r+1 has.  Inside a chunk the rows of the slab and the cells of a row are visited in sweep order, so every cell finds its
+   three neighbours final: the values are those of the serial sweep whatever the interleaving.  The Newton update of a plane
+   (mjr_newton, plane by plane as in invlu_u.for) is applied by each rank to its own slab after rank r-1 has finished sweeping
+   that plane -- the in-plane neighbours (i+1, j+1) of a cell must still be read un-updated, the k neighbour (own slab) updated.
+   prog: 2 * nper counters of finished chunks (lower, upper), zeroed by the caller, one set per zone. */
+#define FO_LU_CHUNK 32
+static inline void lu_wait(const long *p, long v)
+{   /* spin, then give the core away: with more threads than cores the thread waited for may not be running */
+    int spins = 0;
+    while (__atomic_load_n(p, __ATOMIC_ACQUIRE) < v) {
+        if (++spins < 2000) __builtin_ia32_pause(); else { sched_yield(); spins = 0; }
+    }
+}
+void fo_invlu_team(const int *pi, const double *pr, const int box[6], const double *rop, double *rop_out, double *drodm,
+                   const double *coe, const double *ti, const double *tj, const double *tk, int rank, int nper, long *prog)
+{
+    if (box[1] < box[0]) return;
+    if (pi[FO_NB_RELAX] >= 2) {      /* relaxations: serial, by the first thread of the team */
+        if (rank == 0) fo_invlu_impl(pi, pr, box, rop, rop_out, drodm, coe, ti, tj, tk, 0);
+        return;
+    }
+    luctx c;
+    lu_ctx_init(&c, pi, pr, rop, coe, ti, tj, tk);
+    const int overlap = pi[FO_LU_MATCH] == 1;
+    const int ideb = box[0], ifin = box[1], jdeb = box[2], jfin = box[3], kdeb = box[4], kfin = box[5];
+    const int nj = jfin - jdeb + 1, ni = ifin - ideb + 1, nk = kfin - kdeb + 1;
+    const int j0 = jdeb + (int)((long)nj * rank / nper), j1 = jdeb + (int)((long)nj * (rank + 1) / nper) - 1;   /* may be empty */
+    const int nc = (ni + FO_LU_CHUNK - 1) / FO_LU_CHUNK;
+    long *plo = prog, *pup = prog + nper;
+    for (int kk = 0; kk < nk; kk++) {
+        const int k = kdeb + kk;
+        for (int cc = 0; cc < nc; cc++) {
+            const long g = (long)kk * nc + cc;
+            if (rank > 0) lu_wait(plo + rank - 1, g + 1);
+            const int ia = ideb + cc * FO_LU_CHUNK, ib = ia + FO_LU_CHUNK - 1 < ifin ? ia + FO_LU_CHUNK - 1 : ifin;
+            for (int j = j0; j <= j1; j++) for (int i = ia; i <= ib; i++) lu_lower_cell(&c, box, overlap, drodm, i, j, k);
+            __atomic_store_n(plo + rank, g + 1, __ATOMIC_RELEASE);
+        }
+    }
+    int nb[6];
+    for (int q = 0; q < 6; q++) nb[q] = box[q];
+    if (overlap) { nb[0] = 1; nb[1] = pi[FO_IJKV]; nb[2] = 1; nb[3] = pi[FO_IJKV + 1]; nb[4] = 1; nb[5] = pi[FO_IJKV + 2]; }
+    for (int kk = 0; kk < nk; kk++) {
+        const int k = kfin - kk;
+        for (int cc = 0; cc < nc; cc++) {
+            const long g = (long)kk * nc + cc;
+            if (rank < nper - 1) lu_wait(pup + rank + 1, g + 1);
+            const int ib = ifin - cc * FO_LU_CHUNK, ia = ib - FO_LU_CHUNK + 1 > ideb ? ib - FO_LU_CHUNK + 1 : ideb;
+            for (int j = j1; j >= j0; j--) for (int i = ib; i >= ia; i--) lu_upper_cell(&c, box, overlap, drodm, i, j, k);
+            __atomic_store_n(pup + rank, g + 1, __ATOMIC_RELEASE);
+        }
+        if (rank > 0) lu_wait(pup + rank - 1, (long)(kk + 1) * nc);     /* the slab below has read this plane's old state */
+        if (k >= nb[4] && k <= nb[5]) {
+            const int ja = j0 > nb[2] ? j0 : nb[2], jb = j1 < nb[3] ? j1 : nb[3];
+            for (int j = ja; j <= jb; j++) for (int i = nb[0]; i <= nb[1]; i++)
+                mjr_newton(pi, pr, fo_inddm(pi, i, j, k), rop, rop_out, drodm);
+        }
     }
 }
 
@@ -396,12 +483,7 @@ double fo_lu_residual(const int *pi, const double *pr, const int box[6], const d
                       const double *coe, const double *ti, const double *tj, const double *tk)
 {
     luctx c;
-    c.pi = pi; c.rop = rop; c.coe = coe; c.t[0] = ti; c.t[1] = tj; c.t[2] = tk;
-    c.inc[0] = 1; c.inc[1] = pi[FO_NIJK]; c.inc[2] = pi[FO_NIJK] * pi[FO_NIJK + 1];
-    c.incm[0] = pi[FO_NIJK_MTR]; c.incm[1] = pi[FO_NIJK_MTR + 1]; c.incm[2] = pi[FO_NIJK_MTR + 2];
-    c.nd = pi[FO_NDIMDX]; c.nm = pi[FO_NDIMDX_MTR]; c.typ = pi[FO_ITYPZONE]; c.neq = pi[FO_NEQ];
-    c.gam1 = pr[FO_GAMMA]; c.gamm1 = c.gam1 - 1.; c.cp = pr[FO_GAMMA] * pr[FO_CVINF]; c.gam2 = c.gamm1 - 1.;
-    c.tc0[0] = ti[0]; c.tc0[1] = tj[0]; c.tc0[2] = tk[0];
+    lu_ctx_init(&c, pi, pr, rop, coe, ti, tj, tk);
     const int nd = c.nd, neq = c.neq;
     double worst = 0., b[6];
     for (int k = box[4]; k <= box[5]; k++) for (int j = box[2]; j <= box[3]; j++) for (int i = box[0]; i <= box[1]; i++) {

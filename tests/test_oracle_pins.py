@@ -59,23 +59,31 @@ def test_rk2_is_heun_and_lands_in_density():
     assert dist_from_stage1 > 1e3 * err          # ... and it is not the forward-Euler intermediate
 
 
-@pytest.mark.parametrize('case', ['tgv', 'plate_blocks', 'multiblock', 'lamin_plate_homo'])
+@pytest.mark.parametrize('case', ['tgv', 'plate_blocks', 'multiblock', 'lamin_plate_homo', 'plate_full', 'plate_blocks_lumatch', 'plate_ssor'])
 def test_threaded_oracle_is_bit_identical(case):
-    """The thread decomposition of the oracle (k slabs for the rhs, one zone per thread for the LU) used by the full-size GPU
-    parity tests and the timed CPU baseline must not change a single bit of the result."""
+    """The thread decompositions of the oracle -- k slabs for the rhs; for the LU one zone per thread (full-size GPU parity tests)
+    or teams of threads per zone running a (j slab, i chunk) wavefront (timed CPU baseline) -- must not change a single bit."""
     def mk():
         if case == 'tgv': return synth.case_tgv(n=20, perturb=1e-3), None
         if case == 'plate_blocks': return synth.case_flatplate(n=(48, 32, 32), nblocks=(2, 1, 1))
         if case == 'lamin_plate_homo': return synth.case_flatplate(n=(40, 20, 20), model='NSLaminar', ReInf=2.e4)   # 5 equations on 3dhomo metrics
+        if case == 'plate_full': return synth.case_flatplate(n=(70, 20, 12), sheared=True)          # 3dfull SA, several i chunks
+        if case == 'plate_blocks_lumatch': return synth.case_flatplate(n=(24, 16, 8), nblocks=(2, 2, 2), lu_match=1)
+        if case == 'plate_ssor': return synth.case_flatplate(n=(24, 16, 6), nb_relax=2)              # relaxations stay serial
         return synth.case_multiblock(nblk=(2, 1, 2), n=10)
     res = []
-    for nth in (1, 8):
+    for nth, team in ((1, 0), (8, 0), (8, 1), (5, 1)):
         t, j = mk()
         o = oracle_from_tree(t, joins=j)
         nss = int(o.zones[0].pi[V.NSSITER])
-        for it in (1, 2): o.compute(it, 1, nss, 1, nthreads=nth)
+        o.L.fo_set_lu_team(team)       # 1: the threads left over after one per zone sweep the zones in teams (fo_invlu_team)
+        try:
+            for it in (1, 2): o.compute(it, 1, nss, 1, nthreads=nth)
+        finally:
+            o.L.fo_set_lu_team(0)
         res.append([z.lev[0].copy() for z in o.zones])
-    for a, b in zip(*res): assert numpy.array_equal(a, b)
+    for r in res[1:]:
+        for a, b in zip(res[0], r): assert numpy.array_equal(a, b)
 
 
 def test_conservation_periodic():
